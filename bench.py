@@ -1,0 +1,327 @@
+"""Headline benchmark: safeguarded env-steps/s (forward + backward) of the SHAC rollout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--env ...] [--safeguard ...]
+
+One "step" = one SHAC episode pass over the batch: buffer.reset, collect_trajectories (H safeguarded
+environment steps for every environment, policy + target critic inside) and update_policy (loss,
+backward through the whole horizon, clip, Adam) -- src/learning_algorithms/shac.py:87-90,96-151 of the
+reference; the critic fit is excluded.  Workload at N=1: BASELINE.json configs[1],
+BalanceCartPole + boundary projection, 4096 environments, H = 64, policy [128,128], critic [128,128,128].
+Multi-GPU: environments are sharded (4096 per rank, weak scaling); the only collective is the NCCL
+all-reduce of the policy gradients (+ 4 scalars).
+Prints ONE JSON line (see the contract in the task statement / DESIGN.md §Measurement).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+ENV_DEFAULT, SG_DEFAULT = "BalanceCartPole", "boundary_projection"
+N_PER_GPU, HORIZON = 4096, 64
+POLICY_ARCH, VF_ARCH = [128, 128], [128, 128, 128]
+ALG_BYTES = {"BalancePendulum": 105, "BalanceCartPole": 177, "SwingUpCartPole": 177, "BalanceQuadrotor": 273,
+             "ManageHousehold": 309, "NavigateSeeker": 193}     # 4(7n+4m+2o+2)+1, fp32
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--env", default=ENV_DEFAULT)
+    p.add_argument("--safeguard", default=SG_DEFAULT, choices=["none", "boundary_projection", "ray_mask"])
+    p.add_argument("--num-envs", type=int, default=N_PER_GPU, help="environments per GPU")
+    p.add_argument("--horizon", type=int, default=HORIZON)
+    p.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    p.add_argument("--fused", default="auto", choices=["auto", "on", "off"])
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path on the host cores
+# ------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    env_name, sg_kind, n_envs, horizon, episodes, seed = args
+    import torch
+    torch.set_num_threads(1)
+    from oracle.dynamics import OracleEnv
+    from oracle.safeguard import OracleSafeguard
+    from oracle import shac as oshac
+    torch.manual_seed(seed)
+    env = OracleEnv(env_name, n_envs, 240)
+    env.reset(seed=seed)
+    # start inside the feasible box so the bounded sample does not hit infeasible programs
+    env.state = env.state_center + (torch.rand(n_envs, env.state_dim, dtype=torch.float64) * 2 - 1) * env.state_half * 0.5
+    step_fn = env
+    if sg_kind != "none":
+        step_fn = OracleSafeguard(env, sg_kind, gate="reference", strict=False)
+    obs_dim = env.observation().shape[1]
+    pol = oshac.OraclePolicy(obs_dim, env.action_dim, POLICY_ARCH).double()
+    vf = oshac.OracleValue(obs_dim, VF_ARCH).double()
+    opt = torch.optim.Adam(pol.parameters(), lr=4e-4)
+
+    def env_step(action, t):
+        obs, rew, term, trunc = step_fn.step(action)
+        return obs, rew, term | trunc
+
+    t0 = time.perf_counter()
+    for _ in range(episodes):
+        env.cut_computation_graph()
+        opt.zero_grad()
+        eps = torch.randn(horizon, n_envs, env.action_dim, dtype=torch.float64)
+        out = oshac.rollout_loss(env_step, env.observation(), pol, vf, horizon, eps)
+        out["loss"].backward()
+        torch.nn.utils.clip_grad_norm_(pol.parameters(), 1.0)
+        opt.step()
+    return time.perf_counter() - t0
+
+
+def cpu_port_throughput(env_name, sg_kind, n_envs_per_worker, horizon, episodes, workers):
+    """env-steps/s of the oracle port with `workers` processes, each owning its own environment shard."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    jobs = [(env_name, sg_kind, n_envs_per_worker, horizon, episodes, 100 + i) for i in range(workers)]
+    t0 = time.perf_counter()
+    with ctx.Pool(workers) as pool:
+        pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    return workers * n_envs_per_worker * horizon * episodes / wall, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 64))
+    n_w = 8
+    results = []
+    for _ in range(max(1, min(args.steps, 3))):
+        v, wall = cpu_port_throughput(args.env, args.safeguard, n_w, args.horizon, 1, workers)
+        results.append((v, wall))
+    v = sorted(r[0] for r in results)[len(results) // 2]
+    line = {
+        "impl": "reference", "metric": "safeguarded env-steps/s (fwd+bwd)", "value": v, "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": len(results), "warmup": 0, "ms_per_step": 1e3 * results[-1][1],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": workers, "kind": "port",
+                         "sample": f"{workers} processes x {n_w} envs x H={args.horizon} x 1 episode of the same workload "
+                                   "(oracle port of the reference path: per-env HiGHS solves + torch autograd, float64)"},
+        "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, world):
+    return {"workload": f"{args.env}+{args.safeguard}, {args.num_envs} envs/GPU x {world} GPU, H={args.horizon}, "
+                        f"policy {POLICY_ARCH}, critic {VF_ARCH}, SHAC collect_trajectories+update_policy",
+            "env": args.env, "safeguard": args.safeguard, "num_envs_per_gpu": args.num_envs, "horizon": args.horizon,
+            "gate": "reference (Q1 as shipped)", "l2_policy": "working set per episode > L2 not guaranteed; "
+            "a 256 MiB buffer is written between timed episodes to flush L2"}
+
+
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for name, val in zip(names, out[2:]):
+                    if "Active" in val and "Not" not in val:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from safegbpo_b200 import _lib
+    from safegbpo_b200.envs import balance_cartpole, balance_pendulum, swingup_cartpole, balance_quadrotor, manage_household
+    from safegbpo_b200.safeguards.boundary_projection import BoundaryProjectionSafeguard
+    from safegbpo_b200.safeguards.ray_mask import RayMaskSafeguard
+    from safegbpo_b200.learning_algorithms.shac import SHAC
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.float32 if args.dtype == "f32" else torch.float64
+    torch.set_default_dtype(dtype)
+    torch.set_default_device(dev)
+    torch.manual_seed(1234 + rank)
+    env_cls = {"BalanceCartPole": balance_cartpole.BalanceCartPoleEnv, "BalancePendulum": balance_pendulum.BalancePendulumEnv,
+               "SwingUpCartPole": swingup_cartpole.SwingUpCartPoleEnv, "BalanceQuadrotor": balance_quadrotor.BalanceQuadrotorEnv,
+               "ManageHousehold": manage_household.ManageHouseholdEnv}[args.env]
+    N, H = args.num_envs, args.horizon
+    env = env_cls(num_envs=N, num_steps=240)
+    if args.safeguard == "boundary_projection":
+        env = BoundaryProjectionSafeguard(env, strict=False)
+    elif args.safeguard == "ray_mask":
+        env = RayMaskSafeguard(env, linear_projection=True, zonotopic_approximation=True, passthrough=False, strict=False)
+    algo = SHAC(env=env, policy_kwargs={"net_arch": POLICY_ARCH}, policy_optim_kwargs={"lr": 4e-4},
+                vf_kwargs={"net_arch": VF_ARCH}, vf_optim_kwargs={"lr": 2e-3}, regularisation_coefficient=0.1,
+                len_trajectories=H, fused=args.fused)
+    if world > 1:      # replicated networks: broadcast rank 0's parameters; gradients are summed over ranks
+        from safegbpo_b200 import distributed as sgdist
+        sgdist.broadcast_parameters(algo)
+        algo.grad_sync = sgdist.allreduce_policy_grads
+    base = env.env if hasattr(env, "env") else env
+    n = base.state_dim
+    # synthetic batched initial states, pinned on the host (e2e leg copies them in every step)
+    gen = torch.Generator(device="cpu").manual_seed(99 + rank)
+    half = base.state_set.generator[0].diagonal().cpu()
+    ctr = base.state_set.center[0].cpu()
+    s0_host = (ctr + (torch.rand(N, n, generator=gen, device="cpu", dtype=dtype) * 2 - 1) * half * 0.9).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    launches = {"n": 0}
+
+    def episode(from_host: bool):
+        if from_host:
+            base.state = s0_host.to(dev, non_blocking=True)
+            base.steps, base._reset_pending = 0, False
+        algo.buffer.reset()
+        algo.policy_optim.zero_grad()
+        avg_reward = algo.collect_trajectories()
+        loss = algo.update_policy()
+        return loss, avg_reward
+
+    def timed(k, from_host):
+        times = []
+        for _ in range(k):
+            flush.fill_(1.0)                          # L2 flush between timed iterations
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            episode(from_host)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        return times
+
+    base.state = s0_host.to(dev)
+    base.steps, base._reset_pending = 0, False
+    o0 = base.observation
+    algo.buffer.reset(o0, algo.target_value_function(o0).squeeze(1))
+    for _ in range(max(3, args.warmup)):
+        episode(False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    t_dev = timed(args.steps, False)
+    t_e2e = timed(args.steps, True)
+    sampler.stop_flag = True
+    total_ms = sum(t_dev)
+    if world > 1:
+        t = torch.tensor([total_ms, sum(t_e2e)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = float(t[0]), float(t[1])
+    else:
+        e2e_ms = sum(t_e2e)
+    env_steps = N * H * args.steps * world
+    value = env_steps / (total_ms * 1e-3)
+    e2e_value = env_steps / (e2e_ms * 1e-3)
+    engine = algo._fused_engine
+    roof = engine.roofline(args) if engine is not None and hasattr(engine, "roofline") else step_kernel_roofline(args, base, env, dev, dtype)
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except Exception:
+            pass
+        line = {
+            "metric": "safeguarded env-steps/s (fwd+bwd)", "value": value, "unit": "env-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": workload_config(args, world),
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(s0_host.numel() * s0_host.element_size()),
+                    "d2h_bytes_per_step": 2 * (4 if dtype == torch.float32 else 8)},
+            "gpu_launches": roof.pop("launches_per_step", None),
+            "roofline": roof, "clocks": sampler.summary(),
+            "mode": "fused" if engine is not None else "eager (per-step fused safeguard+simulator kernel, torch MLP)",
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            workers = max(1, min(cores, 64))
+            v, wall = cpu_port_throughput(args.env, args.safeguard, 8, H, 1, workers)
+            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": workers, "kind": "port",
+                                    "sample": f"{workers} processes x 8 envs x H={H} x 1 episode ({wall:.1f} s wall), oracle port, float64"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def step_kernel_roofline(args, base, env, dev, dtype):
+    """Roofline of the per-step safeguard+simulator kernels (fwd + bwd) measured live with CUDA events."""
+    import torch
+    from safegbpo_b200 import ops
+    N = args.num_envs
+    consts = env.consts() if hasattr(env, "consts") else base._plain
+    s = base.state.detach().clone().requires_grad_(True)
+    a = (torch.rand(N, base.action_dim) * 2 - 1).requires_grad_(True)
+    w = torch.zeros_like(s)
+    reps = 50
+    g = [torch.ones(N, base.state_dim), torch.ones(N, base.action_dim), torch.ones(N, base.obs_dim), torch.ones(N)]
+    for _ in range(5):
+        out = ops.safeguarded_step(s, a, w, base.env_id, consts, aux=base._aux(), shared=base._shared())
+        torch.autograd.backward(out[:4], g)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = ops.safeguarded_step(s, a, w, base.env_id, consts, aux=base._aux(), shared=base._shared())
+        torch.autograd.backward(out[:4], g)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    bytes_alg = ALG_BYTES[args.env] * (1 if dtype == torch.float32 else 2) * N
+    achieved = bytes_alg / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "kernel": "step_fwd_kernel+step_bwd_kernel (one launch pair per env step; event time includes torch launch gaps)",
+            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+            "launches_per_step": 2 * args.horizon}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -24,12 +24,14 @@ class OracleSafeguard:
     """safeguard.py:21-80.  ``kind``: "boundary_projection" | "ray_mask"."""
 
     def __init__(self, env: OracleEnv, kind: str = "boundary_projection", linear_projection: bool = True,
-                 zonotopic_approximation: bool = True, passthrough: bool = False, gate: str = "reference"):
+                 zonotopic_approximation: bool = True, passthrough: bool = False, gate: str = "reference",
+                 strict: bool = True):
         self.env, self.kind = env, kind
         self.linear_projection = linear_projection
         self.zonotopic = zonotopic_approximation
         self.passthrough = passthrough
         self.gate = gate                    # "reference" (Q1 as shipped) | "intended" | "always"
+        self.strict = strict                # False: keep NaN rows of infeasible programs instead of raising
         self.m, self.n, self.N = env.action_dim, env.state_dim, env.num_envs
         # safeguard.py:54 -- linearised ONCE at construction; env 0's noise/action matrices are baked in (Q4)
         const, _, b_mat, e_mat = env.linear_dynamics()
@@ -65,7 +67,7 @@ class OracleSafeguard:
         else:
             guarded = self.safeguard(action, directions)
             safe_action = self._gate(projectable, action, guarded)
-        if safe_action.isnan().any() or safe_action.isinf().any():
+        if self.strict and (safe_action.isnan().any() or safe_action.isinf().any()):
             raise ValueError("Safe action are NaN.")
         self.safe_action = safe_action
         differs = ~torch.isclose(safe_action, action)
@@ -186,7 +188,9 @@ class OracleSafeguard:
         start = self.boundary_projection(action)
         action_dist = torch.linalg.vector_norm(start - action, dim=1, ord=2, keepdim=True)
         safe = action_dist < 1e-8
-        dirs = (start - action) / action_dist
+        # the reference divides by action_dist itself (ray_mask.py:329); with an exact P1 the distance of an
+        # already-safe action is exactly 0 and 0/0 would poison the gradient, so the masked rows divide by 1
+        dirs = (start - action) / torch.where(safe, torch.ones_like(action_dist), action_dist)
         dist = []
         for i in range(self.N):
             if bool(safe[i]) or self.infeasible[i]:

@@ -1,0 +1,276 @@
+// Per-step kernels + C ABI (include/sgbpo.h).  One thread per environment: n <= 6 states, m <= 2
+// actions, all per-env matrices (B, G_s^-1 rows, duals) live in registers; global traffic is exactly
+// the (N, n)/(N, m)/(N, o) rows, read/written as contiguous per-warp spans.  sm_100a only.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/sgbpo.h"
+#include "sgbpo_step.cuh"
+
+namespace sgbpo {
+
+thread_local char g_err[512] = "";
+static int fail(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+  return SGBPO_E_CUDA;
+}
+
+template <class T> SafeConsts<T> convert_consts(const sgbpo_consts& c) {
+  SafeConsts<T> k;
+  memset(&k, 0, sizeof(k));
+  k.sg_kind = c.sg_kind; k.gate_mode = c.gate_mode;
+  k.rm_linear = c.rm_linear; k.rm_zonotopic = c.rm_zonotopic; k.rm_passthrough = c.rm_passthrough;
+  k.action_constrained = c.action_constrained; k.state_constrained = c.state_constrained;
+  k.state_model = c.state_model; k.disable_clamp = c.disable_clamp;
+  for (int i = 0; i < MAXN; ++i) {
+    k.box_min[i] = T(c.box_min[i]); k.box_max[i] = T(c.box_max[i]); k.noise_center[i] = T(c.noise_center[i]);
+    k.cs_hat[i] = T(c.cs_hat[i]); k.rb[i] = T(c.rb[i]); k.c_s[i] = T(c.c_s[i]);
+  }
+  for (int i = 0; i < MAXN * MAXN; ++i) k.Ginv[i] = T(c.Ginv[i]);
+  for (int i = 0; i < MAXN * MAXM; ++i) k.B0hat_abs[i] = T(c.B0hat_abs[i]);
+  for (int i = 0; i < MAXM; ++i) { k.a_lo[i] = T(c.a_lo[i]); k.a_hi[i] = T(c.a_hi[i]); k.c_a[i] = T(c.c_a[i]); }
+  k.n_act_hp = c.n_act_hp; k.n_k_hp = c.n_k_hp; k.n_q_hp = c.n_q_hp;
+  for (int r = 0; r < MAXHP; ++r) {
+    for (int j = 0; j < 3; ++j) { k.act_hp[r][j] = T(c.act_hp[r][j]); k.q_hp[r][j] = T(c.q_hp[r][j]); }
+    for (int j = 0; j < 2; ++j) k.k_hp[r][j] = T(c.k_hp[r][j]);
+  }
+  return k;
+}
+
+template <class T> StepShared<T> convert_shared(const sgbpo_step_shared* s) {
+  StepShared<T> o;
+  memset(&o, 0, sizeof(o));
+  if (s) {
+    for (int i = 0; i < 20; ++i) o.series[i] = T(s->series[i]);
+    o.load_t = T(s->load_t); o.pv_t = T(s->pv_t); o.price_t = T(s->price_t);
+  }
+  return o;
+}
+
+template <int ROW, class T> __device__ __forceinline__ void load_row(const T* __restrict__ base, int64_t i, T* dst) {
+#pragma unroll
+  for (int q = 0; q < ROW; ++q) dst[q] = base[i * ROW + q];
+}
+
+// ---- forward ------------------------------------------------------------------------------------
+template <int ENV, class T>
+__global__ void __launch_bounds__(128)
+step_fwd_kernel(int64_t N, const __grid_constant__ SafeConsts<T> k, const __grid_constant__ StepShared<T> sh,
+                const T* __restrict__ s, const T* __restrict__ a, const T* __restrict__ w,
+                const T* __restrict__ aux, const T* __restrict__ dirs, const T* __restrict__ reset_state,
+                T* __restrict__ s_next, T* __restrict__ a_exec, T* __restrict__ obs, T* __restrict__ reward,
+                int32_t* __restrict__ flags) {
+  using TASK = Task<ENV>;
+  constexpr int NS = TASK::NS, NA = TASK::NA, NO = TASK::NO, NAUX = TASK::NAUX;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    T sv[NS], av[NA], wv[NS], auxv[NAUX > 0 ? NAUX : 1], dv[NA * 2 * NA], rs[NS];
+    load_row<NS>(s, i, sv);
+    load_row<NA>(a, i, av);
+    load_row<NS>(w, i, wv);
+    if (NAUX > 0) load_row<(NAUX > 0 ? NAUX : 1)>(aux, i, auxv);
+    if (dirs) load_row<NA * 2 * NA>(dirs, i, dv);
+    if (reset_state) load_row<NS>(reset_state, i, rs);
+    T sn[NS], ae[NA], ob[NO], rew;
+    int fl;
+    safeguarded_step<TASK, T, T>(sv, av, wv, auxv, dirs ? dv : nullptr, &sh, k, reset_state != nullptr, rs, sn, ae,
+                                 ob, rew, fl);
+#pragma unroll
+    for (int q = 0; q < NS; ++q) s_next[i * NS + q] = sn[q];
+#pragma unroll
+    for (int q = 0; q < NA; ++q) a_exec[i * NA + q] = ae[q];
+#pragma unroll
+    for (int q = 0; q < NO; ++q) obs[i * NO + q] = ob[q];
+    reward[i] = rew;
+    flags[i] = fl;
+  }
+}
+
+// ---- backward: recompute with duals seeded on (s, a), contract with the cotangents -----------------
+template <int ENV, class T>
+__global__ void __launch_bounds__(128)
+step_bwd_kernel(int64_t N, const __grid_constant__ SafeConsts<T> k, const __grid_constant__ StepShared<T> sh,
+                const T* __restrict__ s, const T* __restrict__ a, const T* __restrict__ w,
+                const T* __restrict__ aux, const T* __restrict__ dirs, const T* __restrict__ reset_state,
+                const T* __restrict__ g_s_next, const T* __restrict__ g_a_exec, const T* __restrict__ g_obs,
+                const T* __restrict__ g_reward, T* __restrict__ gs, T* __restrict__ ga) {
+  using TASK = Task<ENV>;
+  constexpr int NS = TASK::NS, NA = TASK::NA, NO = TASK::NO, NAUX = TASK::NAUX, K = NS + NA;
+  using D = Dual<T, K>;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    T sv[NS], av[NA], wv[NS], auxv[NAUX > 0 ? NAUX : 1], dv[NA * 2 * NA], rs[NS];
+    load_row<NS>(s, i, sv);
+    load_row<NA>(a, i, av);
+    load_row<NS>(w, i, wv);
+    if (NAUX > 0) load_row<(NAUX > 0 ? NAUX : 1)>(aux, i, auxv);
+    if (dirs) load_row<NA * 2 * NA>(dirs, i, dv);
+    if (reset_state) load_row<NS>(reset_state, i, rs);
+    D sd[NS], ad[NA], sn[NS], ae[NA], ob[NO], rew;
+#pragma unroll
+    for (int q = 0; q < NS; ++q) sd[q] = D::seed(sv[q], q);
+#pragma unroll
+    for (int q = 0; q < NA; ++q) ad[q] = D::seed(av[q], NS + q);
+    int fl;
+    safeguarded_step<TASK, D, T>(sd, ad, wv, auxv, dirs ? dv : nullptr, &sh, k, reset_state != nullptr, rs, sn, ae,
+                                 ob, rew, fl);
+    T acc[K];
+#pragma unroll
+    for (int d = 0; d < K; ++d) acc[d] = T(0);
+    if (g_s_next) {
+#pragma unroll
+      for (int q = 0; q < NS; ++q) {
+        const T g = g_s_next[i * NS + q];
+#pragma unroll
+        for (int d = 0; d < K; ++d) acc[d] += g * sn[q].d[d];
+      }
+    }
+    if (g_a_exec) {
+#pragma unroll
+      for (int q = 0; q < NA; ++q) {
+        const T g = g_a_exec[i * NA + q];
+#pragma unroll
+        for (int d = 0; d < K; ++d) acc[d] += g * ae[q].d[d];
+      }
+    }
+    if (g_obs) {
+#pragma unroll
+      for (int q = 0; q < NO; ++q) {
+        const T g = g_obs[i * NO + q];
+#pragma unroll
+        for (int d = 0; d < K; ++d) acc[d] += g * ob[q].d[d];
+      }
+    }
+    if (g_reward) {
+      const T g = g_reward[i];
+#pragma unroll
+      for (int d = 0; d < K; ++d) acc[d] += g * rew.d[d];
+    }
+#pragma unroll
+    for (int q = 0; q < NS; ++q) gs[i * NS + q] = acc[q];
+#pragma unroll
+    for (int q = 0; q < NA; ++q) ga[i * NA + q] = acc[NS + q];
+  }
+}
+
+template <int ENV, class T>
+__global__ void __launch_bounds__(128)
+linearise_kernel(int64_t N, const __grid_constant__ SafeConsts<T> k, const T* __restrict__ s, T* __restrict__ c,
+                 T* __restrict__ A, T* __restrict__ B, T* __restrict__ E) {
+  using TASK = Task<ENV>;
+  constexpr int NS = TASK::NS, NA = TASK::NA;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    T sv[NS], cv[NS], Av[NS * NS], Bv[NS * NA], Ev[NS * NS];
+    load_row<NS>(s, i, sv);
+    linearise_full<TASK, T, T>(sv, k.noise_center, cv, Av, Bv, Ev);
+#pragma unroll
+    for (int q = 0; q < NS; ++q) c[i * NS + q] = cv[q];
+#pragma unroll
+    for (int q = 0; q < NS * NS; ++q) { A[i * NS * NS + q] = Av[q]; E[i * NS * NS + q] = Ev[q]; }
+#pragma unroll
+    for (int q = 0; q < NS * NA; ++q) B[i * NS * NA + q] = Bv[q];
+  }
+}
+
+static int grid_for(int64_t N, int block) {
+  int64_t g = (N + block - 1) / block;
+  const int64_t cap = 148 * 16;      // grid-stride above 16 CTAs per SM
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+template <int ENV, class T> struct Launch {
+  static int fwd(int64_t N, const sgbpo_consts* c, const sgbpo_step_shared* shp, const void* s, const void* a,
+                 const void* w, const void* aux, const void* dirs, const void* reset_state, void* s_next,
+                 void* a_exec, void* obs, void* reward, int32_t* flags, cudaStream_t st) {
+    const SafeConsts<T> k = convert_consts<T>(*c);
+    const StepShared<T> sh = convert_shared<T>(shp);
+    step_fwd_kernel<ENV, T><<<grid_for(N, 128), 128, 0, st>>>(
+        N, k, sh, (const T*)s, (const T*)a, (const T*)w, (const T*)aux, (const T*)dirs, (const T*)reset_state,
+        (T*)s_next, (T*)a_exec, (T*)obs, (T*)reward, flags);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SGBPO_OK : cuda_fail(e, "step_fwd_kernel");
+  }
+  static int bwd(int64_t N, const sgbpo_consts* c, const sgbpo_step_shared* shp, const void* s, const void* a,
+                 const void* w, const void* aux, const void* dirs, const void* reset_state, const void* g_s_next,
+                 const void* g_a_exec, const void* g_obs, const void* g_reward, void* gs, void* ga, cudaStream_t st) {
+    const SafeConsts<T> k = convert_consts<T>(*c);
+    const StepShared<T> sh = convert_shared<T>(shp);
+    step_bwd_kernel<ENV, T><<<grid_for(N, 128), 128, 0, st>>>(
+        N, k, sh, (const T*)s, (const T*)a, (const T*)w, (const T*)aux, (const T*)dirs, (const T*)reset_state,
+        (const T*)g_s_next, (const T*)g_a_exec, (const T*)g_obs, (const T*)g_reward, (T*)gs, (T*)ga);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SGBPO_OK : cuda_fail(e, "step_bwd_kernel");
+  }
+  static int lin(int64_t N, const sgbpo_consts* c, const void* s, void* cc, void* A, void* B, void* E, cudaStream_t st) {
+    const SafeConsts<T> k = convert_consts<T>(*c);
+    linearise_kernel<ENV, T><<<grid_for(N, 128), 128, 0, st>>>(N, k, (const T*)s, (T*)cc, (T*)A, (T*)B, (T*)E);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SGBPO_OK : cuda_fail(e, "linearise_kernel");
+  }
+};
+
+#define SGBPO_DISPATCH(CALL)                                                                     \
+  switch (env_id) {                                                                              \
+    case ENV_BALANCE_PENDULUM: return dtype ? Launch<ENV_BALANCE_PENDULUM, double>::CALL : Launch<ENV_BALANCE_PENDULUM, float>::CALL; \
+    case ENV_BALANCE_CARTPOLE: return dtype ? Launch<ENV_BALANCE_CARTPOLE, double>::CALL : Launch<ENV_BALANCE_CARTPOLE, float>::CALL; \
+    case ENV_SWINGUP_CARTPOLE: return dtype ? Launch<ENV_SWINGUP_CARTPOLE, double>::CALL : Launch<ENV_SWINGUP_CARTPOLE, float>::CALL; \
+    case ENV_BALANCE_QUADROTOR: return dtype ? Launch<ENV_BALANCE_QUADROTOR, double>::CALL : Launch<ENV_BALANCE_QUADROTOR, float>::CALL; \
+    case ENV_MANAGE_HOUSEHOLD: return dtype ? Launch<ENV_MANAGE_HOUSEHOLD, double>::CALL : Launch<ENV_MANAGE_HOUSEHOLD, float>::CALL; \
+    case ENV_NAVIGATE_SEEKER: return dtype ? Launch<ENV_NAVIGATE_SEEKER, double>::CALL : Launch<ENV_NAVIGATE_SEEKER, float>::CALL; \
+    default: return fail(SGBPO_E_ARG, "unknown env_id");                                         \
+  }
+
+}  // namespace sgbpo
+
+using namespace sgbpo;
+
+extern "C" {
+
+const char* sgbpo_version(void) { return "safegbpo-b200 0.1 (sm_100a)"; }
+const char* sgbpo_last_error(void) { return g_err; }
+
+int sgbpo_env_dims(int env_id, int* n, int* m, int* o, int* naux) {
+#define DIMS(E) case E: *n = Task<E>::NS; *m = Task<E>::NA; *o = Task<E>::NO; *naux = Task<E>::NAUX; return SGBPO_OK;
+  switch (env_id) {
+    DIMS(ENV_BALANCE_PENDULUM) DIMS(ENV_BALANCE_CARTPOLE) DIMS(ENV_SWINGUP_CARTPOLE)
+    DIMS(ENV_BALANCE_QUADROTOR) DIMS(ENV_MANAGE_HOUSEHOLD) DIMS(ENV_NAVIGATE_SEEKER)
+    default: return fail(SGBPO_E_ARG, "unknown env_id");
+  }
+#undef DIMS
+}
+
+int sgbpo_step_fwd(int env_id, int dtype, int64_t N, const sgbpo_consts* consts, const sgbpo_step_shared* shared,
+                   const void* s, const void* a, const void* w, const void* aux, const void* dirs,
+                   const void* reset_state, void* s_next, void* a_exec, void* obs, void* reward,
+                   int32_t* flags, void* stream) {
+  if (!consts || !s || !a || !w || !s_next || !a_exec || !obs || !reward || !flags || N < 0)
+    return fail(SGBPO_E_ARG, "sgbpo_step_fwd: null pointer or negative N");
+  if (N == 0) return SGBPO_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  SGBPO_DISPATCH(fwd(N, consts, shared, s, a, w, aux, dirs, reset_state, s_next, a_exec, obs, reward, flags, st))
+}
+
+int sgbpo_step_bwd(int env_id, int dtype, int64_t N, const sgbpo_consts* consts, const sgbpo_step_shared* shared,
+                   const void* s, const void* a, const void* w, const void* aux, const void* dirs,
+                   const void* reset_state, const void* g_s_next, const void* g_a_exec, const void* g_obs,
+                   const void* g_reward, void* gs, void* ga, void* stream) {
+  if (!consts || !s || !a || !w || !gs || !ga || N < 0) return fail(SGBPO_E_ARG, "sgbpo_step_bwd: null pointer or negative N");
+  if (N == 0) return SGBPO_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  SGBPO_DISPATCH(bwd(N, consts, shared, s, a, w, aux, dirs, reset_state, g_s_next, g_a_exec, g_obs, g_reward, gs, ga, st))
+}
+
+int sgbpo_linearise(int env_id, int dtype, int64_t N, const sgbpo_consts* consts, const void* s, void* c, void* A,
+                    void* B, void* E, void* stream) {
+  if (!consts || !s || !c || !A || !B || !E || N < 0) return fail(SGBPO_E_ARG, "sgbpo_linearise: null pointer or negative N");
+  if (N == 0) return SGBPO_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  SGBPO_DISPATCH(lin(N, consts, s, c, A, B, E, st))
+}
+
+}  // extern "C"

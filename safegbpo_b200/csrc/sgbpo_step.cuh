@@ -1,0 +1,90 @@
+// One safeguarded environment step for ONE environment, scalar-generic:
+//   Safeguard.actions (safeguards/interfaces/safeguard.py:61-80)  ->  Simulator.step
+//   (envs/simulators/interfaces/simulator.py:82-108): linearise, gate, safeguard map, execute action
+//   (dynamics + clamp), reset-all substitution (Q6), observation, reward.
+#pragma once
+#include "sgbpo_safeguard.cuh"
+#include "sgbpo_safeguard2.cuh"
+
+namespace sgbpo {
+
+template <class T> SG_HD bool is_close(T a, T b) {   // torch.isclose defaults: rtol 1e-5, atol 1e-8
+  return sg_abs(a - b) <= T(1e-8) + T(1e-5) * sg_abs(b);
+}
+template <class T> SG_HD bool finite_val(T x) { return (x - x) == T(0); }
+
+template <class TASK, class S, class T>
+SG_HD void safeguarded_step(const S* s, const S* a, const T* w, const T* aux, const T* dirs,
+                            const StepShared<T>* sh, const SafeConsts<T>& k, bool reset_now,
+                            const T* reset_state, S* s_next, S* a_exec, S* obs, S& reward, int& flags) {
+  constexpr int NS = TASK::NS, NA = TASK::NA;
+  flags = 0;
+#pragma unroll
+  for (int q = 0; q < NA; ++q) a_exec[q] = a[q];
+  if (k.sg_kind != SG_NONE) {
+    S c_f[NS];
+    S B[NS][MAXM];
+    linearise_cB<TASK>(s, k.noise_center, c_f, B);
+    T cfp[NS];
+    T Bp[NS][MAXM];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      cfp[i] = primal(c_f[i]);
+#pragma unroll
+      for (int q = 0; q < NA; ++q) Bp[i][q] = primal(B[i][q]);
+    }
+    const bool projectable = gate_projectable<TASK>(cfp, Bp, k);
+    S g[NA];
+    bool feasible;
+    if constexpr (NA == 1) feasible = safeguard_m1<TASK>(a[0], c_f, B, k, g[0]);
+    else feasible = safeguard_m2<TASK>(a, c_f, B, dirs, k, g);
+    const bool use_guard = k.gate_mode == GATE_REFERENCE ? !projectable
+                                                         : (k.gate_mode == GATE_INTENDED ? projectable : true);
+    if (projectable) flags |= FL_PROJECTABLE;
+    if (use_guard) {
+      flags |= FL_GUARD_USED;
+      if (!feasible) flags |= FL_INFEASIBLE;
+      const bool straight_through = (k.sg_kind == SG_RAY_MASK) && k.rm_passthrough;   // Q11
+#pragma unroll
+      for (int q = 0; q < NA; ++q) {
+        if (straight_through) a_exec[q] = a[q] + S(primal(g[q]) - primal(a[q]));
+        else a_exec[q] = g[q];
+      }
+    }
+    int differ = 0;
+    bool fin = true;
+#pragma unroll
+    for (int q = 0; q < NA; ++q) {
+      differ += is_close(primal(a_exec[q]), primal(a[q])) ? 0 : 1;
+      fin = fin && finite_val(primal(a_exec[q]));
+    }
+    if (differ == NA) flags |= FL_INTERVENED;
+    if (!fin) flags |= FL_NONFINITE;
+    // verdicts on the executed action
+    T ap[NA];
+#pragma unroll
+    for (int q = 0; q < NA; ++q) ap[q] = primal(a_exec[q]);
+    if (k.action_constrained && action_in_set<TASK>(ap, k)) flags |= FL_ACTION_IN_SET;
+    if (k.state_constrained && next_state_in_set<TASK>(ap, cfp, Bp, k)) flags |= FL_NEXT_IN_SET;
+  }
+  S wS[NS];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) wS[i] = S(w[i]);
+  TASK::Sim::f(s, a_exec, wS, s_next);
+  if (TASK::CLAMP && !k.disable_clamp) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      const T p = primal(s_next[i]);
+      if (p < k.box_min[i]) { s_next[i] = S(k.box_min[i]); flags |= FL_CLAMPED; }
+      else if (p > k.box_max[i]) { s_next[i] = S(k.box_max[i]); flags |= FL_CLAMPED; }
+    }
+  }
+  if (reset_now) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) s_next[i] = S(reset_state[i]);
+  }
+  TASK::observe(s_next, aux, sh, obs);
+  reward = TASK::reward(s_next, a_exec, aux, sh);
+}
+
+}  // namespace sgbpo

@@ -1,0 +1,95 @@
+"""Shared helpers for the parity tests: seeded inputs, the oracle run, consts construction."""
+import numpy as np
+import torch
+
+from oracle.dynamics import OracleEnv, SIMS, ENV_TO_SIM
+from oracle.safeguard import OracleSafeguard
+from safegbpo_b200 import _lib
+from safegbpo_b200.consts import build_consts
+
+ENV_IDS = _lib.ENV_IDS
+F64 = torch.float64
+
+
+def seeded_states(env_name: str, N: int, seed: int, spread: float = 0.97) -> torch.Tensor:
+    """States across the feasible box, some pushed to its boundary so projections bind."""
+    g = torch.Generator().manual_seed(seed)
+    sim = SIMS[ENV_TO_SIM[env_name]]
+    c = torch.tensor(sim.state_center, dtype=F64)
+    h = torch.tensor(sim.state_half, dtype=F64)
+    s = c + (torch.rand(N, sim.n, generator=g, dtype=F64) * 2 - 1) * h * spread
+    edge = torch.rand(N, sim.n, generator=g) < 0.15
+    sign = torch.where(torch.rand(N, sim.n, generator=g) < 0.5, -1.0, 1.0).to(F64)
+    return torch.where(edge, c + sign * h * (0.9 + 0.1 * torch.rand(N, sim.n, generator=g, dtype=F64)), s)
+
+
+def make_case(env_name: str, kind: str, N: int, seed: int, linear=True, zonotopic=True, passthrough=False,
+              gate="always", spread=0.97):
+    """Returns dict with oracle env/safeguard, consts, and seeded inputs (float64 CPU tensors)."""
+    env = OracleEnv(env_name, N, 240)
+    env.reset(seed=seed)
+    st = seeded_states(env_name, N, seed, spread)
+    env.state = st.clone()
+    sg = None
+    sg_kind = {"none": _lib.SG_NONE, "boundary_projection": _lib.SG_BOUNDARY_PROJECTION, "ray_mask": _lib.SG_RAY_MASK}[kind]
+    g = torch.Generator().manual_seed(seed + 17)
+    a = torch.rand(N, env.action_dim, generator=g, dtype=F64) * 2 - 1
+    w = env.noise_sample()
+    dirs = None
+    if kind != "none":
+        sg = OracleSafeguard(env, kind, linear_projection=linear, zonotopic_approximation=zonotopic,
+                             passthrough=passthrough, gate=gate, strict=False)
+        sa = [x.numpy() for x in env.safe_action_set()] if env.action_constrained else None
+        ss = [x.numpy() for x in env.safe_state_set()] if env.state_constrained else None
+        consts = build_consts(env_name, sg_kind, gate_mode=_lib.GATE[gate], rm_linear=linear, rm_zonotopic=zonotopic,
+                              rm_passthrough=passthrough, safe_action=sa, safe_state=ss, G_w=sg.G_w.numpy(),
+                              B0=sg.B0.numpy())
+        if kind == "ray_mask" and zonotopic and env.state_constrained:
+            dirs = sg.draw_directions()
+    else:
+        consts = build_consts(env_name, sg_kind)
+    aux = env.goal.clone() if env.sim.name in ("quadrotor", "seeker") else None
+    cot = dict(g_s_next=torch.rand(N, env.state_dim, generator=g, dtype=F64),
+               g_a_exec=torch.rand(N, env.action_dim, generator=g, dtype=F64),
+               g_obs=torch.rand(N, env.observation().shape[1], generator=g, dtype=F64),
+               g_reward=torch.rand(N, generator=g, dtype=F64))
+    return dict(env=env, sg=sg, consts=consts, s=st, a=a, w=w, dirs=dirs, aux=aux, cot=cot, kind=kind)
+
+
+def oracle_step(case):
+    """Runs the oracle on the case; returns values, gradients of the cotangent functional and masks."""
+    env, sg = case["env"], case["sg"]
+    state = case["s"].clone().requires_grad_(True)
+    act = case["a"].clone().requires_grad_(True)
+    env.state = state
+    env.steps = 0
+    env.scheduled_reset = False
+    if sg is None:
+        obs, rew, _, _ = env.step(act, noise=case["w"])
+        a_exec = act
+        ok = torch.ones(state.shape[0], dtype=torch.bool)
+        proj = infeas = None
+    else:
+        obs, rew, _, _ = sg.step(act, directions=case["dirs"], noise=case["w"])
+        a_exec = sg.safe_action
+        ok = ~sg.infeasible & ~a_exec.detach().isnan().any(dim=1)
+        proj, infeas = sg.projectable.clone(), sg.infeasible.clone()
+    cot = case["cot"]
+    func = ((env.state * cot["g_s_next"]).sum(1) + (a_exec * cot["g_a_exec"]).sum(1) + (obs * cot["g_obs"]).sum(1)
+            + rew * cot["g_reward"])[ok].sum()
+    gs, ga = torch.autograd.grad(func, (state, act), allow_unused=True)
+    return dict(s_next=env.state.detach(), a_exec=a_exec.detach(), obs=obs.detach(), reward=rew.detach(),
+                gs=gs, ga=ga if ga is not None else torch.zeros_like(act), ok=ok, projectable=proj, infeasible=infeas)
+
+
+def shared_for(env, step_index: int):
+    """sgbpo_step_shared for the household series at the post-step index."""
+    if env.sim.name != "household":
+        return None
+    sh = _lib.StepShared()
+    t = step_index
+    vals = torch.cat([env.load[t:t + 5], env.pv[t:t + 5], env.t_out[t:t + 5], env.price[t:t + 5]]).tolist()
+    for i, v in enumerate(vals):
+        sh.series[i] = v
+    sh.load_t, sh.pv_t, sh.price_t = float(env.load[t]), float(env.pv[t]), float(env.price[t])
+    return sh

@@ -1,0 +1,129 @@
+"""GPU: the drop-in classes (envs, safeguards, SHAC) against the reference's golden SHAC episode and the
+oracle's safeguarded episode, with the RNG stream replayed draw by draw."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+class Replay:
+    def __init__(self, draws, dev):
+        self.draws, self.i, self.dev = list(draws), 0, dev
+
+    def __call__(self, kind, shape):
+        k, d = self.draws[self.i]
+        self.i += 1
+        assert k == kind and tuple(d.shape) == tuple(shape), (k, kind, d.shape, shape)
+        return torch.from_numpy(np.asarray(d)).to(self.dev)
+
+
+@pytest.fixture
+def cuda_f64():
+    prev_dtype = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    torch.set_default_device("cuda:0")
+    yield torch.device("cuda:0")
+    torch.set_default_device("cpu")
+    torch.set_default_dtype(prev_dtype)
+    from safegbpo_b200 import rng
+    rng.set_source(None)
+
+
+def test_shac_episode_vs_reference_golden(cuda_f64, golden_dir):
+    """One unsafeguarded SHAC episode (truncation + reset-all inside the horizon): loss, buffer and policy
+    gradients equal the reference's (tests/golden/shac_cartpole_unsafe.npz)."""
+    from safegbpo_b200 import rng
+    from safegbpo_b200.envs.balance_cartpole import BalanceCartPoleEnv
+    from safegbpo_b200.learning_algorithms.shac import SHAC
+    g = np.load(golden_dir / "shac_cartpole_unsafe.npz")
+    keys = sorted(k for k in g.files if k.startswith("draw"))
+    draws = [(k.split("_")[1], g[k]) for k in keys]
+    env = BalanceCartPoleEnv(num_envs=4, num_steps=3)
+    algo = SHAC(env=env, policy_kwargs={"net_arch": [16, 16]}, policy_optim_kwargs={"lr": 1e-3},
+                vf_kwargs={"net_arch": [16, 16, 16]}, vf_optim_kwargs={"lr": 1e-3}, regularisation_coefficient=0.1,
+                len_trajectories=6, fused="off")
+    algo.policy.load_state_dict({k[len("policy."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("policy.")})
+    algo.target_value_function.load_state_dict(
+        {k[len("target_vf."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("target_vf.")})
+    env.state = torch.from_numpy(g["state0"]).to(cuda_f64)
+    obs0 = env.observation
+    algo.buffer.reset(obs0, algo.target_value_function(obs0).squeeze(1))
+    rng.set_source(Replay(draws, cuda_f64))
+    algo.buffer.reset()
+    algo.policy_optim.zero_grad()
+    avg_reward = algo.collect_trajectories()
+    loss = algo.policy_loss()
+    loss.backward()
+    tol = dict(rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(algo.buffer.observations.tensor.detach().cpu().numpy(), g["observations"], **tol)
+    np.testing.assert_allclose(algo.buffer.rewards.tensor.detach().cpu().numpy(), g["rewards"], **tol)
+    np.testing.assert_allclose(algo.buffer.values.tensor.detach().cpu().numpy(), g["values"], **tol)
+    assert np.array_equal(algo.buffer.terminals.tensor.cpu().numpy(), g["terminals"])
+    np.testing.assert_allclose(float(loss), float(g["loss"]), rtol=1e-11)
+    np.testing.assert_allclose(avg_reward, float(g["avg_reward"]), rtol=1e-11)
+    for k, p in algo.policy.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), g[f"grad.{k}"], rtol=1e-8, atol=1e-12, err_msg=k)
+
+
+@pytest.mark.parametrize("sg_name", ["boundary_projection", "ray_mask_orth"])
+def test_safeguarded_episode_vs_oracle(cuda_f64, sg_name):
+    """SwingUpCartPole + safeguard, H = 8, N = 16: eager drop-in classes vs the oracle restatement."""
+    from oracle.dynamics import OracleEnv
+    from oracle.safeguard import OracleSafeguard
+    from oracle import shac as oshac
+    from safegbpo_b200 import rng
+    from safegbpo_b200.envs.swingup_cartpole import SwingUpCartPoleEnv
+    from safegbpo_b200.safeguards.boundary_projection import BoundaryProjectionSafeguard
+    from safegbpo_b200.safeguards.ray_mask import RayMaskSafeguard
+    from safegbpo_b200.learning_algorithms.shac import SHAC
+    N, H = 16, 8
+    gen = torch.Generator().manual_seed(5)
+    s0 = (torch.rand(N, 4, generator=gen, dtype=torch.float64, device="cpu") * 2 - 1) * torch.tensor(
+        [9.5, 3.0, 6.0, 6.0], dtype=torch.float64, device="cpu")
+    eps = torch.randn(H, N, 1, generator=gen, dtype=torch.float64, device="cpu")
+    us = torch.rand(H, N, 1, 4, generator=gen, dtype=torch.float64, device="cpu")
+    # oracle
+    oenv = OracleEnv("SwingUpCartPole", N, 1000, rng=lambda kind, shape: next(it_o))
+    it_o = iter([u for u in us])
+    oenv.state, oenv.scheduled_reset = s0.clone(), False
+    kind = "boundary_projection" if sg_name == "boundary_projection" else "ray_mask"
+    osg = OracleSafeguard(oenv, kind, zonotopic_approximation=False, gate="always", strict=False)
+    pol = oshac.OraclePolicy(5, 1, [32, 32]).double().cpu()
+    vf = oshac.OracleValue(5, [32, 32]).double().cpu()
+
+    def env_step(action, t):
+        obs, rew, term, trunc = osg.step(action)
+        return obs, rew, term | trunc
+    obs0 = oenv.observation()
+    ref = oshac.rollout_loss(env_step, obs0, pol, vf, H, eps, value0=vf(obs0).squeeze(1))
+    ref["loss"].backward()
+    # drop-in classes on the GPU
+    env = SwingUpCartPoleEnv(num_envs=N, num_steps=1000)
+    env.reset()
+    env.state = s0.to(cuda_f64)
+    cls = BoundaryProjectionSafeguard if sg_name == "boundary_projection" else RayMaskSafeguard
+    kw = {} if sg_name == "boundary_projection" else dict(linear_projection=True, zonotopic_approximation=False, passthrough=False)
+    wrapped = cls(env, gate="always", strict=False, **kw)
+    algo = SHAC(env=wrapped, policy_kwargs={"net_arch": [32, 32]}, policy_optim_kwargs={"lr": 1e-3},
+                vf_kwargs={"net_arch": [32, 32]}, vf_optim_kwargs={"lr": 1e-3}, regularisation_coefficient=0.1,
+                len_trajectories=H, fused="off")
+    algo.policy.load_state_dict({k: v.to(cuda_f64) for k, v in pol.state_dict().items()})
+    algo.target_value_function.load_state_dict({k: v.to(cuda_f64) for k, v in vf.state_dict().items()})
+    env.state, env.steps, env._reset_pending = s0.to(cuda_f64), 0, False
+    o0 = env.observation
+    algo.buffer.reset(o0, algo.target_value_function(o0).squeeze(1))
+    draws = []
+    for t in range(H):
+        draws += [("randn", eps[t].numpy()), ("rand", us[t].numpy())]
+    rng.set_source(Replay(draws, cuda_f64))
+    algo.buffer.reset()
+    algo.collect_trajectories()
+    loss = algo.policy_loss()
+    loss.backward()
+    assert not bool(osg.infeasible.any())
+    np.testing.assert_allclose(algo.buffer.observations.tensor.detach().cpu().numpy(), ref["observations"].detach().numpy(),
+                               rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(float(loss), float(ref["loss"]), rtol=1e-10)
+    for (k, p), (k2, p2) in zip(algo.policy.named_parameters(), pol.named_parameters()):
+        np.testing.assert_allclose(p.grad.cpu().numpy(), p2.grad.numpy(), rtol=1e-7, atol=1e-10, err_msg=k)

@@ -1,0 +1,148 @@
+"""GPU: the CUDA kernels, called through the C ABI, against the oracle and the reference goldens.
+
+Tolerances: float64 kernels must agree with the float64 oracle to 1e-9 relative (same algorithm, different
+evaluation order); float32 kernels to 1e-5 relative (the tolerance BASELINE.json's north_star states),
+checked on the environments whose float32 run takes the same branches as the float64 oracle."""
+import numpy as np
+import pytest
+import torch
+
+from common import ENV_IDS, make_case, oracle_step, shared_for
+from safegbpo_b200 import _lib, ops
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("BalanceCartPole", "none", {}), ("BalancePendulum", "none", {}), ("BalanceQuadrotor", "none", {}),
+    ("ManageHousehold", "none", {}), ("SwingUpCartPole", "none", {}),
+    ("BalanceCartPole", "boundary_projection", {}), ("SwingUpCartPole", "boundary_projection", {}),
+    ("BalanceCartPole", "boundary_projection", {"gate": "reference"}),
+    ("SwingUpCartPole", "ray_mask", {"zonotopic": False}), ("SwingUpCartPole", "ray_mask", {"zonotopic": False, "linear": False}),
+    ("SwingUpCartPole", "ray_mask", {"zonotopic": True}), ("BalanceCartPole", "ray_mask", {"zonotopic": True, "linear": False}),
+    ("SwingUpCartPole", "ray_mask", {"zonotopic": False, "passthrough": True}),
+    ("ManageHousehold", "boundary_projection", {}), ("ManageHousehold", "ray_mask", {"zonotopic": False}),
+]
+IDS = [f"{c[0]}-{c[1]}-{'-'.join(f'{k}={v}' for k, v in c[2].items())}" for c in CASES]
+
+
+def run_kernel(case, env_name, dtype, dev):
+    t = lambda x: None if x is None else x.to(device=dev, dtype=dtype)
+    s = t(case["s"]).requires_grad_(True)
+    a = t(case["a"]).requires_grad_(True)
+    out = ops.safeguarded_step(s, a, t(case["w"]), ENV_IDS[env_name], case["consts"], aux=t(case["aux"]),
+                               dirs=t(case["dirs"]), shared=shared_for(case["env"], 1))
+    return s, a, out
+
+
+@pytest.mark.parametrize("env_name,kind,opts", CASES, ids=IDS)
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_step_fwd_bwd_vs_oracle(env_name, kind, opts, dtype):
+    dev = torch.device("cuda:0")
+    zono = kind == "ray_mask" and opts.get("zonotopic", True)
+    N = 12 if zono else 64
+    case = make_case(env_name, kind, N, seed=11, **opts)
+    ref = oracle_step(case)
+    s, a, (s_next, a_exec, obs, reward, flags) = run_kernel(case, env_name, dtype, dev)
+    ok = ref["ok"].to(dev)
+    flags_c = flags.cpu().numpy()
+    if dtype == torch.float32:
+        # fp32 may take a different branch (clamp / active row) when within rounding of a switch: compare
+        # the environments whose flag word equals the float64 kernel's
+        _, _, out64 = run_kernel(case, env_name, torch.float64, dev)
+        same = (out64[4] == flags)
+        assert same.float().mean() > 0.9
+        ok = ok & same
+    cot = {k: v.to(device=dev, dtype=dtype) for k, v in case["cot"].items()}
+    func = ((s_next * cot["g_s_next"]).sum(1) + (a_exec * cot["g_a_exec"]).sum(1) + (obs * cot["g_obs"]).sum(1)
+            + reward * cot["g_reward"])[ok].sum()
+    func.backward()
+    torch.cuda.synchronize()
+    okc = ok.cpu().numpy()
+    if dtype == torch.float64:
+        tol = dict(rtol=1e-7, atol=1e-8) if zono else dict(rtol=1e-9, atol=1e-10)
+        gtol = dict(rtol=1e-5, atol=1e-6) if zono else dict(rtol=1e-8, atol=1e-9)
+    else:
+        tol = dict(rtol=1e-5, atol=2e-5)          # float32: 1e-5 relative (north_star), absolute floor for O(10) states
+        gtol = dict(rtol=2e-4, atol=2e-4)         # first derivatives of fp32 kinks: looser, stated here
+    for name, got in (("a_exec", a_exec), ("s_next", s_next), ("obs", obs), ("reward", reward)):
+        np.testing.assert_allclose(got.detach().cpu().double().numpy()[okc], ref[name].numpy()[okc], err_msg=name, **tol)
+    np.testing.assert_allclose(s.grad.cpu().double().numpy()[okc], ref["gs"].numpy()[okc], err_msg="gs", **gtol)
+    np.testing.assert_allclose(a.grad.cpu().double().numpy()[okc], ref["ga"].numpy()[okc], err_msg="ga", **gtol)
+    if kind != "none" and dtype == torch.float64:
+        assert np.array_equal((flags_c & _lib.FL_PROJECTABLE) != 0, ref["projectable"].numpy())
+        guard = (flags_c & _lib.FL_GUARD_USED) != 0
+        assert np.array_equal(((flags_c & _lib.FL_INFEASIBLE) != 0)[guard], ref["infeasible"].numpy()[guard])
+        # verdicts: every feasible guarded action is inside its sets (zero safety violations)
+        good = guard & ((flags_c & _lib.FL_INFEASIBLE) == 0)
+        env = case["env"]
+        if env.state_constrained and kind == "boundary_projection":
+            assert ((flags_c & _lib.FL_NEXT_IN_SET) != 0)[good].all()
+        if env.action_constrained and kind == "boundary_projection":
+            assert ((flags_c & _lib.FL_ACTION_IN_SET) != 0)[good].all()
+
+
+@pytest.mark.parametrize("env_name", ["BalancePendulum", "BalanceCartPole", "SwingUpCartPole", "BalanceQuadrotor", "ManageHousehold"])
+def test_against_reference_golden(env_name, golden_dir):
+    """Kernel vs the REFERENCE's own outputs (tests/golden/env_*.npz, made from the unmodified reference)."""
+    g = np.load(golden_dir / f"env_{env_name}.npz")
+    dev = torch.device("cuda:0")
+    from safegbpo_b200.consts import build_consts, BOXES, ENV_SIM
+    k = build_consts(env_name, _lib.SG_NONE)
+    eid = ENV_IDS[env_name]
+    s = torch.from_numpy(g["reset_state"]).to(dev)
+    c, A, B, E = ops.linearise(s, eid, k)
+    for got, key in ((c, "lin_c"), (A, "lin_A"), (B, "lin_B"), (E, "lin_E")):
+        np.testing.assert_allclose(got.cpu().numpy(), g[key], rtol=1e-12, atol=1e-12, err_msg=key)
+    bc, bh, nc, nh = (np.asarray(x, dtype=np.float64) for x in BOXES[ENV_SIM[env_name]])
+    from oracle.dynamics import OracleEnv
+    oenv = OracleEnv(env_name, 5, 100)
+    for t in range(3):
+        st = torch.from_numpy(g[f"s{t}"]).to(dev).requires_grad_(True)
+        ac = torch.from_numpy(g[f"a{t}"]).to(dev).requires_grad_(True)
+        noise = nc + nh * (2 * g[f"u{t}"][:, 0, :] - 1)
+        step_idx = int(g[f"steps{t}"])
+        if env_name == "ManageHousehold":
+            noise[:, 1] = float(oenv.t_out[step_idx - 1])
+        aux = torch.from_numpy(g[f"goal{t}"]).to(dev) if f"goal{t}" in g.files and env_name == "BalanceQuadrotor" else None
+        s_next, a_exec, obs, rew, flags = ops.safeguarded_step(st, ac, torch.from_numpy(noise).to(dev), eid, k, aux=aux,
+                                                               shared=shared_for(oenv, step_idx))
+        np.testing.assert_allclose(s_next.detach().cpu().numpy(), g[f"next{t}"], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(obs.detach().cpu().numpy(), g[f"obs{t}"], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(rew.detach().cpu().numpy(), g[f"rew{t}"], rtol=1e-12, atol=1e-12)
+        func = (obs * torch.from_numpy(g[f"cot_o{t}"]).to(dev)).sum() + (rew * torch.from_numpy(g[f"cot_r{t}"]).to(dev)).sum()
+        func.backward()
+        np.testing.assert_allclose(st.grad.cpu().numpy(), g[f"gs{t}"], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(ac.grad.cpu().numpy(), g[f"ga{t}"], rtol=1e-9, atol=1e-11)
+
+
+def test_empty_batch_and_bad_args():
+    dev = torch.device("cuda:0")
+    from safegbpo_b200.consts import build_consts
+    k = build_consts("BalanceCartPole", _lib.SG_NONE)
+    z = lambda *s: torch.zeros(*s, device=dev)
+    out = ops.safeguarded_step(z(0, 4), z(0, 1), z(0, 4), 1, k)
+    assert out[0].shape == (0, 4) and out[4].shape == (0,)
+    with pytest.raises(_lib.SgbpoError):
+        ops.safeguarded_step(z(3, 4), z(3, 2), z(3, 4), 1, k)
+    with pytest.raises(_lib.SgbpoError):
+        ops.safeguarded_step(z(3, 4).cpu(), z(3, 1).cpu(), z(3, 4).cpu(), 1, k)
+
+
+def test_large_batch_properties():
+    """BASELINE full size (N = 4096 .. 65536): size-independent properties of the projection."""
+    dev = torch.device("cuda:0")
+    for N in (4096, 65536):
+        case = make_case("BalanceCartPole", "boundary_projection", 8, seed=3)
+        g = torch.Generator().manual_seed(N)
+        s = ((torch.rand(N, 4, generator=g, dtype=torch.float64) * 2 - 1) * torch.tensor([10.0, 3.1, 10.0, 10.0], dtype=torch.float64)).to(dev)
+        a = (torch.rand(N, 1, generator=g, dtype=torch.float64) * 2 - 1).to(dev)
+        w = torch.zeros(N, 4, dtype=torch.float64, device=dev)
+        s_next, a1, obs, rew, fl = ops.safeguarded_step(s, a, w, 1, case["consts"])
+        _, a2, _, _, fl2 = ops.safeguarded_step(s, a1.detach(), w, 1, case["consts"])
+        feas = (fl & _lib.FL_INFEASIBLE) == 0
+        assert torch.allclose(a1[feas], a2[feas], rtol=0, atol=1e-12)            # projection is idempotent
+        assert (((fl & _lib.FL_NEXT_IN_SET) != 0) | ~feas).all()                 # zero violations where feasible
+        assert (a1[feas].abs() <= 1 + 1e-12).all()
+        assert ((s_next - torch.tensor([10.0, 3.141592653589793, 10.0, 10.0], device=dev, dtype=torch.float64)) <= 1e-12).all()
+        inside = feas & (((fl & _lib.FL_INTERVENED) == 0))
+        assert torch.equal(a1[inside], a[inside])                                # already-safe actions pass unchanged

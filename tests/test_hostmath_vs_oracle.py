@@ -1,0 +1,58 @@
+"""CPU: the device math (csrc/*.cuh compiled for the host, test-only) against the oracle.
+Values, gradients (incl. the second-order terms through B = df/da) and verdict bits."""
+import numpy as np
+import pytest
+import torch
+
+import hostmath_util as hm
+from common import ENV_IDS, make_case, oracle_step, shared_for
+from safegbpo_b200 import _lib
+
+CASES = [
+    ("BalanceCartPole", "none", {}), ("BalancePendulum", "none", {}), ("BalanceQuadrotor", "none", {}),
+    ("ManageHousehold", "none", {}), ("SwingUpCartPole", "none", {}),
+    ("BalanceCartPole", "boundary_projection", {}), ("SwingUpCartPole", "boundary_projection", {}),
+    ("BalanceCartPole", "boundary_projection", {"gate": "reference"}),
+    ("SwingUpCartPole", "ray_mask", {"zonotopic": False}), ("SwingUpCartPole", "ray_mask", {"zonotopic": False, "linear": False}),
+    ("BalanceCartPole", "ray_mask", {"zonotopic": False}),
+    ("SwingUpCartPole", "ray_mask", {"zonotopic": True}), ("BalanceCartPole", "ray_mask", {"zonotopic": True, "linear": False}),
+    ("SwingUpCartPole", "ray_mask", {"zonotopic": False, "passthrough": True}),
+    ("ManageHousehold", "boundary_projection", {}), ("ManageHousehold", "ray_mask", {"zonotopic": False}),
+]
+
+
+@pytest.mark.parametrize("env_name,kind,opts", CASES, ids=[f"{c[0]}-{c[1]}-{'-'.join(f'{k}={v}' for k, v in c[2].items())}" for c in CASES])
+def test_step_matches_oracle(env_name, kind, opts):
+    N = 10 if (kind == "ray_mask" and opts.get("zonotopic", True)) else 24
+    case = make_case(env_name, kind, N, seed=5, **opts)
+    ref = oracle_step(case)
+    env = case["env"]
+    out = hm.step(ENV_IDS[env_name], case["consts"], case["s"].numpy(), case["a"].numpy(), case["w"].numpy(),
+                  aux=None if case["aux"] is None else case["aux"].numpy(),
+                  dirs=None if case["dirs"] is None else case["dirs"].numpy(), shared=shared_for(env, 1),
+                  cot={k: v.numpy() for k, v in case["cot"].items()})
+    ok = ref["ok"].numpy()
+    assert ok.sum() >= N // 2
+    tol = dict(rtol=1e-7, atol=1e-8) if (kind == "ray_mask" and opts.get("zonotopic", True)) else dict(rtol=1e-10, atol=1e-11)
+    for key in ("a_exec", "s_next", "obs", "reward"):
+        np.testing.assert_allclose(out[key][ok], ref[key].numpy()[ok], err_msg=key, **tol)
+    gtol = dict(rtol=1e-5, atol=1e-6) if (kind == "ray_mask" and opts.get("zonotopic", True)) else dict(rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(out["gs"][ok], ref["gs"].numpy()[ok], err_msg="gs", **gtol)
+    np.testing.assert_allclose(out["ga"][ok], ref["ga"].numpy()[ok], err_msg="ga", **gtol)
+    if kind != "none":
+        flags = out["flags"]
+        assert np.array_equal((flags & _lib.FL_PROJECTABLE) != 0, ref["projectable"].numpy())
+        guard = (flags & _lib.FL_GUARD_USED) != 0
+        assert np.array_equal(((flags & _lib.FL_INFEASIBLE) != 0)[guard], ref["infeasible"].numpy()[guard])
+
+
+def test_float32_close_to_float64():
+    case = make_case("BalanceCartPole", "boundary_projection", 64, seed=2)
+    args = (ENV_IDS["BalanceCartPole"], case["consts"], case["s"].numpy(), case["a"].numpy(), case["w"].numpy())
+    cot = {k: v.numpy() for k, v in case["cot"].items()}
+    o64 = hm.step(*args, cot=cot, dtype=np.float64)
+    o32 = hm.step(*args, cot=cot, dtype=np.float32)
+    same = o64["flags"] == o32["flags"]
+    assert same.mean() > 0.9
+    for key in ("a_exec", "s_next", "obs", "reward"):
+        np.testing.assert_allclose(o32[key][same], o64[key][same], rtol=1e-5, atol=1e-5, err_msg=key)   # fp32 tolerance
