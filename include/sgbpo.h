@@ -93,6 +93,60 @@ int sgbpo_step_bwd(int env_id, int dtype, int64_t N, const sgbpo_consts* consts,
 int sgbpo_linearise(int env_id, int dtype, int64_t N, const sgbpo_consts* consts, const void* s,
                     void* c, void* A, void* B, void* E, void* stream);
 
+/* ---- whole-horizon fused rollout (SHAC.collect_trajectories + reverse pass, shac.py:96-151) ------------ */
+
+/* MLP parameters on the DEVICE in the kernels' layout (policy.py:50-60 / value_function.py:38-48:
+ * Linear -> ELU -> LayerNorm per hidden layer, then Linear).  All hidden layers share one width. */
+typedef struct sgbpo_mlp {
+  int32_t in_dim, width, n_hidden, out_dim;
+  const void* w_in;    /* [in_dim][width]            = Linear.weight^T of the first layer */
+  const void* w_hid;   /* [n_hidden-1][width][width]  = Linear.weight^T of the hidden->hidden layers */
+  const void* w_out;   /* [width][out_dim] */
+  const void* b_hid;   /* [n_hidden][width] */
+  const void* gamma;   /* [n_hidden][width] LayerNorm weight */
+  const void* beta;    /* [n_hidden][width] LayerNorm bias */
+  const void* b_out;   /* [out_dim] */
+  const void* log_std; /* [out_dim] policy only, else NULL */
+} sgbpo_mlp;
+
+/* Rollout buffers, time-major like CoupledBuffer's (T, N, .) tensors (coupled_buffer.py:79-92). */
+typedef struct sgbpo_rollout {
+  int64_t N;
+  int32_t H, reserved;
+  const void* eps;           /* [H][N][m]   policy draws (Normal.rsample, policy.py:84-85) */
+  const void* noise;         /* [H][N][n]   noise_set.sample() per step (simulator.py:181) */
+  const void* dirs;          /* [H][N][m][2m] ray-mask directions (ray_mask.py:184-185) or NULL */
+  const void* aux0;          /* [N][naux] or NULL */
+  const void* reset_states;  /* [R][N][n] states drawn by reset() inside the horizon (Q6) or NULL */
+  const int32_t* reset_idx;  /* [H] device: -1 or r: s_{t+1} := reset_states[r] */
+  const int32_t* aux_src;    /* [H] device: -1 -> aux0, r -> reset_states[r][:, :naux] in effect after step t */
+  const void* shared;        /* [H][23] per-step shared scalars (layout of sgbpo_step_shared in dtype) or NULL */
+  void* states;              /* [H+1][N][n]  row 0 = s_0 (input) */
+  void* obs;                 /* [H+2][N][o]  row 0 = obs_0 (input) */
+  void* actions;             /* [H+1][N][m] */
+  void* exec_actions;        /* [H][N][m] */
+  void* rewards;             /* [H+2][N] */
+  int32_t* flags;            /* [H][N] */
+} sgbpo_rollout;
+
+typedef struct sgbpo_rollout_grads {
+  const void* grw;             /* [H]  d loss / d rewards[t] */
+  const void* gobs_term;       /* [K][N][o] d(terminal value terms)/d obs rows, or NULL */
+  const int32_t* term_of_row;  /* [H+2] device: -1 or k */
+  void* h1_out;                /* [H][N][width]  } operands of the hidden-hidden weight gradient */
+  void* dz2_out;               /* [H][N][width]  }   dW_hid = h1^T dz2 (one GEMM by the caller) */
+  void* g_w_in; void* g_w_out; void* g_b_hid; void* g_gamma; void* g_beta; void* g_b_out; void* g_log_std;
+} sgbpo_rollout_grads;
+
+/* forward over the whole horizon: policy MLP + safeguarded step per environment per t (one launch) */
+int sgbpo_rollout_fwd(int env_id, int dtype, const sgbpo_consts* consts, const sgbpo_mlp* policy,
+                      const sgbpo_rollout* r, void* stream);
+/* reverse pass over the whole horizon (replaces autograd's H-long chain) */
+int sgbpo_rollout_bwd(int env_id, int dtype, const sgbpo_consts* consts, const sgbpo_mlp* policy,
+                      const sgbpo_rollout* r, const sgbpo_rollout_grads* g, void* stream);
+/* batched MLP forward over M rows (target critic over the buffer's observation rows, shac.py:111) */
+int sgbpo_mlp_rows(int dtype, int64_t M, const sgbpo_mlp* net, const void* x, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

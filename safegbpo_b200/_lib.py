@@ -47,6 +47,30 @@ class StepShared(C.Structure):
     _fields_ = [("series", C.c_double * 20), ("load_t", C.c_double), ("pv_t", C.c_double), ("price_t", C.c_double)]
 
 
+class Mlp(C.Structure):
+    """Mirror of ``struct sgbpo_mlp``."""
+    _fields_ = [("in_dim", C.c_int32), ("width", C.c_int32), ("n_hidden", C.c_int32), ("out_dim", C.c_int32),
+                ("w_in", C.c_void_p), ("w_hid", C.c_void_p), ("w_out", C.c_void_p), ("b_hid", C.c_void_p),
+                ("gamma", C.c_void_p), ("beta", C.c_void_p), ("b_out", C.c_void_p), ("log_std", C.c_void_p)]
+
+
+class Rollout(C.Structure):
+    """Mirror of ``struct sgbpo_rollout``."""
+    _fields_ = [("N", C.c_int64), ("H", C.c_int32), ("reserved", C.c_int32),
+                ("eps", C.c_void_p), ("noise", C.c_void_p), ("dirs", C.c_void_p), ("aux0", C.c_void_p),
+                ("reset_states", C.c_void_p), ("reset_idx", C.c_void_p), ("aux_src", C.c_void_p), ("shared", C.c_void_p),
+                ("states", C.c_void_p), ("obs", C.c_void_p), ("actions", C.c_void_p), ("exec_actions", C.c_void_p),
+                ("rewards", C.c_void_p), ("flags", C.c_void_p)]
+
+
+class RolloutGrads(C.Structure):
+    """Mirror of ``struct sgbpo_rollout_grads``."""
+    _fields_ = [("grw", C.c_void_p), ("gobs_term", C.c_void_p), ("term_of_row", C.c_void_p),
+                ("h1_out", C.c_void_p), ("dz2_out", C.c_void_p), ("g_w_in", C.c_void_p), ("g_w_out", C.c_void_p),
+                ("g_b_hid", C.c_void_p), ("g_gamma", C.c_void_p), ("g_beta", C.c_void_p), ("g_b_out", C.c_void_p),
+                ("g_log_std", C.c_void_p)]
+
+
 ENV_IDS = {"BalancePendulum": 0, "BalanceCartPole": 1, "SwingUpCartPole": 2, "BalanceQuadrotor": 3,
            "ManageHousehold": 4, "NavigateSeeker": 5}
 SG_NONE, SG_BOUNDARY_PROJECTION, SG_RAY_MASK = 0, 1, 2
@@ -64,6 +88,10 @@ _SIGNATURES = {
     "sgbpo_step_bwd": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.POINTER(Consts), C.POINTER(StepShared)]
                        + [_VP] * 6 + [_VP] * 4 + [_VP, _VP, _VP]),
     "sgbpo_linearise": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.POINTER(Consts)] + [_VP] * 5 + [_VP]),
+    "sgbpo_rollout_fwd": (C.c_int, [C.c_int, C.c_int, C.POINTER(Consts), C.POINTER(Mlp), C.POINTER(Rollout), _VP]),
+    "sgbpo_rollout_bwd": (C.c_int, [C.c_int, C.c_int, C.POINTER(Consts), C.POINTER(Mlp), C.POINTER(Rollout),
+                                    C.POINTER(RolloutGrads), _VP]),
+    "sgbpo_mlp_rows": (C.c_int, [C.c_int, C.c_int64, C.POINTER(Mlp), _VP, _VP, _VP]),
 }
 EXPORTED = tuple(_SIGNATURES)
 _lib = None
@@ -74,19 +102,38 @@ def sources() -> list[Path]:
 
 
 def build(verbose: bool = False) -> Path:
-    """Compile every CUDA source for sm_100a into libsgbpo.so (in-tree, so it travels with the repo)."""
+    """Compile every CUDA source for sm_100a into libsgbpo.so (in-tree, so it travels with the repo).
+    One object per translation unit, compiled in parallel, then linked."""
+    from concurrent.futures import ThreadPoolExecutor
     srcs = sources()
-    newest = max(p.stat().st_mtime for p in list(CSRC.glob("*")) + [PKG.parent / "include" / "sgbpo.h"])
-    if LIB_PATH.exists() and LIB_PATH.stat().st_mtime >= newest:
-        return LIB_PATH
-    cmd = ["nvcc", *NVCC_FLAGS, "-o", str(LIB_PATH), *map(str, srcs)]
+    headers = list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "sgbpo.h"]
+    newest_hdr = max(p.stat().st_mtime for p in headers)
+    objdir = PKG / "build"
+    objdir.mkdir(exist_ok=True)
+    compile_flags = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
+                     "-Xcompiler", "-fPIC", "-c"]
+
+    def compile_one(src: Path):
+        obj = objdir / (src.stem + ".o")
+        if obj.exists() and obj.stat().st_mtime >= max(newest_hdr, src.stat().st_mtime):
+            return obj, ""
+        cmd = ["nvcc", *compile_flags, *( ["-Xptxas=-v"] if verbose else []), "-o", str(obj), str(src)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise SgbpoError(f"nvcc failed on {src.name}:\n{res.stderr[-4000:]}")
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, srcs))
+    objs = [o for o, _ in results]
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise SgbpoError(f"nvcc failed:\n{res.stderr[-4000:]}")
-    if verbose:
-        print(res.stderr)
+        for _, log in results:
+            print(log)
+    if not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < max(o.stat().st_mtime for o in objs):
+        res = subprocess.run(["nvcc", "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB_PATH),
+                              *map(str, objs)], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise SgbpoError(f"nvcc link failed:\n{res.stderr[-4000:]}")
     return LIB_PATH
 
 

@@ -7,6 +7,7 @@
 
 #include "../../include/sgbpo.h"
 #include "sgbpo_step.cuh"
+#include "sgbpo_host.cuh"
 
 namespace sgbpo {
 
@@ -18,38 +19,6 @@ static int fail(int code, const char* msg) {
 static int cuda_fail(cudaError_t e, const char* where) {
   snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
   return SGBPO_E_CUDA;
-}
-
-template <class T> SafeConsts<T> convert_consts(const sgbpo_consts& c) {
-  SafeConsts<T> k;
-  memset(&k, 0, sizeof(k));
-  k.sg_kind = c.sg_kind; k.gate_mode = c.gate_mode;
-  k.rm_linear = c.rm_linear; k.rm_zonotopic = c.rm_zonotopic; k.rm_passthrough = c.rm_passthrough;
-  k.action_constrained = c.action_constrained; k.state_constrained = c.state_constrained;
-  k.state_model = c.state_model; k.disable_clamp = c.disable_clamp;
-  for (int i = 0; i < MAXN; ++i) {
-    k.box_min[i] = T(c.box_min[i]); k.box_max[i] = T(c.box_max[i]); k.noise_center[i] = T(c.noise_center[i]);
-    k.cs_hat[i] = T(c.cs_hat[i]); k.rb[i] = T(c.rb[i]); k.c_s[i] = T(c.c_s[i]);
-  }
-  for (int i = 0; i < MAXN * MAXN; ++i) k.Ginv[i] = T(c.Ginv[i]);
-  for (int i = 0; i < MAXN * MAXM; ++i) k.B0hat_abs[i] = T(c.B0hat_abs[i]);
-  for (int i = 0; i < MAXM; ++i) { k.a_lo[i] = T(c.a_lo[i]); k.a_hi[i] = T(c.a_hi[i]); k.c_a[i] = T(c.c_a[i]); }
-  k.n_act_hp = c.n_act_hp; k.n_k_hp = c.n_k_hp; k.n_q_hp = c.n_q_hp;
-  for (int r = 0; r < MAXHP; ++r) {
-    for (int j = 0; j < 3; ++j) { k.act_hp[r][j] = T(c.act_hp[r][j]); k.q_hp[r][j] = T(c.q_hp[r][j]); }
-    for (int j = 0; j < 2; ++j) k.k_hp[r][j] = T(c.k_hp[r][j]);
-  }
-  return k;
-}
-
-template <class T> StepShared<T> convert_shared(const sgbpo_step_shared* s) {
-  StepShared<T> o;
-  memset(&o, 0, sizeof(o));
-  if (s) {
-    for (int i = 0; i < 20; ++i) o.series[i] = T(s->series[i]);
-    o.load_t = T(s->load_t); o.pv_t = T(s->pv_t); o.price_t = T(s->price_t);
-  }
-  return o;
 }
 
 template <int ROW, class T> __device__ __forceinline__ void load_row(const T* __restrict__ base, int64_t i, T* dst) {
@@ -248,9 +217,9 @@ int sgbpo_step_fwd(int env_id, int dtype, int64_t N, const sgbpo_consts* consts,
                    const void* s, const void* a, const void* w, const void* aux, const void* dirs,
                    const void* reset_state, void* s_next, void* a_exec, void* obs, void* reward,
                    int32_t* flags, void* stream) {
+  if (N == 0) return SGBPO_OK;
   if (!consts || !s || !a || !w || !s_next || !a_exec || !obs || !reward || !flags || N < 0)
     return fail(SGBPO_E_ARG, "sgbpo_step_fwd: null pointer or negative N");
-  if (N == 0) return SGBPO_OK;
   cudaStream_t st = (cudaStream_t)stream;
   SGBPO_DISPATCH(fwd(N, consts, shared, s, a, w, aux, dirs, reset_state, s_next, a_exec, obs, reward, flags, st))
 }
@@ -259,16 +228,16 @@ int sgbpo_step_bwd(int env_id, int dtype, int64_t N, const sgbpo_consts* consts,
                    const void* s, const void* a, const void* w, const void* aux, const void* dirs,
                    const void* reset_state, const void* g_s_next, const void* g_a_exec, const void* g_obs,
                    const void* g_reward, void* gs, void* ga, void* stream) {
-  if (!consts || !s || !a || !w || !gs || !ga || N < 0) return fail(SGBPO_E_ARG, "sgbpo_step_bwd: null pointer or negative N");
   if (N == 0) return SGBPO_OK;
+  if (!consts || !s || !a || !w || !gs || !ga || N < 0) return fail(SGBPO_E_ARG, "sgbpo_step_bwd: null pointer or negative N");
   cudaStream_t st = (cudaStream_t)stream;
   SGBPO_DISPATCH(bwd(N, consts, shared, s, a, w, aux, dirs, reset_state, g_s_next, g_a_exec, g_obs, g_reward, gs, ga, st))
 }
 
 int sgbpo_linearise(int env_id, int dtype, int64_t N, const sgbpo_consts* consts, const void* s, void* c, void* A,
                     void* B, void* E, void* stream) {
-  if (!consts || !s || !c || !A || !B || !E || N < 0) return fail(SGBPO_E_ARG, "sgbpo_linearise: null pointer or negative N");
   if (N == 0) return SGBPO_OK;
+  if (!consts || !s || !c || !A || !B || !E || N < 0) return fail(SGBPO_E_ARG, "sgbpo_linearise: null pointer or negative N");
   cudaStream_t st = (cudaStream_t)stream;
   SGBPO_DISPATCH(lin(N, consts, s, c, A, B, E, st))
 }

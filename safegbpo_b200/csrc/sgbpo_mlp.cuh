@@ -1,0 +1,223 @@
+// Warp-autonomous MLP tiles for the fused rollout (policy.py:50-89, value_function.py:38-66 of the
+// reference: Linear -> ELU -> LayerNorm per hidden layer, then Linear).
+//
+// One warp owns R = 8 rows (environments).  Lane l owns output columns {l, l+32, ...} (CPL = W/32 per
+// lane) of every hidden layer, i.e. an 8 x CPL register tile; the 8 input activations of one k are a
+// 32-byte broadcast read from the warp's private shared-memory tile laid out [k][8]; the weights are
+// shared by the CTA in shared memory as [k][LD] with LD = W + 1, so the forward read (lanes along
+// columns) AND the transposed read of the data-gradient GEMM (lanes along k) are both conflict-free.
+// LayerNorm row reductions are warp shuffles.  No __syncthreads inside the time loop.
+//
+// fp32 (or fp64) FMA on purpose: the parity bar is 1e-5 relative on actions/states/gradients through a
+// 64-step unstable rollout; single-pass TF32/BF16 tensor-core MMA (~1e-3) does not meet it.
+#pragma once
+#include "sgbpo_dual.cuh"
+
+namespace sgbpo {
+
+constexpr int MLP_R = 8;          // rows per warp
+constexpr int MAX_HIDDEN = 4;
+
+template <class T> struct MlpParams {
+  int in_dim, width, n_hidden, out_dim;
+  const T* w_in;    // [in_dim][width]            (= torch Linear.weight^T)
+  const T* w_hid;   // [n_hidden-1][width][width]  (k-major: [k][c])
+  const T* w_out;   // [width][out_dim]
+  const T* b_hid;   // [n_hidden][width]
+  const T* gamma;   // [n_hidden][width]
+  const T* beta;    // [n_hidden][width]
+  const T* b_out;   // [out_dim]
+  const T* log_std; // [out_dim] (policy only, else nullptr)
+};
+
+template <class T, int W> struct NetSmem {
+  static constexpr int LD = W + 1;
+  T* w_in; T* w_hid; T* w_out; T* b_hid; T* gamma; T* beta; T* b_out;
+  int in_dim, n_hidden, out_dim;
+  __host__ __device__ static size_t floats(int in_dim, int n_hidden, int out_dim) {
+    return (size_t)in_dim * LD + (size_t)(n_hidden - 1) * W * LD + (size_t)W * out_dim + 3 * (size_t)n_hidden * W + out_dim;
+  }
+  // carve `base` and copy the parameters in (whole CTA cooperates); returns the next free address
+  __device__ T* load(T* base, const MlpParams<T>& p) {
+    in_dim = p.in_dim; n_hidden = p.n_hidden; out_dim = p.out_dim;
+    w_in = base; base += in_dim * LD;
+    w_hid = base; base += (n_hidden - 1) * W * LD;
+    w_out = base; base += W * out_dim;
+    b_hid = base; base += n_hidden * W;
+    gamma = base; base += n_hidden * W;
+    beta = base; base += n_hidden * W;
+    b_out = base; base += out_dim;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < in_dim * W; i += nt) w_in[(i / W) * LD + (i % W)] = p.w_in[i];
+    for (int i = tid; i < (n_hidden - 1) * W * W; i += nt) {
+      const int l = i / (W * W), rem = i % (W * W);
+      w_hid[l * W * LD + (rem / W) * LD + (rem % W)] = p.w_hid[i];
+    }
+    for (int i = tid; i < W * out_dim; i += nt) w_out[i] = p.w_out[i];
+    for (int i = tid; i < n_hidden * W; i += nt) { b_hid[i] = p.b_hid[i]; gamma[i] = p.gamma[i]; beta[i] = p.beta[i]; }
+    for (int i = tid; i < out_dim; i += nt) b_out[i] = p.b_out[i];
+    return base;
+  }
+};
+
+template <class T> __device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float sg_expm1(float x) { return expm1f(x); }
+__device__ __forceinline__ double sg_expm1(double x) { return expm1(x); }
+__device__ __forceinline__ float sg_rsqrt(float x) { return 1.0f / sqrtf(x); }
+__device__ __forceinline__ double sg_rsqrt(double x) { return 1.0 / sqrt(x); }
+
+// 8 contiguous row values of one k: vector loads (the warp tiles are 32-byte aligned)
+__device__ __forceinline__ void load8(const float* __restrict__ p, float (&a)[MLP_R]) {
+  const float4 v0 = *reinterpret_cast<const float4*>(p), v1 = *reinterpret_cast<const float4*>(p + 4);
+  a[0] = v0.x; a[1] = v0.y; a[2] = v0.z; a[3] = v0.w; a[4] = v1.x; a[5] = v1.y; a[6] = v1.z; a[7] = v1.w;
+}
+__device__ __forceinline__ void load8(const double* __restrict__ p, double (&a)[MLP_R]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double2 v = *reinterpret_cast<const double2*>(p + 2 * i);
+    a[2 * i] = v.x; a[2 * i + 1] = v.y;
+  }
+}
+
+// acc[r][j] = bias + sum_k inT[k][r] * Wsm[k][lane + 32 j]
+template <class T, int W>
+__device__ __forceinline__ void tile_gemm(const T* __restrict__ inT, int K, const T* __restrict__ Wsm,
+                                          const T* __restrict__ bias, int lane, T (&acc)[MLP_R][W / 32]) {
+  constexpr int CPL = W / 32, LD = W + 1;
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    const T b = bias ? bias[lane + 32 * j] : T(0);
+#pragma unroll
+    for (int r = 0; r < MLP_R; ++r) acc[r][j] = b;
+  }
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    T a[MLP_R], w[CPL];
+    load8(inT + k * MLP_R, a);
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) w[j] = Wsm[k * LD + lane + 32 * j];
+#pragma unroll
+    for (int r = 0; r < MLP_R; ++r)
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) acc[r][j] = fma(a[r], w[j], acc[r][j]);
+  }
+}
+
+// transposed product for the data gradient: out[r][j] = sum_c gT[c][r] * Wsm[lane + 32 j][c]
+template <class T, int W>
+__device__ __forceinline__ void tile_gemm_t(const T* __restrict__ gT, const T* __restrict__ Wsm, int lane,
+                                            T (&acc)[MLP_R][W / 32]) {
+  constexpr int CPL = W / 32, LD = W + 1;
+#pragma unroll
+  for (int j = 0; j < CPL; ++j)
+#pragma unroll
+    for (int r = 0; r < MLP_R; ++r) acc[r][j] = T(0);
+#pragma unroll 4
+  for (int c = 0; c < W; ++c) {
+    T a[MLP_R], w[CPL];
+    load8(gT + c * MLP_R, a);
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) w[j] = Wsm[(lane + 32 * j) * LD + c];
+#pragma unroll
+    for (int r = 0; r < MLP_R; ++r)
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) acc[r][j] = fma(a[r], w[j], acc[r][j]);
+  }
+}
+
+// ELU + LayerNorm (eps 1e-5, biased variance) on the register tile.  z is overwritten by h.
+// xhat / egrad / rstd are produced for the backward pass when SAVE.
+template <class T, int W, bool SAVE>
+__device__ __forceinline__ void elu_layernorm(T (&z)[MLP_R][W / 32], const T* __restrict__ gamma,
+                                              const T* __restrict__ beta, int lane, T (&xhat)[MLP_R][W / 32],
+                                              T (&egrad)[MLP_R][W / 32], T (&rstd)[MLP_R]) {
+  constexpr int CPL = W / 32;
+  T g[CPL], b[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) { g[j] = gamma[lane + 32 * j]; b[j] = beta[lane + 32 * j]; }
+#pragma unroll
+  for (int r = 0; r < MLP_R; ++r) {
+    T s = T(0);
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      const T v = z[r][j];
+      const T e = v > T(0) ? v : sg_expm1(v);
+      if (SAVE) egrad[r][j] = v > T(0) ? T(1) : e + T(1);
+      z[r][j] = e;
+      s += e;
+    }
+    const T mean = warp_sum(s) / T(W);
+    T q = T(0);
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) { z[r][j] -= mean; q += z[r][j] * z[r][j]; }
+    const T rs = sg_rsqrt(warp_sum(q) / T(W) + T(1e-5));
+    if (SAVE) rstd[r] = rs;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      const T xh = z[r][j] * rs;
+      if (SAVE) xhat[r][j] = xh;
+      z[r][j] = xh * g[j] + b[j];
+    }
+  }
+}
+
+// register tile -> warp-private shared tile [c][8]
+template <class T, int W>
+__device__ __forceinline__ void store_tile(T* __restrict__ dstT, int lane, const T (&h)[MLP_R][W / 32]) {
+#pragma unroll
+  for (int j = 0; j < W / 32; ++j)
+#pragma unroll
+    for (int r = 0; r < MLP_R; ++r) dstT[(lane + 32 * j) * MLP_R + r] = h[r][j];
+}
+template <class T, int W>
+__device__ __forceinline__ void load_tile(const T* __restrict__ srcT, int lane, T (&h)[MLP_R][W / 32]) {
+#pragma unroll
+  for (int j = 0; j < W / 32; ++j)
+#pragma unroll
+    for (int r = 0; r < MLP_R; ++r) h[r][j] = srcT[(lane + 32 * j) * MLP_R + r];
+}
+
+// out[r][q] = b_out[q] + sum_c h[r][c] w_out[c][q]; every lane receives every (r, q)
+template <class T, int W, int OUT>
+__device__ __forceinline__ void out_layer(const T (&h)[MLP_R][W / 32], const T* __restrict__ w_out,
+                                          const T* __restrict__ b_out, int lane, T (&mu)[MLP_R][OUT]) {
+#pragma unroll
+  for (int q = 0; q < OUT; ++q) {
+    T w[W / 32];
+#pragma unroll
+    for (int j = 0; j < W / 32; ++j) w[j] = w_out[(lane + 32 * j) * OUT + q];
+#pragma unroll
+    for (int r = 0; r < MLP_R; ++r) {
+      T p = T(0);
+#pragma unroll
+      for (int j = 0; j < W / 32; ++j) p = fma(h[r][j], w[j], p);
+      mu[r][q] = warp_sum(p) + b_out[q];
+    }
+  }
+}
+
+// whole-network forward for 8 rows whose inputs sit in inT ([in_dim][8]); bufA/bufB: warp-private
+// ping-pong tiles [W][8].  Returns the last hidden activations in h.
+template <class T, int W>
+__device__ __forceinline__ void net_forward(const NetSmem<T, W>& net, const T* inT, T* bufA, T* bufB, int lane,
+                                            T (&h)[MLP_R][W / 32]) {
+  T dummy_x[MLP_R][W / 32], dummy_e[MLP_R][W / 32], dummy_r[MLP_R];
+  tile_gemm<T, W>(inT, net.in_dim, net.w_in, net.b_hid, lane, h);
+  elu_layernorm<T, W, false>(h, net.gamma, net.beta, lane, dummy_x, dummy_e, dummy_r);
+  T* cur = bufA;
+  T* nxt = bufB;
+  for (int l = 1; l < net.n_hidden; ++l) {
+    store_tile<T, W>(cur, lane, h);
+    __syncwarp();
+    tile_gemm<T, W>(cur, W, net.w_hid + (size_t)(l - 1) * W * (W + 1), net.b_hid + l * W, lane, h);
+    elu_layernorm<T, W, false>(h, net.gamma + l * W, net.beta + l * W, lane, dummy_x, dummy_e, dummy_r);
+    T* t = cur; cur = nxt; nxt = t;
+  }
+}
+
+}  // namespace sgbpo

@@ -1,0 +1,668 @@
+// Whole-horizon fused rollout: SHAC.collect_trajectories + the reverse pass of update_policy
+// (reference: src/learning_algorithms/shac.py:96-151) for N environments and H steps in THREE launches:
+//
+//   rollout_fwd_kernel   persistent over t = 0..H-1.  A warp owns 8 environments for the whole horizon:
+//                        policy MLP (weights in shared memory, fp32/fp64 FMA register tiles) -> tanh-Gaussian
+//                        action -> fused safeguarded step (sgbpo_step.cuh) on lanes 0..7 -> the next
+//                        observation goes straight back into the warp's shared tile.  State never leaves
+//                        registers between steps; HBM sees only the rollout-buffer rows (coalesced 8-env spans).
+//   mlp_rows_kernel      target critic over all (H x N) observation rows, batched (not on the sequential chain).
+//   rollout_bwd_kernel   persistent over t = H-1..0: recompute the policy forward, dual-number Jacobian of the
+//                        step contracted with the carried cotangents, policy data-gradient; small parameter
+//                        gradients accumulate in registers, the hidden-hidden operands (h1, dz2) are streamed
+//                        out for one split-K GEMM.
+//
+// Environments are independent, so there is no inter-CTA synchronisation anywhere; the reset-all of Q6
+// is uniform over environments and is resolved on the host into a per-step schedule.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/sgbpo.h"
+#include "sgbpo_mlp.cuh"
+#include "sgbpo_step.cuh"
+#include "sgbpo_host.cuh"
+
+namespace sgbpo {
+
+extern thread_local char g_err[512];
+
+template <class T> struct RolloutArgs {
+  int64_t N;
+  int H;
+  // inputs
+  const T* eps;           // [H][N][m]   standard normal draws of the policy
+  const T* noise;         // [H][N][n]   noise samples w_t (centre included; household: T_out already substituted)
+  const T* dirs;          // [H][N][m][2m] or null
+  const T* aux0;          // [N][naux] or null
+  const T* reset_states;  // [R][N][n] or null
+  const int* reset_idx;   // [H]: -1, or the index r of the reset state that REPLACES s_{t+1}
+  const int* aux_src;     // [H]: -1 -> aux0, else r -> reset_states[r][:, 0:naux] is the aux in effect after step t
+  const StepShared<T>* shared;   // [H] or null (household)
+  // rollout buffers
+  T* states;              // [H+1][N][n]   row 0 = s_0 (input), rows 1..H written
+  T* obs;                 // [H+2][N][o]   row 0 = obs_0 (input), rows 1..H written
+  T* actions;             // [H+1][N][m]   policy actions a_t, rows 0..H-1 written
+  T* exec_actions;        // [H][N][m]     executed (safeguarded) actions
+  T* rewards;             // [H+2][N]      rows 0..H-1 written
+  int32_t* flags;         // [H][N]
+};
+
+template <class T> struct BackwardArgs {
+  const T* grw;           // [H]   d loss / d reward[t]  (0 on rows replaced by the critic value)
+  const T* gobs_term;     // [K][N][o] gradient of the terminal-value terms w.r.t. obs rows, or null
+  const int* term_of_row; // [H+2]: -1 or k
+  T* h1_out;              // [H][N][W]   layer-2 input activations      } operands of dW_hid = h1^T dz2
+  T* dz2_out;             // [H][N][W]   layer-2 pre-activation grads   }
+  // parameter gradients (accumulated with atomics, caller zero-fills)
+  T* g_w_in;              // [o][W]
+  T* g_w_out;             // [W][m]
+  T* g_b_hid;             // [2][W]
+  T* g_gamma;             // [2][W]
+  T* g_beta;              // [2][W]
+  T* g_b_out;             // [m]
+  T* g_log_std;           // [m]
+};
+
+constexpr int ROLLOUT_WARPS = 4;
+
+// ---------------------------------------------------------------------------------------------------------
+template <int ENV, class T, int W>
+__global__ void __launch_bounds__(ROLLOUT_WARPS * 32)
+rollout_fwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_constant__ MlpParams<T> P,
+                   const __grid_constant__ SafeConsts<T> k) {
+  using TASK = Task<ENV>;
+  constexpr int NS = TASK::NS, NA = TASK::NA, NO = TASK::NO, NAUX = TASK::NAUX, CPL = W / 32;
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  T* smem = reinterpret_cast<T*>(smem_raw);
+  NetSmem<T, W> net;                       // same carve in every thread: pointers stay in registers
+  T* after = net.load(smem, P);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp-private tiles (32-byte aligned): obsT [NO][8], bufA/bufB [W][8]
+  size_t off = (size_t)(after - smem);
+  off = (off + 7) & ~size_t(7);
+  const size_t per_warp = (size_t)(NO + 2 * W) * MLP_R;
+  T* obsT = smem + off + warp * per_warp;
+  T* bufA = obsT + NO * MLP_R;
+  T* bufB = bufA + W * MLP_R;
+  const int64_t env = ((int64_t)blockIdx.x * ROLLOUT_WARPS + warp) * MLP_R + lane;
+  const bool owner = lane < MLP_R;
+  const bool valid = owner && env < A.N;
+  const int64_t N = A.N;
+
+  T s[NS], aux[NAUX > 0 ? NAUX : 1];
+  T sigma[NA];
+#pragma unroll
+  for (int q = 0; q < NA; ++q) sigma[q] = sg_exp(P.log_std[q]);
+#pragma unroll
+  for (int i = 0; i < NS; ++i) s[i] = valid ? A.states[env * NS + i] : T(0);
+  if (NAUX > 0) {
+#pragma unroll
+    for (int i = 0; i < NAUX; ++i) aux[i] = valid ? A.aux0[env * NAUX + i] : T(0);
+  }
+  if (owner) {
+#pragma unroll
+    for (int i = 0; i < NO; ++i) obsT[i * MLP_R + lane] = valid ? A.obs[env * NO + i] : T(0);
+  }
+  __syncwarp();
+
+  for (int t = 0; t < A.H; ++t) {
+    // issue this step's streaming loads before the MLP so their latency hides behind it
+    T epsv[NA], wv[NS], dv[NA * 2 * NA], rs[NS];
+    const int ridx = A.reset_idx ? A.reset_idx[t] : -1;
+    if (valid) {
+#pragma unroll
+      for (int q = 0; q < NA; ++q) epsv[q] = A.eps[((int64_t)t * N + env) * NA + q];
+#pragma unroll
+      for (int i = 0; i < NS; ++i) wv[i] = A.noise[((int64_t)t * N + env) * NS + i];
+      if (A.dirs) {
+#pragma unroll
+        for (int i = 0; i < NA * 2 * NA; ++i) dv[i] = A.dirs[((int64_t)t * N + env) * (NA * 2 * NA) + i];
+      }
+      if (ridx >= 0) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) rs[i] = A.reset_states[((int64_t)ridx * N + env) * NS + i];
+      }
+    }
+    // ---- policy forward -------------------------------------------------------------------------
+    T h[MLP_R][CPL];
+    net_forward<T, W>(net, obsT, bufA, bufB, lane, h);
+    T mu[MLP_R][NA];
+    out_layer<T, W, NA>(h, net.w_out, net.b_out, lane, mu);
+    // ---- environment step on the owner lanes ---------------------------------------------------
+    __syncwarp();
+    if (owner) {
+      T a[NA];
+#pragma unroll
+      for (int q = 0; q < NA; ++q) {
+        T m = T(0);
+#pragma unroll
+        for (int r = 0; r < MLP_R; ++r) m = (lane == r) ? mu[r][q] : m;
+        a[q] = valid ? sg_tanh(m + sigma[q] * epsv[q]) : T(0);
+      }
+      if (!valid) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) wv[i] = T(0);
+      }
+      if (NAUX > 0 && ridx >= 0 && valid) {     // quadrotor / seeker: goal = reset position
+#pragma unroll
+        for (int i = 0; i < NAUX; ++i) aux[i] = rs[i];
+      }
+      T sn[NS], ae[NA], ob[NO], rew;
+      int fl;
+      const StepShared<T>* sh = A.shared ? A.shared + t : nullptr;
+      StepShared<T> empty;
+      if (!sh) { memset(&empty, 0, sizeof(empty)); sh = &empty; }
+      safeguarded_step<TASK, T, T>(s, a, wv, aux, A.dirs ? dv : nullptr, sh, k, ridx >= 0, rs, sn, ae, ob, rew, fl);
+#pragma unroll
+      for (int i = 0; i < NS; ++i) s[i] = sn[i];
+#pragma unroll
+      for (int i = 0; i < NO; ++i) obsT[i * MLP_R + lane] = ob[i];
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) A.states[((int64_t)(t + 1) * N + env) * NS + i] = sn[i];
+#pragma unroll
+        for (int i = 0; i < NO; ++i) A.obs[((int64_t)(t + 1) * N + env) * NO + i] = ob[i];
+#pragma unroll
+        for (int q = 0; q < NA; ++q) {
+          A.actions[((int64_t)t * N + env) * NA + q] = a[q];
+          A.exec_actions[((int64_t)t * N + env) * NA + q] = ae[q];
+        }
+        A.rewards[(int64_t)t * N + env] = rew;
+        A.flags[(int64_t)t * N + env] = fl;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// batched MLP forward over M rows: out[row] = net(x[row]) (critic: out_dim = 1).
+template <class T, int W>
+__global__ void __launch_bounds__(256)
+mlp_rows_kernel(int64_t M, int in_dim, const T* __restrict__ x, T* __restrict__ out,
+                const __grid_constant__ MlpParams<T> P) {
+  constexpr int CPL = W / 32;
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  T* smem = reinterpret_cast<T*>(smem_raw);
+  NetSmem<T, W> net;                       // same carve in every thread: pointers stay in registers
+  T* after = net.load(smem, P);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  size_t off = (size_t)(after - smem);
+  off = (off + 7) & ~size_t(7);
+  const size_t per_warp = (size_t)(in_dim + 2 * W) * MLP_R;
+  T* inT = smem + off + warp * per_warp;
+  T* bufA = inT + in_dim * MLP_R;
+  T* bufB = bufA + W * MLP_R;
+  const int64_t n_blocks = (M + MLP_R - 1) / MLP_R;
+  for (int64_t blk = (int64_t)blockIdx.x * nwarps + warp; blk < n_blocks; blk += (int64_t)gridDim.x * nwarps) {
+    const int64_t row0 = blk * MLP_R;
+    const int total = in_dim * MLP_R;
+    for (int i = lane; i < total; i += 32) {        // contiguous 8-row span, coalesced
+      const int r = i / in_dim, c = i % in_dim;
+      inT[c * MLP_R + r] = (row0 + r < M) ? x[row0 * in_dim + i] : T(0);
+    }
+    __syncwarp();
+    T h[MLP_R][CPL];
+    net_forward<T, W>(net, inT, bufA, bufB, lane, h);
+    T v[MLP_R][1];
+    out_layer<T, W, 1>(h, net.w_out, net.b_out, lane, v);
+    if (lane < MLP_R && row0 + lane < M) {
+      T mine = T(0);
+#pragma unroll
+      for (int r = 0; r < MLP_R; ++r) mine = (lane == r) ? v[r][0] : mine;
+      out[row0 + lane] = mine;
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+template <int ENV, class T, int W>
+__global__ void __launch_bounds__(ROLLOUT_WARPS * 32)
+rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_constant__ BackwardArgs<T> G,
+                   const __grid_constant__ MlpParams<T> P, const __grid_constant__ SafeConsts<T> k) {
+  using TASK = Task<ENV>;
+  constexpr int NS = TASK::NS, NA = TASK::NA, NO = TASK::NO, NAUX = TASK::NAUX, CPL = W / 32, KD = NS + NA;
+  using D = Dual<T, KD>;
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  T* smem = reinterpret_cast<T*>(smem_raw);
+  NetSmem<T, W> net;                       // same carve in every thread: pointers stay in registers
+  T* after = net.load(smem, P);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  size_t off = (size_t)(after - smem);
+  off = (off + 7) & ~size_t(7);
+  // warp-private: obsT [NO][8], h1T [W][8], g2T [W][8], stash x1/e1/x2/e2 [W][8] each
+  const size_t per_warp = (size_t)(NO + 6 * W) * MLP_R;
+  T* obsT = smem + off + warp * per_warp;
+  T* h1T = obsT + NO * MLP_R;
+  T* g2T = h1T + W * MLP_R;
+  T* x1S = g2T + W * MLP_R;
+  T* e1S = x1S + W * MLP_R;
+  T* x2S = e1S + W * MLP_R;
+  T* e2S = x2S + W * MLP_R;
+  const int64_t N = A.N;
+  const int64_t env = ((int64_t)blockIdx.x * ROLLOUT_WARPS + warp) * MLP_R + lane;
+  const bool owner = lane < MLP_R;
+  const bool valid = owner && env < N;
+  const int64_t env0 = ((int64_t)blockIdx.x * ROLLOUT_WARPS + warp) * MLP_R;   // first env of this warp
+
+  T sigma[NA];
+#pragma unroll
+  for (int q = 0; q < NA; ++q) sigma[q] = sg_exp(P.log_std[q]);
+  const T* Whid = net.w_hid;                 // single hidden-hidden layer (n_hidden == 2)
+  // carried cotangents (owner lanes)
+  T gs[NS], gobs[NO];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) gs[i] = T(0);
+#pragma unroll
+  for (int i = 0; i < NO; ++i) gobs[i] = T(0);
+  // per-lane parameter-gradient accumulators
+  T a_b1[CPL], a_g1[CPL], a_be1[CPL], a_b2[CPL], a_g2[CPL], a_be2[CPL], a_wout[CPL][NA], a_win[NO][CPL];
+  T a_bout[NA], a_lstd[NA];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    a_b1[j] = a_g1[j] = a_be1[j] = a_b2[j] = a_g2[j] = a_be2[j] = T(0);
+#pragma unroll
+    for (int q = 0; q < NA; ++q) a_wout[j][q] = T(0);
+#pragma unroll
+    for (int i = 0; i < NO; ++i) a_win[i][j] = T(0);
+  }
+#pragma unroll
+  for (int q = 0; q < NA; ++q) a_bout[q] = a_lstd[q] = T(0);
+
+  for (int t = A.H - 1; t >= 0; --t) {
+    // ---- loads (owner lanes) ------------------------------------------------------------------------
+    T sv[NS], epsv[NA], wv[NS], dv[NA * 2 * NA], rs[NS], aux[NAUX > 0 ? NAUX : 1];
+    const int ridx = A.reset_idx ? A.reset_idx[t] : -1;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) { sv[i] = T(0); wv[i] = T(0); rs[i] = T(0); }
+#pragma unroll
+    for (int q = 0; q < NA; ++q) epsv[q] = T(0);
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < NS; ++i) sv[i] = A.states[((int64_t)t * N + env) * NS + i];
+#pragma unroll
+      for (int q = 0; q < NA; ++q) epsv[q] = A.eps[((int64_t)t * N + env) * NA + q];
+#pragma unroll
+      for (int i = 0; i < NS; ++i) wv[i] = A.noise[((int64_t)t * N + env) * NS + i];
+      if (A.dirs) {
+#pragma unroll
+        for (int i = 0; i < NA * 2 * NA; ++i) dv[i] = A.dirs[((int64_t)t * N + env) * (NA * 2 * NA) + i];
+      }
+      if (ridx >= 0) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) rs[i] = A.reset_states[((int64_t)ridx * N + env) * NS + i];
+      }
+      if (NAUX > 0) {
+        const int src = A.aux_src ? A.aux_src[t] : -1;
+#pragma unroll
+        for (int i = 0; i < NAUX; ++i)
+          aux[i] = src < 0 ? A.aux0[env * NAUX + i] : A.reset_states[((int64_t)src * N + env) * NS + i];
+      }
+    }
+    if (owner) {
+#pragma unroll
+      for (int i = 0; i < NO; ++i) obsT[i * MLP_R + lane] = valid ? A.obs[((int64_t)t * N + env) * NO + i] : T(0);
+    }
+    __syncwarp();
+    // ---- recompute the policy forward, stashing what the backward needs ----------------------------------
+    T rstd1[MLP_R], rstd2[MLP_R];
+    T mu[MLP_R][NA];
+    {
+      T z[MLP_R][CPL], xh[MLP_R][CPL], eg[MLP_R][CPL];
+      tile_gemm<T, W>(obsT, NO, net.w_in, net.b_hid, lane, z);
+      elu_layernorm<T, W, true>(z, net.gamma, net.beta, lane, xh, eg, rstd1);
+      store_tile<T, W>(h1T, lane, z);
+      store_tile<T, W>(x1S, lane, xh);
+      store_tile<T, W>(e1S, lane, eg);
+      __syncwarp();
+      tile_gemm<T, W>(h1T, W, Whid, net.b_hid + W, lane, z);
+      elu_layernorm<T, W, true>(z, net.gamma + W, net.beta + W, lane, xh, eg, rstd2);
+      out_layer<T, W, NA>(z, net.w_out, net.b_out, lane, mu);
+      store_tile<T, W>(x2S, lane, xh);
+      store_tile<T, W>(e2S, lane, eg);
+      // stream h1 (layer-2 input) out for the dW_hid GEMM: [t][env][W], 8-env span of this warp
+#pragma unroll
+      for (int r = 0; r < MLP_R; ++r) {
+        if (env0 + r < N) {
+          T hrow[CPL];
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) hrow[j] = h1T[(lane + 32 * j) * MLP_R + r];
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) G.h1_out[((int64_t)t * N + env0 + r) * W + lane + 32 * j] = hrow[j];
+        }
+      }
+    }
+    __syncwarp();
+    // ---- step Jacobian (duals) contracted with the carried cotangents, on the owner lanes -----------------
+    T ga_pre[NA];          // d loss / d (mu + sigma eps)   (after the tanh)
+#pragma unroll
+    for (int q = 0; q < NA; ++q) ga_pre[q] = T(0);
+    T act[NA];
+#pragma unroll
+    for (int q = 0; q < NA; ++q) act[q] = T(0);
+    if (owner) {
+#pragma unroll
+      for (int q = 0; q < NA; ++q) {
+        T m = T(0);
+#pragma unroll
+        for (int r = 0; r < MLP_R; ++r) m = (lane == r) ? mu[r][q] : m;
+        act[q] = valid ? sg_tanh(m + sigma[q] * epsv[q]) : T(0);
+      }
+      D sd[NS], ad[NA], sn[NS], ae[NA], ob[NO], rew;
+#pragma unroll
+      for (int i = 0; i < NS; ++i) sd[i] = D::seed(sv[i], i);
+#pragma unroll
+      for (int q = 0; q < NA; ++q) ad[q] = D::seed(act[q], NS + q);
+      int fl;
+      const StepShared<T>* sh = A.shared ? A.shared + t : nullptr;
+      StepShared<T> empty;
+      if (!sh) { memset(&empty, 0, sizeof(empty)); sh = &empty; }
+      safeguarded_step<TASK, D, T>(sd, ad, wv, aux, A.dirs ? dv : nullptr, sh, k, ridx >= 0, rs, sn, ae, ob, rew, fl);
+      // cotangent of obs_{t+1}: carried policy-input gradient + terminal-value term of row t+1
+      T go[NO];
+#pragma unroll
+      for (int i = 0; i < NO; ++i) go[i] = gobs[i];
+      const int kt = G.term_of_row ? G.term_of_row[t + 1] : -1;
+      if (kt >= 0 && valid) {
+#pragma unroll
+        for (int i = 0; i < NO; ++i) go[i] += G.gobs_term[((int64_t)kt * N + env) * NO + i];
+      }
+      const T gr = G.grw[t];
+      T acc[KD];
+#pragma unroll
+      for (int d = 0; d < KD; ++d) {
+        T v = gr * rew.d[d];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) v += gs[i] * sn[i].d[d];
+#pragma unroll
+        for (int i = 0; i < NO; ++i) v += go[i] * ob[i].d[d];
+        acc[d] = valid ? v : T(0);
+      }
+#pragma unroll
+      for (int i = 0; i < NS; ++i) gs[i] = acc[i];
+#pragma unroll
+      for (int q = 0; q < NA; ++q) ga_pre[q] = acc[NS + q] * (T(1) - act[q] * act[q]);
+    }
+    // broadcast d mu to the whole warp: dmu[r][q] from lane r
+    T dmu[MLP_R][NA];
+#pragma unroll
+    for (int r = 0; r < MLP_R; ++r)
+#pragma unroll
+      for (int q = 0; q < NA; ++q) dmu[r][q] = __shfl_sync(0xffffffffu, ga_pre[q], r);
+    if (owner) {
+#pragma unroll
+      for (int q = 0; q < NA; ++q) {
+        a_bout[q] += ga_pre[q];
+        a_lstd[q] += ga_pre[q] * epsv[q] * sigma[q];
+      }
+    }
+    // ---- policy backward ---------------------------------------------------------------------------------
+    T gcarry[MLP_R][CPL];       // gradient flowing into the current layer's output
+    {
+      // output layer: dh2 = dmu w_out^T ; dW_out += h2^T dmu (h2 = xhat2 * gamma2 + beta2)
+      T xh[MLP_R][CPL], eg[MLP_R][CPL];
+      load_tile<T, W>(x2S, lane, xh);
+      load_tile<T, W>(e2S, lane, eg);
+      T wo[CPL][NA], g2[CPL], b2[CPL];
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        g2[j] = net.gamma[W + lane + 32 * j];
+        b2[j] = net.beta[W + lane + 32 * j];
+#pragma unroll
+        for (int q = 0; q < NA; ++q) wo[j][q] = net.w_out[(lane + 32 * j) * NA + q];
+      }
+#pragma unroll
+      for (int r = 0; r < MLP_R; ++r)
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          T dh = T(0);
+          const T h2 = xh[r][j] * g2[j] + b2[j];
+#pragma unroll
+          for (int q = 0; q < NA; ++q) { dh = fma(dmu[r][q], wo[j][q], dh); a_wout[j][q] = fma(h2, dmu[r][q], a_wout[j][q]); }
+          gcarry[r][j] = dh;
+        }
+      // LayerNorm 2 + ELU 2 backward -> dz2
+#pragma unroll
+      for (int r = 0; r < MLP_R; ++r) {
+        T s1 = T(0), s2 = T(0);
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          a_g2[j] = fma(gcarry[r][j], xh[r][j], a_g2[j]);
+          a_be2[j] += gcarry[r][j];
+          const T dx = gcarry[r][j] * g2[j];
+          gcarry[r][j] = dx;
+          s1 += dx;
+          s2 = fma(dx, xh[r][j], s2);
+        }
+        s1 = warp_sum(s1) / T(W);
+        s2 = warp_sum(s2) / T(W);
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          const T de = rstd2[r] * (gcarry[r][j] - s1 - xh[r][j] * s2);
+          const T dz = de * eg[r][j];
+          gcarry[r][j] = dz;
+          a_b2[j] += dz;
+        }
+      }
+      store_tile<T, W>(g2T, lane, gcarry);
+      __syncwarp();
+      // stream dz2 out for the dW_hid GEMM
+#pragma unroll
+      for (int r = 0; r < MLP_R; ++r) {
+        if (env0 + r < N) {
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) G.dz2_out[((int64_t)t * N + env0 + r) * W + lane + 32 * j] = gcarry[r][j];
+        }
+      }
+      // dh1 = dz2 W_hid^T
+      tile_gemm_t<T, W>(g2T, Whid, lane, gcarry);
+      // LayerNorm 1 + ELU 1 backward -> dz1
+      load_tile<T, W>(x1S, lane, xh);
+      load_tile<T, W>(e1S, lane, eg);
+      T g1[CPL];
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) g1[j] = net.gamma[lane + 32 * j];
+#pragma unroll
+      for (int r = 0; r < MLP_R; ++r) {
+        T s1 = T(0), s2 = T(0);
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          a_g1[j] = fma(gcarry[r][j], xh[r][j], a_g1[j]);
+          a_be1[j] += gcarry[r][j];
+          const T dx = gcarry[r][j] * g1[j];
+          gcarry[r][j] = dx;
+          s1 += dx;
+          s2 = fma(dx, xh[r][j], s2);
+        }
+        s1 = warp_sum(s1) / T(W);
+        s2 = warp_sum(s2) / T(W);
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          const T de = rstd1[r] * (gcarry[r][j] - s1 - xh[r][j] * s2);
+          const T dz = de * eg[r][j];
+          gcarry[r][j] = dz;
+          a_b1[j] += dz;
+        }
+      }
+    }
+    // input layer: dW_in += obs^T dz1 ; dobs = dz1 W_in^T (reduced over columns across the warp)
+    T gobs_new[NO];
+#pragma unroll
+    for (int i = 0; i < NO; ++i) {
+      T wi[CPL];
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) wi[j] = net.w_in[i * (W + 1) + lane + 32 * j];
+      T mine = T(0);
+#pragma unroll
+      for (int r = 0; r < MLP_R; ++r) {
+        const T ob_r = obsT[i * MLP_R + r];
+        T p = T(0);
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) { p = fma(gcarry[r][j], wi[j], p); a_win[i][j] = fma(ob_r, gcarry[r][j], a_win[i][j]); }
+        p = warp_sum(p);
+        mine = (lane == r) ? p : mine;
+      }
+      gobs_new[i] = mine;
+    }
+    if (owner) {
+#pragma unroll
+      for (int i = 0; i < NO; ++i) gobs[i] = valid ? gobs_new[i] : T(0);
+    }
+    __syncwarp();
+  }
+  // ---- flush the per-lane parameter gradients ----------------------------------------------------------------
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    const int c = lane + 32 * j;
+    atomicAdd(G.g_b_hid + c, a_b1[j]);  atomicAdd(G.g_b_hid + W + c, a_b2[j]);
+    atomicAdd(G.g_gamma + c, a_g1[j]);  atomicAdd(G.g_gamma + W + c, a_g2[j]);
+    atomicAdd(G.g_beta + c, a_be1[j]);  atomicAdd(G.g_beta + W + c, a_be2[j]);
+#pragma unroll
+    for (int q = 0; q < NA; ++q) atomicAdd(G.g_w_out + c * NA + q, a_wout[j][q]);
+#pragma unroll
+    for (int i = 0; i < NO; ++i) atomicAdd(G.g_w_in + i * W + c, a_win[i][j]);
+  }
+  if (owner) {
+#pragma unroll
+    for (int q = 0; q < NA; ++q) { atomicAdd(G.g_b_out + q, a_bout[q]); atomicAdd(G.g_log_std + q, a_lstd[q]); }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+template <class T, int W> size_t fwd_smem(int in_dim, int n_hidden, int out_dim, int no) {
+  size_t f = NetSmem<T, W>::floats(in_dim, n_hidden, out_dim);
+  f = (f + 7) & ~size_t(7);
+  f += (size_t)ROLLOUT_WARPS * (no + 2 * W) * MLP_R;
+  return f * sizeof(T) + 32;
+}
+template <class T, int W> size_t bwd_smem(int in_dim, int n_hidden, int out_dim, int no) {
+  size_t f = NetSmem<T, W>::floats(in_dim, n_hidden, out_dim);
+  f = (f + 7) & ~size_t(7);
+  f += (size_t)ROLLOUT_WARPS * (no + 6 * W) * MLP_R;
+  return f * sizeof(T) + 32;
+}
+template <class T, int W> size_t rows_smem(int in_dim, int n_hidden, int out_dim, int warps) {
+  size_t f = NetSmem<T, W>::floats(in_dim, n_hidden, out_dim);
+  f = (f + 7) & ~size_t(7);
+  f += (size_t)warps * (in_dim + 2 * W) * MLP_R;
+  return f * sizeof(T) + 32;
+}
+
+static int cuda_fail2(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+  return SGBPO_E_CUDA;
+}
+static int fail2(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+
+template <class T> MlpParams<T> convert_mlp(const sgbpo_mlp& m) {
+  MlpParams<T> p;
+  p.in_dim = m.in_dim; p.width = m.width; p.n_hidden = m.n_hidden; p.out_dim = m.out_dim;
+  p.w_in = (const T*)m.w_in; p.w_hid = (const T*)m.w_hid; p.w_out = (const T*)m.w_out;
+  p.b_hid = (const T*)m.b_hid; p.gamma = (const T*)m.gamma; p.beta = (const T*)m.beta;
+  p.b_out = (const T*)m.b_out; p.log_std = (const T*)m.log_std;
+  return p;
+}
+template <class T> RolloutArgs<T> convert_rollout(const sgbpo_rollout& r) {
+  RolloutArgs<T> a;
+  a.N = r.N; a.H = r.H;
+  a.eps = (const T*)r.eps; a.noise = (const T*)r.noise; a.dirs = (const T*)r.dirs; a.aux0 = (const T*)r.aux0;
+  a.reset_states = (const T*)r.reset_states; a.reset_idx = r.reset_idx; a.aux_src = r.aux_src;
+  a.shared = (const StepShared<T>*)r.shared;
+  a.states = (T*)r.states; a.obs = (T*)r.obs; a.actions = (T*)r.actions; a.exec_actions = (T*)r.exec_actions;
+  a.rewards = (T*)r.rewards; a.flags = r.flags;
+  return a;
+}
+template <class T> BackwardArgs<T> convert_backward(const sgbpo_rollout_grads& g) {
+  BackwardArgs<T> b;
+  b.grw = (const T*)g.grw; b.gobs_term = (const T*)g.gobs_term; b.term_of_row = g.term_of_row;
+  b.h1_out = (T*)g.h1_out; b.dz2_out = (T*)g.dz2_out;
+  b.g_w_in = (T*)g.g_w_in; b.g_w_out = (T*)g.g_w_out; b.g_b_hid = (T*)g.g_b_hid; b.g_gamma = (T*)g.g_gamma;
+  b.g_beta = (T*)g.g_beta; b.g_b_out = (T*)g.g_b_out; b.g_log_std = (T*)g.g_log_std;
+  return b;
+}
+
+template <int ENV, class T, int W> struct RolloutLaunch {
+  static int fwd(const sgbpo_consts* c, const sgbpo_mlp* pol, const sgbpo_rollout* r, cudaStream_t st) {
+    using TASK = Task<ENV>;
+    if (pol->in_dim != TASK::NO || pol->out_dim != TASK::NA) return fail2(SGBPO_E_ARG, "policy dims do not match the environment");
+    const size_t smem = fwd_smem<T, W>(pol->in_dim, pol->n_hidden, pol->out_dim, TASK::NO);
+    if (smem > 227 * 1024) return fail2(SGBPO_E_UNSUPPORTED, "policy does not fit in shared memory");
+    auto kern = rollout_fwd_kernel<ENV, T, W>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail2(e, "cudaFuncSetAttribute(rollout_fwd)");
+    const int64_t per_cta = ROLLOUT_WARPS * MLP_R;
+    const int grid = (int)((r->N + per_cta - 1) / per_cta);
+    kern<<<grid, ROLLOUT_WARPS * 32, smem, st>>>(convert_rollout<T>(*r), convert_mlp<T>(*pol), convert_consts<T>(*c));
+    e = cudaGetLastError();
+    return e == cudaSuccess ? SGBPO_OK : cuda_fail2(e, "rollout_fwd_kernel");
+  }
+  static int bwd(const sgbpo_consts* c, const sgbpo_mlp* pol, const sgbpo_rollout* r, const sgbpo_rollout_grads* g,
+                 cudaStream_t st) {
+    using TASK = Task<ENV>;
+    if (pol->n_hidden != 2) return fail2(SGBPO_E_UNSUPPORTED, "fused backward supports policies with two hidden layers");
+    const size_t smem = bwd_smem<T, W>(pol->in_dim, pol->n_hidden, pol->out_dim, TASK::NO);
+    if (smem > 227 * 1024) return fail2(SGBPO_E_UNSUPPORTED, "policy does not fit in shared memory (backward)");
+    auto kern = rollout_bwd_kernel<ENV, T, W>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail2(e, "cudaFuncSetAttribute(rollout_bwd)");
+    const int64_t per_cta = ROLLOUT_WARPS * MLP_R;
+    const int grid = (int)((r->N + per_cta - 1) / per_cta);
+    kern<<<grid, ROLLOUT_WARPS * 32, smem, st>>>(convert_rollout<T>(*r), convert_backward<T>(*g), convert_mlp<T>(*pol),
+                                                 convert_consts<T>(*c));
+    e = cudaGetLastError();
+    return e == cudaSuccess ? SGBPO_OK : cuda_fail2(e, "rollout_bwd_kernel");
+  }
+};
+
+template <class T, int W> int launch_rows(int64_t M, const sgbpo_mlp* net, const void* x, void* out, cudaStream_t st) {
+  const int warps = 8;
+  const size_t smem = rows_smem<T, W>(net->in_dim, net->n_hidden, net->out_dim, warps);
+  if (smem > 227 * 1024) return fail2(SGBPO_E_UNSUPPORTED, "network does not fit in shared memory");
+  auto kern = mlp_rows_kernel<T, W>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail2(e, "cudaFuncSetAttribute(mlp_rows)");
+  int64_t blocks = (M + MLP_R * warps - 1) / (MLP_R * warps);
+  const int64_t cap = 148 * (smem > 110 * 1024 ? 1 : 2);
+  if (blocks > cap) blocks = cap;
+  kern<<<(int)blocks, warps * 32, smem, st>>>(M, net->in_dim, (const T*)x, (T*)out, convert_mlp<T>(*net));
+  e = cudaGetLastError();
+  return e == cudaSuccess ? SGBPO_OK : cuda_fail2(e, "mlp_rows_kernel");
+}
+
+
+// per-environment entry points (one translation unit each, so nvcc compiles them in parallel)
+template <int ENV> int rollout_fwd_env(int dtype, int width, const sgbpo_consts* c, const sgbpo_mlp* pol,
+                                       const sgbpo_rollout* r, cudaStream_t st);
+template <int ENV> int rollout_bwd_env(int dtype, int width, const sgbpo_consts* c, const sgbpo_mlp* pol,
+                                       const sgbpo_rollout* r, const sgbpo_rollout_grads* g, cudaStream_t st);
+
+#define SGBPO_INSTANTIATE_ROLLOUT_ENV(E)                                                                       \
+  template <> int rollout_fwd_env<E>(int dtype, int width, const sgbpo_consts* c, const sgbpo_mlp* pol,          \
+                                     const sgbpo_rollout* r, cudaStream_t st) {                                   \
+    switch (width) {                                                                                              \
+      case 32: return dtype ? RolloutLaunch<E, double, 32>::fwd(c, pol, r, st) : RolloutLaunch<E, float, 32>::fwd(c, pol, r, st);   \
+      case 64: return dtype ? RolloutLaunch<E, double, 64>::fwd(c, pol, r, st) : RolloutLaunch<E, float, 64>::fwd(c, pol, r, st);   \
+      case 128: return dtype ? RolloutLaunch<E, double, 128>::fwd(c, pol, r, st) : RolloutLaunch<E, float, 128>::fwd(c, pol, r, st); \
+      default: return fail2(SGBPO_E_UNSUPPORTED, "fused rollout supports hidden widths 32, 64, 128");            \
+    }                                                                                                             \
+  }                                                                                                               \
+  template <> int rollout_bwd_env<E>(int dtype, int width, const sgbpo_consts* c, const sgbpo_mlp* pol,          \
+                                     const sgbpo_rollout* r, const sgbpo_rollout_grads* g, cudaStream_t st) {     \
+    switch (width) {                                                                                              \
+      case 32: return dtype ? RolloutLaunch<E, double, 32>::bwd(c, pol, r, g, st) : RolloutLaunch<E, float, 32>::bwd(c, pol, r, g, st);   \
+      case 64: return dtype ? RolloutLaunch<E, double, 64>::bwd(c, pol, r, g, st) : RolloutLaunch<E, float, 64>::bwd(c, pol, r, g, st);   \
+      case 128: return dtype ? RolloutLaunch<E, double, 128>::bwd(c, pol, r, g, st) : RolloutLaunch<E, float, 128>::bwd(c, pol, r, g, st); \
+      default: return fail2(SGBPO_E_UNSUPPORTED, "fused rollout supports hidden widths 32, 64, 128");            \
+    }                                                                                                             \
+  }
+
+}  // namespace sgbpo

@@ -1,7 +1,325 @@
-"""Whole-horizon fused rollout engine (placeholder until csrc/sgbpo_rollout.cu lands)."""
+"""Whole-horizon fused engine behind ``SHAC.collect_trajectories`` / ``SHAC.update_policy``.
+
+Host side of csrc/sgbpo_rollout*.cu: resolves the episode schedule (reset-all of Q6, terminal rows,
+household series), draws the random inputs in the reference's order, launches
+
+    sgbpo_rollout_fwd  ->  sgbpo_mlp_rows (target critic over all rows)          [collect_trajectories]
+    (critic input-gradient on the terminal rows) -> sgbpo_rollout_bwd -> one GEMM   [update_policy backward]
+
+and maps the results back onto the reference's objects (CoupledBuffer tensors, ``policy.*.grad``).
+Everything numeric runs in libsgbpo.so except two plain library calls: the critic's input gradient on the
+K terminal rows (torch autograd on N x o inputs) and dW_hid = h1^T dz2 (cuBLAS through torch.matmul).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from .. import _lib, rng
+from .._lib import Mlp, Rollout, RolloutGrads, check, dtype_code, stream_ptr
+
+FUSED_ENVS = {"BalancePendulum", "BalanceCartPole", "SwingUpCartPole", "BalanceQuadrotor"}
+WIDTHS = (32, 64, 128)
+
+
+def _mlp_layout(model: nn.Sequential):
+    """(linears, norms) of a Linear/ELU/LayerNorm stack, or None if the module is not of that form."""
+    mods = list(model)
+    if len(mods) < 4 or (len(mods) - 1) % 3:
+        return None
+    n_hidden = (len(mods) - 1) // 3
+    lin, norm = [], []
+    for l in range(n_hidden):
+        a, b, c = mods[3 * l: 3 * l + 3]
+        if not (isinstance(a, nn.Linear) and isinstance(b, nn.ELU) and isinstance(c, nn.LayerNorm)):
+            return None
+        if b.alpha != 1.0 or abs(c.eps - 1e-5) > 0 or not c.elementwise_affine:
+            return None
+        lin.append(a)
+        norm.append(c)
+    if not isinstance(mods[-1], nn.Linear):
+        return None
+    lin.append(mods[-1])
+    widths = {l.out_features for l in lin[:-1]}
+    if len(widths) != 1 or next(iter(widths)) not in WIDTHS:
+        return None
+    return lin, norm
+
+
+class PackedMlp:
+    """Device copies of an MLP's parameters in the kernels' layout + the ctypes descriptor."""
+
+    def __init__(self, model: nn.Sequential, log_std: Optional[Tensor] = None):
+        self.lin, self.norm = _mlp_layout(model)
+        self.log_std = log_std
+        self.n_hidden = len(self.norm)
+        self.width = self.lin[0].out_features
+        self.in_dim, self.out_dim = self.lin[0].in_features, self.lin[-1].out_features
+        self.refresh()
+
+    @torch.no_grad()
+    def refresh(self):
+        lin, norm = self.lin, self.norm
+        self.w_in = lin[0].weight.t().contiguous()
+        if self.n_hidden > 1:
+            self.w_hid = torch.stack([l.weight.t() for l in lin[1:-1]]).contiguous()
+        else:
+            self.w_hid = torch.zeros(1, dtype=self.w_in.dtype, device=self.w_in.device)
+        self.w_out = lin[-1].weight.t().contiguous()
+        self.b_hid = torch.stack([l.bias for l in lin[:-1]]).contiguous()
+        self.gamma = torch.stack([n.weight for n in norm]).contiguous()
+        self.beta = torch.stack([n.bias for n in norm]).contiguous()
+        self.b_out = lin[-1].bias.contiguous()
+        d = Mlp()
+        d.in_dim, d.width, d.n_hidden, d.out_dim = self.in_dim, self.width, self.n_hidden, self.out_dim
+        d.w_in, d.w_hid, d.w_out = self.w_in.data_ptr(), self.w_hid.data_ptr(), self.w_out.data_ptr()
+        d.b_hid, d.gamma, d.beta, d.b_out = (self.b_hid.data_ptr(), self.gamma.data_ptr(), self.beta.data_ptr(),
+                                             self.b_out.data_ptr())
+        if self.log_std is not None:
+            self._ls = self.log_std.detach().contiguous()
+            d.log_std = self._ls.data_ptr()
+        self.desc = d
 
 
 class FusedRollout:
+    def __init__(self, algo):
+        self.algo = algo
+        self.wrapper = algo.env if hasattr(algo.env, "consts") else None
+        self.base = algo.env.env if self.wrapper is not None else algo.env
+        self.rng_mode = "reference"        # "reference": per-step draws in the reference's order; "batched": 2 draws
+        self.policy_pack = PackedMlp(algo.policy.model, algo.policy.log_std)
+        self.vf_pack = PackedMlp(algo.target_value_function.model)
+        self._grad_bufs = None
+        self.last = None
+        self.launches_per_episode = 3          # rollout_fwd, mlp_rows, rollout_bwd (our kernels)
+        self.profile = False                   # record CUDA events around each of our kernels
+        self.kernel_ms = {"rollout_fwd": [], "mlp_rows": [], "rollout_bwd": []}
+
+    def _timed(self, name, fn):
+        if not self.profile:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        self.kernel_ms[name].append((e0, e1))
+        return out
+
+    def kernel_times(self) -> dict:
+        """Average duration (ms) of each kernel over the recorded launches (call after a synchronize)."""
+        return {k: (sum(a.elapsed_time(b) for a, b in v) / len(v) if v else None) for k, v in self.kernel_ms.items()}
+
+    # ------------------------------------------------------------------------------------------------------
     @staticmethod
-    def try_create(algo):
-        return None
+    def try_create(algo) -> Optional["FusedRollout"]:
+        env = algo.env
+        base = env.env if hasattr(env, "consts") else env
+        if getattr(base, "ENV_NAME", None) not in FUSED_ENVS:
+            return None
+        if not torch.cuda.is_available() or base.state.device.type != "cuda":
+            return None
+        if base.state.dtype not in (torch.float32, torch.float64):
+            return None
+        pol = algo.policy
+        if not pol.stochastic or _mlp_layout(pol.model) is None or _mlp_layout(algo.target_value_function.model) is None:
+            return None
+        if len(_mlp_layout(pol.model)[1]) != 2:          # fused backward: two hidden layers
+            return None
+        if algo.buffer.store_safe_actions:
+            return None
+        if hasattr(env, "consts"):
+            try:
+                env.consts()
+            except NotImplementedError:
+                return None
+        return FusedRollout(algo)
+
+    def _consts(self):
+        return self.wrapper.consts() if self.wrapper is not None else self.base._plain
+
+    # ------------------------------------------------------------------------------------------------------
+    def _draw_inputs(self, H: int):
+        """Random inputs + episode schedule, in the reference's order."""
+        base, wrapper = self.base, self.wrapper
+        N, n, m = base.num_envs, base.state_dim, base.action_dim
+        dt, dev = base.state.dtype, base.state.device
+        want_dirs = (wrapper is not None and wrapper.SG_KIND == _lib.SG_RAY_MASK
+                     and getattr(wrapper, "zonotopic_approximation", False) and wrapper.state_constrained)
+        eps, noise, dirs, resets = [], [], [], []
+        reset_idx, aux_src, terminal_rows, shared_rows = [-1] * H, [-1] * H, [False] * (H + 2), []
+        pending, cur_aux = base._reset_pending, -1
+        if self.rng_mode == "batched" and not pending and base.steps + H < base.num_steps and base._shared() is None:
+            eps_t = rng.randn(H, N, m).to(dt)
+            u = rng.rand(H, N, 1, n).to(dt)
+            noise_t = base.noise_set.center.to(dt).unsqueeze(0) + (base.noise_set.generator.to(dt).unsqueeze(0) * (2 * u - 1)).sum(dim=3)
+            dirs_t = None
+            if want_dirs:
+                d = rng.rand(H, N, m, 2 * m).to(dt) * 2 - 1
+                dirs_t = d / torch.linalg.vector_norm(d, dim=2, keepdim=True)
+            base.steps += H
+            terminal_rows[H] = True
+            return eps_t, noise_t, dirs_t, None, reset_idx, aux_src, terminal_rows, None
+        for t in range(H):
+            eps.append(rng.randn(N, m).to(dt))
+            if want_dirs:
+                dirs.append(wrapper._directions().to(dt))
+            noise.append(base._noise().to(dt))
+            base.steps += 1
+            if pending:
+                base.reset()                      # draws; sets steps = 0 and the task's aux (goal)
+                resets.append(base.state.detach().to(dt))
+                reset_idx[t] = cur_aux = len(resets) - 1
+            aux_src[t] = cur_aux
+            sh = base._shared()
+            if sh is not None:
+                shared_rows.append(list(sh.series) + [sh.load_t, sh.pv_t, sh.price_t])
+            pending = base.steps >= base.num_steps
+            terminal_rows[t + 1] = pending
+        terminal_rows[H] = True
+        base._reset_pending = pending
+        eps_t, noise_t = torch.stack(eps), torch.stack(noise)
+        dirs_t = torch.stack(dirs) if dirs else None
+        resets_t = torch.stack(resets) if resets else None
+        shared_t = torch.tensor(shared_rows, dtype=dt, device=dev) if shared_rows else None
+        return eps_t, noise_t, dirs_t, resets_t, reset_idx, aux_src, terminal_rows, shared_t
+
+    # ------------------------------------------------------------------------------------------------------
+    def collect_trajectories(self) -> float:
+        algo, base = self.algo, self.base
+        H, N = algo.len_trajectories, base.num_envs
+        n, m, o = base.state_dim, base.action_dim, base.obs_dim
+        dt, dev = base.state.dtype, base.state.device
+        base.cut_computation_graph()
+        s0 = base.state.detach().contiguous()
+        aux0 = base._aux()
+        aux0 = None if aux0 is None else aux0.detach().to(dt).contiguous()
+        buf = algo.buffer
+        obs0 = buf.observations.tensor[0].detach()
+        val0 = buf.values.tensor[0].detach()
+        eps, noise, dirs, resets, reset_idx, aux_src, terminal_rows, shared = self._draw_inputs(H)
+        opts = dict(dtype=dt, device=dev)
+        states = torch.empty(H + 1, N, n, **opts)
+        obs = torch.zeros(H + 2, N, o, **opts)
+        actions = torch.zeros(H + 1, N, m, **opts)
+        exec_actions = torch.empty(H, N, m, **opts)
+        rewards = torch.zeros(H + 2, N, **opts)
+        values = torch.zeros(H + 2, N, **opts)
+        flags = torch.empty(H, N, dtype=torch.int32, device=dev)
+        states[0], obs[0], values[0] = s0, obs0, val0
+        i32 = lambda lst: torch.tensor(lst, dtype=torch.int32, device=dev)
+        reset_idx_t, aux_src_t = i32(reset_idx), i32(aux_src)
+        self.policy_pack.refresh()
+        self.vf_pack.refresh()
+        r = Rollout()
+        r.N, r.H = N, H
+        keep = [eps, noise, dirs, aux0, resets, reset_idx_t, aux_src_t, shared]
+        p = lambda t: None if t is None else t.contiguous().data_ptr()
+        eps, noise = eps.contiguous(), noise.contiguous()
+        r.eps, r.noise, r.dirs, r.aux0 = p(eps), p(noise), p(dirs), p(aux0)
+        r.reset_states, r.reset_idx, r.aux_src, r.shared = p(resets), p(reset_idx_t), p(aux_src_t), p(shared)
+        r.states, r.obs, r.actions, r.exec_actions = states.data_ptr(), obs.data_ptr(), actions.data_ptr(), exec_actions.data_ptr()
+        r.rewards, r.flags = rewards.data_ptr(), flags.data_ptr()
+        lib = _lib.lib()
+        self._timed("rollout_fwd", lambda: check(
+            lib.sgbpo_rollout_fwd(base.env_id, dtype_code(dt), C.byref(self._consts()), C.byref(self.policy_pack.desc),
+                                  C.byref(r), stream_ptr()), "sgbpo_rollout_fwd"))
+        self._timed("mlp_rows", lambda: check(
+            lib.sgbpo_mlp_rows(dtype_code(dt), H * N, C.byref(self.vf_pack.desc), C.c_void_p(obs[1].data_ptr()),
+                               C.c_void_p(values[1].data_ptr()), stream_ptr()), "sgbpo_mlp_rows"))
+        # hand the results to the reference's objects
+        term = torch.zeros(H + 2, N, dtype=torch.bool, device=dev)
+        rows = [j for j, f in enumerate(terminal_rows) if f]
+        term[rows] = True
+        buf.observations.tensor, buf.values.tensor, buf.rewards.tensor = obs, values, rewards
+        buf.actions.tensor, buf.terminals.tensor = actions, term
+        buf.t = torch.full_like(buf.t, H)
+        base.state = states[H]
+        base.scheduled_reset = torch.full_like(base.scheduled_reset, bool(base._reset_pending))
+        base.last_flags, base.last_exec_action = flags[H - 1], exec_actions[H - 1]
+        if self.wrapper is not None:
+            w = self.wrapper
+            w.safe_action = exec_actions[H - 1]
+            w._interventions = w._interventions + ((flags & _lib.FL_INTERVENED) != 0).sum()
+            bad = ((flags & (_lib.FL_NONFINITE | _lib.FL_INFEASIBLE)) != 0).any()
+            if w.strict:
+                if bool(bad):
+                    raise ValueError("a safeguarded step produced a non-finite action or an infeasible program "
+                                     "(the reference raises here: safeguard.py:68-75 / solver error)")
+            else:
+                w._status = w._status | bad.to(torch.int32)
+        self.last = dict(r=r, keep=keep + [eps, noise, states, obs, actions, exec_actions, rewards, flags, values],
+                         terminal_rows=terminal_rows, obs=obs, values=values, rewards=rewards, flags=flags,
+                         exec_actions=exec_actions, states=states)
+        return float(rewards.sum()) / N / H
+
+    # ------------------------------------------------------------------------------------------------------
+    def _weights(self, terminal_rows, H: int, N: int):
+        """Per-row discount of shac.py:131-139 (uniform over environments) and the normaliser."""
+        gamma = self.algo.GAMMA
+        exponent, drop = [], 0
+        for r in range(H + 2):
+            exponent.append(r - drop)
+            if terminal_rows[r]:
+                drop += r + 1                      # cumulative, as shipped (see SHAC.discount_weights)
+        disc = [gamma ** e for e in exponent]
+        norm = N * H + N * sum(terminal_rows)
+        return disc, norm
+
+    def backward(self) -> Tensor:
+        algo, base, last = self.algo, self.base, self.last
+        H, N = algo.len_trajectories, base.num_envs
+        o, m, W = base.obs_dim, base.action_dim, self.policy_pack.width
+        dt, dev = base.state.dtype, base.state.device
+        terminal_rows = last["terminal_rows"]
+        disc, norm = self._weights(terminal_rows, H, N)
+        disc_t = torch.tensor(disc, dtype=dt, device=dev)
+        term_mask = torch.tensor(terminal_rows, dtype=torch.bool, device=dev)
+        picked = torch.where(term_mask.unsqueeze(1), last["values"], last["rewards"])
+        loss = -(disc_t.unsqueeze(1) * picked).sum() / norm
+        grw = torch.tensor([0.0 if terminal_rows[t] else -disc[t] / norm for t in range(H)], dtype=dt, device=dev)
+        # critic input-gradient on the terminal rows (N x o inputs each): plain autograd through the target critic
+        rows = [j for j in range(1, H + 1) if terminal_rows[j]]
+        term_of_row = [-1] * (H + 2)
+        gterm = []
+        for kk, j in enumerate(rows):
+            x = last["obs"][j].detach().clone().requires_grad_(True)
+            v = algo.target_value_function(x).sum() * (-disc[j] / norm)
+            gterm.append(torch.autograd.grad(v, x)[0])
+            term_of_row[j] = kk
+        gobs_term = torch.stack(gterm).contiguous()
+        term_of_row_t = torch.tensor(term_of_row, dtype=torch.int32, device=dev)
+        if self._grad_bufs is None or self._grad_bufs["h1"].shape != (H, N, W):
+            self._grad_bufs = dict(h1=torch.empty(H, N, W, dtype=dt, device=dev), dz2=torch.empty(H, N, W, dtype=dt, device=dev))
+        h1, dz2 = self._grad_bufs["h1"], self._grad_bufs["dz2"]
+        sizes = [o * W, W * m, 2 * W, 2 * W, 2 * W, m, m]
+        flat = torch.zeros(sum(sizes), dtype=dt, device=dev)
+        parts = torch.split(flat, sizes)
+        g = RolloutGrads()
+        g.grw, g.gobs_term, g.term_of_row = grw.data_ptr(), gobs_term.data_ptr(), term_of_row_t.data_ptr()
+        g.h1_out, g.dz2_out = h1.data_ptr(), dz2.data_ptr()
+        (g.g_w_in, g.g_w_out, g.g_b_hid, g.g_gamma, g.g_beta, g.g_b_out, g.g_log_std) = [x.data_ptr() for x in parts]
+        self._timed("rollout_bwd", lambda: check(
+            _lib.lib().sgbpo_rollout_bwd(base.env_id, dtype_code(dt), C.byref(self._consts()),
+                                         C.byref(self.policy_pack.desc), C.byref(last["r"]), C.byref(g), stream_ptr()),
+            "sgbpo_rollout_bwd"))
+        dw_hid = h1.view(H * N, W).t() @ dz2.view(H * N, W)          # [k][c]; plain library GEMM
+        g_w_in, g_w_out, g_b_hid, g_gamma, g_beta, g_b_out, g_log_std = parts
+        pack = self.policy_pack
+        grads = {
+            pack.lin[0].weight: g_w_in.view(o, W).t(), pack.lin[0].bias: g_b_hid.view(2, W)[0],
+            pack.norm[0].weight: g_gamma.view(2, W)[0], pack.norm[0].bias: g_beta.view(2, W)[0],
+            pack.lin[1].weight: dw_hid.t(), pack.lin[1].bias: g_b_hid.view(2, W)[1],
+            pack.norm[1].weight: g_gamma.view(2, W)[1], pack.norm[1].bias: g_beta.view(2, W)[1],
+            pack.lin[2].weight: g_w_out.view(W, m).t(), pack.lin[2].bias: g_b_out,
+            algo.policy.log_std: g_log_std,
+        }
+        for prm, val in grads.items():
+            val = val.contiguous()
+            prm.grad = val if prm.grad is None else prm.grad + val
+        return loss.detach()
+

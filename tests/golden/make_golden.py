@@ -94,8 +94,8 @@ def shac_golden():
     torch.manual_seed(7)
     env = BalanceCartPoleEnv(num_envs=4, num_steps=3)
     DRAWS.clear()
-    algo = SHAC(env=env, policy_kwargs={"net_arch": [16, 16]}, policy_optim_kwargs={"lr": 1e-3},
-                vf_kwargs={"net_arch": [16, 16, 16]}, vf_optim_kwargs={"lr": 1e-3},
+    algo = SHAC(env=env, policy_kwargs={"net_arch": [32, 32]}, policy_optim_kwargs={"lr": 1e-3},
+                vf_kwargs={"net_arch": [32, 32, 32]}, vf_optim_kwargs={"lr": 1e-3},
                 regularisation_coefficient=0.1, len_trajectories=6)
     out = {}
     for k, v in algo.policy.state_dict().items():

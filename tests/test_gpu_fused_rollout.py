@@ -1,0 +1,189 @@
+"""GPU: the whole-horizon fused rollout (csrc/sgbpo_rollout*.cu) against (a) the reference's golden SHAC
+episode, (b) the eager per-step path fed the same replayed RNG stream, in float64 (tight) and float32."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+class Replay:
+    def __init__(self, draws, dev):
+        self.draws, self.i, self.dev = list(draws), 0, dev
+
+    def __call__(self, kind, shape):
+        k, d = self.draws[self.i]
+        self.i += 1
+        assert k == kind and tuple(d.shape) == tuple(shape), (k, kind, tuple(d.shape), shape)
+        return d.to(self.dev) if isinstance(d, torch.Tensor) else torch.from_numpy(np.asarray(d)).to(self.dev)
+
+
+class Recorder:
+    def __init__(self):
+        self.draws = []
+
+    def __call__(self, kind, shape):
+        t = torch.rand(*shape) if kind == "rand" else torch.randn(*shape)
+        self.draws.append((kind, t.detach().clone()))
+        return t
+
+
+@pytest.fixture
+def cuda_default():
+    prev = torch.get_default_dtype()
+    torch.set_default_device("cuda:0")
+    yield torch.device("cuda:0")
+    torch.set_default_device("cpu")
+    torch.set_default_dtype(prev)
+    from safegbpo_b200 import rng
+    rng.set_source(None)
+
+
+def test_fused_episode_vs_reference_golden(cuda_default, golden_dir):
+    from safegbpo_b200 import rng
+    from safegbpo_b200.envs.balance_cartpole import BalanceCartPoleEnv
+    from safegbpo_b200.learning_algorithms.shac import SHAC
+    torch.set_default_dtype(torch.float64)
+    dev = cuda_default
+    g = np.load(golden_dir / "shac_cartpole_unsafe.npz")
+    keys = sorted(k for k in g.files if k.startswith("draw"))
+    draws = [(k.split("_")[1], g[k]) for k in keys]
+    env = BalanceCartPoleEnv(num_envs=4, num_steps=3)
+    algo = SHAC(env=env, policy_kwargs={"net_arch": [32, 32]}, policy_optim_kwargs={"lr": 1e-3},
+                vf_kwargs={"net_arch": [32, 32, 32]}, vf_optim_kwargs={"lr": 1e-3}, regularisation_coefficient=0.1,
+                len_trajectories=6, fused="on")
+    algo.policy.load_state_dict({k[len("policy."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("policy.")})
+    algo.target_value_function.load_state_dict(
+        {k[len("target_vf."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("target_vf.")})
+    env.state = torch.from_numpy(g["state0"]).to(dev)
+    o0 = env.observation
+    algo.buffer.reset(o0, algo.target_value_function(o0).squeeze(1))
+    rng.set_source(Replay(draws, dev))
+    algo.buffer.reset()
+    algo.policy_optim.zero_grad()
+    avg_reward = algo.collect_trajectories()
+    assert algo._fused_engine is not None
+    loss = algo._fused_engine.backward()
+    tol = dict(rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(algo.buffer.observations.tensor.cpu().numpy(), g["observations"], **tol)
+    np.testing.assert_allclose(algo.buffer.rewards.tensor.cpu().numpy(), g["rewards"], **tol)
+    np.testing.assert_allclose(algo.buffer.values.tensor.cpu().numpy(), g["values"], **tol)
+    np.testing.assert_allclose(algo.buffer.actions.tensor.cpu().numpy(), g["actions"], **tol)
+    assert np.array_equal(algo.buffer.terminals.tensor.cpu().numpy(), g["terminals"])
+    np.testing.assert_allclose(env.state.cpu().numpy(), g["final_state"], **tol)
+    np.testing.assert_allclose(float(loss), float(g["loss"]), rtol=1e-11)
+    np.testing.assert_allclose(avg_reward, float(g["avg_reward"]), rtol=1e-11)
+    for k, p in algo.policy.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), g[f"grad.{k}"], rtol=1e-8, atol=1e-12, err_msg=k)
+
+
+CONFIGS = [
+    ("BalanceCartPole", "bp", {"gate": "reference"}, 64, 5),
+    ("BalanceCartPole", "bp", {"gate": "always"}, 64, 1000),
+    ("SwingUpCartPole", "rm", {"gate": "always", "zono": True, "linear": True}, 64, 1000),
+    ("SwingUpCartPole", "rm", {"gate": "always", "zono": False, "linear": False}, 32, 1000),
+    ("BalancePendulum", "none", {}, 64, 7),
+    ("BalanceQuadrotor", "none", {}, 32, 6),
+]
+
+
+def build(env_name, sg, opts, width, num_steps, N, H, fused, dev):
+    from safegbpo_b200.envs.balance_cartpole import BalanceCartPoleEnv
+    from safegbpo_b200.envs.swingup_cartpole import SwingUpCartPoleEnv
+    from safegbpo_b200.envs.balance_pendulum import BalancePendulumEnv
+    from safegbpo_b200.envs.balance_quadrotor import BalanceQuadrotorEnv
+    from safegbpo_b200.safeguards.boundary_projection import BoundaryProjectionSafeguard
+    from safegbpo_b200.safeguards.ray_mask import RayMaskSafeguard
+    from safegbpo_b200.learning_algorithms.shac import SHAC
+    cls = {"BalanceCartPole": BalanceCartPoleEnv, "SwingUpCartPole": SwingUpCartPoleEnv,
+           "BalancePendulum": BalancePendulumEnv, "BalanceQuadrotor": BalanceQuadrotorEnv}[env_name]
+    env = cls(num_envs=N, num_steps=num_steps)
+    wrapped = env
+    if sg == "bp":
+        wrapped = BoundaryProjectionSafeguard(env, gate=opts["gate"], strict=False)
+    elif sg == "rm":
+        wrapped = RayMaskSafeguard(env, linear_projection=opts["linear"], zonotopic_approximation=opts["zono"],
+                                   passthrough=False, gate=opts["gate"], strict=False)
+    algo = SHAC(env=wrapped, policy_kwargs={"net_arch": [width, width]}, policy_optim_kwargs={"lr": 1e-3},
+                vf_kwargs={"net_arch": [width, width, width]}, vf_optim_kwargs={"lr": 1e-3}, regularisation_coefficient=0.1,
+                len_trajectories=H, fused=fused)
+    return env, wrapped, algo
+
+
+@pytest.mark.parametrize("env_name,sg,opts,width,num_steps", CONFIGS,
+                         ids=[f"{c[0]}-{c[1]}-w{c[3]}-T{c[4]}" for c in CONFIGS])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_fused_equals_eager(cuda_default, env_name, sg, opts, width, num_steps, dtype):
+    """Same weights, same initial states, same replayed draws: the fused kernels and the eager per-step path
+    must produce the same buffers, loss and policy gradients (resets inside the horizon included)."""
+    from safegbpo_b200 import rng
+    torch.set_default_dtype(dtype)
+    dev = cuda_default
+    N, H = 40, 12        # N not a multiple of 8 x 4: exercises the ragged last warp / CTA
+    torch.manual_seed(3)
+    env_e, wrap_e, algo_e = build(env_name, sg, opts, width, num_steps, N, H, "off", dev)
+    env_f, wrap_f, algo_f = build(env_name, sg, opts, width, num_steps, N, H, "on", dev)
+    algo_f.policy.load_state_dict(algo_e.policy.state_dict())
+    algo_f.target_value_function.load_state_dict(algo_e.target_value_function.state_dict())
+    # start inside the feasible box (RCI resets put cartpole far outside; keep programs feasible for the comparison)
+    half = env_e.state_set.generator[0].diagonal()
+    s0 = env_e.state_set.center[0] + (torch.rand(N, env_e.state_dim) * 2 - 1) * half * 0.6
+    for env, algo in ((env_e, algo_e), (env_f, algo_f)):
+        env.state, env.steps, env._reset_pending = s0.clone(), 2, False
+        if hasattr(env, "goal"):
+            env.goal = s0[:, :2].clone()
+        o0 = env.observation
+        algo.buffer.reset(o0, algo.target_value_function(o0).squeeze(1))
+    rec = Recorder()
+    rng.set_source(rec)
+    algo_e.buffer.reset()
+    algo_e.policy_optim.zero_grad()
+    r_e = algo_e.collect_trajectories()
+    loss_e = algo_e.policy_loss()
+    loss_e.backward()
+    rng.set_source(Replay(rec.draws, dev))
+    algo_f.buffer.reset()
+    algo_f.policy_optim.zero_grad()
+    r_f = algo_f.collect_trajectories()
+    loss_f = algo_f._fused_engine.backward()
+    torch.cuda.synchronize()
+    if dtype == torch.float64:
+        tol, gtol = dict(rtol=1e-9, atol=1e-10), dict(rtol=1e-7, atol=1e-9)
+    else:
+        tol, gtol = dict(rtol=2e-4, atol=2e-4), dict(rtol=5e-3, atol=5e-4)      # fp32 over 12 chained steps
+    be, bf = algo_e.buffer, algo_f.buffer
+    assert torch.equal(be.terminals.tensor, bf.terminals.tensor)
+    finite = torch.isfinite(be.observations.tensor).all(dim=2).all(dim=0) & torch.isfinite(bf.observations.tensor).all(dim=2).all(dim=0)
+    assert finite.float().mean() > 0.9
+    np.testing.assert_allclose(bf.observations.tensor[:, finite].cpu().numpy(), be.observations.tensor[:, finite].detach().cpu().numpy(), **tol)
+    np.testing.assert_allclose(bf.actions.tensor[:, finite].cpu().numpy(), be.actions.tensor[:, finite].detach().cpu().numpy(), **tol)
+    np.testing.assert_allclose(bf.rewards.tensor[:, finite].cpu().numpy(), be.rewards.tensor[:, finite].detach().cpu().numpy(), **tol)
+    np.testing.assert_allclose(bf.values.tensor[:, finite].cpu().numpy(), be.values.tensor[:, finite].detach().cpu().numpy(), **tol)
+    if bool(finite.all()):
+        np.testing.assert_allclose(float(loss_f), float(loss_e), rtol=tol["rtol"])
+        np.testing.assert_allclose(r_f, r_e, rtol=tol["rtol"])
+        for (k, pe), (_, pf) in zip(algo_e.policy.named_parameters(), algo_f.policy.named_parameters()):
+            scale = float(pe.grad.abs().max()) + 1e-30
+            np.testing.assert_allclose(pf.grad.cpu().numpy() / scale, pe.grad.cpu().numpy() / scale, err_msg=k,
+                                       rtol=gtol["rtol"], atol=gtol["atol"])
+        if wrap_e is not env_e:
+            assert wrap_e.interventions == wrap_f.interventions
+
+
+def test_mlp_rows_matches_torch(cuda_default):
+    import ctypes as C
+    from safegbpo_b200 import _lib
+    from safegbpo_b200.learning_algorithms.components.value_function import ValueFunction
+    from safegbpo_b200.learning_algorithms.fused_rollout import PackedMlp
+    for dtype, tol in ((torch.float64, 1e-11), (torch.float32, 2e-5)):
+        torch.set_default_dtype(dtype)
+        for width, depth, M in ((32, 1, 5), (64, 2, 1000), (128, 3, 4099)):
+            vf = ValueFunction(5, net_arch=[width] * depth)
+            x = torch.randn(M, 5) * 3
+            ref = vf(x).squeeze(1)
+            pack = PackedMlp(vf.model)
+            out = torch.empty(M)
+            _lib.check(_lib.lib().sgbpo_mlp_rows(_lib.dtype_code(dtype), M, C.byref(pack.desc), C.c_void_p(x.data_ptr()),
+                                                 C.c_void_p(out.data_ptr()), _lib.stream_ptr()), "sgbpo_mlp_rows")
+            torch.cuda.synchronize()
+            np.testing.assert_allclose(out.cpu().numpy(), ref.detach().cpu().numpy(), rtol=tol, atol=tol)

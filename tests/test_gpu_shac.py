@@ -40,8 +40,8 @@ def test_shac_episode_vs_reference_golden(cuda_f64, golden_dir):
     keys = sorted(k for k in g.files if k.startswith("draw"))
     draws = [(k.split("_")[1], g[k]) for k in keys]
     env = BalanceCartPoleEnv(num_envs=4, num_steps=3)
-    algo = SHAC(env=env, policy_kwargs={"net_arch": [16, 16]}, policy_optim_kwargs={"lr": 1e-3},
-                vf_kwargs={"net_arch": [16, 16, 16]}, vf_optim_kwargs={"lr": 1e-3}, regularisation_coefficient=0.1,
+    algo = SHAC(env=env, policy_kwargs={"net_arch": [32, 32]}, policy_optim_kwargs={"lr": 1e-3},
+                vf_kwargs={"net_arch": [32, 32, 32]}, vf_optim_kwargs={"lr": 1e-3}, regularisation_coefficient=0.1,
                 len_trajectories=6, fused="off")
     algo.policy.load_state_dict({k[len("policy."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("policy.")})
     algo.target_value_function.load_state_dict(
@@ -80,24 +80,25 @@ def test_safeguarded_episode_vs_oracle(cuda_f64, sg_name):
     N, H = 16, 8
     gen = torch.Generator().manual_seed(5)
     s0 = (torch.rand(N, 4, generator=gen, dtype=torch.float64, device="cpu") * 2 - 1) * torch.tensor(
-        [9.5, 3.0, 6.0, 6.0], dtype=torch.float64, device="cpu")
+        [5.0, 3.0, 9.0, 9.0], dtype=torch.float64, device="cpu")
     eps = torch.randn(H, N, 1, generator=gen, dtype=torch.float64, device="cpu")
     us = torch.rand(H, N, 1, 4, generator=gen, dtype=torch.float64, device="cpu")
-    # oracle
-    oenv = OracleEnv("SwingUpCartPole", N, 1000, rng=lambda kind, shape: next(it_o))
-    it_o = iter([u for u in us])
-    oenv.state, oenv.scheduled_reset = s0.clone(), False
-    kind = "boundary_projection" if sg_name == "boundary_projection" else "ray_mask"
-    osg = OracleSafeguard(oenv, kind, zonotopic_approximation=False, gate="always", strict=False)
-    pol = oshac.OraclePolicy(5, 1, [32, 32]).double().cpu()
-    vf = oshac.OracleValue(5, [32, 32]).double().cpu()
+    # oracle (float64, CPU)
+    with torch.device("cpu"):
+        oenv = OracleEnv("SwingUpCartPole", N, 1000, rng=lambda kind, shape: next(it_o))
+        it_o = iter([u for u in us])
+        oenv.state, oenv.scheduled_reset = s0.clone(), False
+        kind = "boundary_projection" if sg_name == "boundary_projection" else "ray_mask"
+        osg = OracleSafeguard(oenv, kind, zonotopic_approximation=False, gate="always", strict=False)
+        pol = oshac.OraclePolicy(5, 1, [32, 32]).double().cpu()
+        vf = oshac.OracleValue(5, [32, 32]).double().cpu()
 
-    def env_step(action, t):
-        obs, rew, term, trunc = osg.step(action)
-        return obs, rew, term | trunc
-    obs0 = oenv.observation()
-    ref = oshac.rollout_loss(env_step, obs0, pol, vf, H, eps, value0=vf(obs0).squeeze(1))
-    ref["loss"].backward()
+        def env_step(action, t):
+            obs, rew, term, trunc = osg.step(action)
+            return obs, rew, term | trunc
+        obs0 = oenv.observation()
+        ref = oshac.rollout_loss(env_step, obs0, pol, vf, H, eps, value0=vf(obs0).squeeze(1))
+        ref["loss"].backward()
     # drop-in classes on the GPU
     env = SwingUpCartPoleEnv(num_envs=N, num_steps=1000)
     env.reset()

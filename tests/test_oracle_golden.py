@@ -67,8 +67,8 @@ def test_shac_episode_matches_reference(golden_dir):
     env = OracleEnv("BalanceCartPole", 4, 3, rng=Replay([(k, d) for k, d in draws if k == "rand"]))
     env.state = torch.from_numpy(g["state0"]).clone()
     env.scheduled_reset = False
-    policy = oshac.OraclePolicy(5, 1, [16, 16]).double()
-    vf = oshac.OracleValue(5, [16, 16, 16]).double()
+    policy = oshac.OraclePolicy(5, 1, [32, 32]).double()
+    vf = oshac.OracleValue(5, [32, 32, 32]).double()
     policy.load_state_dict({k[len("policy."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("policy.")})
     vf.load_state_dict({k[len("target_vf."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("target_vf.")})
 
