@@ -45,6 +45,8 @@ def parse():
     p.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     p.add_argument("--fused", default="auto", choices=["auto", "on", "off"])
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--rng-order", default="batched", choices=["batched", "reference"],
+                   help="batched: 3 RNG draws per episode (same distributions); reference: the reference's per-step order")
     return p.parse_args()
 
 
@@ -128,7 +130,7 @@ def workload_config(args, world):
     return {"workload": f"{args.env}+{args.safeguard}, {args.num_envs} envs/GPU x {world} GPU, H={args.horizon}, "
                         f"policy {POLICY_ARCH}, critic {VF_ARCH}, SHAC collect_trajectories+update_policy",
             "env": args.env, "safeguard": args.safeguard, "num_envs_per_gpu": args.num_envs, "horizon": args.horizon,
-            "gate": "reference (Q1 as shipped)", "l2_policy": "working set per episode > L2 not guaranteed; "
+            "gate": "reference (Q1 as shipped)", "rng_order": args.rng_order, "l2_policy": "working set per episode > L2 not guaranteed; "
             "a 256 MiB buffer is written between timed episodes to flush L2"}
 
 
@@ -191,7 +193,7 @@ def run_ours(args):
         env = RayMaskSafeguard(env, linear_projection=True, zonotopic_approximation=True, passthrough=False, strict=False)
     algo = SHAC(env=env, policy_kwargs={"net_arch": POLICY_ARCH}, policy_optim_kwargs={"lr": 4e-4},
                 vf_kwargs={"net_arch": VF_ARCH}, vf_optim_kwargs={"lr": 2e-3}, regularisation_coefficient=0.1,
-                len_trajectories=H, fused=args.fused)
+                len_trajectories=H, fused=args.fused, rng_order=args.rng_order)
     if world > 1:      # replicated networks: broadcast rank 0's parameters; gradients are summed over ranks
         from safegbpo_b200 import distributed as sgdist
         sgdist.broadcast_parameters(algo)

@@ -410,3 +410,105 @@ def _polish_sum_log(model: Model, x_np: np.ndarray, lv: slice, iters: int = 30) 
         for _ in range(iters):
             x = newton(x, C, r)
     return newton(x.detach(), C, r)
+
+
+# ------------------------------------------------------------------------------------------------
+# parametrised fast path (what cvxpylayers does: canonicalise once, refill the data per environment)
+# ------------------------------------------------------------------------------------------------
+class ParametricP1M1:
+    """P1 for m = 1 with the lifted LP canonicalised ONCE: A(theta) = A0 + sum_i theta_i A_i with
+    theta = (c_f, B[:, 0]) -- exactly affine, so the decomposition is read off n_theta + 1 builds of the
+    generic model above.  Per environment: two HiGHS solves; gradients by the Lagrangian identity."""
+
+    def __init__(self, template: SafeSets):
+        self.n = template.n
+        self.state = template.G_s is not None
+        n_theta = 2 * self.n if self.state else 0
+        self.n_theta = n_theta
+
+        def build(theta: Tensor):
+            s = SafeSets(m=1, n=template.n, c_a=template.c_a, G_a=template.G_a, c_s=template.c_s, G_s=template.G_s,
+                         G_w=template.G_w, a_lin=template.a_lin)
+            if self.state:
+                s.c_f, s.B = theta[:self.n], theta[self.n:].reshape(self.n, 1)
+            model = Model()
+            av = model.var("a_s", 1)
+            _constrain_action(model, [[(av.start, 1.0)]], [torch.zeros((), dtype=F64)], s)
+            model.finalize()
+            return model, av.start
+
+        base, self.a_idx = build(torch.zeros(n_theta, dtype=F64))
+        self.nvar = base.nvar
+        self.A_ub0, self.b_ub0 = base.A_ub.numpy().copy(), base.b_ub.numpy().copy()
+        self.A_eq0, self.b_eq0 = base.A_eq.numpy().copy(), base.b_eq.numpy().copy()
+        self.dA_ub, self.db_ub, self.dA_eq, self.db_eq = [], [], [], []
+        for i in range(n_theta):
+            e = torch.zeros(n_theta, dtype=F64)
+            e[i] = 1.0
+            m_i, _ = build(e)
+            self.dA_ub.append(m_i.A_ub.numpy() - self.A_ub0)
+            self.db_ub.append(m_i.b_ub.numpy() - self.b_ub0)
+            self.dA_eq.append(m_i.A_eq.numpy() - self.A_eq0)
+            self.db_eq.append(m_i.b_eq.numpy() - self.b_eq0)
+        if n_theta:
+            self.dA_ub, self.db_ub = np.stack(self.dA_ub), np.stack(self.db_ub)
+            self.dA_eq, self.db_eq = np.stack(self.dA_eq), np.stack(self.db_eq)
+        self.cost = np.zeros(self.nvar)
+        self.cost[self.a_idx] = 1.0
+
+    def bounds(self, theta: np.ndarray):
+        """(lo, hi, dlo/dtheta, dhi/dtheta) for one environment; raises Infeasible."""
+        if self.n_theta:
+            A_ub = self.A_ub0 + np.tensordot(theta, self.dA_ub, axes=1)
+            b_ub = self.b_ub0 + theta @ self.db_ub
+            A_eq = self.A_eq0 + np.tensordot(theta, self.dA_eq, axes=1)
+            b_eq = self.b_eq0 + theta @ self.db_eq
+        else:
+            A_ub, b_ub, A_eq, b_eq = self.A_ub0, self.b_ub0, self.A_eq0, self.b_eq0
+        out = []
+        for sign in (1.0, -1.0):
+            res = linprog(sign * self.cost, A_ub=A_ub, b_ub=b_ub, A_eq=A_eq if len(b_eq) else None,
+                          b_eq=b_eq if len(b_eq) else None, bounds=[(None, None)] * self.nvar, method="highs")
+            if res.status == 2:
+                raise Infeasible("LP infeasible")
+            if res.status != 0:
+                raise RuntimeError(f"HiGHS status {res.status}: {res.message}")
+            grad = np.zeros(self.n_theta)
+            if self.n_theta:
+                y_ub, y_eq = np.asarray(res.ineqlin.marginals), np.asarray(res.eqlin.marginals)
+                grad = (self.db_ub - self.dA_ub @ res.x) @ y_ub + (self.db_eq - self.dA_eq @ res.x) @ y_eq
+            out.append((sign * res.fun, sign * grad))
+        return out[0][0], out[1][0], out[0][1], out[1][1]
+
+
+class _IntervalFn(torch.autograd.Function):
+    """(lo, hi) of every environment as a differentiable function of theta (N, n_theta)."""
+
+    @staticmethod
+    def forward(ctx, theta: Tensor, prog: ParametricP1M1):
+        th = theta.detach().numpy()
+        N = th.shape[0]
+        lo, hi = np.full(N, np.nan), np.full(N, np.nan)
+        glo, ghi = np.zeros_like(th), np.zeros_like(th)
+        infeasible = np.zeros(N, dtype=bool)
+        for i in range(N):
+            try:
+                lo[i], hi[i], glo[i], ghi[i] = prog.bounds(th[i])
+            except Infeasible:
+                infeasible[i] = True
+        ctx.save_for_backward(torch.from_numpy(glo), torch.from_numpy(ghi))
+        ctx.infeasible = infeasible
+        return torch.from_numpy(lo), torch.from_numpy(hi), torch.from_numpy(infeasible)
+
+    @staticmethod
+    def backward(ctx, g_lo, g_hi, _g_inf):
+        glo, ghi = ctx.saved_tensors
+        return g_lo.unsqueeze(1) * glo + g_hi.unsqueeze(1) * ghi, None
+
+
+def p1_projection_batch_m1(action: Tensor, prog: ParametricP1M1, theta: Tensor):
+    """Batched P1 (m = 1): returns (a_s (N,1) with NaN rows where infeasible, infeasible mask)."""
+    lo, hi, infeasible = _IntervalFn.apply(theta, prog)
+    a_s = torch.minimum(torch.maximum(action[:, 0], lo), hi)
+    a_s = torch.where(infeasible, torch.full_like(a_s, float("nan")), a_s)
+    return a_s.unsqueeze(1), infeasible

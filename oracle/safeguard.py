@@ -32,6 +32,8 @@ class OracleSafeguard:
         self.passthrough = passthrough
         self.gate = gate                    # "reference" (Q1 as shipped) | "intended" | "always"
         self.strict = strict                # False: keep NaN rows of infeasible programs instead of raising
+        self.fast = True                    # m = 1 boundary projection through the canonicalise-once path
+        self._p1_prog = None
         self.m, self.n, self.N = env.action_dim, env.state_dim, env.num_envs
         # safeguard.py:54 -- linearised ONCE at construction; env 0's noise/action matrices are baked in (Q4)
         const, _, b_mat, e_mat = env.linear_dynamics()
@@ -99,6 +101,17 @@ class OracleSafeguard:
     def boundary_projection(self, action: Tensor) -> Tensor:
         """boundary_projection.py:54-55: one P1 per environment."""
         const, b_mat = self._linear()
+        if self.m == 1 and self.fast:
+            # canonicalise once (like the CvxpyLayer built at the first call), refill (c_f, B) per environment
+            if self._p1_prog is None:
+                self._p1_prog = P.ParametricP1M1(self._sets(0, torch.zeros(self.N, self.n, dtype=F64),
+                                                            torch.zeros(self.N, self.n, 1, dtype=F64))
+                                                 if self.env.state_constrained else self._sets(0, None, None))
+            theta = torch.cat([const, b_mat[:, :, 0]], dim=1) if self.env.state_constrained \
+                else torch.zeros(self.N, 0, dtype=F64)
+            a_s, infeasible = P.p1_projection_batch_m1(action, self._p1_prog, theta)
+            self.infeasible = infeasible
+            return a_s
         out = []
         self.infeasible = torch.zeros(self.N, dtype=torch.bool)
         for i in range(self.N):

@@ -143,49 +143,79 @@ class FusedRollout:
         return self.wrapper.consts() if self.wrapper is not None else self.base._plain
 
     # ------------------------------------------------------------------------------------------------------
+    def _schedule(self, H: int):
+        """Episode schedule (pure host logic, no draws): which steps trigger the reset-all of Q6
+        (simulator.py:100-106), which buffer rows are terminal, and the shared step counter per step."""
+        base = self.base
+        pending, steps = base._reset_pending, base.steps
+        reset_at, terminal_rows, pre_steps, post_steps = [], [False] * (H + 2), [], []
+        for t in range(H):
+            pre_steps.append(steps)               # household: T_out index used by execute_action (household.py:176)
+            steps += 1
+            if pending:
+                reset_at.append(t)
+                steps = 0
+            post_steps.append(steps)              # household: series index of observation / reward
+            pending = steps >= base.num_steps
+            terminal_rows[t + 1] = pending
+        terminal_rows[H] = True
+        return reset_at, terminal_rows, pre_steps, post_steps, pending, steps
+
     def _draw_inputs(self, H: int):
-        """Random inputs + episode schedule, in the reference's order."""
+        """Random inputs in the reference's order or, with rng_mode="batched", in three
+        batched draws (same distributions, different stream order)."""
         base, wrapper = self.base, self.wrapper
         N, n, m = base.num_envs, base.state_dim, base.action_dim
         dt, dev = base.state.dtype, base.state.device
         want_dirs = (wrapper is not None and wrapper.SG_KIND == _lib.SG_RAY_MASK
                      and getattr(wrapper, "zonotopic_approximation", False) and wrapper.state_constrained)
-        eps, noise, dirs, resets = [], [], [], []
-        reset_idx, aux_src, terminal_rows, shared_rows = [-1] * H, [-1] * H, [False] * (H + 2), []
-        pending, cur_aux = base._reset_pending, -1
-        if self.rng_mode == "batched" and not pending and base.steps + H < base.num_steps and base._shared() is None:
+        reset_at, terminal_rows, pre_steps, post_steps, pending_end, steps_end = self._schedule(H)
+        reset_idx, aux_src = [-1] * H, [-1] * H
+        resets = []
+        household = base._shared() is not None
+        if self.rng_mode == "batched":
             eps_t = rng.randn(H, N, m).to(dt)
-            u = rng.rand(H, N, 1, n).to(dt)
-            noise_t = base.noise_set.center.to(dt).unsqueeze(0) + (base.noise_set.generator.to(dt).unsqueeze(0) * (2 * u - 1)).sum(dim=3)
+            u = rng.rand(H, N, n).to(dt)
+            ctr = base.noise_set.center[0].to(dt)
+            half = base.noise_set.generator[0].diagonal().to(dt)
+            noise_t = ctr + half * (2 * u - 1)
             dirs_t = None
             if want_dirs:
                 d = rng.rand(H, N, m, 2 * m).to(dt) * 2 - 1
                 dirs_t = d / torch.linalg.vector_norm(d, dim=2, keepdim=True)
-            base.steps += H
-            terminal_rows[H] = True
-            return eps_t, noise_t, dirs_t, None, reset_idx, aux_src, terminal_rows, None
-        for t in range(H):
-            eps.append(rng.randn(N, m).to(dt))
-            if want_dirs:
-                dirs.append(wrapper._directions().to(dt))
-            noise.append(base._noise().to(dt))
-            base.steps += 1
-            if pending:
-                base.reset()                      # draws; sets steps = 0 and the task's aux (goal)
+            for t in reset_at:
+                base.reset()
                 resets.append(base.state.detach().to(dt))
-                reset_idx[t] = cur_aux = len(resets) - 1
-            aux_src[t] = cur_aux
-            sh = base._shared()
-            if sh is not None:
-                shared_rows.append(list(sh.series) + [sh.load_t, sh.pv_t, sh.price_t])
-            pending = base.steps >= base.num_steps
-            terminal_rows[t + 1] = pending
-        terminal_rows[H] = True
-        base._reset_pending = pending
-        eps_t, noise_t = torch.stack(eps), torch.stack(noise)
-        dirs_t = torch.stack(dirs) if dirs else None
+        else:
+            eps, noise, dirs = [], [], []
+            for t in range(H):
+                eps.append(rng.randn(N, m).to(dt))
+                if want_dirs:
+                    dirs.append(wrapper._directions().to(dt))
+                noise.append(base.noise_set.sample().to(dt))
+                if t in reset_at:
+                    base.reset()                  # draws in the reference's position of the stream
+                    resets.append(base.state.detach().to(dt))
+            eps_t, noise_t = torch.stack(eps), torch.stack(noise)
+            dirs_t = torch.stack(dirs) if dirs else None
+        cur = -1
+        for t in range(H):
+            if t in reset_at:
+                cur = reset_at.index(t)
+                reset_idx[t] = cur
+            aux_src[t] = cur
+        shared_t = None
+        if household:
+            tout = torch.tensor([float(base._t_out[s]) for s in pre_steps], dtype=dt, device=dev)
+            noise_t = noise_t.clone()
+            noise_t[:, :, 1] = tout.unsqueeze(1)                      # household.py:175-176
+            rows = []
+            for s in post_steps:
+                rows.append(np.concatenate([base._load[s:s + 5], base._pv[s:s + 5], base._t_out[s:s + 5], base._price[s:s + 5],
+                                            [base._load[s], base._pv[s], base._price[s]]]))
+            shared_t = torch.tensor(np.stack(rows), dtype=dt, device=dev)
+        base.steps, base._reset_pending = steps_end, pending_end
         resets_t = torch.stack(resets) if resets else None
-        shared_t = torch.tensor(shared_rows, dtype=dt, device=dev) if shared_rows else None
         return eps_t, noise_t, dirs_t, resets_t, reset_idx, aux_src, terminal_rows, shared_t
 
     # ------------------------------------------------------------------------------------------------------
@@ -205,14 +235,14 @@ class FusedRollout:
         opts = dict(dtype=dt, device=dev)
         states = torch.empty(H + 1, N, n, **opts)
         obs = torch.zeros(H + 2, N, o, **opts)
-        actions = torch.zeros(H + 1, N, m, **opts)
+        actions = torch.zeros(H + 2, N, m, **opts)
         exec_actions = torch.empty(H, N, m, **opts)
         rewards = torch.zeros(H + 2, N, **opts)
         values = torch.zeros(H + 2, N, **opts)
         flags = torch.empty(H, N, dtype=torch.int32, device=dev)
         states[0], obs[0], values[0] = s0, obs0, val0
-        i32 = lambda lst: torch.tensor(lst, dtype=torch.int32, device=dev)
-        reset_idx_t, aux_src_t = i32(reset_idx), i32(aux_src)
+        sched = torch.tensor([reset_idx, aux_src], dtype=torch.int32, device=dev)      # one small H2D copy
+        reset_idx_t, aux_src_t = sched[0], sched[1]
         self.policy_pack.refresh()
         self.vf_pack.refresh()
         r = Rollout()

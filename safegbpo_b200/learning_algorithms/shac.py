@@ -25,7 +25,8 @@ class SHAC(LearningAlgorithm):
 
     def __init__(self, env, policy_kwargs: dict, policy_optim_kwargs: dict, vf_kwargs: dict, vf_optim_kwargs: dict,
                  regularisation_coefficient: float, len_trajectories: int, polyak_target: float = 0.995,
-                 td_weight: float = 0.95, vf_num_fits: int = 16, vf_fit_num_batches: int = 4, fused: str = "auto"):
+                 td_weight: float = 0.95, vf_num_fits: int = 16, vf_fit_num_batches: int = 4, fused: str = "auto",
+                 rng_order: str = "reference"):
         super().__init__(env, policy_kwargs, policy_optim_kwargs, vf_kwargs, vf_optim_kwargs,
                          regularisation_coefficient, False)
         self.len_trajectories = len_trajectories
@@ -40,6 +41,7 @@ class SHAC(LearningAlgorithm):
         self.buffer.reset(reset_observation, reset_value)
         self.interactions_per_episode = len_trajectories * self.env.num_envs
         self.fused = fused
+        self.rng_order = rng_order      # "reference": draws in the reference's call order; "batched": 3 draws per episode
         self._fused_engine = None
         # data-parallel hook: called between backward and clip/Adam (distributed.allreduce_policy_grads)
         self.grad_sync = None
@@ -60,6 +62,8 @@ class SHAC(LearningAlgorithm):
         if self._fused_engine is None:
             from .fused_rollout import FusedRollout
             self._fused_engine = FusedRollout.try_create(self)
+            if self._fused_engine is not None:
+                self._fused_engine.rng_mode = self.rng_order
             if self._fused_engine is None and self.fused == "on":
                 raise RuntimeError("fused='on' but this env/safeguard/network combination has no fused rollout")
             if self._fused_engine is None:
