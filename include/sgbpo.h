@@ -99,14 +99,13 @@ int sgbpo_linearise(int env_id, int dtype, int64_t N, const sgbpo_consts* consts
  * Linear -> ELU -> LayerNorm per hidden layer, then Linear).  All hidden layers share one width. */
 typedef struct sgbpo_mlp {
   int32_t in_dim, width, n_hidden, out_dim;
-  const void* w_in;    /* [in_dim][width]            = Linear.weight^T of the first layer */
-  const void* w_hid;   /* [n_hidden-1][width][width]  = Linear.weight^T of the hidden->hidden layers */
-  const void* w_out;   /* [width][out_dim] */
-  const void* b_hid;   /* [n_hidden][width] */
-  const void* gamma;   /* [n_hidden][width] LayerNorm weight */
-  const void* beta;    /* [n_hidden][width] LayerNorm bias */
-  const void* b_out;   /* [out_dim] */
-  const void* log_std; /* [out_dim] policy only, else NULL */
+  /* parameters exactly as torch stores them (no repacking): Linear.weight of layer l is [out_l][in_l]
+   * row-major; l = 0..n_hidden-1 are the hidden layers, l = n_hidden is the output layer */
+  const void* weight[5];
+  const void* bias[5];
+  const void* ln_weight[4];  /* LayerNorm weight / bias of hidden layer l: [width] */
+  const void* ln_bias[4];
+  const void* log_std;       /* [out_dim] policy only, else NULL */
 } sgbpo_mlp;
 
 /* Rollout buffers, time-major like CoupledBuffer's (T, N, .) tensors (coupled_buffer.py:79-92). */
@@ -134,7 +133,9 @@ typedef struct sgbpo_rollout_grads {
   const void* gobs_term;       /* [K][N][o] d(terminal value terms)/d obs rows, or NULL */
   const int32_t* term_of_row;  /* [H+2] device: -1 or k */
   void* h1_out;                /* [H][N][width]  } operands of the hidden-hidden weight gradient */
-  void* dz2_out;               /* [H][N][width]  }   dW_hid = h1^T dz2 (one GEMM by the caller) */
+  void* dz2_out;               /* [H][N][width]  }   Linear.weight.grad = dz2^T h1 (one GEMM by the caller) */
+  /* parameter gradients, accumulated (caller zero-fills), in torch's layouts:
+   * g_w_in [width][in_dim], g_w_out [out_dim][width], g_b_hid/g_gamma/g_beta [2][width], g_b_out/g_log_std [out_dim] */
   void* g_w_in; void* g_w_out; void* g_b_hid; void* g_gamma; void* g_beta; void* g_b_out; void* g_log_std;
 } sgbpo_rollout_grads;
 

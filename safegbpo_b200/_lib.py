@@ -48,10 +48,10 @@ class StepShared(C.Structure):
 
 
 class Mlp(C.Structure):
-    """Mirror of ``struct sgbpo_mlp``."""
+    """Mirror of ``struct sgbpo_mlp`` (pointers to the torch parameters themselves, no repacking)."""
     _fields_ = [("in_dim", C.c_int32), ("width", C.c_int32), ("n_hidden", C.c_int32), ("out_dim", C.c_int32),
-                ("w_in", C.c_void_p), ("w_hid", C.c_void_p), ("w_out", C.c_void_p), ("b_hid", C.c_void_p),
-                ("gamma", C.c_void_p), ("beta", C.c_void_p), ("b_out", C.c_void_p), ("log_std", C.c_void_p)]
+                ("weight", C.c_void_p * 5), ("bias", C.c_void_p * 5), ("ln_weight", C.c_void_p * 4),
+                ("ln_bias", C.c_void_p * 4), ("log_std", C.c_void_p)]
 
 
 class Rollout(C.Structure):

@@ -44,6 +44,21 @@ SG_HD float sg_abs(float x) { return fabsf(x); }
 SG_HD double sg_abs(double x) { return fabs(x); }
 SG_HD float primal(float x) { return x; }
 SG_HD double primal(double x) { return x; }
+// sine and cosine from ONE range reduction (every simulator needs both of the same angle)
+SG_HD void sg_sincos(float x, float& s, float& c) {
+#if defined(__CUDA_ARCH__)
+  sincosf(x, &s, &c);
+#else
+  s = sinf(x); c = cosf(x);
+#endif
+}
+SG_HD void sg_sincos(double x, double& s, double& c) {
+#if defined(__CUDA_ARCH__)
+  sincos(x, &s, &c);
+#else
+  s = sin(x); c = cos(x);
+#endif
+}
 
 // ---- Dual -------------------------------------------------------------------------------------
 template <class S, int K> struct Dual {
@@ -122,6 +137,12 @@ template <class S, int K> SG_HD Dual<S, K> chain(const Dual<S, K>& x, const S& f
 }
 template <class S, int K> SG_HD Dual<S, K> sg_sin(const Dual<S, K>& x) { return chain(x, sg_sin(x.v), sg_cos(x.v)); }
 template <class S, int K> SG_HD Dual<S, K> sg_cos(const Dual<S, K>& x) { return chain(x, sg_cos(x.v), -sg_sin(x.v)); }
+template <class S, int K> SG_HD void sg_sincos(const Dual<S, K>& x, Dual<S, K>& s, Dual<S, K>& c) {
+  S sv, cv;
+  sg_sincos(x.v, sv, cv);
+  s = chain(x, sv, cv);
+  c = chain(x, cv, -sv);
+}
 template <class S, int K> SG_HD Dual<S, K> sg_sqrt(const Dual<S, K>& x) {
   using B = typename Traits<S>::base;
   S r = sg_sqrt(x.v);
@@ -169,6 +190,10 @@ template <class S> SG_HD S sg_clamp_const(const S& x, double lo, double hi) {
   if (p > B(hi)) return C<S>(hi);
   return x;
 }
-template <class S> SG_HD S wrap_angle(const S& x) { return sg_atan2(sg_sin(x), sg_cos(x)); }
+template <class S> SG_HD S wrap_angle(const S& x) {
+  S s, c;
+  sg_sincos(x, s, c);
+  return sg_atan2(s, c);
+}
 
 }  // namespace sgbpo

@@ -43,7 +43,8 @@ struct PendulumSim {
 struct CartPoleSim {
   static constexpr int NS = 4, NA = 1;
   template <class S> SG_HD static void f(const S* s, const S* a, const S* w, S* o) {
-    const S sn = sg_sin(s[1]), cs = sg_cos(s[1]);
+    S sn, cs;
+    sg_sincos(s[1], sn, cs);
     const S tmp = (a[0] * C<S>(10.0) + C<S>(0.1 * 0.5) * (s[3] * s[3]) * sn) / C<S>(1.1);
     const S thdd = C<S>(2.0) * ((C<S>(9.8) * sn + tmp * cs) / (C<S>(4.0 / 3.0) - C<S>(0.1 / 1.1) * (cs * cs)) + w[0]);
     const S xdd = tmp - C<S>(0.1 * 0.5 / 1.1) * cs * thdd;
@@ -59,8 +60,10 @@ struct QuadrotorSim {
   template <class S> SG_HD static void f(const S* s, const S* a, const S* w, S* o) {
     const S thrust = a[0] * C<S>(6.0 / 7.0) + C<S>(9.81);
     const S roll_cmd = a[1] * C<S>(3.14159265358979323846 / 12.0);
-    const S xdd = thrust * sg_sin(s[2]) + w[3];
-    const S zdd = thrust * sg_cos(s[2]) - C<S>(9.81) + w[4];
+    S sr, cr;
+    sg_sincos(s[2], sr, cr);
+    const S xdd = thrust * sr + w[3];
+    const S zdd = thrust * cr - C<S>(9.81) + w[4];
     const S rdd = roll_cmd * C<S>(55.0) - C<S>(70.0) * s[2] - C<S>(17.0) * s[5];
     o[3] = s[3] + C<S>(0.05) * xdd;
     o[4] = s[4] + C<S>(0.05) * zdd;
@@ -105,7 +108,7 @@ template <> struct Task<ENV_BALANCE_PENDULUM> {
   static constexpr int NS = 2, NA = 1, NO = 3, NAUX = 0;
   static constexpr bool CLAMP = true;
   template <class S, class T> SG_HD static void observe(const S* s, const T*, const StepShared<T>*, S* o) {
-    o[0] = sg_sin(s[0]); o[1] = sg_cos(s[0]); o[2] = s[1];
+    sg_sincos(s[0], o[0], o[1]); o[2] = s[1];
   }
   template <class S, class T> SG_HD static S reward(const S* s, const S* a, const T*, const StepShared<T>*) {
     return -(s[0] * s[0]) - C<S>(0.1) * (s[1] * s[1]) - C<S>(0.001) * (a[0] * a[0]);
@@ -117,7 +120,7 @@ template <int ENV> struct CartPoleTask {
   static constexpr int NS = 4, NA = 1, NO = 5, NAUX = 0;
   static constexpr bool CLAMP = true;
   template <class S, class T> SG_HD static void observe(const S* s, const T*, const StepShared<T>*, S* o) {
-    o[0] = s[0]; o[1] = sg_sin(s[1]); o[2] = sg_cos(s[1]); o[3] = s[2]; o[4] = s[3];
+    o[0] = s[0]; sg_sincos(s[1], o[1], o[2]); o[3] = s[2]; o[4] = s[3];
   }
   template <class S, class T> SG_HD static S reward(const S* s, const S* a, const T*, const StepShared<T>*) {
     return -(C<S>(0.05) * (s[0] * s[0])) - C<S>(0.1) * (s[2] * s[2]) - (s[1] * s[1]) - C<S>(0.1) * (s[3] * s[3])

@@ -20,14 +20,11 @@ constexpr int MAX_HIDDEN = 4;
 
 template <class T> struct MlpParams {
   int in_dim, width, n_hidden, out_dim;
-  const T* w_in;    // [in_dim][width]            (= torch Linear.weight^T)
-  const T* w_hid;   // [n_hidden-1][width][width]  (k-major: [k][c])
-  const T* w_out;   // [width][out_dim]
-  const T* b_hid;   // [n_hidden][width]
-  const T* gamma;   // [n_hidden][width]
-  const T* beta;    // [n_hidden][width]
-  const T* b_out;   // [out_dim]
-  const T* log_std; // [out_dim] (policy only, else nullptr)
+  const T* weight[MAX_HIDDEN + 1];   // torch layout [out][in]; index n_hidden = output layer
+  const T* bias[MAX_HIDDEN + 1];
+  const T* ln_weight[MAX_HIDDEN];
+  const T* ln_bias[MAX_HIDDEN];
+  const T* log_std;                  // [out_dim] (policy only, else nullptr)
 };
 
 template <class T, int W> struct NetSmem {
@@ -47,15 +44,20 @@ template <class T, int W> struct NetSmem {
     gamma = base; base += n_hidden * W;
     beta = base; base += n_hidden * W;
     b_out = base; base += out_dim;
+    // global reads walk torch's [out][in] layout contiguously; the transpose into [k][LD] happens on the
+    // shared-memory side, where a stride of LD = W + 1 words is conflict-free
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int i = tid; i < in_dim * W; i += nt) w_in[(i / W) * LD + (i % W)] = p.w_in[i];
-    for (int i = tid; i < (n_hidden - 1) * W * W; i += nt) {
-      const int l = i / (W * W), rem = i % (W * W);
-      w_hid[l * W * LD + (rem / W) * LD + (rem % W)] = p.w_hid[i];
-    }
-    for (int i = tid; i < W * out_dim; i += nt) w_out[i] = p.w_out[i];
-    for (int i = tid; i < n_hidden * W; i += nt) { b_hid[i] = p.b_hid[i]; gamma[i] = p.gamma[i]; beta[i] = p.beta[i]; }
-    for (int i = tid; i < out_dim; i += nt) b_out[i] = p.b_out[i];
+    for (int i = tid; i < in_dim * W; i += nt) w_in[(i % in_dim) * LD + (i / in_dim)] = p.weight[0][i];
+    for (int l = 0; l + 1 < n_hidden; ++l)
+      for (int i = tid; i < W * W; i += nt) w_hid[l * W * LD + (i % W) * LD + (i / W)] = p.weight[l + 1][i];
+    for (int i = tid; i < W * out_dim; i += nt) w_out[(i % W) * out_dim + (i / W)] = p.weight[n_hidden][i];
+    for (int l = 0; l < n_hidden; ++l)
+      for (int i = tid; i < W; i += nt) {
+        b_hid[l * W + i] = p.bias[l][i];
+        gamma[l * W + i] = p.ln_weight[l][i];
+        beta[l * W + i] = p.ln_bias[l][i];
+      }
+    for (int i = tid; i < out_dim; i += nt) b_out[i] = p.bias[n_hidden][i];
     return base;
   }
 };
@@ -66,10 +68,23 @@ template <class T> __device__ __forceinline__ T warp_sum(T v) {
   return v;
 }
 
-__device__ __forceinline__ float sg_expm1(float x) { return expm1f(x); }
-__device__ __forceinline__ double sg_expm1(double x) { return expm1(x); }
-__device__ __forceinline__ float sg_rsqrt(float x) { return 1.0f / sqrtf(x); }
+// ELU negative branch exactly as ATen evaluates it: exp(x) - 1 (not expm1); LayerNorm's rsqrt likewise
+__device__ __forceinline__ float sg_elu_neg(float x) { return expf(x) - 1.0f; }
+__device__ __forceinline__ double sg_elu_neg(double x) { return exp(x) - 1.0; }
+__device__ __forceinline__ float sg_rsqrt(float x) { return rsqrtf(x); }
 __device__ __forceinline__ double sg_rsqrt(double x) { return 1.0 / sqrt(x); }
+
+// all-reduce of R independent values: the R shuffle chains are interleaved so their latencies overlap
+template <class T, int R> __device__ __forceinline__ void warp_sum_rows(T (&v)[R]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    T t[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) t[r] = __shfl_xor_sync(0xffffffffu, v[r], o);
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] += t[r];
+  }
+}
 
 // 8 contiguous row values of one k: vector loads (the warp tiles are 32-byte aligned)
 __device__ __forceinline__ void load8(const float* __restrict__ p, float (&a)[MLP_R]) {
@@ -140,22 +155,34 @@ __device__ __forceinline__ void elu_layernorm(T (&z)[MLP_R][W / 32], const T* __
   T g[CPL], b[CPL];
 #pragma unroll
   for (int j = 0; j < CPL; ++j) { g[j] = gamma[lane + 32 * j]; b[j] = beta[lane + 32 * j]; }
+  T sum[MLP_R];
 #pragma unroll
   for (int r = 0; r < MLP_R; ++r) {
     T s = T(0);
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
       const T v = z[r][j];
-      const T e = v > T(0) ? v : sg_expm1(v);
+      const T e = v > T(0) ? v : sg_elu_neg(v);
       if (SAVE) egrad[r][j] = v > T(0) ? T(1) : e + T(1);
       z[r][j] = e;
       s += e;
     }
-    const T mean = warp_sum(s) / T(W);
+    sum[r] = s;
+  }
+  warp_sum_rows<T, MLP_R>(sum);
+  T sq[MLP_R];
+#pragma unroll
+  for (int r = 0; r < MLP_R; ++r) {
+    const T mean = sum[r] / T(W);
     T q = T(0);
 #pragma unroll
     for (int j = 0; j < CPL; ++j) { z[r][j] -= mean; q += z[r][j] * z[r][j]; }
-    const T rs = sg_rsqrt(warp_sum(q) / T(W) + T(1e-5));
+    sq[r] = q;
+  }
+  warp_sum_rows<T, MLP_R>(sq);
+#pragma unroll
+  for (int r = 0; r < MLP_R; ++r) {
+    const T rs = sg_rsqrt(sq[r] / T(W) + T(1e-5));
     if (SAVE) rstd[r] = rs;
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
@@ -166,20 +193,34 @@ __device__ __forceinline__ void elu_layernorm(T (&z)[MLP_R][W / 32], const T* __
   }
 }
 
-// register tile -> warp-private shared tile [c][8]
+// register tile <-> warp-private shared tile [c][8]: the 8 row values of one column are contiguous (vector access)
+__device__ __forceinline__ void store8(float* __restrict__ p, const float (&a)[MLP_R]) {
+  *reinterpret_cast<float4*>(p) = make_float4(a[0], a[1], a[2], a[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(a[4], a[5], a[6], a[7]);
+}
+__device__ __forceinline__ void store8(double* __restrict__ p, const double (&a)[MLP_R]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<double2*>(p + 2 * i) = make_double2(a[2 * i], a[2 * i + 1]);
+}
 template <class T, int W>
 __device__ __forceinline__ void store_tile(T* __restrict__ dstT, int lane, const T (&h)[MLP_R][W / 32]) {
 #pragma unroll
-  for (int j = 0; j < W / 32; ++j)
+  for (int j = 0; j < W / 32; ++j) {
+    T col[MLP_R];
 #pragma unroll
-    for (int r = 0; r < MLP_R; ++r) dstT[(lane + 32 * j) * MLP_R + r] = h[r][j];
+    for (int r = 0; r < MLP_R; ++r) col[r] = h[r][j];
+    store8(dstT + (lane + 32 * j) * MLP_R, col);
+  }
 }
 template <class T, int W>
 __device__ __forceinline__ void load_tile(const T* __restrict__ srcT, int lane, T (&h)[MLP_R][W / 32]) {
 #pragma unroll
-  for (int j = 0; j < W / 32; ++j)
+  for (int j = 0; j < W / 32; ++j) {
+    T col[MLP_R];
+    load8(srcT + (lane + 32 * j) * MLP_R, col);
 #pragma unroll
-    for (int r = 0; r < MLP_R; ++r) h[r][j] = srcT[(lane + 32 * j) * MLP_R + r];
+    for (int r = 0; r < MLP_R; ++r) h[r][j] = col[r];
+  }
 }
 
 // out[r][q] = b_out[q] + sum_c h[r][c] w_out[c][q]; every lane receives every (r, q)
@@ -191,13 +232,16 @@ __device__ __forceinline__ void out_layer(const T (&h)[MLP_R][W / 32], const T* 
     T w[W / 32];
 #pragma unroll
     for (int j = 0; j < W / 32; ++j) w[j] = w_out[(lane + 32 * j) * OUT + q];
+    T p[MLP_R];
 #pragma unroll
     for (int r = 0; r < MLP_R; ++r) {
-      T p = T(0);
+      p[r] = T(0);
 #pragma unroll
-      for (int j = 0; j < W / 32; ++j) p = fma(h[r][j], w[j], p);
-      mu[r][q] = warp_sum(p) + b_out[q];
+      for (int j = 0; j < W / 32; ++j) p[r] = fma(h[r][j], w[j], p[r]);
     }
+    warp_sum_rows<T, MLP_R>(p);
+#pragma unroll
+    for (int r = 0; r < MLP_R; ++r) mu[r][q] = p[r] + b_out[q];
   }
 }
 

@@ -56,8 +56,8 @@ template <class T> struct BackwardArgs {
   T* h1_out;              // [H][N][W]   layer-2 input activations      } operands of dW_hid = h1^T dz2
   T* dz2_out;             // [H][N][W]   layer-2 pre-activation grads   }
   // parameter gradients (accumulated with atomics, caller zero-fills)
-  T* g_w_in;              // [o][W]
-  T* g_w_out;             // [W][m]
+  T* g_w_in;              // [W][o]  (torch layout of Linear.weight)
+  T* g_w_out;             // [m][W]
   T* g_b_hid;             // [2][W]
   T* g_gamma;             // [2][W]
   T* g_beta;              // [2][W]
@@ -428,26 +428,33 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
           gcarry[r][j] = dh;
         }
       // LayerNorm 2 + ELU 2 backward -> dz2
+      {
+        T s1[MLP_R], s2[MLP_R];
 #pragma unroll
-      for (int r = 0; r < MLP_R; ++r) {
-        T s1 = T(0), s2 = T(0);
+        for (int r = 0; r < MLP_R; ++r) {
+          s1[r] = T(0); s2[r] = T(0);
 #pragma unroll
-        for (int j = 0; j < CPL; ++j) {
-          a_g2[j] = fma(gcarry[r][j], xh[r][j], a_g2[j]);
-          a_be2[j] += gcarry[r][j];
-          const T dx = gcarry[r][j] * g2[j];
-          gcarry[r][j] = dx;
-          s1 += dx;
-          s2 = fma(dx, xh[r][j], s2);
+          for (int j = 0; j < CPL; ++j) {
+            a_g2[j] = fma(gcarry[r][j], xh[r][j], a_g2[j]);
+            a_be2[j] += gcarry[r][j];
+            const T dx = gcarry[r][j] * g2[j];
+            gcarry[r][j] = dx;
+            s1[r] += dx;
+            s2[r] = fma(dx, xh[r][j], s2[r]);
+          }
         }
-        s1 = warp_sum(s1) / T(W);
-        s2 = warp_sum(s2) / T(W);
+        warp_sum_rows<T, MLP_R>(s1);
+        warp_sum_rows<T, MLP_R>(s2);
 #pragma unroll
-        for (int j = 0; j < CPL; ++j) {
-          const T de = rstd2[r] * (gcarry[r][j] - s1 - xh[r][j] * s2);
-          const T dz = de * eg[r][j];
-          gcarry[r][j] = dz;
-          a_b2[j] += dz;
+        for (int r = 0; r < MLP_R; ++r) {
+          const T m1 = s1[r] / T(W), m2 = s2[r] / T(W);
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) {
+            const T de = rstd2[r] * (gcarry[r][j] - m1 - xh[r][j] * m2);
+            const T dz = de * eg[r][j];
+            gcarry[r][j] = dz;
+            a_b2[j] += dz;
+          }
         }
       }
       store_tile<T, W>(g2T, lane, gcarry);
@@ -468,26 +475,33 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
       T g1[CPL];
 #pragma unroll
       for (int j = 0; j < CPL; ++j) g1[j] = net.gamma[lane + 32 * j];
+      {
+        T s1[MLP_R], s2[MLP_R];
 #pragma unroll
-      for (int r = 0; r < MLP_R; ++r) {
-        T s1 = T(0), s2 = T(0);
+        for (int r = 0; r < MLP_R; ++r) {
+          s1[r] = T(0); s2[r] = T(0);
 #pragma unroll
-        for (int j = 0; j < CPL; ++j) {
-          a_g1[j] = fma(gcarry[r][j], xh[r][j], a_g1[j]);
-          a_be1[j] += gcarry[r][j];
-          const T dx = gcarry[r][j] * g1[j];
-          gcarry[r][j] = dx;
-          s1 += dx;
-          s2 = fma(dx, xh[r][j], s2);
+          for (int j = 0; j < CPL; ++j) {
+            a_g1[j] = fma(gcarry[r][j], xh[r][j], a_g1[j]);
+            a_be1[j] += gcarry[r][j];
+            const T dx = gcarry[r][j] * g1[j];
+            gcarry[r][j] = dx;
+            s1[r] += dx;
+            s2[r] = fma(dx, xh[r][j], s2[r]);
+          }
         }
-        s1 = warp_sum(s1) / T(W);
-        s2 = warp_sum(s2) / T(W);
+        warp_sum_rows<T, MLP_R>(s1);
+        warp_sum_rows<T, MLP_R>(s2);
 #pragma unroll
-        for (int j = 0; j < CPL; ++j) {
-          const T de = rstd1[r] * (gcarry[r][j] - s1 - xh[r][j] * s2);
-          const T dz = de * eg[r][j];
-          gcarry[r][j] = dz;
-          a_b1[j] += dz;
+        for (int r = 0; r < MLP_R; ++r) {
+          const T m1 = s1[r] / T(W), m2 = s2[r] / T(W);
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) {
+            const T de = rstd1[r] * (gcarry[r][j] - m1 - xh[r][j] * m2);
+            const T dz = de * eg[r][j];
+            gcarry[r][j] = dz;
+            a_b1[j] += dz;
+          }
         }
       }
     }
@@ -498,16 +512,18 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
       T wi[CPL];
 #pragma unroll
       for (int j = 0; j < CPL; ++j) wi[j] = net.w_in[i * (W + 1) + lane + 32 * j];
-      T mine = T(0);
+      T p[MLP_R], obr[MLP_R];
+      load8(obsT + i * MLP_R, obr);
 #pragma unroll
       for (int r = 0; r < MLP_R; ++r) {
-        const T ob_r = obsT[i * MLP_R + r];
-        T p = T(0);
+        p[r] = T(0);
 #pragma unroll
-        for (int j = 0; j < CPL; ++j) { p = fma(gcarry[r][j], wi[j], p); a_win[i][j] = fma(ob_r, gcarry[r][j], a_win[i][j]); }
-        p = warp_sum(p);
-        mine = (lane == r) ? p : mine;
+        for (int j = 0; j < CPL; ++j) { p[r] = fma(gcarry[r][j], wi[j], p[r]); a_win[i][j] = fma(obr[r], gcarry[r][j], a_win[i][j]); }
       }
+      warp_sum_rows<T, MLP_R>(p);
+      T mine = T(0);
+#pragma unroll
+      for (int r = 0; r < MLP_R; ++r) mine = (lane == r) ? p[r] : mine;
       gobs_new[i] = mine;
     }
     if (owner) {
@@ -524,9 +540,9 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
     atomicAdd(G.g_gamma + c, a_g1[j]);  atomicAdd(G.g_gamma + W + c, a_g2[j]);
     atomicAdd(G.g_beta + c, a_be1[j]);  atomicAdd(G.g_beta + W + c, a_be2[j]);
 #pragma unroll
-    for (int q = 0; q < NA; ++q) atomicAdd(G.g_w_out + c * NA + q, a_wout[j][q]);
+    for (int q = 0; q < NA; ++q) atomicAdd(G.g_w_out + q * W + c, a_wout[j][q]);
 #pragma unroll
-    for (int i = 0; i < NO; ++i) atomicAdd(G.g_w_in + i * W + c, a_win[i][j]);
+    for (int i = 0; i < NO; ++i) atomicAdd(G.g_w_in + c * NO + i, a_win[i][j]);
   }
   if (owner) {
 #pragma unroll
@@ -566,9 +582,9 @@ static int fail2(int code, const char* msg) {
 template <class T> MlpParams<T> convert_mlp(const sgbpo_mlp& m) {
   MlpParams<T> p;
   p.in_dim = m.in_dim; p.width = m.width; p.n_hidden = m.n_hidden; p.out_dim = m.out_dim;
-  p.w_in = (const T*)m.w_in; p.w_hid = (const T*)m.w_hid; p.w_out = (const T*)m.w_out;
-  p.b_hid = (const T*)m.b_hid; p.gamma = (const T*)m.gamma; p.beta = (const T*)m.beta;
-  p.b_out = (const T*)m.b_out; p.log_std = (const T*)m.log_std;
+  for (int l = 0; l <= MAX_HIDDEN; ++l) { p.weight[l] = (const T*)m.weight[l]; p.bias[l] = (const T*)m.bias[l]; }
+  for (int l = 0; l < MAX_HIDDEN; ++l) { p.ln_weight[l] = (const T*)m.ln_weight[l]; p.ln_bias[l] = (const T*)m.ln_bias[l]; }
+  p.log_std = (const T*)m.log_std;
   return p;
 }
 template <class T> RolloutArgs<T> convert_rollout(const sgbpo_rollout& r) {
@@ -594,6 +610,7 @@ template <int ENV, class T, int W> struct RolloutLaunch {
   static int fwd(const sgbpo_consts* c, const sgbpo_mlp* pol, const sgbpo_rollout* r, cudaStream_t st) {
     using TASK = Task<ENV>;
     if (pol->in_dim != TASK::NO || pol->out_dim != TASK::NA) return fail2(SGBPO_E_ARG, "policy dims do not match the environment");
+    if (pol->n_hidden < 1 || pol->n_hidden > MAX_HIDDEN) return fail2(SGBPO_E_UNSUPPORTED, "1..4 hidden layers");
     const size_t smem = fwd_smem<T, W>(pol->in_dim, pol->n_hidden, pol->out_dim, TASK::NO);
     if (smem > 227 * 1024) return fail2(SGBPO_E_UNSUPPORTED, "policy does not fit in shared memory");
     auto kern = rollout_fwd_kernel<ENV, T, W>;
@@ -608,6 +625,7 @@ template <int ENV, class T, int W> struct RolloutLaunch {
   static int bwd(const sgbpo_consts* c, const sgbpo_mlp* pol, const sgbpo_rollout* r, const sgbpo_rollout_grads* g,
                  cudaStream_t st) {
     using TASK = Task<ENV>;
+    if (pol->n_hidden < 1 || pol->n_hidden > MAX_HIDDEN) return fail2(SGBPO_E_UNSUPPORTED, "1..4 hidden layers");
     if (pol->n_hidden != 2) return fail2(SGBPO_E_UNSUPPORTED, "fused backward supports policies with two hidden layers");
     const size_t smem = bwd_smem<T, W>(pol->in_dim, pol->n_hidden, pol->out_dim, TASK::NO);
     if (smem > 227 * 1024) return fail2(SGBPO_E_UNSUPPORTED, "policy does not fit in shared memory (backward)");
@@ -625,6 +643,7 @@ template <int ENV, class T, int W> struct RolloutLaunch {
 
 template <class T, int W> int launch_rows(int64_t M, const sgbpo_mlp* net, const void* x, void* out, cudaStream_t st) {
   const int warps = 8;
+  if (net->n_hidden < 1 || net->n_hidden > MAX_HIDDEN) return fail2(SGBPO_E_UNSUPPORTED, "1..4 hidden layers");
   const size_t smem = rows_smem<T, W>(net->in_dim, net->n_hidden, net->out_dim, warps);
   if (smem > 227 * 1024) return fail2(SGBPO_E_UNSUPPORTED, "network does not fit in shared memory");
   auto kern = mlp_rows_kernel<T, W>;

@@ -51,8 +51,28 @@ def _mlp_layout(model: nn.Sequential):
     return lin, norm
 
 
+SMEM_LIMIT = 227 * 1024
+
+
+def net_smem_floats(in_dim: int, width: int, n_hidden: int, out_dim: int) -> int:
+    """NetSmem<T, W>::floats of csrc/sgbpo_mlp.cuh (weights as [k][W+1] + biases + LayerNorm parameters)."""
+    ld = width + 1
+    f = in_dim * ld + (n_hidden - 1) * width * ld + width * out_dim + 3 * n_hidden * width + out_dim
+    return (f + 7) & ~7
+
+
+def mlp_rows_fits(dtype, in_dim: int, width: int, n_hidden: int, out_dim: int = 1, warps: int = 8) -> bool:
+    size = 4 if dtype == torch.float32 else 8
+    return (net_smem_floats(in_dim, width, n_hidden, out_dim) + warps * (in_dim + 2 * width) * 8) * size + 32 <= SMEM_LIMIT
+
+
+def rollout_fits(dtype, obs_dim: int, width: int, n_hidden: int, act_dim: int) -> bool:
+    size = 4 if dtype == torch.float32 else 8
+    return (net_smem_floats(obs_dim, width, n_hidden, act_dim) + 4 * (obs_dim + 6 * width) * 8) * size + 32 <= SMEM_LIMIT
+
+
 class PackedMlp:
-    """Device copies of an MLP's parameters in the kernels' layout + the ctypes descriptor."""
+    """ctypes descriptor pointing at an MLP's torch parameters (the kernels read torch's layout directly)."""
 
     def __init__(self, model: nn.Sequential, log_std: Optional[Tensor] = None):
         self.lin, self.norm = _mlp_layout(model)
@@ -62,27 +82,19 @@ class PackedMlp:
         self.in_dim, self.out_dim = self.lin[0].in_features, self.lin[-1].out_features
         self.refresh()
 
-    @torch.no_grad()
     def refresh(self):
-        lin, norm = self.lin, self.norm
-        self.w_in = lin[0].weight.t().contiguous()
-        if self.n_hidden > 1:
-            self.w_hid = torch.stack([l.weight.t() for l in lin[1:-1]]).contiguous()
-        else:
-            self.w_hid = torch.zeros(1, dtype=self.w_in.dtype, device=self.w_in.device)
-        self.w_out = lin[-1].weight.t().contiguous()
-        self.b_hid = torch.stack([l.bias for l in lin[:-1]]).contiguous()
-        self.gamma = torch.stack([n.weight for n in norm]).contiguous()
-        self.beta = torch.stack([n.bias for n in norm]).contiguous()
-        self.b_out = lin[-1].bias.contiguous()
+        """Re-read the data pointers (parameters are updated in place by the optimisers, so this is only
+        needed if a parameter tensor was replaced)."""
         d = Mlp()
         d.in_dim, d.width, d.n_hidden, d.out_dim = self.in_dim, self.width, self.n_hidden, self.out_dim
-        d.w_in, d.w_hid, d.w_out = self.w_in.data_ptr(), self.w_hid.data_ptr(), self.w_out.data_ptr()
-        d.b_hid, d.gamma, d.beta, d.b_out = (self.b_hid.data_ptr(), self.gamma.data_ptr(), self.beta.data_ptr(),
-                                             self.b_out.data_ptr())
+        for l, lin in enumerate(self.lin):
+            if not (lin.weight.is_contiguous() and lin.bias.is_contiguous()):
+                raise _lib.SgbpoError("MLP parameters must be contiguous")
+            d.weight[l], d.bias[l] = lin.weight.data_ptr(), lin.bias.data_ptr()
+        for l, norm in enumerate(self.norm):
+            d.ln_weight[l], d.ln_bias[l] = norm.weight.data_ptr(), norm.bias.data_ptr()
         if self.log_std is not None:
-            self._ls = self.log_std.detach().contiguous()
-            d.log_std = self._ls.data_ptr()
+            d.log_std = self.log_std.data_ptr()
         self.desc = d
 
 
@@ -94,6 +106,9 @@ class FusedRollout:
         self.rng_mode = "reference"        # "reference": per-step draws in the reference's order; "batched": 2 draws
         self.policy_pack = PackedMlp(algo.policy.model, algo.policy.log_std)
         self.vf_pack = PackedMlp(algo.target_value_function.model)
+        vp = self.vf_pack
+        # critic too large for shared memory in this dtype (e.g. float64 [128]x3): evaluate it with torch
+        self.vf_native = mlp_rows_fits(self.base.state.dtype, vp.in_dim, vp.width, vp.n_hidden)
         self._grad_bufs = None
         self.last = None
         self.launches_per_episode = 3          # rollout_fwd, mlp_rows, rollout_bwd (our kernels)
@@ -131,6 +146,9 @@ class FusedRollout:
         if len(_mlp_layout(pol.model)[1]) != 2:          # fused backward: two hidden layers
             return None
         if algo.buffer.store_safe_actions:
+            return None
+        pw = _mlp_layout(pol.model)[0][0].out_features
+        if not rollout_fits(base.state.dtype, base.obs_dim, pw, 2, base.action_dim):
             return None
         if hasattr(env, "consts"):
             try:
@@ -243,8 +261,6 @@ class FusedRollout:
         states[0], obs[0], values[0] = s0, obs0, val0
         sched = torch.tensor([reset_idx, aux_src], dtype=torch.int32, device=dev)      # one small H2D copy
         reset_idx_t, aux_src_t = sched[0], sched[1]
-        self.policy_pack.refresh()
-        self.vf_pack.refresh()
         r = Rollout()
         r.N, r.H = N, H
         keep = [eps, noise, dirs, aux0, resets, reset_idx_t, aux_src_t, shared]
@@ -258,9 +274,13 @@ class FusedRollout:
         self._timed("rollout_fwd", lambda: check(
             lib.sgbpo_rollout_fwd(base.env_id, dtype_code(dt), C.byref(self._consts()), C.byref(self.policy_pack.desc),
                                   C.byref(r), stream_ptr()), "sgbpo_rollout_fwd"))
-        self._timed("mlp_rows", lambda: check(
-            lib.sgbpo_mlp_rows(dtype_code(dt), H * N, C.byref(self.vf_pack.desc), C.c_void_p(obs[1].data_ptr()),
-                               C.c_void_p(values[1].data_ptr()), stream_ptr()), "sgbpo_mlp_rows"))
+        if self.vf_native:
+            self._timed("mlp_rows", lambda: check(
+                lib.sgbpo_mlp_rows(dtype_code(dt), H * N, C.byref(self.vf_pack.desc), C.c_void_p(obs[1].data_ptr()),
+                                   C.c_void_p(values[1].data_ptr()), stream_ptr()), "sgbpo_mlp_rows"))
+        else:
+            with torch.no_grad():
+                values[1:H + 1] = algo.target_value_function(obs[1:H + 1].reshape(H * N, o)).view(H, N)
         # hand the results to the reference's objects
         term = torch.zeros(H + 2, N, dtype=torch.bool, device=dev)
         rows = [j for j, f in enumerate(terminal_rows) if f]
@@ -337,19 +357,18 @@ class FusedRollout:
             _lib.lib().sgbpo_rollout_bwd(base.env_id, dtype_code(dt), C.byref(self._consts()),
                                          C.byref(self.policy_pack.desc), C.byref(last["r"]), C.byref(g), stream_ptr()),
             "sgbpo_rollout_bwd"))
-        dw_hid = h1.view(H * N, W).t() @ dz2.view(H * N, W)          # [k][c]; plain library GEMM
+        dw_hid = dz2.view(H * N, W).t() @ h1.view(H * N, W)          # Linear.weight.grad [out][in]; plain library GEMM
         g_w_in, g_w_out, g_b_hid, g_gamma, g_beta, g_b_out, g_log_std = parts
         pack = self.policy_pack
         grads = {
-            pack.lin[0].weight: g_w_in.view(o, W).t(), pack.lin[0].bias: g_b_hid.view(2, W)[0],
+            pack.lin[0].weight: g_w_in.view(W, o), pack.lin[0].bias: g_b_hid.view(2, W)[0],
             pack.norm[0].weight: g_gamma.view(2, W)[0], pack.norm[0].bias: g_beta.view(2, W)[0],
-            pack.lin[1].weight: dw_hid.t(), pack.lin[1].bias: g_b_hid.view(2, W)[1],
+            pack.lin[1].weight: dw_hid, pack.lin[1].bias: g_b_hid.view(2, W)[1],
             pack.norm[1].weight: g_gamma.view(2, W)[1], pack.norm[1].bias: g_beta.view(2, W)[1],
-            pack.lin[2].weight: g_w_out.view(W, m).t(), pack.lin[2].bias: g_b_out,
+            pack.lin[2].weight: g_w_out.view(m, W), pack.lin[2].bias: g_b_out,
             algo.policy.log_std: g_log_std,
         }
         for prm, val in grads.items():
-            val = val.contiguous()
             prm.grad = val if prm.grad is None else prm.grad + val
         return loss.detach()
 

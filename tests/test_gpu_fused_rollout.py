@@ -174,10 +174,12 @@ def test_mlp_rows_matches_torch(cuda_default):
     import ctypes as C
     from safegbpo_b200 import _lib
     from safegbpo_b200.learning_algorithms.components.value_function import ValueFunction
-    from safegbpo_b200.learning_algorithms.fused_rollout import PackedMlp
+    from safegbpo_b200.learning_algorithms.fused_rollout import PackedMlp, mlp_rows_fits
     for dtype, tol in ((torch.float64, 1e-11), (torch.float32, 2e-5)):
         torch.set_default_dtype(dtype)
         for width, depth, M in ((32, 1, 5), (64, 2, 1000), (128, 3, 4099)):
+            if not mlp_rows_fits(dtype, 5, width, depth):
+                continue
             vf = ValueFunction(5, net_arch=[width] * depth)
             x = torch.randn(M, 5) * 3
             ref = vf(x).squeeze(1)

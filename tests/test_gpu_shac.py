@@ -80,7 +80,7 @@ def test_safeguarded_episode_vs_oracle(cuda_f64, sg_name):
     N, H = 16, 8
     gen = torch.Generator().manual_seed(5)
     s0 = (torch.rand(N, 4, generator=gen, dtype=torch.float64, device="cpu") * 2 - 1) * torch.tensor(
-        [5.0, 3.0, 9.0, 9.0], dtype=torch.float64, device="cpu")
+        [3.0, 3.0, 7.0, 7.0], dtype=torch.float64, device="cpu")
     eps = torch.randn(H, N, 1, generator=gen, dtype=torch.float64, device="cpu")
     us = torch.rand(H, N, 1, 4, generator=gen, dtype=torch.float64, device="cpu")
     # oracle (float64, CPU)
