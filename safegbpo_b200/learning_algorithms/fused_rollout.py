@@ -71,6 +71,20 @@ def rollout_fits(dtype, obs_dim: int, width: int, n_hidden: int, act_dim: int) -
     return (net_smem_floats(obs_dim, width, n_hidden, act_dim) + 4 * (obs_dim + 6 * width) * 8) * size + 32 <= SMEM_LIMIT
 
 
+def _tall_skinny_gram(a: Tensor, b: Tensor) -> Tensor:
+    """a^T b for (M, W) operands with M >> W: a plain library GEMM, split over M so that more than a
+    handful of CTAs work on it (cuBLAS picks a 64x64 tile without split-K for this shape)."""
+    M, W = a.shape
+    split = 1
+    for cand in (256, 128, 64, 32, 16, 8):
+        if M % cand == 0 and M // cand >= 256:
+            split = cand
+            break
+    if split == 1:
+        return a.t() @ b
+    return torch.bmm(a.view(split, M // split, W).transpose(1, 2), b.view(split, M // split, W)).sum(dim=0)
+
+
 class PackedMlp:
     """ctypes descriptor pointing at an MLP's torch parameters (the kernels read torch's layout directly)."""
 
@@ -357,7 +371,7 @@ class FusedRollout:
             _lib.lib().sgbpo_rollout_bwd(base.env_id, dtype_code(dt), C.byref(self._consts()),
                                          C.byref(self.policy_pack.desc), C.byref(last["r"]), C.byref(g), stream_ptr()),
             "sgbpo_rollout_bwd"))
-        dw_hid = dz2.view(H * N, W).t() @ h1.view(H * N, W)          # Linear.weight.grad [out][in]; plain library GEMM
+        dw_hid = _tall_skinny_gram(dz2.view(H * N, W), h1.view(H * N, W))   # Linear.weight.grad [out][in]
         g_w_in, g_w_out, g_b_hid, g_gamma, g_beta, g_b_out, g_log_std = parts
         pack = self.policy_pack
         grads = {
