@@ -126,6 +126,10 @@ class FusedRollout:
         self._grad_bufs = None
         self.last = None
         self.launches_per_episode = 3          # rollout_fwd, mlp_rows, rollout_bwd (our kernels)
+        self.use_graphs = True                 # replay the episode as two CUDA graphs when its schedule allows
+        self.graph_warmup = 2                  # eager episodes before capture (optimizer state, cuBLAS handles)
+        self._episodes = 0
+        self._g = None                         # static buffers + captured graphs
         self.profile = False                   # record CUDA events around each of our kernels
         self.kernel_ms = {"rollout_fwd": [], "mlp_rows": [], "rollout_bwd": []}
 
@@ -250,12 +254,194 @@ class FusedRollout:
         resets_t = torch.stack(resets) if resets else None
         return eps_t, noise_t, dirs_t, resets_t, reset_idx, aux_src, terminal_rows, shared_t
 
+
+    # ======================================================================================================
+    # CUDA-graph path: an episode whose schedule has no reset inside the horizon is always the same sequence
+    # of launches on the same buffers, so it is captured once (two graphs: collect / update) and replayed.
+    # ======================================================================================================
+    def _graphable(self, reset_at) -> bool:
+        base = self.base
+        return (self.use_graphs and not self.profile and rng._source is None and not reset_at
+                and base._shared() is None and self._episodes >= self.graph_warmup
+                and getattr(self.algo.policy_optim, "defaults", {}).get("capturable", False))
+
+    def _alloc_static(self, H: int):
+        base, algo = self.base, self.algo
+        N, n, m, o, W = base.num_envs, base.state_dim, base.action_dim, base.obs_dim, self.policy_pack.width
+        dt, dev = base.state.dtype, base.state.device
+        z = lambda *shape, dtype=dt: torch.zeros(*shape, dtype=dtype, device=dev)
+        want_dirs = (self.wrapper is not None and self.wrapper.SG_KIND == _lib.SG_RAY_MASK
+                     and getattr(self.wrapper, "zonotopic_approximation", False) and self.wrapper.state_constrained)
+        g = dict(H=H, eps=z(H, N, m), u=z(H, N, n), noise=z(H, N, n), dirs=z(H, N, m, 2 * m) if want_dirs else None,
+                 states=z(H + 1, N, n), obs=z(H + 2, N, o), actions=z(H + 2, N, m), exec_actions=z(H, N, m),
+                 rewards=z(H + 2, N), values=z(H + 2, N), flags=z(H, N, dtype=torch.int32),
+                 term=z(H + 2, N, dtype=torch.bool), reward_sum=z(()), n_interv=z((), dtype=torch.int64),
+                 bad=z((), dtype=torch.int32), aux0=None if base._aux() is None else z(N, base._aux().shape[1]),
+                 h1=z(H, N, W), dz2=z(H, N, W), loss=z(()), fwd_graph=None, bwd_graph=None)
+        terminal_rows = [False] * (H + 2)
+        terminal_rows[H] = True
+        disc, norm = self._weights(terminal_rows, H, N)
+        g["terminal_rows"], g["disc"], g["norm"] = terminal_rows, disc, norm
+        g["term"][H] = True
+        g["disc_t"] = torch.tensor(disc, dtype=dt, device=dev)
+        g["term_mask"] = torch.tensor(terminal_rows, dtype=torch.bool, device=dev)
+        g["grw"] = torch.tensor([0.0 if terminal_rows[t] else -disc[t] / norm for t in range(H)], dtype=dt, device=dev)
+        tor = [-1] * (H + 2)
+        tor[H] = 0
+        g["term_of_row"] = torch.tensor(tor, dtype=torch.int32, device=dev)
+        g["gobs_term"] = z(1, N, o)
+        sizes = [o * W, W * m, 2 * W, 2 * W, 2 * W, m, m]
+        g["flat"] = z(sum(sizes))
+        g["parts"] = torch.split(g["flat"], sizes)
+        g["dw_hid"] = z(W, W)
+        g["ctr"] = base.noise_set.center[0].to(dt).clone()
+        g["half"] = base.noise_set.generator[0].diagonal().to(dt).clone()
+        r = Rollout()
+        r.N, r.H = N, H
+        p = lambda t: None if t is None else t.data_ptr()
+        r.eps, r.noise, r.dirs, r.aux0 = p(g["eps"]), p(g["noise"]), p(g["dirs"]), p(g["aux0"])
+        r.states, r.obs, r.actions, r.exec_actions = p(g["states"]), p(g["obs"]), p(g["actions"]), p(g["exec_actions"])
+        r.rewards, r.flags = p(g["rewards"]), p(g["flags"])
+        g["r"] = r
+        gr = RolloutGrads()
+        gr.grw, gr.gobs_term, gr.term_of_row = p(g["grw"]), p(g["gobs_term"]), p(g["term_of_row"])
+        gr.h1_out, gr.dz2_out = p(g["h1"]), p(g["dz2"])
+        (gr.g_w_in, gr.g_w_out, gr.g_b_hid, gr.g_gamma, gr.g_beta, gr.g_b_out, gr.g_log_std) = [x.data_ptr() for x in g["parts"]]
+        g["gr"] = gr
+        g_w_in, g_w_out, g_b_hid, g_gamma, g_beta, g_b_out, g_log_std = g["parts"]
+        pack = self.policy_pack
+        g["grads"] = {
+            pack.lin[0].weight: g_w_in.view(W, o), pack.lin[0].bias: g_b_hid.view(2, W)[0],
+            pack.norm[0].weight: g_gamma.view(2, W)[0], pack.norm[0].bias: g_beta.view(2, W)[0],
+            pack.lin[1].weight: g["dw_hid"], pack.lin[1].bias: g_b_hid.view(2, W)[1],
+            pack.norm[1].weight: g_gamma.view(2, W)[1], pack.norm[1].bias: g_beta.view(2, W)[1],
+            pack.lin[2].weight: g_w_out.view(m, W), pack.lin[2].bias: g_b_out,
+            algo.policy.log_std: g_log_std,
+        }
+        self._g = g
+        return g
+
+    def _fwd_body(self, g):
+        """Everything of collect_trajectories that touches the device, on static buffers (capturable)."""
+        base, algo, H = self.base, self.algo, g["H"]
+        N, o = base.num_envs, base.obs_dim
+        dt = base.state.dtype
+        lib = _lib.lib()
+        g["states"][0].copy_(g["states"][H])    # the episode starts where the previous one ended
+        if self.rng_mode == "batched":
+            g["eps"].normal_()
+            g["u"].uniform_()
+            if g["dirs"] is not None:
+                g["dirs"].uniform_(-1.0, 1.0)
+        else:                                   # the reference's per-step order: policy draw, directions, noise
+            for t in range(H):
+                g["eps"][t].normal_()
+                if g["dirs"] is not None:
+                    g["dirs"][t].uniform_(-1.0, 1.0)
+                g["u"][t].uniform_()
+        torch.addcmul(g["ctr"] - g["half"], g["u"], 2.0 * g["half"], out=g["noise"])
+        if g["dirs"] is not None:
+            g["dirs"].div_(torch.linalg.vector_norm(g["dirs"], dim=2, keepdim=True))
+        check(lib.sgbpo_rollout_fwd(base.env_id, dtype_code(dt), C.byref(self._consts()), C.byref(self.policy_pack.desc),
+                                    C.byref(g["r"]), stream_ptr()), "sgbpo_rollout_fwd")
+        if self.vf_native:
+            check(lib.sgbpo_mlp_rows(dtype_code(dt), H * N, C.byref(self.vf_pack.desc), C.c_void_p(g["obs"][1].data_ptr()),
+                                     C.c_void_p(g["values"][1].data_ptr()), stream_ptr()), "sgbpo_mlp_rows")
+        else:
+            with torch.no_grad():
+                g["values"][1:H + 1] = algo.target_value_function(g["obs"][1:H + 1].reshape(H * N, o)).view(H, N)
+        torch.sum(g["rewards"], out=g["reward_sum"])
+        if self.wrapper is not None:
+            g["n_interv"].copy_(((g["flags"] & _lib.FL_INTERVENED) != 0).sum())
+            g["bad"].copy_(((g["flags"] & (_lib.FL_NONFINITE | _lib.FL_INFEASIBLE)) != 0).any())
+
+    def _bwd_body(self, g):
+        """Loss, terminal-value gradient, fused reverse pass, weight-gradient GEMM (capturable)."""
+        base, algo, H = self.base, self.algo, g["H"]
+        N = base.num_envs
+        dt = base.state.dtype
+        W = self.policy_pack.width
+        picked = torch.where(g["term_mask"].unsqueeze(1), g["values"], g["rewards"])
+        g["loss"].copy_(-(g["disc_t"].unsqueeze(1) * picked).sum() / g["norm"])
+        x = g["obs"][H].detach().clone().requires_grad_(True)
+        v = algo.target_value_function(x).sum() * (-g["disc"][H] / g["norm"])
+        g["gobs_term"][0].copy_(torch.autograd.grad(v, x)[0])
+        g["flat"].zero_()
+        check(_lib.lib().sgbpo_rollout_bwd(base.env_id, dtype_code(dt), C.byref(self._consts()),
+                                           C.byref(self.policy_pack.desc), C.byref(g["r"]), C.byref(g["gr"]), stream_ptr()),
+              "sgbpo_rollout_bwd")
+        g["dw_hid"].copy_(_tall_skinny_gram(g["dz2"].view(H * N, W), g["h1"].view(H * N, W)))
+
+    def _capture(self, body, g):
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):            # warm-up on a side stream, as torch.cuda.graph requires
+            body(g)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            body(g)
+        return graph
+
+    def _collect_graph(self, H: int, steps_end: int, pending_end: bool) -> float:
+        base, algo = self.base, self.algo
+        g = self._g if self._g is not None and self._g["H"] == H else self._alloc_static(H)
+        buf = algo.buffer
+        base.cut_computation_graph()
+        if base.state.data_ptr() != g["states"][H].data_ptr():
+            g["states"][H].copy_(base.state)
+        g["obs"][0].copy_(buf.observations.tensor[0])
+        g["values"][0].copy_(buf.values.tensor[0])
+        if g["aux0"] is not None:
+            g["aux0"].copy_(base._aux())
+        if g["fwd_graph"] is None:
+            rng_state = torch.cuda.get_rng_state()
+            g["fwd_graph"] = self._capture(self._fwd_body, g)
+            torch.cuda.set_rng_state(rng_state)          # the warm-up + capture passes must not consume the stream
+        g["fwd_graph"].replay()
+        buf.observations.tensor, buf.values.tensor, buf.rewards.tensor = g["obs"], g["values"], g["rewards"]
+        buf.actions.tensor, buf.terminals.tensor = g["actions"], g["term"]
+        buf.t = torch.full_like(buf.t, H)
+        base.state = g["states"][H]
+        base.steps, base._reset_pending = steps_end, pending_end
+        base.last_flags, base.last_exec_action = g["flags"][H - 1], g["exec_actions"][H - 1]
+        if self.wrapper is not None:
+            w = self.wrapper
+            w.safe_action = g["exec_actions"][H - 1]
+            w._interventions = w._interventions + g["n_interv"]
+            if w.strict:
+                if int(g["bad"]):
+                    raise ValueError("a safeguarded step produced a non-finite action or an infeasible program "
+                                     "(the reference raises here: safeguard.py:68-75 / solver error)")
+            else:
+                w._status = w._status | g["bad"]
+        self.last = dict(graph=True, terminal_rows=g["terminal_rows"])
+        return float(g["reward_sum"]) / base.num_envs / H
+
+    def _backward_graph(self) -> Tensor:
+        g, algo = self._g, self.algo
+        for prm, buf in g["grads"].items():
+            if prm.grad is None:
+                prm.grad = buf
+            elif prm.grad.data_ptr() != buf.data_ptr():
+                raise _lib.SgbpoError("fused graph path: policy gradients must be zeroed (set_to_none) before the episode")
+        if g["bwd_graph"] is None:
+            g["bwd_graph"] = self._capture(self._bwd_body, g)
+        g["bwd_graph"].replay()
+        return g["loss"]
+
     # ------------------------------------------------------------------------------------------------------
     def collect_trajectories(self) -> float:
         algo, base = self.algo, self.base
         H, N = algo.len_trajectories, base.num_envs
         n, m, o = base.state_dim, base.action_dim, base.obs_dim
         dt, dev = base.state.dtype, base.state.device
+        self._episodes += 1
+        reset_at, _, _, _, pending_end, steps_end = self._schedule(H)
+        if self._graphable(reset_at):
+            return self._collect_graph(H, steps_end, pending_end)
         base.cut_computation_graph()
         s0 = base.state.detach().contiguous()
         aux0 = base._aux()
@@ -336,6 +522,8 @@ class FusedRollout:
 
     def backward(self) -> Tensor:
         algo, base, last = self.algo, self.base, self.last
+        if last.get("graph"):
+            return self._backward_graph()
         H, N = algo.len_trajectories, base.num_envs
         o, m, W = base.obs_dim, base.action_dim, self.policy_pack.width
         dt, dev = base.state.dtype, base.state.device

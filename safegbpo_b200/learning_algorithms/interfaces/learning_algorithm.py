@@ -19,6 +19,9 @@ class LearningAlgorithm(ABC):
         self.env = env
         self.policy = Policy(env.obs_dim, env.action_dim, **policy_kwargs)
         self.value_function = ValueFunction(env.obs_dim + (env.action_dim if q_function else 0), **vf_kwargs)
+        if torch.cuda.is_available() and next(self.policy.parameters()).is_cuda:
+            # device-side step counter: same arithmetic, lets the update be replayed inside a CUDA graph
+            policy_optim_kwargs = {"capturable": True, **policy_optim_kwargs}
         self.policy_optim = torch.optim.Adam(self.policy.parameters(), **policy_optim_kwargs)
         self.value_function_optim = torch.optim.Adam(self.value_function.parameters(), **vf_optim_kwargs)
         self.regularisation_coefficient = regularisation_coefficient
