@@ -350,7 +350,7 @@ class FusedRollout:
         else:
             with torch.no_grad():
                 g["values"][1:H + 1] = algo.target_value_function(g["obs"][1:H + 1].reshape(H * N, o)).view(H, N)
-        torch.sum(g["rewards"], out=g["reward_sum"])
+        g["reward_sum"].copy_(g["rewards"].sum())
         if self.wrapper is not None:
             g["n_interv"].copy_(((g["flags"] & _lib.FL_INTERVENED) != 0).sum())
             g["bad"].copy_(((g["flags"] & (_lib.FL_NONFINITE | _lib.FL_INFEASIBLE)) != 0).any())

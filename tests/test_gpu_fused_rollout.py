@@ -83,6 +83,9 @@ CONFIGS = [
     ("SwingUpCartPole", "rm", {"gate": "always", "zono": True, "linear": True}, 64, 1000),
     ("SwingUpCartPole", "rm", {"gate": "always", "zono": False, "linear": False}, 32, 1000),
     ("BalancePendulum", "none", {}, 64, 7),
+    ("BalancePendulum", "rm", {"gate": "reference", "zono": True, "linear": True}, 64, 1000),     # BASELINE configs[0]
+    ("BalancePendulum", "rm", {"gate": "always", "zono": True, "linear": True}, 32, 1000),
+    ("BalancePendulum", "bp", {"gate": "always"}, 32, 9),
     ("BalanceQuadrotor", "none", {}, 32, 6),
 ]
 

@@ -21,6 +21,8 @@ CASES = [
     ("SwingUpCartPole", "ray_mask", {"zonotopic": True}), ("BalanceCartPole", "ray_mask", {"zonotopic": True, "linear": False}),
     ("SwingUpCartPole", "ray_mask", {"zonotopic": False, "passthrough": True}),
     ("ManageHousehold", "boundary_projection", {}), ("ManageHousehold", "ray_mask", {"zonotopic": False}),
+    ("BalancePendulum", "boundary_projection", {}), ("BalancePendulum", "ray_mask", {"zonotopic": False}),
+    ("BalancePendulum", "ray_mask", {"zonotopic": True}), ("BalancePendulum", "ray_mask", {"zonotopic": True, "gate": "reference"}),
 ]
 IDS = [f"{c[0]}-{c[1]}-{'-'.join(f'{k}={v}' for k, v in c[2].items())}" for c in CASES]
 

@@ -18,6 +18,8 @@ CASES = [
     ("SwingUpCartPole", "ray_mask", {"zonotopic": True}), ("BalanceCartPole", "ray_mask", {"zonotopic": True, "linear": False}),
     ("SwingUpCartPole", "ray_mask", {"zonotopic": False, "passthrough": True}),
     ("ManageHousehold", "boundary_projection", {}), ("ManageHousehold", "ray_mask", {"zonotopic": False}),
+    ("BalancePendulum", "boundary_projection", {}), ("BalancePendulum", "ray_mask", {"zonotopic": False}),
+    ("BalancePendulum", "ray_mask", {"zonotopic": True}), ("BalancePendulum", "ray_mask", {"zonotopic": True, "gate": "reference"}),
 ]
 
 
