@@ -273,7 +273,7 @@ class FusedRollout:
         want_dirs = (self.wrapper is not None and self.wrapper.SG_KIND == _lib.SG_RAY_MASK
                      and getattr(self.wrapper, "zonotopic_approximation", False) and self.wrapper.state_constrained)
         g = dict(H=H, eps=z(H, N, m), u=z(H, N, n), noise=z(H, N, n), dirs=z(H, N, m, 2 * m) if want_dirs else None,
-                 states=z(H + 1, N, n), obs=z(H + 2, N, o), actions=z(H + 2, N, m), exec_actions=z(H, N, m),
+                 s_start=z(N, n), states=z(H + 1, N, n), obs=z(H + 2, N, o), actions=z(H + 2, N, m), exec_actions=z(H, N, m),
                  rewards=z(H + 2, N), values=z(H + 2, N), flags=z(H, N, dtype=torch.int32),
                  term=z(H + 2, N, dtype=torch.bool), reward_sum=z(()), n_interv=z((), dtype=torch.int64),
                  bad=z((), dtype=torch.int32), aux0=None if base._aux() is None else z(N, base._aux().shape[1]),
@@ -327,7 +327,7 @@ class FusedRollout:
         N, o = base.num_envs, base.obs_dim
         dt = base.state.dtype
         lib = _lib.lib()
-        g["states"][0].copy_(g["states"][H])    # the episode starts where the previous one ended
+        g["states"][0].copy_(g["s_start"])      # (separate input buffer: the body must be idempotent for capture)
         if self.rng_mode == "batched":
             g["eps"].normal_()
             g["u"].uniform_()
@@ -390,8 +390,7 @@ class FusedRollout:
         g = self._g if self._g is not None and self._g["H"] == H else self._alloc_static(H)
         buf = algo.buffer
         base.cut_computation_graph()
-        if base.state.data_ptr() != g["states"][H].data_ptr():
-            g["states"][H].copy_(base.state)
+        g["s_start"].copy_(base.state)
         g["obs"][0].copy_(buf.observations.tensor[0])
         g["values"][0].copy_(buf.values.tensor[0])
         if g["aux0"] is not None:

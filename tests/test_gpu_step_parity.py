@@ -61,8 +61,9 @@ def test_step_fwd_bwd_vs_oracle(env_name, kind, opts, dtype):
     torch.cuda.synchronize()
     okc = ok.cpu().numpy()
     if dtype == torch.float64:
-        tol = dict(rtol=1e-7, atol=1e-8) if zono else dict(rtol=1e-9, atol=1e-10)
-        gtol = dict(rtol=1e-5, atol=1e-6) if zono else dict(rtol=1e-8, atol=1e-9)
+        # zonotopic ray mask: the ORACLE's P2 is an SLSQP + Newton-polish solve, accurate to ~1e-6
+        tol = dict(rtol=1e-5, atol=2e-6) if zono else dict(rtol=1e-9, atol=1e-10)
+        gtol = dict(rtol=1e-4, atol=1e-5) if zono else dict(rtol=1e-8, atol=1e-9)
     else:
         tol = dict(rtol=1e-5, atol=2e-5)          # float32: 1e-5 relative (north_star), absolute floor for O(10) states
         gtol = dict(rtol=2e-4, atol=2e-4)         # first derivatives of fp32 kinks: looser, stated here

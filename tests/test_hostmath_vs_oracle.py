@@ -35,10 +35,10 @@ def test_step_matches_oracle(env_name, kind, opts):
                   cot={k: v.numpy() for k, v in case["cot"].items()})
     ok = ref["ok"].numpy()
     assert ok.sum() >= N // 2
-    tol = dict(rtol=1e-7, atol=1e-8) if (kind == "ray_mask" and opts.get("zonotopic", True)) else dict(rtol=1e-10, atol=1e-11)
+    tol = dict(rtol=1e-5, atol=2e-6) if (kind == "ray_mask" and opts.get("zonotopic", True)) else dict(rtol=1e-10, atol=1e-11)
     for key in ("a_exec", "s_next", "obs", "reward"):
         np.testing.assert_allclose(out[key][ok], ref[key].numpy()[ok], err_msg=key, **tol)
-    gtol = dict(rtol=1e-5, atol=1e-6) if (kind == "ray_mask" and opts.get("zonotopic", True)) else dict(rtol=1e-8, atol=1e-9)
+    gtol = dict(rtol=1e-4, atol=1e-5) if (kind == "ray_mask" and opts.get("zonotopic", True)) else dict(rtol=1e-8, atol=1e-9)
     np.testing.assert_allclose(out["gs"][ok], ref["gs"].numpy()[ok], err_msg="gs", **gtol)
     np.testing.assert_allclose(out["ga"][ok], ref["ga"].numpy()[ok], err_msg="ga", **gtol)
     if kind != "none":
