@@ -214,7 +214,7 @@ class FusedRollout:
             u = rng.rand(H, N, n).to(dt)
             ctr = base.noise_set.center[0].to(dt)
             half = base.noise_set.generator[0].diagonal().to(dt)
-            noise_t = ctr + half * (2 * u - 1)
+            noise_t = torch.addcmul(ctr - half, u, 2.0 * half)      # = ctr + half (2u - 1), same form as the graph body
             dirs_t = None
             if want_dirs:
                 d = rng.rand(H, N, m, 2 * m).to(dt) * 2 - 1
