@@ -33,7 +33,8 @@ enum { SGBPO_SG_NONE = 0, SGBPO_SG_BOUNDARY_PROJECTION = 1, SGBPO_SG_RAY_MASK = 
 enum { SGBPO_GATE_REFERENCE = 0, SGBPO_GATE_INTENDED = 1, SGBPO_GATE_ALWAYS = 2 };
 enum {
   SGBPO_FL_PROJECTABLE = 1, SGBPO_FL_INFEASIBLE = 2, SGBPO_FL_INTERVENED = 4, SGBPO_FL_NONFINITE = 8,
-  SGBPO_FL_GUARD_USED = 16, SGBPO_FL_ACTION_IN_SET = 32, SGBPO_FL_NEXT_IN_SET = 64, SGBPO_FL_CLAMPED = 128
+  SGBPO_FL_GUARD_USED = 16, SGBPO_FL_ACTION_IN_SET = 32, SGBPO_FL_NEXT_IN_SET = 64, SGBPO_FL_CLAMPED = 128,
+  SGBPO_FL_COLLIDED = 256
 };
 
 /* Constant set data, registered once per wrapper (replaces the numpy constants cvxpy bakes into the
@@ -42,7 +43,8 @@ typedef struct sgbpo_consts {
   int32_t sg_kind, gate_mode;
   int32_t rm_linear, rm_zonotopic, rm_passthrough;
   int32_t action_constrained, state_constrained, state_model; /* 0: G_s invertible, 1: polygon (n = 2) */
-  int32_t disable_clamp, reserved0;                          /* 1: raw dynamics (Simulator.dynamics), no box clamp */
+  int32_t disable_clamp, n_obstacles;                        /* 1: raw dynamics (no clamp); obstacles in aux (Navigate*) */
+  int32_t act_set_mode, reserved1;                           /* 0: constant safe action set; 1: NavigateSeeker per-step set (P5) */
   double box_min[SGBPO_MAXN], box_max[SGBPO_MAXN];           /* feasible state box */
   double noise_center[SGBPO_MAXN];
   double a_lo[SGBPO_MAXM], a_hi[SGBPO_MAXM];                 /* m = 1 safe action interval */
@@ -92,6 +94,12 @@ int sgbpo_step_bwd(int env_id, int dtype, int64_t N, const sgbpo_consts* consts,
 /* K2: Simulator.linear_dynamics (simulator.py:206-230): c (N,n), A (N,n,n), B (N,n,m), E (N,n,n). */
 int sgbpo_linearise(int env_id, int dtype, int64_t N, const sgbpo_consts* consts, const void* s,
                     void* c, void* A, void* B, void* E, void* stream);
+
+/* K11: NavigateSeekerEnv.safe_action_set / compute_generator (envs/navigate_seeker.py:398-477, program P5):
+ * generator (N,2,2) of the per-environment safe action zonotope Z(0, U diag(len)); aux (N, 2 + 3*3) holds
+ * goal then (cx, cy, r) per obstacle; status (N) int32: 0 ok, 1 degenerate/infeasible. */
+int sgbpo_seeker_action_set(int dtype, int64_t N, const sgbpo_consts* consts, const void* s, const void* aux,
+                            void* generator, int32_t* status, void* stream);
 
 /* ---- whole-horizon fused rollout (SHAC.collect_trajectories + reverse pass, shac.py:96-151) ------------ */
 

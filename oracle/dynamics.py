@@ -168,6 +168,7 @@ class OracleEnv:
             p = RCI_ENVS[env_name]
             self.ctrl = (assets[f"{p}_ctrl_center"], assets[f"{p}_ctrl_generators"])
             self.rci = (assets[f"{p}_rci_center"], assets[f"{p}_rci_generators"])
+        self.obstacles = []                                 # NavigateSeeker: list of (center (N,2), radius (N))
         if self.sim.name == "household":                   # household.py:59-66, 95-98
             s0 = HOUSEHOLD_START
             self.load = assets["load_data"][s0:]
@@ -185,7 +186,14 @@ class OracleEnv:
         return self.env_name != "NavigateSeeker"
 
     def safe_action_set(self):
-        """(center (m,), generator (m,p)) -- rci_env.py:38-45."""
+        """(center (m,), generator (m,p)) -- rci_env.py:38-45.  NavigateSeeker: per-environment
+        (center (N,m), generator (N,m,2)) from program P5 (navigate_seeker.py:398-477, no_grad)."""
+        if self.env_name == "NavigateSeeker":
+            from .programs import p5_seeker_generator
+            with torch.no_grad():
+                gens = [p5_seeker_generator(self.state[i].detach(), [(c[i], r[i]) for c, r in self.obstacles],
+                                            self.state_min, self.state_max) for i in range(self.num_envs)]
+            return torch.zeros(self.num_envs, 2, dtype=torch.float64), torch.stack(gens)
         return self.ctrl
 
     def safe_state_set(self):
@@ -232,9 +240,43 @@ class OracleEnv:
         """simulator.py:174-182; household.py:168-177."""
         w = self.noise_sample() if noise is None else noise
         self.last_noise = w
+        prev = self.state
         self.state = self.dynamics(self.state, action, w)
+        if self.obstacles:
+            self.state = self._collision_operator(prev, self.state)
         if self.sim.clamp:
             self.state = torch.clamp(self.state, self.state_min, self.state_max)
+
+    def _collision_operator(self, prev: Tensor, free: Tensor) -> Tensor:
+        """navigate_seeker.py:233-296: elastic bounce off the LAST obstacle the free state entered."""
+        N = self.num_envs
+        collided = torch.stack([torch.linalg.vector_norm(free - c, dim=1) <= r for c, r in self.obstacles], dim=1)
+        self.collided = collided
+        mask = collided.any(dim=1)
+        if not bool(mask.any()):
+            return free
+        which = torch.zeros(N, dtype=torch.long)
+        for j in range(len(self.obstacles)):
+            which = torch.where(collided[:, j], torch.full_like(which, j), which)
+        centers = torch.stack([c for c, _ in self.obstacles])[which, torch.arange(N)]
+        radii = torch.stack([r for _, r in self.obstacles])[which, torch.arange(N)].unsqueeze(1)
+        safe_mask = mask.unsqueeze(1)
+        to_start = prev - centers
+        vel = free - prev
+        a = (vel * vel).sum(1, keepdim=True)
+        b = 2 * (to_start * vel).sum(1, keepdim=True)
+        c = (to_start * to_start).sum(1, keepdim=True) - radii ** 2
+        disc = torch.where(safe_mask, b ** 2 - 4 * a * c, torch.ones_like(a))
+        a_safe = torch.where(safe_mask, a, torch.ones_like(a))
+        t = (-b - torch.sqrt(disc)) / (2 * a_safe)
+        inter = prev + t * vel
+        normal = inter - centers
+        nn = torch.where(safe_mask, torch.linalg.vector_norm(normal, dim=1, keepdim=True), torch.ones_like(a))
+        normal = normal / nn
+        vdn = (vel * normal).sum(1, keepdim=True)
+        refl = vel - 2 * vdn * normal
+        bounced = inter + refl * ((1 - t) * 0.1)
+        return torch.where(safe_mask, bounced, free)
 
     def step(self, action: Tensor, noise: Optional[Tensor] = None):
         """simulator.py:82-108 (Q6: reset-all, reward on the post-reset state)."""
@@ -254,8 +296,9 @@ class OracleEnv:
             return torch.cat([torch.sin(s[:, 0:1]), torch.cos(s[:, 0:1]), s[:, 1:2]], dim=1)
         if self.sim.name == "cartpole":      # cartpole.py:83-88
             return torch.cat([s[:, 0:1], torch.sin(s[:, 1:2]), torch.cos(s[:, 1:2]), s[:, 2:4]], dim=1)
-        if self.sim.name in ("quadrotor", "seeker"):   # quadrotor.py:132, seeker.py:113
-            return torch.cat([s, self.goal], dim=1)
+        if self.sim.name in ("quadrotor", "seeker"):   # quadrotor.py:132, seeker.py:113, navigate_seeker.py:189-197
+            extra = [torch.cat([c, r.unsqueeze(1)], dim=1) for c, r in self.obstacles]
+            return torch.cat([s, self.goal] + extra, dim=1)
         t = self.steps                        # household.py:109-113
         series = torch.cat([self.load[t:t + 5], self.pv[t:t + 5], self.t_out[t:t + 5], self.price[t:t + 5]])
         return torch.cat([s, series.unsqueeze(0).expand(self.num_envs, -1)], dim=1)

@@ -512,3 +512,43 @@ def p1_projection_batch_m1(action: Tensor, prog: ParametricP1M1, theta: Tensor):
     a_s = torch.minimum(torch.maximum(action[:, 0], lo), hi)
     a_s = torch.where(infeasible, torch.full_like(a_s, float("nan")), a_s)
     return a_s.unsqueeze(1), infeasible
+
+
+
+def p5_seeker_generator(state: Tensor, obstacles, box_min: Tensor, box_max: Tensor) -> Tensor:
+    """P5, navigate_seeker.py:415-477 for ONE environment: generator U diag(len) of the safe action zonotope,
+    len = argmax geo_mean(len) under state-box feasibility, len <= 1 and one support constraint per obstacle.
+    Solved generically (SLSQP on sum(log len), then an exact re-solve on the identified active set)."""
+    U = torch.eye(2, dtype=F64)
+    min_dist = torch.linalg.vector_norm(state.abs() - box_max)
+    rows = []
+    for center, radius in obstacles:
+        direction = center - state
+        distance = torch.linalg.vector_norm(direction)
+        to_obs = direction / distance
+        distance = distance - radius
+        if distance < min_dist:
+            U = torch.stack([to_obs, torch.stack([to_obs[1], -to_obs[0]])], dim=1)
+            min_dist = distance
+    A, b = [], []
+    for d in range(2):
+        A.append(U[d].abs()); b.append(state[d] - box_min[d])
+        A.append(U[d].abs()); b.append(box_max[d] - state[d])
+    A.append(torch.tensor([1.0, 0.0], dtype=F64)); b.append(torch.tensor(1.0, dtype=F64))
+    A.append(torch.tensor([0.0, 1.0], dtype=F64)); b.append(torch.tensor(1.0, dtype=F64))
+    for center, radius in obstacles:
+        direction = center - state
+        distance = torch.linalg.vector_norm(direction)
+        A.append((direction / distance @ U).abs()); b.append(distance - radius)
+    A, b = torch.stack(A).numpy(), torch.stack(b).numpy()
+    x0 = np.full(2, 0.25 * min(1.0, float(np.min(b / np.maximum(A.sum(1), 1e-12)))))
+    res = minimize(lambda x: -np.sum(np.log(x)), x0, jac=lambda x: -1.0 / x,
+                   constraints=[{"type": "ineq", "fun": lambda x: b - A @ x, "jac": lambda x: -A}],
+                   bounds=[(1e-12, None)] * 2, method="SLSQP", options={"maxiter": 500, "ftol": 1e-16})
+    x = res.x
+    act = np.where(b - A @ x <= 1e-7 * (1 + np.abs(b)))[0]
+    if len(act) >= 2:                      # vertex
+        x = np.linalg.lstsq(A[act], b[act], rcond=None)[0]
+    elif len(act) == 1:                    # edge optimum of the product: x_j = b / (2 a_j)
+        x = b[act[0]] / (2 * A[act[0]])
+    return U * torch.from_numpy(x)

@@ -32,6 +32,7 @@ class OracleSafeguard:
         self.passthrough = passthrough
         self.gate = gate                    # "reference" (Q1 as shipped) | "intended" | "always"
         self.strict = strict                # False: keep NaN rows of infeasible programs instead of raising
+        self._action_set = None             # per-call cache of a per-environment safe action set (NavigateSeeker)
         self.fast = True                    # m = 1 boundary projection through the canonicalise-once path
         self._p1_prog = None
         self.m, self.n, self.N = env.action_dim, env.state_dim, env.num_envs
@@ -49,7 +50,8 @@ class OracleSafeguard:
         env = self.env
         s = P.SafeSets(m=self.m, n=self.n)
         if env.action_constrained:
-            s.c_a, s.G_a = env.safe_action_set()
+            c_a, G_a = self._action_set if self._action_set is not None else env.safe_action_set()
+            s.c_a, s.G_a = (c_a[i], G_a[i]) if G_a.dim() == 3 else (c_a, G_a)
         if env.state_constrained:
             s.c_s, s.G_s = env.safe_state_set()
             s.c_f, s.B, s.G_w = const[i], b_mat[i], self.G_w
@@ -88,6 +90,7 @@ class OracleSafeguard:
 
     # -- the maps -------------------------------------------------------------------------------
     def safeguard(self, action: Tensor, directions: Optional[Tensor] = None) -> Tensor:
+        self._action_set = self.env.safe_action_set() if self.env.env_name == "NavigateSeeker" else None
         if self.kind == "boundary_projection":
             return self.boundary_projection(action)
         return self.ray_mask(action, directions)
@@ -132,9 +135,9 @@ class OracleSafeguard:
             else:
                 center, safe_dist, feas_dist = self.orthogonal_approximation(action)
         else:
-            c_a, g_a = env.safe_action_set()
-            center = c_a.expand(self.N, -1)
-            safe_dist, feas_dist = self.compute_distances(action, center, g_a.expand(self.N, -1, -1))
+            c_a, g_a = self._action_set if self._action_set is not None else env.safe_action_set()
+            center = c_a if c_a.dim() == 2 else c_a.expand(self.N, -1)
+            safe_dist, feas_dist = self.compute_distances(action, center, g_a if g_a.dim() == 3 else g_a.expand(self.N, -1, -1))
         action_dist = torch.linalg.vector_norm(action - center, dim=1, ord=2, keepdim=True)
         dirs = (action - center) / (action_dist + 1e-8)
         central = action_dist < 1e-8

@@ -31,7 +31,7 @@ class Consts(C.Structure):
         ("sg_kind", C.c_int32), ("gate_mode", C.c_int32),
         ("rm_linear", C.c_int32), ("rm_zonotopic", C.c_int32), ("rm_passthrough", C.c_int32),
         ("action_constrained", C.c_int32), ("state_constrained", C.c_int32), ("state_model", C.c_int32),
-        ("disable_clamp", C.c_int32), ("reserved0", C.c_int32),
+        ("disable_clamp", C.c_int32), ("n_obstacles", C.c_int32), ("act_set_mode", C.c_int32), ("reserved1", C.c_int32),
         ("box_min", C.c_double * MAXN), ("box_max", C.c_double * MAXN), ("noise_center", C.c_double * MAXN),
         ("a_lo", C.c_double * MAXM), ("a_hi", C.c_double * MAXM),
         ("n_act_hp", C.c_int32), ("act_hp", (C.c_double * 3) * MAXHP), ("c_a", C.c_double * MAXM),
@@ -76,7 +76,7 @@ ENV_IDS = {"BalancePendulum": 0, "BalanceCartPole": 1, "SwingUpCartPole": 2, "Ba
 SG_NONE, SG_BOUNDARY_PROJECTION, SG_RAY_MASK = 0, 1, 2
 GATE = {"reference": 0, "intended": 1, "always": 2}
 FL_PROJECTABLE, FL_INFEASIBLE, FL_INTERVENED, FL_NONFINITE = 1, 2, 4, 8
-FL_GUARD_USED, FL_ACTION_IN_SET, FL_NEXT_IN_SET, FL_CLAMPED = 16, 32, 64, 128
+FL_GUARD_USED, FL_ACTION_IN_SET, FL_NEXT_IN_SET, FL_CLAMPED, FL_COLLIDED = 16, 32, 64, 128, 256
 
 _VP = C.c_void_p
 _SIGNATURES = {
@@ -88,6 +88,7 @@ _SIGNATURES = {
     "sgbpo_step_bwd": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.POINTER(Consts), C.POINTER(StepShared)]
                        + [_VP] * 6 + [_VP] * 4 + [_VP, _VP, _VP]),
     "sgbpo_linearise": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.POINTER(Consts)] + [_VP] * 5 + [_VP]),
+    "sgbpo_seeker_action_set": (C.c_int, [C.c_int, C.c_int64, C.POINTER(Consts)] + [_VP] * 5),
     "sgbpo_rollout_fwd": (C.c_int, [C.c_int, C.c_int, C.POINTER(Consts), C.POINTER(Mlp), C.POINTER(Rollout), _VP]),
     "sgbpo_rollout_bwd": (C.c_int, [C.c_int, C.c_int, C.POINTER(Consts), C.POINTER(Mlp), C.POINTER(Rollout),
                                     C.POINTER(RolloutGrads), _VP]),

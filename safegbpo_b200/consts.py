@@ -140,7 +140,8 @@ def polytope_facets(G_s: np.ndarray, fixed_cols: np.ndarray, free_col: Optional[
 def build_consts(env_name: str, sg_kind: int, *, gate_mode: int = 0, rm_linear: bool = True,
                  rm_zonotopic: bool = True, rm_passthrough: bool = False,
                  safe_action: Optional[tuple] = None, safe_state: Optional[tuple] = None,
-                 G_w: Optional[np.ndarray] = None, B0: Optional[np.ndarray] = None) -> Consts:
+                 G_w: Optional[np.ndarray] = None, B0: Optional[np.ndarray] = None,
+                 dynamic_action_set: bool = False, n_obstacles: int = 0) -> Consts:
     """Fill ``struct sgbpo_consts``.  safe_action / safe_state: (center, generator) numpy float64 or None."""
     sim = ENV_SIM[env_name]
     bc, bh, nc, _ = (np.asarray(x, dtype=np.float64) for x in BOXES[sim])
@@ -150,7 +151,9 @@ def build_consts(env_name: str, sg_kind: int, *, gate_mode: int = 0, rm_linear: 
     k.rm_linear, k.rm_zonotopic, k.rm_passthrough = int(rm_linear), int(rm_zonotopic), int(rm_passthrough)
     for i in range(n):
         k.box_min[i], k.box_max[i], k.noise_center[i] = bc[i] - bh[i], bc[i] + bh[i], nc[i]
-    k.action_constrained = int(safe_action is not None)
+    k.action_constrained = int(safe_action is not None or dynamic_action_set)
+    k.n_obstacles = int(n_obstacles)
+    k.act_set_mode = int(dynamic_action_set)
     k.state_constrained = int(safe_state is not None)
     if safe_action is not None:
         c_a, G_a = (np.asarray(x, dtype=np.float64) for x in safe_action)

@@ -166,16 +166,21 @@ template <> struct Task<ENV_MANAGE_HOUSEHOLD> {
   }
 };
 
+constexpr int SEEKER_MAXK = 3;   // obstacles carried in aux: goal (2) then (cx, cy, r) per obstacle
+
 template <> struct Task<ENV_NAVIGATE_SEEKER> {
   using Sim = SeekerSim;
-  static constexpr int NS = 2, NA = 2, NO = 4, NAUX = 2;   // aux = goal; obstacles: appended by the host side
+  // observation written by the kernel: (state, goal); the constant obstacle columns are appended by the host
+  static constexpr int NS = 2, NA = 2, NO = 4, NAUX = 2 + 3 * SEEKER_MAXK;
   static constexpr bool CLAMP = true;
   template <class S, class T> SG_HD static void observe(const S* s, const T* aux, const StepShared<T>*, S* o) {
     o[0] = s[0]; o[1] = s[1]; o[2] = S(aux[0]); o[3] = S(aux[1]);
   }
   template <class S, class T> SG_HD static S reward(const S* s, const S*, const T* aux, const StepShared<T>*) {
     const S dx = S(aux[0]) - s[0], dz = S(aux[1]) - s[1];
-    return -(C<S>(2.0) * sg_sqrt(dx * dx + dz * dz));
+    const S q = dx * dx + dz * dz;
+    if (primal(q) == T(0)) return C<S>(0.0);
+    return -(C<S>(2.0) * sg_sqrt(q));
   }
 };
 

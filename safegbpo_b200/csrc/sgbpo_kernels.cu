@@ -144,6 +144,22 @@ linearise_kernel(int64_t N, const __grid_constant__ SafeConsts<T> k, const T* __
   }
 }
 
+template <class T>
+__global__ void __launch_bounds__(128)
+seeker_action_set_kernel(int64_t N, const __grid_constant__ SafeConsts<T> k, const T* __restrict__ s,
+                         const T* __restrict__ aux, T* __restrict__ gen, int32_t* __restrict__ status) {
+  constexpr int NAUX = Task<ENV_NAVIGATE_SEEKER>::NAUX;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    T sv[2], av[NAUX], U[2][2], len[2];
+    load_row<2>(s, i, sv);
+    load_row<NAUX>(aux, i, av);
+    const bool ok = seeker_action_set<T>(sv, av, k, U, len);
+    gen[i * 4 + 0] = U[0][0] * len[0]; gen[i * 4 + 1] = U[0][1] * len[1];
+    gen[i * 4 + 2] = U[1][0] * len[0]; gen[i * 4 + 3] = U[1][1] * len[1];
+    status[i] = ok ? 0 : 1;
+  }
+}
+
 static int grid_for(int64_t N, int block) {
   int64_t g = (N + block - 1) / block;
   const int64_t cap = 148 * 16;      // grid-stride above 16 CTAs per SM
@@ -232,6 +248,22 @@ int sgbpo_step_bwd(int env_id, int dtype, int64_t N, const sgbpo_consts* consts,
   if (!consts || !s || !a || !w || !gs || !ga || N < 0) return fail(SGBPO_E_ARG, "sgbpo_step_bwd: null pointer or negative N");
   cudaStream_t st = (cudaStream_t)stream;
   SGBPO_DISPATCH(bwd(N, consts, shared, s, a, w, aux, dirs, reset_state, g_s_next, g_a_exec, g_obs, g_reward, gs, ga, st))
+}
+
+int sgbpo_seeker_action_set(int dtype, int64_t N, const sgbpo_consts* consts, const void* s, const void* aux,
+                            void* generator, int32_t* status, void* stream) {
+  if (N == 0) return SGBPO_OK;
+  if (!consts || !s || !aux || !generator || !status || N < 0) return fail(SGBPO_E_ARG, "sgbpo_seeker_action_set: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype) {
+    seeker_action_set_kernel<double><<<grid_for(N, 128), 128, 0, st>>>(N, convert_consts<double>(*consts), (const double*)s,
+                                                                      (const double*)aux, (double*)generator, status);
+  } else {
+    seeker_action_set_kernel<float><<<grid_for(N, 128), 128, 0, st>>>(N, convert_consts<float>(*consts), (const float*)s,
+                                                                     (const float*)aux, (float*)generator, status);
+  }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? SGBPO_OK : cuda_fail(e, "seeker_action_set_kernel");
 }
 
 int sgbpo_linearise(int env_id, int dtype, int64_t N, const sgbpo_consts* consts, const void* s, void* c, void* A,

@@ -162,8 +162,9 @@ __device__ __forceinline__ void elu_layernorm(T (&z)[MLP_R][W / 32], const T* __
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
       const T v = z[r][j];
-      const T e = v > T(0) ? v : sg_elu_neg(v);
-      if (SAVE) egrad[r][j] = v > T(0) ? T(1) : e + T(1);
+      const T en = sg_elu_neg(v < T(0) ? v : T(0));     // branch-free: exp() is evaluated for every element
+      const T e = v > T(0) ? v : en;
+      if (SAVE) egrad[r][j] = v > T(0) ? T(1) : en + T(1);
       z[r][j] = e;
       s += e;
     }

@@ -320,23 +320,21 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
       store_tile<T, W>(h1T, lane, z);
       store_tile<T, W>(x1S, lane, xh);
       store_tile<T, W>(e1S, lane, eg);
+      // stream h1 (layer-2 input) out for the dW_hid GEMM straight from the register tile:
+      // [t][env][W], 128-byte row segments per (r, j)
+#pragma unroll
+      for (int r = 0; r < MLP_R; ++r) {
+        if (env0 + r < N) {
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) G.h1_out[((int64_t)t * N + env0 + r) * W + lane + 32 * j] = z[r][j];
+        }
+      }
       __syncwarp();
       tile_gemm<T, W>(h1T, W, Whid, net.b_hid + W, lane, z);
       elu_layernorm<T, W, true>(z, net.gamma + W, net.beta + W, lane, xh, eg, rstd2);
       out_layer<T, W, NA>(z, net.w_out, net.b_out, lane, mu);
       store_tile<T, W>(x2S, lane, xh);
       store_tile<T, W>(e2S, lane, eg);
-      // stream h1 (layer-2 input) out for the dW_hid GEMM: [t][env][W], 8-env span of this warp
-#pragma unroll
-      for (int r = 0; r < MLP_R; ++r) {
-        if (env0 + r < N) {
-          T hrow[CPL];
-#pragma unroll
-          for (int j = 0; j < CPL; ++j) hrow[j] = h1T[(lane + 32 * j) * MLP_R + r];
-#pragma unroll
-          for (int j = 0; j < CPL; ++j) G.h1_out[((int64_t)t * N + env0 + r) * W + lane + 32 * j] = hrow[j];
-        }
-      }
     }
     __syncwarp();
     // ---- step Jacobian (duals) contracted with the carried cotangents, on the owner lanes -----------------

@@ -38,14 +38,16 @@ enum Flag : int {
   FL_GUARD_USED = 16,        // the safeguarded action (not the raw one) was executed
   FL_ACTION_IN_SET = 32,     // verdict: executed action inside the safe action set (where one exists)
   FL_NEXT_IN_SET = 64,       // verdict: linearised next-state zonotope inside the safe state set
-  FL_CLAMPED = 128           // execute_action clamped the state to the feasible box
+  FL_CLAMPED = 128,          // execute_action clamped the state to the feasible box
+  FL_COLLIDED = 256          // Navigate*: the free step entered an obstacle (collision operator applied)
 };
 
 template <class T> struct SafeConsts {
   int sg_kind, gate_mode;
   int rm_linear, rm_zonotopic, rm_passthrough;
   int action_constrained, state_constrained, state_model;
-  int disable_clamp, reserved0;
+  int disable_clamp, n_obstacles;
+  int act_set_mode, reserved1;
   T box_min[MAXN], box_max[MAXN];      // feasible state box: gate (box.py:139-154) and clamp
   T noise_center[MAXN];
   // action block

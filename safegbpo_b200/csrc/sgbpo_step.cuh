@@ -13,6 +13,35 @@ template <class T> SG_HD bool is_close(T a, T b) {   // torch.isclose defaults: 
 }
 template <class T> SG_HD bool finite_val(T x) { return (x - x) == T(0); }
 
+// Navigate* environments: elastic collision with the (last) obstacle the free step entered
+// (envs/navigate_seeker.py:251-296; the remaining-time factor (1 - t) * DT is kept as shipped).
+template <class TASK, class S, class T>
+SG_HD void collision_operator(const S* s_prev, S* s_next, const T* aux, const SafeConsts<T>& k, int& flags) {
+  int hit = -1;
+  for (int i = 0; i < k.n_obstacles && i < SEEKER_MAXK; ++i) {
+    const T dx = primal(s_next[0]) - aux[2 + 3 * i], dy = primal(s_next[1]) - aux[3 + 3 * i];
+    if (sg_sqrt(dx * dx + dy * dy) <= aux[4 + 3 * i]) hit = i;
+  }
+  if (hit < 0) return;
+  flags |= FL_COLLIDED;
+  const S cx = S(aux[2 + 3 * hit]), cy = S(aux[3 + 3 * hit]), rad = S(aux[4 + 3 * hit]);
+  const S tx = s_prev[0] - cx, ty = s_prev[1] - cy;
+  const S vx = s_next[0] - s_prev[0], vy = s_next[1] - s_prev[1];
+  const S qa = vx * vx + vy * vy;
+  const S qb = C<S>(2.0) * (tx * vx + ty * vy);
+  const S qc = tx * tx + ty * ty - rad * rad;
+  const S t = (-qb - sg_sqrt(qb * qb - C<S>(4.0) * qa * qc)) / (C<S>(2.0) * qa);
+  const S ix = s_prev[0] + t * vx, iy = s_prev[1] + t * vy;
+  S nx = ix - cx, ny = iy - cy;
+  const S nn = sg_sqrt(nx * nx + ny * ny);
+  nx = nx / nn; ny = ny / nn;
+  const S vdn = vx * nx + vy * ny;
+  const S rx = vx - C<S>(2.0) * vdn * nx, ry = vy - C<S>(2.0) * vdn * ny;
+  const S rem = (C<S>(1.0) - t) * C<S>(0.1);
+  s_next[0] = ix + rx * rem;
+  s_next[1] = iy + ry * rem;
+}
+
 template <class TASK, class S, class T>
 SG_HD void safeguarded_step(const S* s, const S* a, const T* w, const T* aux, const T* dirs,
                             const StepShared<T>* sh, const SafeConsts<T>& k, bool reset_now,
@@ -36,8 +65,21 @@ SG_HD void safeguarded_step(const S* s, const S* a, const T* w, const T* aux, co
     const bool projectable = gate_projectable<TASK>(cfp, Bp, k);
     S g[NA];
     bool feasible;
-    if constexpr (NA == 1) feasible = safeguard_m1<TASK>(a[0], c_f, B, k, g[0]);
-    else feasible = safeguard_m2<TASK>(a, c_f, B, dirs, k, g);
+    ActRows<T> dyn;
+    dyn.count = 0;
+    if constexpr (NA == 1) {
+      feasible = safeguard_m1<TASK>(a[0], c_f, B, k, g[0]);
+    } else {
+      bool set_ok = true;
+      if (k.act_set_mode == 1) {                 // NavigateSeeker: the safe action set is rebuilt every step (P5)
+        T sp[NS], U[2][2], len[2];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) sp[i] = primal(s[i]);
+        set_ok = seeker_action_set<T>(sp, aux, k, U, len);
+        seeker_rows<T>(U, len, dyn);
+      }
+      feasible = safeguard_m2<TASK>(a, c_f, B, dirs, k, &dyn, g) && set_ok;
+    }
     const bool use_guard = k.gate_mode == GATE_REFERENCE ? !projectable
                                                          : (k.gate_mode == GATE_INTENDED ? projectable : true);
     if (projectable) flags |= FL_PROJECTABLE;
@@ -64,13 +106,16 @@ SG_HD void safeguarded_step(const S* s, const S* a, const T* w, const T* aux, co
     T ap[NA];
 #pragma unroll
     for (int q = 0; q < NA; ++q) ap[q] = primal(a_exec[q]);
-    if (k.action_constrained && action_in_set<TASK>(ap, k)) flags |= FL_ACTION_IN_SET;
+    if (k.action_constrained && action_in_set<TASK>(ap, k, &dyn)) flags |= FL_ACTION_IN_SET;
     if (k.state_constrained && next_state_in_set<TASK>(ap, cfp, Bp, k)) flags |= FL_NEXT_IN_SET;
   }
   S wS[NS];
 #pragma unroll
   for (int i = 0; i < NS; ++i) wS[i] = S(w[i]);
   TASK::Sim::f(s, a_exec, wS, s_next);
+  if constexpr (TASK::NAUX > 2) {
+    if (k.n_obstacles > 0) collision_operator<TASK>(s, s_next, aux, k, flags);
+  }
   if (TASK::CLAMP && !k.disable_clamp) {
 #pragma unroll
     for (int i = 0; i < NS; ++i) {

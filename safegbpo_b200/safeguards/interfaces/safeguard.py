@@ -48,7 +48,8 @@ class Safeguard:
             env = self.env
             f64 = lambda t: t.detach().to(torch.float64).cpu().numpy()
             sa = ss = None
-            if self.action_constrained:
+            dynamic = bool(getattr(env, "DYNAMIC_ACTION_SET", False))
+            if self.action_constrained and not dynamic:
                 z = env.safe_action_set()
                 sa = getattr(env, "_ctrl64", None) or (f64(z.center[0]), f64(z.generator[0]))
             if self.state_constrained:
@@ -56,7 +57,8 @@ class Safeguard:
                 ss = getattr(env, "_rci64", None) or (f64(z.center[0]), f64(z.generator[0]))
             G_w = f64(self.noise_mat[0]) @ f64(env.noise_set.generator[0])
             self._consts = build_consts(env.ENV_NAME, self.SG_KIND, gate_mode=_lib.GATE[self.gate], safe_action=sa,
-                                        safe_state=ss, G_w=G_w, B0=f64(self.action_mat[0]), **self._rm_flags())
+                                        safe_state=ss, G_w=G_w, B0=f64(self.action_mat[0]), dynamic_action_set=dynamic,
+                                        n_obstacles=int(getattr(env, "num_obstacles", 0)), **self._rm_flags())
         return self._consts
 
     def _directions(self) -> Optional[Tensor]:

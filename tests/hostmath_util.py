@@ -8,7 +8,7 @@ import numpy as np
 from safegbpo_b200._lib import Consts, StepShared
 
 HERE = Path(__file__).resolve().parent / "hostmath"
-DIMS = {0: (2, 1, 3, 0), 1: (4, 1, 5, 0), 2: (4, 1, 5, 0), 3: (6, 2, 8, 2), 4: (3, 2, 23, 0), 5: (2, 2, 4, 2)}
+DIMS = {0: (2, 1, 3, 0), 1: (4, 1, 5, 0), 2: (4, 1, 5, 0), 3: (6, 2, 8, 2), 4: (3, 2, 23, 0), 5: (2, 2, 4, 11)}
 _lib = None
 
 
