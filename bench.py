@@ -264,6 +264,13 @@ def run_ours(args):
         roof = fused_roofline(args, engine, episode, dtype)
     else:
         roof = step_kernel_roofline(args, base, env, dev, dtype)
+    stress = None
+    if rank == 0:
+        try:
+            stress = step_kernel_roofline(args, base, env, dev, dtype, n_envs=1 << 20)
+            stress.pop("launches_per_step", None)
+        except Exception as exc:      # the stress variant is additional evidence, never fatal
+            stress = {"error": str(exc)[:200]}
     if rank == 0:
         peaks = {}
         try:
@@ -280,6 +287,7 @@ def run_ours(args):
             "gpu_launches": roof.pop("launches_per_step", None),
             "roofline": roof, "clocks": {**sampler.summary(), "n_samples": len(sampler.samples),
                                          "sampled_beyond_timed_region": extended},
+            "roofline_stress": stress,
             "mode": "fused" if engine is not None else "eager (per-step fused safeguard+simulator kernel, torch MLP)",
         }
         if not args.no_cpu_baseline and world == 1:
@@ -330,39 +338,40 @@ def fused_roofline(args, engine, episode, dtype):
             "launches_per_step": engine.launches_per_episode}
 
 
-def step_kernel_roofline(args, base, env, dev, dtype):
-    """Roofline of the per-step safeguard+simulator kernels (fwd + bwd) measured live with CUDA events."""
+def step_kernel_roofline(args, base, env, dev, dtype, n_envs=None):
+    """Roofline of the per-step safeguard+simulator kernels (step_fwd_kernel + step_bwd_kernel, policy bypassed:
+    the stress variant of SURVEY §8d), timed live with CUDA events.  These two kernels ARE HBM-bound."""
     import torch
     from safegbpo_b200 import ops
-    N = args.num_envs
+    N = n_envs or args.num_envs
     consts = env.consts() if hasattr(env, "consts") else base._plain
-    s = base.state.detach().clone().requires_grad_(True)
+    half = base.state_set.generator[0].diagonal()
+    s = (base.state_set.center[0] + (torch.rand(N, base.state_dim) * 2 - 1) * half * 0.9).requires_grad_(True)
     a = (torch.rand(N, base.action_dim) * 2 - 1).requires_grad_(True)
     w = torch.zeros_like(s)
-    reps = 50
+    aux = base._aux()
+    aux = None if aux is None else aux[:1].expand(N, -1).contiguous()
+    reps = 20
     g = [torch.ones(N, base.state_dim), torch.ones(N, base.action_dim), torch.ones(N, base.obs_dim), torch.ones(N)]
     for _ in range(5):
-        out = ops.safeguarded_step(s, a, w, base.env_id, consts, aux=base._aux(), shared=base._shared())
+        out = ops.safeguarded_step(s, a, w, base.env_id, consts, aux=aux, shared=base._shared())
         torch.autograd.backward(out[:4], g)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        out = ops.safeguarded_step(s, a, w, base.env_id, consts, aux=base._aux(), shared=base._shared())
+        out = ops.safeguarded_step(s, a, w, base.env_id, consts, aux=aux, shared=base._shared())
         torch.autograd.backward(out[:4], g)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    peaks = {}
-    try:
-        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-    except Exception:
-        pass
+    peaks = _peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))
     bytes_alg = ALG_BYTES[args.env] * (1 if dtype == torch.float32 else 2) * N
     achieved = bytes_alg / (ms * 1e-3) / 1e9
     return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
             "kernel": "step_fwd_kernel+step_bwd_kernel (one launch pair per env step; event time includes torch launch gaps)",
+            "n_envs": N, "ms_per_pair": ms, "env_steps_per_s": N / (ms * 1e-3),
             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
             "launches_per_step": 2 * args.horizon}
 

@@ -107,8 +107,9 @@ def build(verbose: bool = False) -> Path:
     One object per translation unit, compiled in parallel, then linked."""
     from concurrent.futures import ThreadPoolExecutor
     srcs = sources()
-    headers = list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "sgbpo.h"]
-    newest_hdr = max(p.stat().st_mtime for p in headers)
+    import hashlib
+    headers = sorted(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "sgbpo.h"]
+    hdr_hash = hashlib.sha1(b"".join(p.read_bytes() for p in headers)).hexdigest()
     objdir = PKG / "build"
     objdir.mkdir(exist_ok=True)
     compile_flags = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
@@ -116,12 +117,18 @@ def build(verbose: bool = False) -> Path:
 
     def compile_one(src: Path):
         obj = objdir / (src.stem + ".o")
-        if obj.exists() and obj.stat().st_mtime >= max(newest_hdr, src.stat().st_mtime):
+        stamp = objdir / (src.stem + ".sha1")
+        # content hash of the unit and every header (mtimes are not trusted: a concurrent or interrupted build
+        # could leave a newer object compiled from older headers)
+        want = hashlib.sha1((hdr_hash + hashlib.sha1(src.read_bytes()).hexdigest() + " ".join(compile_flags)).encode()).hexdigest()
+        if obj.exists() and stamp.exists() and stamp.read_text() == want:
             return obj, ""
+        stamp.unlink(missing_ok=True)
         cmd = ["nvcc", *compile_flags, *( ["-Xptxas=-v"] if verbose else []), "-o", str(obj), str(src)]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise SgbpoError(f"nvcc failed on {src.name}:\n{res.stderr[-4000:]}")
+        stamp.write_text(want)
         return obj, res.stderr
 
     with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 1)) as pool:
@@ -130,11 +137,14 @@ def build(verbose: bool = False) -> Path:
     if verbose:
         for _, log in results:
             print(log)
-    if not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < max(o.stat().st_mtime for o in objs):
+    link_want = hashlib.sha1("".join((objdir / (s.stem + ".sha1")).read_text() for s in srcs).encode()).hexdigest()
+    link_stamp = objdir / "libsgbpo.sha1"
+    if not LIB_PATH.exists() or not link_stamp.exists() or link_stamp.read_text() != link_want:
         res = subprocess.run(["nvcc", "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB_PATH),
                               *map(str, objs)], capture_output=True, text=True)
         if res.returncode != 0:
             raise SgbpoError(f"nvcc link failed:\n{res.stderr[-4000:]}")
+        link_stamp.write_text(link_want)
     return LIB_PATH
 
 

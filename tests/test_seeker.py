@@ -73,10 +73,10 @@ def test_gpu_env_class_reset_step_and_action_set():
         assert not ball.contains(env.state).any() and not ball.contains(env.goal).any()
         assert (torch.linalg.vector_norm(env.goal - env.state, dim=1) >= 8.0).all()
         z = env.safe_action_set()
-        oenv = OracleEnv("NavigateSeeker", N, 400)
-        oenv.state, oenv.goal = env.state.cpu(), env.goal.cpu()
-        oenv.obstacles = [(ball.center.cpu(), ball.radius.cpu())]
         with torch.device("cpu"):
+            oenv = OracleEnv("NavigateSeeker", N, 400)
+            oenv.state, oenv.goal = env.state.cpu(), env.goal.cpu()
+            oenv.obstacles = [(ball.center.cpu(), ball.radius.cpu())]
             _, gen = oenv.safe_action_set()
         np.testing.assert_allclose(z.generator.cpu().numpy(), gen.numpy(), rtol=1e-6, atol=1e-8)
         wrapped = BoundaryProjectionSafeguard(env, gate="always", strict=False)
