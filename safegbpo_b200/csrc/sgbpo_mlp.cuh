@@ -1,9 +1,11 @@
 // Warp-autonomous MLP tiles for the fused rollout (policy.py:50-89, value_function.py:38-66 of the
 // reference: Linear -> ELU -> LayerNorm per hidden layer, then Linear).
 //
-// One warp owns R = 8 rows (environments).  Lane l owns output columns {l, l+32, ...} (CPL = W/32 per
-// lane) of every hidden layer, i.e. an 8 x CPL register tile; the 8 input activations of one k are a
-// 32-byte broadcast read from the warp's private shared-memory tile laid out [k][8]; the weights are
+// One warp owns R rows (environments; R = 8, 4 or 2 is a template parameter chosen at launch so that every
+// SM sub-partition has several warps to interleave -- few rows per warp for small batches, 8 for large
+// ones).  Lane l owns output columns {l, l+32, ...} (CPL = W/32 per lane) of every hidden layer, i.e. an
+// R x CPL register tile; the R input activations of one k are one broadcast vector read from the warp's
+// private shared-memory tile laid out [k][R]; the weights are
 // shared by the CTA in shared memory as [k][LD] with LD = W + 1, so the forward read (lanes along
 // columns) AND the transposed read of the data-gradient GEMM (lanes along k) are both conflict-free.
 // LayerNorm row reductions are warp shuffles.  No __syncthreads inside the time loop.
@@ -15,7 +17,7 @@
 
 namespace sgbpo {
 
-constexpr int MLP_R = 8;          // rows per warp
+constexpr int MLP_R_MAX = 8;      // rows per warp: template parameter R in {2, 4, 8}
 constexpr int MAX_HIDDEN = 4;
 
 template <class T> struct MlpParams {
@@ -86,181 +88,209 @@ template <class T, int R> __device__ __forceinline__ void warp_sum_rows(T (&v)[R
   }
 }
 
-// 8 contiguous row values of one k: vector loads (the warp tiles are 32-byte aligned)
-__device__ __forceinline__ void load8(const float* __restrict__ p, float (&a)[MLP_R]) {
-  const float4 v0 = *reinterpret_cast<const float4*>(p), v1 = *reinterpret_cast<const float4*>(p + 4);
-  a[0] = v0.x; a[1] = v0.y; a[2] = v0.z; a[3] = v0.w; a[4] = v1.x; a[5] = v1.y; a[6] = v1.z; a[7] = v1.w;
+// R contiguous row values of one k: vector loads (the warp tiles are 32-byte aligned, R*sizeof(T) >= 8)
+template <int R> __device__ __forceinline__ void load_rows(const float* __restrict__ p, float (&a)[R]) {
+  if constexpr (R == 8) {
+    const float4 v0 = *reinterpret_cast<const float4*>(p), v1 = *reinterpret_cast<const float4*>(p + 4);
+    a[0] = v0.x; a[1] = v0.y; a[2] = v0.z; a[3] = v0.w; a[4] = v1.x; a[5] = v1.y; a[6] = v1.z; a[7] = v1.w;
+  } else if constexpr (R == 4) {
+    const float4 v0 = *reinterpret_cast<const float4*>(p);
+    a[0] = v0.x; a[1] = v0.y; a[2] = v0.z; a[3] = v0.w;
+  } else {
+    static_assert(R == 2, "rows per warp: 2, 4 or 8");
+    const float2 v0 = *reinterpret_cast<const float2*>(p);
+    a[0] = v0.x; a[1] = v0.y;
+  }
 }
-__device__ __forceinline__ void load8(const double* __restrict__ p, double (&a)[MLP_R]) {
+template <int R> __device__ __forceinline__ void load_rows(const double* __restrict__ p, double (&a)[R]) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < R / 2; ++i) {
     const double2 v = *reinterpret_cast<const double2*>(p + 2 * i);
     a[2 * i] = v.x; a[2 * i + 1] = v.y;
   }
 }
 
 // acc[r][j] = bias + sum_k inT[k][r] * Wsm[k][lane + 32 j]
-template <class T, int W>
+template <class T, int W, int R>
 __device__ __forceinline__ void tile_gemm(const T* __restrict__ inT, int K, const T* __restrict__ Wsm,
-                                          const T* __restrict__ bias, int lane, T (&acc)[MLP_R][W / 32]) {
+                                          const T* __restrict__ bias, int lane, T (&acc)[R][W / 32]) {
   constexpr int CPL = W / 32, LD = W + 1;
 #pragma unroll
   for (int j = 0; j < CPL; ++j) {
     const T b = bias ? bias[lane + 32 * j] : T(0);
 #pragma unroll
-    for (int r = 0; r < MLP_R; ++r) acc[r][j] = b;
+    for (int r = 0; r < R; ++r) acc[r][j] = b;
   }
 #pragma unroll 4
   for (int k = 0; k < K; ++k) {
-    T a[MLP_R], w[CPL];
-    load8(inT + k * MLP_R, a);
+    T a[R], w[CPL];
+    load_rows<R>(inT + k * R, a);
 #pragma unroll
     for (int j = 0; j < CPL; ++j) w[j] = Wsm[k * LD + lane + 32 * j];
 #pragma unroll
-    for (int r = 0; r < MLP_R; ++r)
+    for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int j = 0; j < CPL; ++j) acc[r][j] = fma(a[r], w[j], acc[r][j]);
   }
 }
 
 // transposed product for the data gradient: out[r][j] = sum_c gT[c][r] * Wsm[lane + 32 j][c]
-template <class T, int W>
+template <class T, int W, int R>
 __device__ __forceinline__ void tile_gemm_t(const T* __restrict__ gT, const T* __restrict__ Wsm, int lane,
-                                            T (&acc)[MLP_R][W / 32]) {
+                                            T (&acc)[R][W / 32]) {
   constexpr int CPL = W / 32, LD = W + 1;
 #pragma unroll
   for (int j = 0; j < CPL; ++j)
 #pragma unroll
-    for (int r = 0; r < MLP_R; ++r) acc[r][j] = T(0);
+    for (int r = 0; r < R; ++r) acc[r][j] = T(0);
 #pragma unroll 4
   for (int c = 0; c < W; ++c) {
-    T a[MLP_R], w[CPL];
-    load8(gT + c * MLP_R, a);
+    T a[R], w[CPL];
+    load_rows<R>(gT + c * R, a);
 #pragma unroll
     for (int j = 0; j < CPL; ++j) w[j] = Wsm[(lane + 32 * j) * LD + c];
 #pragma unroll
-    for (int r = 0; r < MLP_R; ++r)
+    for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int j = 0; j < CPL; ++j) acc[r][j] = fma(a[r], w[j], acc[r][j]);
   }
 }
 
 // ELU + LayerNorm (eps 1e-5, biased variance) on the register tile.  z is overwritten by h.
-// xhat / egrad / rstd are produced for the backward pass when SAVE.
-template <class T, int W, bool SAVE>
-__device__ __forceinline__ void elu_layernorm(T (&z)[MLP_R][W / 32], const T* __restrict__ gamma,
-                                              const T* __restrict__ beta, int lane, T (&xhat)[MLP_R][W / 32],
-                                              T (&egrad)[MLP_R][W / 32], T (&rstd)[MLP_R]) {
+// When SAVE, the ELU output e (the LayerNorm input), the row mean and the reciprocal standard deviation are
+// kept for the backward pass: xhat = (e - mean) * rstd and dELU/dz = (e > 0 ? 1 : e + 1) are re-derived
+// from e with the forward's own operations (bitwise the same values), so e is the only tile stashed.
+template <class T, int W, int R, bool SAVE>
+__device__ __forceinline__ void elu_layernorm(T (&z)[R][W / 32], const T* __restrict__ gamma,
+                                              const T* __restrict__ beta, int lane, T (&ev)[R][W / 32],
+                                              T (&mean_out)[R], T (&rstd)[R]) {
   constexpr int CPL = W / 32;
   T g[CPL], b[CPL];
 #pragma unroll
   for (int j = 0; j < CPL; ++j) { g[j] = gamma[lane + 32 * j]; b[j] = beta[lane + 32 * j]; }
-  T sum[MLP_R];
+  T sum[R];
 #pragma unroll
-  for (int r = 0; r < MLP_R; ++r) {
+  for (int r = 0; r < R; ++r) {
     T s = T(0);
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
       const T v = z[r][j];
       const T en = sg_elu_neg(v < T(0) ? v : T(0));     // branch-free: exp() is evaluated for every element
       const T e = v > T(0) ? v : en;
-      if (SAVE) egrad[r][j] = v > T(0) ? T(1) : en + T(1);
+      if (SAVE) ev[r][j] = e;
       z[r][j] = e;
       s += e;
     }
     sum[r] = s;
   }
-  warp_sum_rows<T, MLP_R>(sum);
-  T sq[MLP_R];
+  warp_sum_rows<T, R>(sum);
+  T sq[R];
 #pragma unroll
-  for (int r = 0; r < MLP_R; ++r) {
+  for (int r = 0; r < R; ++r) {
     const T mean = sum[r] / T(W);
+    if (SAVE) mean_out[r] = mean;
     T q = T(0);
 #pragma unroll
     for (int j = 0; j < CPL; ++j) { z[r][j] -= mean; q += z[r][j] * z[r][j]; }
     sq[r] = q;
   }
-  warp_sum_rows<T, MLP_R>(sq);
+  warp_sum_rows<T, R>(sq);
 #pragma unroll
-  for (int r = 0; r < MLP_R; ++r) {
+  for (int r = 0; r < R; ++r) {
     const T rs = sg_rsqrt(sq[r] / T(W) + T(1e-5));
     if (SAVE) rstd[r] = rs;
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) {
-      const T xh = z[r][j] * rs;
-      if (SAVE) xhat[r][j] = xh;
-      z[r][j] = xh * g[j] + b[j];
-    }
+    for (int j = 0; j < CPL; ++j) z[r][j] = (z[r][j] * rs) * g[j] + b[j];
   }
 }
 
-// register tile <-> warp-private shared tile [c][8]: the 8 row values of one column are contiguous (vector access)
-__device__ __forceinline__ void store8(float* __restrict__ p, const float (&a)[MLP_R]) {
-  *reinterpret_cast<float4*>(p) = make_float4(a[0], a[1], a[2], a[3]);
-  *reinterpret_cast<float4*>(p + 4) = make_float4(a[4], a[5], a[6], a[7]);
+// backward-side inverse of the stash: xhat and dELU/dz from the stored ELU output
+template <class T, int W, int R>
+__device__ __forceinline__ void unstash(const T (&ev)[R][W / 32], const T (&mean)[R], const T (&rstd)[R],
+                                        T (&xhat)[R][W / 32], T (&egrad)[R][W / 32]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int j = 0; j < W / 32; ++j) {
+      const T e = ev[r][j];
+      xhat[r][j] = (e - mean[r]) * rstd[r];
+      egrad[r][j] = e > T(0) ? T(1) : e + T(1);
+    }
 }
-__device__ __forceinline__ void store8(double* __restrict__ p, const double (&a)[MLP_R]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) *reinterpret_cast<double2*>(p + 2 * i) = make_double2(a[2 * i], a[2 * i + 1]);
-}
-template <class T, int W>
-__device__ __forceinline__ void store_tile(T* __restrict__ dstT, int lane, const T (&h)[MLP_R][W / 32]) {
-#pragma unroll
-  for (int j = 0; j < W / 32; ++j) {
-    T col[MLP_R];
-#pragma unroll
-    for (int r = 0; r < MLP_R; ++r) col[r] = h[r][j];
-    store8(dstT + (lane + 32 * j) * MLP_R, col);
+
+// register tile <-> warp-private shared tile [c][R]: the R row values of one column are contiguous (vector access)
+template <int R> __device__ __forceinline__ void store_rows(float* __restrict__ p, const float (&a)[R]) {
+  if constexpr (R == 8) {
+    *reinterpret_cast<float4*>(p) = make_float4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(a[4], a[5], a[6], a[7]);
+  } else if constexpr (R == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(a[0], a[1], a[2], a[3]);
+  } else {
+    *reinterpret_cast<float2*>(p) = make_float2(a[0], a[1]);
   }
 }
-template <class T, int W>
-__device__ __forceinline__ void load_tile(const T* __restrict__ srcT, int lane, T (&h)[MLP_R][W / 32]) {
+template <int R> __device__ __forceinline__ void store_rows(double* __restrict__ p, const double (&a)[R]) {
+#pragma unroll
+  for (int i = 0; i < R / 2; ++i) *reinterpret_cast<double2*>(p + 2 * i) = make_double2(a[2 * i], a[2 * i + 1]);
+}
+template <class T, int W, int R>
+__device__ __forceinline__ void store_tile(T* __restrict__ dstT, int lane, const T (&h)[R][W / 32]) {
 #pragma unroll
   for (int j = 0; j < W / 32; ++j) {
-    T col[MLP_R];
-    load8(srcT + (lane + 32 * j) * MLP_R, col);
+    T col[R];
 #pragma unroll
-    for (int r = 0; r < MLP_R; ++r) h[r][j] = col[r];
+    for (int r = 0; r < R; ++r) col[r] = h[r][j];
+    store_rows<R>(dstT + (lane + 32 * j) * R, col);
+  }
+}
+template <class T, int W, int R>
+__device__ __forceinline__ void load_tile(const T* __restrict__ srcT, int lane, T (&h)[R][W / 32]) {
+#pragma unroll
+  for (int j = 0; j < W / 32; ++j) {
+    T col[R];
+    load_rows<R>(srcT + (lane + 32 * j) * R, col);
+#pragma unroll
+    for (int r = 0; r < R; ++r) h[r][j] = col[r];
   }
 }
 
 // out[r][q] = b_out[q] + sum_c h[r][c] w_out[c][q]; every lane receives every (r, q)
-template <class T, int W, int OUT>
-__device__ __forceinline__ void out_layer(const T (&h)[MLP_R][W / 32], const T* __restrict__ w_out,
-                                          const T* __restrict__ b_out, int lane, T (&mu)[MLP_R][OUT]) {
+template <class T, int W, int R, int OUT>
+__device__ __forceinline__ void out_layer(const T (&h)[R][W / 32], const T* __restrict__ w_out,
+                                          const T* __restrict__ b_out, int lane, T (&mu)[R][OUT]) {
 #pragma unroll
   for (int q = 0; q < OUT; ++q) {
     T w[W / 32];
 #pragma unroll
     for (int j = 0; j < W / 32; ++j) w[j] = w_out[(lane + 32 * j) * OUT + q];
-    T p[MLP_R];
+    T p[R];
 #pragma unroll
-    for (int r = 0; r < MLP_R; ++r) {
+    for (int r = 0; r < R; ++r) {
       p[r] = T(0);
 #pragma unroll
       for (int j = 0; j < W / 32; ++j) p[r] = fma(h[r][j], w[j], p[r]);
     }
-    warp_sum_rows<T, MLP_R>(p);
+    warp_sum_rows<T, R>(p);
 #pragma unroll
-    for (int r = 0; r < MLP_R; ++r) mu[r][q] = p[r] + b_out[q];
+    for (int r = 0; r < R; ++r) mu[r][q] = p[r] + b_out[q];
   }
 }
 
-// whole-network forward for 8 rows whose inputs sit in inT ([in_dim][8]); bufA/bufB: warp-private
-// ping-pong tiles [W][8].  Returns the last hidden activations in h.
-template <class T, int W>
+// whole-network forward for R rows whose inputs sit in inT ([in_dim][R]); bufA/bufB: warp-private
+// ping-pong tiles [W][R].  Returns the last hidden activations in h.
+template <class T, int W, int R>
 __device__ __forceinline__ void net_forward(const NetSmem<T, W>& net, const T* inT, T* bufA, T* bufB, int lane,
-                                            T (&h)[MLP_R][W / 32]) {
-  T dummy_x[MLP_R][W / 32], dummy_e[MLP_R][W / 32], dummy_r[MLP_R];
-  tile_gemm<T, W>(inT, net.in_dim, net.w_in, net.b_hid, lane, h);
-  elu_layernorm<T, W, false>(h, net.gamma, net.beta, lane, dummy_x, dummy_e, dummy_r);
+                                            T (&h)[R][W / 32]) {
+  T dummy_e[R][W / 32], dummy_m[R], dummy_r[R];
+  tile_gemm<T, W, R>(inT, net.in_dim, net.w_in, net.b_hid, lane, h);
+  elu_layernorm<T, W, R, false>(h, net.gamma, net.beta, lane, dummy_e, dummy_m, dummy_r);
   T* cur = bufA;
   T* nxt = bufB;
   for (int l = 1; l < net.n_hidden; ++l) {
-    store_tile<T, W>(cur, lane, h);
+    store_tile<T, W, R>(cur, lane, h);
     __syncwarp();
-    tile_gemm<T, W>(cur, W, net.w_hid + (size_t)(l - 1) * W * (W + 1), net.b_hid + l * W, lane, h);
-    elu_layernorm<T, W, false>(h, net.gamma + l * W, net.beta + l * W, lane, dummy_x, dummy_e, dummy_r);
+    tile_gemm<T, W, R>(cur, W, net.w_hid + (size_t)(l - 1) * W * (W + 1), net.b_hid + l * W, lane, h);
+    elu_layernorm<T, W, R, false>(h, net.gamma + l * W, net.beta + l * W, lane, dummy_e, dummy_m, dummy_r);
     T* t = cur; cur = nxt; nxt = t;
   }
 }

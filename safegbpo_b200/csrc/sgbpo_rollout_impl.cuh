@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "../../include/sgbpo.h"
 #include "sgbpo_mlp.cuh"
@@ -65,11 +66,14 @@ template <class T> struct BackwardArgs {
   T* g_log_std;           // [m]
 };
 
-constexpr int ROLLOUT_WARPS = 4;
+// launch bounds per rows-per-warp R: fewer rows -> smaller register tiles -> more resident warps
+template <int R> struct RolloutShape {
+  static constexpr int MAX_WARPS = R == 8 ? 8 : (R == 4 ? 12 : 16);
+};
 
 // ---------------------------------------------------------------------------------------------------------
-template <int ENV, class T, int W>
-__global__ void __launch_bounds__(ROLLOUT_WARPS * 32)
+template <int ENV, class T, int W, int R>
+__global__ void __launch_bounds__(RolloutShape<R>::MAX_WARPS * 32)
 rollout_fwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_constant__ MlpParams<T> P,
                    const __grid_constant__ SafeConsts<T> k) {
   using TASK = Task<ENV>;
@@ -79,16 +83,16 @@ rollout_fwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
   NetSmem<T, W> net;                       // same carve in every thread: pointers stay in registers
   T* after = net.load(smem, P);
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // warp-private tiles (32-byte aligned): obsT [NO][8], bufA/bufB [W][8]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  // warp-private tiles (32-byte aligned): obsT [NO][R], bufA/bufB [W][R]
   size_t off = (size_t)(after - smem);
   off = (off + 7) & ~size_t(7);
-  const size_t per_warp = (size_t)(NO + 2 * W) * MLP_R;
+  const size_t per_warp = ((size_t)(NO + 2 * W) * R + 7) & ~size_t(7);
   T* obsT = smem + off + warp * per_warp;
-  T* bufA = obsT + NO * MLP_R;
-  T* bufB = bufA + W * MLP_R;
-  const int64_t env = ((int64_t)blockIdx.x * ROLLOUT_WARPS + warp) * MLP_R + lane;
-  const bool owner = lane < MLP_R;
+  T* bufA = obsT + NO * R;
+  T* bufB = bufA + W * R;
+  const int64_t env = ((int64_t)blockIdx.x * nwarps + warp) * R + lane;
+  const bool owner = lane < R;
   const bool valid = owner && env < A.N;
   const int64_t N = A.N;
 
@@ -104,7 +108,7 @@ rollout_fwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
   }
   if (owner) {
 #pragma unroll
-    for (int i = 0; i < NO; ++i) obsT[i * MLP_R + lane] = valid ? A.obs[env * NO + i] : T(0);
+    for (int i = 0; i < NO; ++i) obsT[i * R + lane] = valid ? A.obs[env * NO + i] : T(0);
   }
   __syncwarp();
 
@@ -127,10 +131,10 @@ rollout_fwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
       }
     }
     // ---- policy forward -------------------------------------------------------------------------
-    T h[MLP_R][CPL];
-    net_forward<T, W>(net, obsT, bufA, bufB, lane, h);
-    T mu[MLP_R][NA];
-    out_layer<T, W, NA>(h, net.w_out, net.b_out, lane, mu);
+    T h[R][CPL];
+    net_forward<T, W, R>(net, obsT, bufA, bufB, lane, h);
+    T mu[R][NA];
+    out_layer<T, W, R, NA>(h, net.w_out, net.b_out, lane, mu);
     // ---- environment step on the owner lanes ---------------------------------------------------
     __syncwarp();
     if (owner) {
@@ -139,7 +143,7 @@ rollout_fwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
       for (int q = 0; q < NA; ++q) {
         T m = T(0);
 #pragma unroll
-        for (int r = 0; r < MLP_R; ++r) m = (lane == r) ? mu[r][q] : m;
+        for (int r = 0; r < R; ++r) m = (lane == r) ? mu[r][q] : m;
         a[q] = valid ? sg_tanh(m + sigma[q] * epsv[q]) : T(0);
       }
       if (!valid) {
@@ -159,7 +163,7 @@ rollout_fwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
 #pragma unroll
       for (int i = 0; i < NS; ++i) s[i] = sn[i];
 #pragma unroll
-      for (int i = 0; i < NO; ++i) obsT[i * MLP_R + lane] = ob[i];
+      for (int i = 0; i < NO; ++i) obsT[i * R + lane] = ob[i];
       if (valid) {
 #pragma unroll
         for (int i = 0; i < NS; ++i) A.states[((int64_t)(t + 1) * N + env) * NS + i] = sn[i];
@@ -180,8 +184,8 @@ rollout_fwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
 
 // ---------------------------------------------------------------------------------------------------------
 // batched MLP forward over M rows: out[row] = net(x[row]) (critic: out_dim = 1).
-template <class T, int W>
-__global__ void __launch_bounds__(256)
+template <class T, int W, int R>
+__global__ void __launch_bounds__(R == 8 ? 256 : 512)
 mlp_rows_kernel(int64_t M, int in_dim, const T* __restrict__ x, T* __restrict__ out,
                 const __grid_constant__ MlpParams<T> P) {
   constexpr int CPL = W / 32;
@@ -193,27 +197,27 @@ mlp_rows_kernel(int64_t M, int in_dim, const T* __restrict__ x, T* __restrict__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   size_t off = (size_t)(after - smem);
   off = (off + 7) & ~size_t(7);
-  const size_t per_warp = (size_t)(in_dim + 2 * W) * MLP_R;
+  const size_t per_warp = ((size_t)(in_dim + 2 * W) * R + 7) & ~size_t(7);
   T* inT = smem + off + warp * per_warp;
-  T* bufA = inT + in_dim * MLP_R;
-  T* bufB = bufA + W * MLP_R;
-  const int64_t n_blocks = (M + MLP_R - 1) / MLP_R;
+  T* bufA = inT + in_dim * R;
+  T* bufB = bufA + W * R;
+  const int64_t n_blocks = (M + R - 1) / R;
   for (int64_t blk = (int64_t)blockIdx.x * nwarps + warp; blk < n_blocks; blk += (int64_t)gridDim.x * nwarps) {
-    const int64_t row0 = blk * MLP_R;
-    const int total = in_dim * MLP_R;
-    for (int i = lane; i < total; i += 32) {        // contiguous 8-row span, coalesced
+    const int64_t row0 = blk * R;
+    const int total = in_dim * R;
+    for (int i = lane; i < total; i += 32) {        // contiguous R-row span, coalesced
       const int r = i / in_dim, c = i % in_dim;
-      inT[c * MLP_R + r] = (row0 + r < M) ? x[row0 * in_dim + i] : T(0);
+      inT[c * R + r] = (row0 + r < M) ? x[row0 * in_dim + i] : T(0);
     }
     __syncwarp();
-    T h[MLP_R][CPL];
-    net_forward<T, W>(net, inT, bufA, bufB, lane, h);
-    T v[MLP_R][1];
-    out_layer<T, W, 1>(h, net.w_out, net.b_out, lane, v);
-    if (lane < MLP_R && row0 + lane < M) {
+    T h[R][CPL];
+    net_forward<T, W, R>(net, inT, bufA, bufB, lane, h);
+    T v[R][1];
+    out_layer<T, W, R, 1>(h, net.w_out, net.b_out, lane, v);
+    if (lane < R && row0 + lane < M) {
       T mine = T(0);
 #pragma unroll
-      for (int r = 0; r < MLP_R; ++r) mine = (lane == r) ? v[r][0] : mine;
+      for (int r = 0; r < R; ++r) mine = (lane == r) ? v[r][0] : mine;
       out[row0 + lane] = mine;
     }
     __syncwarp();
@@ -221,8 +225,8 @@ mlp_rows_kernel(int64_t M, int in_dim, const T* __restrict__ x, T* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-template <int ENV, class T, int W>
-__global__ void __launch_bounds__(ROLLOUT_WARPS * 32)
+template <int ENV, class T, int W, int R>
+__global__ void __launch_bounds__(RolloutShape<R>::MAX_WARPS * 32)
 rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_constant__ BackwardArgs<T> G,
                    const __grid_constant__ MlpParams<T> P, const __grid_constant__ SafeConsts<T> k) {
   using TASK = Task<ENV>;
@@ -233,23 +237,21 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
   NetSmem<T, W> net;                       // same carve in every thread: pointers stay in registers
   T* after = net.load(smem, P);
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   size_t off = (size_t)(after - smem);
   off = (off + 7) & ~size_t(7);
-  // warp-private: obsT [NO][8], h1T [W][8], g2T [W][8], stash x1/e1/x2/e2 [W][8] each
-  const size_t per_warp = (size_t)(NO + 6 * W) * MLP_R;
+  // warp-private: obsT [NO][R], h1T [W][R], g2T [W][R], stash of the two ELU outputs e1S / e2S [W][R] each
+  const size_t per_warp = ((size_t)(NO + 4 * W) * R + 7) & ~size_t(7);
   T* obsT = smem + off + warp * per_warp;
-  T* h1T = obsT + NO * MLP_R;
-  T* g2T = h1T + W * MLP_R;
-  T* x1S = g2T + W * MLP_R;
-  T* e1S = x1S + W * MLP_R;
-  T* x2S = e1S + W * MLP_R;
-  T* e2S = x2S + W * MLP_R;
+  T* h1T = obsT + NO * R;
+  T* g2T = h1T + W * R;
+  T* e1S = g2T + W * R;
+  T* e2S = e1S + W * R;
   const int64_t N = A.N;
-  const int64_t env = ((int64_t)blockIdx.x * ROLLOUT_WARPS + warp) * MLP_R + lane;
-  const bool owner = lane < MLP_R;
+  const int64_t env0 = ((int64_t)blockIdx.x * nwarps + warp) * R;      // first env of this warp
+  const int64_t env = env0 + lane;
+  const bool owner = lane < R;
   const bool valid = owner && env < N;
-  const int64_t env0 = ((int64_t)blockIdx.x * ROLLOUT_WARPS + warp) * MLP_R;   // first env of this warp
 
   T sigma[NA];
 #pragma unroll
@@ -307,34 +309,32 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
     }
     if (owner) {
 #pragma unroll
-      for (int i = 0; i < NO; ++i) obsT[i * MLP_R + lane] = valid ? A.obs[((int64_t)t * N + env) * NO + i] : T(0);
+      for (int i = 0; i < NO; ++i) obsT[i * R + lane] = valid ? A.obs[((int64_t)t * N + env) * NO + i] : T(0);
     }
     __syncwarp();
     // ---- recompute the policy forward, stashing what the backward needs ----------------------------------
-    T rstd1[MLP_R], rstd2[MLP_R];
-    T mu[MLP_R][NA];
+    T mean1[R], rstd1[R], mean2[R], rstd2[R];
+    T mu[R][NA];
     {
-      T z[MLP_R][CPL], xh[MLP_R][CPL], eg[MLP_R][CPL];
-      tile_gemm<T, W>(obsT, NO, net.w_in, net.b_hid, lane, z);
-      elu_layernorm<T, W, true>(z, net.gamma, net.beta, lane, xh, eg, rstd1);
-      store_tile<T, W>(h1T, lane, z);
-      store_tile<T, W>(x1S, lane, xh);
-      store_tile<T, W>(e1S, lane, eg);
+      T z[R][CPL], ev[R][CPL];
+      tile_gemm<T, W, R>(obsT, NO, net.w_in, net.b_hid, lane, z);
+      elu_layernorm<T, W, R, true>(z, net.gamma, net.beta, lane, ev, mean1, rstd1);
+      store_tile<T, W, R>(h1T, lane, z);
+      store_tile<T, W, R>(e1S, lane, ev);
       // stream h1 (layer-2 input) out for the dW_hid GEMM straight from the register tile:
       // [t][env][W], 128-byte row segments per (r, j)
 #pragma unroll
-      for (int r = 0; r < MLP_R; ++r) {
+      for (int r = 0; r < R; ++r) {
         if (env0 + r < N) {
 #pragma unroll
           for (int j = 0; j < CPL; ++j) G.h1_out[((int64_t)t * N + env0 + r) * W + lane + 32 * j] = z[r][j];
         }
       }
       __syncwarp();
-      tile_gemm<T, W>(h1T, W, Whid, net.b_hid + W, lane, z);
-      elu_layernorm<T, W, true>(z, net.gamma + W, net.beta + W, lane, xh, eg, rstd2);
-      out_layer<T, W, NA>(z, net.w_out, net.b_out, lane, mu);
-      store_tile<T, W>(x2S, lane, xh);
-      store_tile<T, W>(e2S, lane, eg);
+      tile_gemm<T, W, R>(h1T, W, Whid, net.b_hid + W, lane, z);
+      elu_layernorm<T, W, R, true>(z, net.gamma + W, net.beta + W, lane, ev, mean2, rstd2);
+      out_layer<T, W, R, NA>(z, net.w_out, net.b_out, lane, mu);
+      store_tile<T, W, R>(e2S, lane, ev);
     }
     __syncwarp();
     // ---- step Jacobian (duals) contracted with the carried cotangents, on the owner lanes -----------------
@@ -349,7 +349,7 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
       for (int q = 0; q < NA; ++q) {
         T m = T(0);
 #pragma unroll
-        for (int r = 0; r < MLP_R; ++r) m = (lane == r) ? mu[r][q] : m;
+        for (int r = 0; r < R; ++r) m = (lane == r) ? mu[r][q] : m;
         act[q] = valid ? sg_tanh(m + sigma[q] * epsv[q]) : T(0);
       }
       D sd[NS], ad[NA], sn[NS], ae[NA], ob[NO], rew;
@@ -388,9 +388,9 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
       for (int q = 0; q < NA; ++q) ga_pre[q] = acc[NS + q] * (T(1) - act[q] * act[q]);
     }
     // broadcast d mu to the whole warp: dmu[r][q] from lane r
-    T dmu[MLP_R][NA];
+    T dmu[R][NA];
 #pragma unroll
-    for (int r = 0; r < MLP_R; ++r)
+    for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int q = 0; q < NA; ++q) dmu[r][q] = __shfl_sync(0xffffffffu, ga_pre[q], r);
     if (owner) {
@@ -401,12 +401,12 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
       }
     }
     // ---- policy backward ---------------------------------------------------------------------------------
-    T gcarry[MLP_R][CPL];       // gradient flowing into the current layer's output
+    T gcarry[R][CPL];       // gradient flowing into the current layer's output
     {
       // output layer: dh2 = dmu w_out^T ; dW_out += h2^T dmu (h2 = xhat2 * gamma2 + beta2)
-      T xh[MLP_R][CPL], eg[MLP_R][CPL];
-      load_tile<T, W>(x2S, lane, xh);
-      load_tile<T, W>(e2S, lane, eg);
+      T xh[R][CPL], eg[R][CPL];
+      load_tile<T, W, R>(e2S, lane, eg);
+      unstash<T, W, R>(eg, mean2, rstd2, xh, eg);
       T wo[CPL][NA], g2[CPL], b2[CPL];
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
@@ -416,7 +416,7 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
         for (int q = 0; q < NA; ++q) wo[j][q] = net.w_out[(lane + 32 * j) * NA + q];
       }
 #pragma unroll
-      for (int r = 0; r < MLP_R; ++r)
+      for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
           T dh = T(0);
@@ -427,9 +427,9 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
         }
       // LayerNorm 2 + ELU 2 backward -> dz2
       {
-        T s1[MLP_R], s2[MLP_R];
+        T s1[R], s2[R];
 #pragma unroll
-        for (int r = 0; r < MLP_R; ++r) {
+        for (int r = 0; r < R; ++r) {
           s1[r] = T(0); s2[r] = T(0);
 #pragma unroll
           for (int j = 0; j < CPL; ++j) {
@@ -441,10 +441,10 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
             s2[r] = fma(dx, xh[r][j], s2[r]);
           }
         }
-        warp_sum_rows<T, MLP_R>(s1);
-        warp_sum_rows<T, MLP_R>(s2);
+        warp_sum_rows<T, R>(s1);
+        warp_sum_rows<T, R>(s2);
 #pragma unroll
-        for (int r = 0; r < MLP_R; ++r) {
+        for (int r = 0; r < R; ++r) {
           const T m1 = s1[r] / T(W), m2 = s2[r] / T(W);
 #pragma unroll
           for (int j = 0; j < CPL; ++j) {
@@ -455,28 +455,28 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
           }
         }
       }
-      store_tile<T, W>(g2T, lane, gcarry);
+      store_tile<T, W, R>(g2T, lane, gcarry);
       __syncwarp();
       // stream dz2 out for the dW_hid GEMM
 #pragma unroll
-      for (int r = 0; r < MLP_R; ++r) {
+      for (int r = 0; r < R; ++r) {
         if (env0 + r < N) {
 #pragma unroll
           for (int j = 0; j < CPL; ++j) G.dz2_out[((int64_t)t * N + env0 + r) * W + lane + 32 * j] = gcarry[r][j];
         }
       }
       // dh1 = dz2 W_hid^T
-      tile_gemm_t<T, W>(g2T, Whid, lane, gcarry);
+      tile_gemm_t<T, W, R>(g2T, Whid, lane, gcarry);
       // LayerNorm 1 + ELU 1 backward -> dz1
-      load_tile<T, W>(x1S, lane, xh);
-      load_tile<T, W>(e1S, lane, eg);
+      load_tile<T, W, R>(e1S, lane, eg);
+      unstash<T, W, R>(eg, mean1, rstd1, xh, eg);
       T g1[CPL];
 #pragma unroll
       for (int j = 0; j < CPL; ++j) g1[j] = net.gamma[lane + 32 * j];
       {
-        T s1[MLP_R], s2[MLP_R];
+        T s1[R], s2[R];
 #pragma unroll
-        for (int r = 0; r < MLP_R; ++r) {
+        for (int r = 0; r < R; ++r) {
           s1[r] = T(0); s2[r] = T(0);
 #pragma unroll
           for (int j = 0; j < CPL; ++j) {
@@ -488,10 +488,10 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
             s2[r] = fma(dx, xh[r][j], s2[r]);
           }
         }
-        warp_sum_rows<T, MLP_R>(s1);
-        warp_sum_rows<T, MLP_R>(s2);
+        warp_sum_rows<T, R>(s1);
+        warp_sum_rows<T, R>(s2);
 #pragma unroll
-        for (int r = 0; r < MLP_R; ++r) {
+        for (int r = 0; r < R; ++r) {
           const T m1 = s1[r] / T(W), m2 = s2[r] / T(W);
 #pragma unroll
           for (int j = 0; j < CPL; ++j) {
@@ -510,18 +510,18 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
       T wi[CPL];
 #pragma unroll
       for (int j = 0; j < CPL; ++j) wi[j] = net.w_in[i * (W + 1) + lane + 32 * j];
-      T p[MLP_R], obr[MLP_R];
-      load8(obsT + i * MLP_R, obr);
+      T p[R], obr[R];
+      load_rows<R>(obsT + i * R, obr);
 #pragma unroll
-      for (int r = 0; r < MLP_R; ++r) {
+      for (int r = 0; r < R; ++r) {
         p[r] = T(0);
 #pragma unroll
         for (int j = 0; j < CPL; ++j) { p[r] = fma(gcarry[r][j], wi[j], p[r]); a_win[i][j] = fma(obr[r], gcarry[r][j], a_win[i][j]); }
       }
-      warp_sum_rows<T, MLP_R>(p);
+      warp_sum_rows<T, R>(p);
       T mine = T(0);
 #pragma unroll
-      for (int r = 0; r < MLP_R; ++r) mine = (lane == r) ? p[r] : mine;
+      for (int r = 0; r < R; ++r) mine = (lane == r) ? p[r] : mine;
       gobs_new[i] = mine;
     }
     if (owner) {
@@ -549,24 +549,70 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------------------
-template <class T, int W> size_t fwd_smem(int in_dim, int n_hidden, int out_dim, int no) {
+// launch shapes.  Shared memory per CTA = network parameters (shared by the CTA's warps) + per-warp tiles.
+constexpr size_t SMEM_CAP = 227 * 1024;
+
+template <class T, int W> size_t net_bytes(int in_dim, int n_hidden, int out_dim) {
   size_t f = NetSmem<T, W>::floats(in_dim, n_hidden, out_dim);
   f = (f + 7) & ~size_t(7);
-  f += (size_t)ROLLOUT_WARPS * (no + 2 * W) * MLP_R;
   return f * sizeof(T) + 32;
 }
-template <class T, int W> size_t bwd_smem(int in_dim, int n_hidden, int out_dim, int no) {
-  size_t f = NetSmem<T, W>::floats(in_dim, n_hidden, out_dim);
+template <class T> size_t warp_bytes(int leading, int tiles, int W, int R) {      // (leading + tiles * W) * R, 32-byte granules
+  size_t f = (size_t)(leading + tiles * W) * R;
   f = (f + 7) & ~size_t(7);
-  f += (size_t)ROLLOUT_WARPS * (no + 6 * W) * MLP_R;
-  return f * sizeof(T) + 32;
+  return f * sizeof(T);
 }
-template <class T, int W> size_t rows_smem(int in_dim, int n_hidden, int out_dim, int warps) {
-  size_t f = NetSmem<T, W>::floats(in_dim, n_hidden, out_dim);
-  f = (f + 7) & ~size_t(7);
-  f += (size_t)warps * (in_dim + 2 * W) * MLP_R;
-  return f * sizeof(T) + 32;
+
+inline int env_int(const char* name) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : 0;
 }
+inline int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+struct Shape { int R, warps, grid; size_t smem; };
+
+// Rows per warp and warps per CTA for `units` independent rows (environments).  The time loop is a serial
+// dependency chain per warp, so throughput comes from interleaving warps on every SM sub-partition: prefer
+// 8 rows per warp (most FMAs per shared-memory weight read) when that still gives every SM >= 6 warps,
+// otherwise fewer rows per warp.  SGBPO_ROLLOUT_R / SGBPO_ROLLOUT_WARPS override (tuning, tests).
+template <class T>
+Shape pick_shape(int64_t units, size_t fixed_bytes, int leading, int tiles, int W, const int* max_warps_of_R,
+                 bool rows_kernel = false) {
+  const int forced_R = env_int(rows_kernel ? "SGBPO_ROWS_R" : "SGBPO_ROLLOUT_R");
+  const int forced_w = env_int(rows_kernel ? "SGBPO_ROWS_WARPS" : "SGBPO_ROLLOUT_WARPS");
+  const int enough = env_int("SGBPO_ROLLOUT_ENOUGH") > 0 ? env_int("SGBPO_ROLLOUT_ENOUGH") : 6;
+  const int sms = sm_count();
+  Shape best{0, 0, 0, 0};
+  const int cand[3] = {8, 4, 2};
+  for (int ci = 0; ci < 3; ++ci) {
+    const int R = cand[ci];
+    if (forced_R && R != forced_R) continue;
+    const size_t wb = warp_bytes<T>(leading, tiles, W, R);
+    if (fixed_bytes + wb > SMEM_CAP) continue;
+    int wmax = (int)((SMEM_CAP - fixed_bytes) / wb);
+    if (wmax > max_warps_of_R[ci]) wmax = max_warps_of_R[ci];
+    if (wmax < 1) continue;
+    const int64_t total = (units + R - 1) / R;
+    int w = (int)((total + sms - 1) / sms);
+    if (w < 1) w = 1;
+    if (w > wmax) w = wmax;
+    if (forced_w) w = forced_w < wmax ? forced_w : wmax;
+    const Shape s{R, w, (int)((total + w - 1) / w), fixed_bytes + (size_t)w * wb};
+    if (!best.R || w > best.warps) best = s;
+    if (w >= enough) break;
+  }
+  return best;
+}
+
+template <int R> struct RowsShape { static constexpr int MAX_WARPS = R == 8 ? 8 : 16; };
 
 static int cuda_fail2(cudaError_t e, const char* where) {
   snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
@@ -605,54 +651,74 @@ template <class T> BackwardArgs<T> convert_backward(const sgbpo_rollout_grads& g
 }
 
 template <int ENV, class T, int W> struct RolloutLaunch {
+  template <int R>
+  static int fwd_R(const Shape& sh, const sgbpo_consts* c, const sgbpo_mlp* pol, const sgbpo_rollout* r, cudaStream_t st) {
+    auto kern = rollout_fwd_kernel<ENV, T, W, R>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
+    if (e != cudaSuccess) return cuda_fail2(e, "cudaFuncSetAttribute(rollout_fwd)");
+    kern<<<sh.grid, sh.warps * 32, sh.smem, st>>>(convert_rollout<T>(*r), convert_mlp<T>(*pol), convert_consts<T>(*c));
+    e = cudaGetLastError();
+    return e == cudaSuccess ? SGBPO_OK : cuda_fail2(e, "rollout_fwd_kernel");
+  }
+  template <int R>
+  static int bwd_R(const Shape& sh, const sgbpo_consts* c, const sgbpo_mlp* pol, const sgbpo_rollout* r,
+                   const sgbpo_rollout_grads* g, cudaStream_t st) {
+    auto kern = rollout_bwd_kernel<ENV, T, W, R>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
+    if (e != cudaSuccess) return cuda_fail2(e, "cudaFuncSetAttribute(rollout_bwd)");
+    kern<<<sh.grid, sh.warps * 32, sh.smem, st>>>(convert_rollout<T>(*r), convert_backward<T>(*g), convert_mlp<T>(*pol),
+                                                  convert_consts<T>(*c));
+    e = cudaGetLastError();
+    return e == cudaSuccess ? SGBPO_OK : cuda_fail2(e, "rollout_bwd_kernel");
+  }
   static int fwd(const sgbpo_consts* c, const sgbpo_mlp* pol, const sgbpo_rollout* r, cudaStream_t st) {
     using TASK = Task<ENV>;
     if (pol->in_dim != TASK::NO || pol->out_dim != TASK::NA) return fail2(SGBPO_E_ARG, "policy dims do not match the environment");
     if (pol->n_hidden < 1 || pol->n_hidden > MAX_HIDDEN) return fail2(SGBPO_E_UNSUPPORTED, "1..4 hidden layers");
-    const size_t smem = fwd_smem<T, W>(pol->in_dim, pol->n_hidden, pol->out_dim, TASK::NO);
-    if (smem > 227 * 1024) return fail2(SGBPO_E_UNSUPPORTED, "policy does not fit in shared memory");
-    auto kern = rollout_fwd_kernel<ENV, T, W>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail2(e, "cudaFuncSetAttribute(rollout_fwd)");
-    const int64_t per_cta = ROLLOUT_WARPS * MLP_R;
-    const int grid = (int)((r->N + per_cta - 1) / per_cta);
-    kern<<<grid, ROLLOUT_WARPS * 32, smem, st>>>(convert_rollout<T>(*r), convert_mlp<T>(*pol), convert_consts<T>(*c));
-    e = cudaGetLastError();
-    return e == cudaSuccess ? SGBPO_OK : cuda_fail2(e, "rollout_fwd_kernel");
+    const int caps[3] = {RolloutShape<8>::MAX_WARPS, RolloutShape<4>::MAX_WARPS, RolloutShape<2>::MAX_WARPS};
+    const Shape sh = pick_shape<T>(r->N, net_bytes<T, W>(pol->in_dim, pol->n_hidden, pol->out_dim), TASK::NO, 2, W, caps);
+    if (!sh.R) return fail2(SGBPO_E_UNSUPPORTED, "policy does not fit in shared memory");
+    switch (sh.R) {
+      case 8: return fwd_R<8>(sh, c, pol, r, st);
+      case 4: return fwd_R<4>(sh, c, pol, r, st);
+      default: return fwd_R<2>(sh, c, pol, r, st);
+    }
   }
   static int bwd(const sgbpo_consts* c, const sgbpo_mlp* pol, const sgbpo_rollout* r, const sgbpo_rollout_grads* g,
                  cudaStream_t st) {
     using TASK = Task<ENV>;
     if (pol->n_hidden < 1 || pol->n_hidden > MAX_HIDDEN) return fail2(SGBPO_E_UNSUPPORTED, "1..4 hidden layers");
     if (pol->n_hidden != 2) return fail2(SGBPO_E_UNSUPPORTED, "fused backward supports policies with two hidden layers");
-    const size_t smem = bwd_smem<T, W>(pol->in_dim, pol->n_hidden, pol->out_dim, TASK::NO);
-    if (smem > 227 * 1024) return fail2(SGBPO_E_UNSUPPORTED, "policy does not fit in shared memory (backward)");
-    auto kern = rollout_bwd_kernel<ENV, T, W>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail2(e, "cudaFuncSetAttribute(rollout_bwd)");
-    const int64_t per_cta = ROLLOUT_WARPS * MLP_R;
-    const int grid = (int)((r->N + per_cta - 1) / per_cta);
-    kern<<<grid, ROLLOUT_WARPS * 32, smem, st>>>(convert_rollout<T>(*r), convert_backward<T>(*g), convert_mlp<T>(*pol),
-                                                 convert_consts<T>(*c));
-    e = cudaGetLastError();
-    return e == cudaSuccess ? SGBPO_OK : cuda_fail2(e, "rollout_bwd_kernel");
+    const int caps[3] = {RolloutShape<8>::MAX_WARPS, RolloutShape<4>::MAX_WARPS, RolloutShape<2>::MAX_WARPS};
+    const Shape sh = pick_shape<T>(r->N, net_bytes<T, W>(pol->in_dim, pol->n_hidden, pol->out_dim), TASK::NO, 4, W, caps);
+    if (!sh.R) return fail2(SGBPO_E_UNSUPPORTED, "policy does not fit in shared memory (backward)");
+    switch (sh.R) {
+      case 8: return bwd_R<8>(sh, c, pol, r, g, st);
+      case 4: return bwd_R<4>(sh, c, pol, r, g, st);
+      default: return bwd_R<2>(sh, c, pol, r, g, st);
+    }
   }
 };
 
-template <class T, int W> int launch_rows(int64_t M, const sgbpo_mlp* net, const void* x, void* out, cudaStream_t st) {
-  const int warps = 8;
-  if (net->n_hidden < 1 || net->n_hidden > MAX_HIDDEN) return fail2(SGBPO_E_UNSUPPORTED, "1..4 hidden layers");
-  const size_t smem = rows_smem<T, W>(net->in_dim, net->n_hidden, net->out_dim, warps);
-  if (smem > 227 * 1024) return fail2(SGBPO_E_UNSUPPORTED, "network does not fit in shared memory");
-  auto kern = mlp_rows_kernel<T, W>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <class T, int W, int R>
+int launch_rows_R(const Shape& sh, int64_t M, const sgbpo_mlp* net, const void* x, void* out, cudaStream_t st) {
+  auto kern = mlp_rows_kernel<T, W, R>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
   if (e != cudaSuccess) return cuda_fail2(e, "cudaFuncSetAttribute(mlp_rows)");
-  int64_t blocks = (M + MLP_R * warps - 1) / (MLP_R * warps);
-  const int64_t cap = 148 * (smem > 110 * 1024 ? 1 : 2);
+  int64_t blocks = sh.grid;
+  const int64_t cap = (int64_t)sm_count() * (sh.smem > 110 * 1024 ? 1 : 2);     // persistent: warps stride over row blocks
   if (blocks > cap) blocks = cap;
-  kern<<<(int)blocks, warps * 32, smem, st>>>(M, net->in_dim, (const T*)x, (T*)out, convert_mlp<T>(*net));
+  kern<<<(int)blocks, sh.warps * 32, sh.smem, st>>>(M, net->in_dim, (const T*)x, (T*)out, convert_mlp<T>(*net));
   e = cudaGetLastError();
   return e == cudaSuccess ? SGBPO_OK : cuda_fail2(e, "mlp_rows_kernel");
+}
+
+template <class T, int W> int launch_rows(int64_t M, const sgbpo_mlp* net, const void* x, void* out, cudaStream_t st) {
+  if (net->n_hidden < 1 || net->n_hidden > MAX_HIDDEN) return fail2(SGBPO_E_UNSUPPORTED, "1..4 hidden layers");
+  const int caps[3] = {RowsShape<8>::MAX_WARPS, RowsShape<4>::MAX_WARPS, 0};
+  const Shape sh = pick_shape<T>(M, net_bytes<T, W>(net->in_dim, net->n_hidden, net->out_dim), net->in_dim, 2, W, caps, true);
+  if (!sh.R) return fail2(SGBPO_E_UNSUPPORTED, "network does not fit in shared memory");
+  return sh.R == 8 ? launch_rows_R<T, W, 8>(sh, M, net, x, out, st) : launch_rows_R<T, W, 4>(sh, M, net, x, out, st);
 }
 
 

@@ -61,14 +61,16 @@ def net_smem_floats(in_dim: int, width: int, n_hidden: int, out_dim: int) -> int
     return (f + 7) & ~7
 
 
-def mlp_rows_fits(dtype, in_dim: int, width: int, n_hidden: int, out_dim: int = 1, warps: int = 8) -> bool:
+def mlp_rows_fits(dtype, in_dim: int, width: int, n_hidden: int, out_dim: int = 1) -> bool:
+    """At least one warp of 4 rows next to the parameters (csrc/sgbpo_rollout_impl.cuh::pick_shape)."""
     size = 4 if dtype == torch.float32 else 8
-    return (net_smem_floats(in_dim, width, n_hidden, out_dim) + warps * (in_dim + 2 * width) * 8) * size + 32 <= SMEM_LIMIT
+    return (net_smem_floats(in_dim, width, n_hidden, out_dim) + (in_dim + 2 * width) * 4 + 8) * size + 32 <= SMEM_LIMIT
 
 
 def rollout_fits(dtype, obs_dim: int, width: int, n_hidden: int, act_dim: int) -> bool:
+    """At least one warp of 2 rows of the backward kernel (4 tiles of W + the observation tile) fits."""
     size = 4 if dtype == torch.float32 else 8
-    return (net_smem_floats(obs_dim, width, n_hidden, act_dim) + 4 * (obs_dim + 6 * width) * 8) * size + 32 <= SMEM_LIMIT
+    return (net_smem_floats(obs_dim, width, n_hidden, act_dim) + (obs_dim + 4 * width) * 2 + 8) * size + 32 <= SMEM_LIMIT
 
 
 def _tall_skinny_gram(a: Tensor, b: Tensor) -> Tensor:

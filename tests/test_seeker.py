@@ -83,9 +83,13 @@ def test_gpu_env_class_reset_step_and_action_set():
         for _ in range(30):                      # drive straight at the obstacle
             to_obs = ball.center - env.state
             action = to_obs / torch.linalg.vector_norm(to_obs, dim=1, keepdim=True)
+            pre = torch.linalg.vector_norm(to_obs, dim=1) - ball.radius
             o, r, term, trunc, _ = wrapped.step(action)
             assert o.shape == (N, 7)
-        assert not env.collided.any()
+            # P5 bounds the ACTION support by the distance (displacement = DT * a = a / 10) and ignores the
+            # noise, so the free step can only enter the obstacle when the noise (|w| <= 0.05 sqrt 2)
+            # exceeds the 0.9 * distance the safe action leaves: collided => pre-step distance < 0.08
+            assert (pre[env.collided[:, 0]] < 0.08).all()
         dist = torch.linalg.vector_norm(env.state - ball.center, dim=1) - ball.radius
         assert (dist > -0.06).all()              # noise (+-0.05) is not part of the reference's safe set (P5 ignores it)
         assert wrapped.interventions > 0
