@@ -209,10 +209,14 @@ def run_ours(args):
     launches = {"n": 0}
 
     def episode(from_host: bool):
-        if from_host:
+        if from_host:      # e2e: the caller hands over host initial states; row 0 of the buffer is rebuilt from them
             base.state = s0_host.to(dev, non_blocking=True)
             base.steps, base._reset_pending = 0, False
-        algo.buffer.reset()
+            o0 = base.observation
+            with torch.no_grad():
+                algo.buffer.reset(o0, algo.target_value_function(o0).squeeze(1))
+        else:
+            algo.buffer.reset()
         algo.policy_optim.zero_grad()
         avg_reward = algo.collect_trajectories()
         loss = algo.update_policy()

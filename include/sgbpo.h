@@ -156,6 +156,21 @@ int sgbpo_rollout_bwd(int env_id, int dtype, const sgbpo_consts* consts, const s
 /* batched MLP forward over M rows (target critic over the buffer's observation rows, shac.py:111) */
 int sgbpo_mlp_rows(int dtype, int64_t M, const sgbpo_mlp* net, const void* x, void* out, void* stream);
 
+/* ---- policy update tail (shac.py:148-149: clip_grad_norm_(policy, max_norm) + torch.optim.Adam.step()) ---- */
+#define SGBPO_OPT_MAX_TENSORS 24
+typedef struct sgbpo_optim {
+  int32_t n_tensors, reserved;
+  void* param[SGBPO_OPT_MAX_TENSORS];       /* parameter tensors (updated in place) */
+  void* grad[SGBPO_OPT_MAX_TENSORS];        /* their gradients (scaled in place by the clip coefficient, like torch) */
+  void* exp_avg[SGBPO_OPT_MAX_TENSORS];     /* torch.optim.Adam state tensors, updated in place */
+  void* exp_avg_sq[SGBPO_OPT_MAX_TENSORS];
+  void* step[SGBPO_OPT_MAX_TENSORS];        /* 0-dim device step counters (capturable=True), dtype step_dtype */
+  int64_t numel[SGBPO_OPT_MAX_TENSORS];
+  double lr, beta1, beta2, eps, max_norm;
+} sgbpo_optim;
+/* one launch: global gradient norm -> clip -> Adam (no weight decay / amsgrad); total_norm_out: 1 element of dtype or NULL */
+int sgbpo_clip_adam(int dtype, int step_dtype, const sgbpo_optim* o, void* total_norm_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,5 @@
+// fused rollout kernels instantiated for one environment and one dtype (parallel compilation unit)
+#include "sgbpo_rollout_impl.cuh"
+namespace sgbpo {
+SGBPO_INSTANTIATE_ROLLOUT_ENV_T(ENV_SWINGUP_CARTPOLE, double)
+}

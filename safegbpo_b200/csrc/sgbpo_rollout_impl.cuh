@@ -722,30 +722,39 @@ template <class T, int W> int launch_rows(int64_t M, const sgbpo_mlp* net, const
 }
 
 
-// per-environment entry points (one translation unit each, so nvcc compiles them in parallel)
-template <int ENV> int rollout_fwd_env(int dtype, int width, const sgbpo_consts* c, const sgbpo_mlp* pol,
-                                       const sgbpo_rollout* r, cudaStream_t st);
-template <int ENV> int rollout_bwd_env(int dtype, int width, const sgbpo_consts* c, const sgbpo_mlp* pol,
-                                       const sgbpo_rollout* r, const sgbpo_rollout_grads* g, cudaStream_t st);
+// one translation unit per (environment, dtype): SGBPO_INSTANTIATE_ROLLOUT_ENV_T(E, T, SUFFIX) in sgbpo_rollout_env<E>_<f|d>.cu
+template <int ENV, class T> int rollout_fwd_env_t(int width, const sgbpo_consts* c, const sgbpo_mlp* pol,
+                                                  const sgbpo_rollout* r, cudaStream_t st);
+template <int ENV, class T> int rollout_bwd_env_t(int width, const sgbpo_consts* c, const sgbpo_mlp* pol,
+                                                  const sgbpo_rollout* r, const sgbpo_rollout_grads* g, cudaStream_t st);
 
-#define SGBPO_INSTANTIATE_ROLLOUT_ENV(E)                                                                       \
-  template <> int rollout_fwd_env<E>(int dtype, int width, const sgbpo_consts* c, const sgbpo_mlp* pol,          \
-                                     const sgbpo_rollout* r, cudaStream_t st) {                                   \
+#define SGBPO_INSTANTIATE_ROLLOUT_ENV_T(E, T)                                                                  \
+  template <> int rollout_fwd_env_t<E, T>(int width, const sgbpo_consts* c, const sgbpo_mlp* pol,                \
+                                          const sgbpo_rollout* r, cudaStream_t st) {                              \
     switch (width) {                                                                                              \
-      case 32: return dtype ? RolloutLaunch<E, double, 32>::fwd(c, pol, r, st) : RolloutLaunch<E, float, 32>::fwd(c, pol, r, st);   \
-      case 64: return dtype ? RolloutLaunch<E, double, 64>::fwd(c, pol, r, st) : RolloutLaunch<E, float, 64>::fwd(c, pol, r, st);   \
-      case 128: return dtype ? RolloutLaunch<E, double, 128>::fwd(c, pol, r, st) : RolloutLaunch<E, float, 128>::fwd(c, pol, r, st); \
+      case 32: return RolloutLaunch<E, T, 32>::fwd(c, pol, r, st);                                                \
+      case 64: return RolloutLaunch<E, T, 64>::fwd(c, pol, r, st);                                                \
+      case 128: return RolloutLaunch<E, T, 128>::fwd(c, pol, r, st);                                              \
       default: return fail2(SGBPO_E_UNSUPPORTED, "fused rollout supports hidden widths 32, 64, 128");            \
     }                                                                                                             \
   }                                                                                                               \
-  template <> int rollout_bwd_env<E>(int dtype, int width, const sgbpo_consts* c, const sgbpo_mlp* pol,          \
-                                     const sgbpo_rollout* r, const sgbpo_rollout_grads* g, cudaStream_t st) {     \
+  template <> int rollout_bwd_env_t<E, T>(int width, const sgbpo_consts* c, const sgbpo_mlp* pol,                \
+                                          const sgbpo_rollout* r, const sgbpo_rollout_grads* g, cudaStream_t st) { \
     switch (width) {                                                                                              \
-      case 32: return dtype ? RolloutLaunch<E, double, 32>::bwd(c, pol, r, g, st) : RolloutLaunch<E, float, 32>::bwd(c, pol, r, g, st);   \
-      case 64: return dtype ? RolloutLaunch<E, double, 64>::bwd(c, pol, r, g, st) : RolloutLaunch<E, float, 64>::bwd(c, pol, r, g, st);   \
-      case 128: return dtype ? RolloutLaunch<E, double, 128>::bwd(c, pol, r, g, st) : RolloutLaunch<E, float, 128>::bwd(c, pol, r, g, st); \
+      case 32: return RolloutLaunch<E, T, 32>::bwd(c, pol, r, g, st);                                             \
+      case 64: return RolloutLaunch<E, T, 64>::bwd(c, pol, r, g, st);                                             \
+      case 128: return RolloutLaunch<E, T, 128>::bwd(c, pol, r, g, st);                                           \
       default: return fail2(SGBPO_E_UNSUPPORTED, "fused rollout supports hidden widths 32, 64, 128");            \
     }                                                                                                             \
   }
+
+template <int ENV> inline int rollout_fwd_env(int dtype, int width, const sgbpo_consts* c, const sgbpo_mlp* pol,
+                                              const sgbpo_rollout* r, cudaStream_t st) {
+  return dtype ? rollout_fwd_env_t<ENV, double>(width, c, pol, r, st) : rollout_fwd_env_t<ENV, float>(width, c, pol, r, st);
+}
+template <int ENV> inline int rollout_bwd_env(int dtype, int width, const sgbpo_consts* c, const sgbpo_mlp* pol,
+                                              const sgbpo_rollout* r, const sgbpo_rollout_grads* g, cudaStream_t st) {
+  return dtype ? rollout_bwd_env_t<ENV, double>(width, c, pol, r, g, st) : rollout_bwd_env_t<ENV, float>(width, c, pol, r, g, st);
+}
 
 }  // namespace sgbpo

@@ -20,6 +20,7 @@ class CoupledBuffer:
         self.store_log_probs, self.store_safe_actions = store_log_probs, store_safe_actions
         self.batch_size, self.gamma, self.gae_lambda = batch_size, gamma, gae_lambda
         rows = len_trajectories + 1
+        self.fast_reset = None          # set by the fused rollout engine while its static buffers back this object
         self.t = torch.zeros(num_envs, dtype=torch.int64)
         self.observations = CoupledTensor(rows, num_envs, obs_dim)
         if store_values:
@@ -40,6 +41,8 @@ class CoupledBuffer:
         return [getattr(self, n) for n in names if hasattr(self, n)]
 
     def reset(self, reset_observation: Optional[Tensor] = None, reset_value: Optional[Tensor] = None) -> None:
+        if reset_observation is None and self.fast_reset is not None and self.fast_reset():
+            return      # the fused engine owns the storage: last row -> row 0 in place, nothing re-allocated
         if reset_observation is None:
             reset_observation = self.observations[self.t].detach()
             if self.store_values:

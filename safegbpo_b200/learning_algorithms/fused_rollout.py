@@ -133,6 +133,7 @@ class FusedRollout:
         self._episodes = 0
         self._g = None                         # static buffers + captured graphs
         self.profile = False                   # record CUDA events around each of our kernels
+        self.speculative_backward = True       # graph path: enqueue the backward graph right behind the forward graph
         self.kernel_ms = {"rollout_fwd": [], "mlp_rows": [], "rollout_bwd": []}
 
     def _timed(self, name, fn):
@@ -279,7 +280,9 @@ class FusedRollout:
                  rewards=z(H + 2, N), values=z(H + 2, N), flags=z(H, N, dtype=torch.int32),
                  term=z(H + 2, N, dtype=torch.bool), reward_sum=z(()), n_interv=z((), dtype=torch.int64),
                  bad=z((), dtype=torch.int32), aux0=None if base._aux() is None else z(N, base._aux().shape[1]),
-                 h1=z(H, N, W), dz2=z(H, N, W), loss=z(()), fwd_graph=None, bwd_graph=None)
+                 h1=z(H, N, W), dz2=z(H, N, W), loss=z(()), fwd_graph=None, bwd_graph=None,
+                 scal=z(2, dtype=torch.float64), scal_host=torch.zeros(2, dtype=torch.float64, device="cpu").pin_memory(),
+                 side=torch.cuda.Stream(), ev_fwd=torch.cuda.Event(), ev_side=torch.cuda.Event())
         terminal_rows = [False] * (H + 2)
         terminal_rows[H] = True
         disc, norm = self._weights(terminal_rows, H, N)
@@ -353,9 +356,11 @@ class FusedRollout:
             with torch.no_grad():
                 g["values"][1:H + 1] = algo.target_value_function(g["obs"][1:H + 1].reshape(H * N, o)).view(H, N)
         g["reward_sum"].copy_(g["rewards"].sum())
+        g["scal"][0].copy_(g["reward_sum"])
         if self.wrapper is not None:
             g["n_interv"].copy_(((g["flags"] & _lib.FL_INTERVENED) != 0).sum())
             g["bad"].copy_(((g["flags"] & (_lib.FL_NONFINITE | _lib.FL_INFEASIBLE)) != 0).any())
+            g["scal"][1].copy_(g["bad"])
 
     def _bwd_body(self, g):
         """Loss, terminal-value gradient, fused reverse pass, weight-gradient GEMM (capturable)."""
@@ -393,8 +398,10 @@ class FusedRollout:
         buf = algo.buffer
         base.cut_computation_graph()
         g["s_start"].copy_(base.state)
-        g["obs"][0].copy_(buf.observations.tensor[0])
-        g["values"][0].copy_(buf.values.tensor[0])
+        if not g.get("row0_ready"):
+            g["obs"][0].copy_(buf.observations.tensor[0])
+            g["values"][0].copy_(buf.values.tensor[0])
+        g["row0_ready"] = False
         if g["aux0"] is not None:
             g["aux0"].copy_(base._aux())
         if g["fwd_graph"] is None:
@@ -402,9 +409,27 @@ class FusedRollout:
             g["fwd_graph"] = self._capture(self._fwd_body, g)
             torch.cuda.set_rng_state(rng_state)          # the warm-up + capture passes must not consume the stream
         g["fwd_graph"].replay()
+        # speculative reverse pass: update_policy always follows collect_trajectories in SHAC._learn_episode and the
+        # policy does not change in between, so the backward graph is enqueued right behind the forward one and
+        # runs while the host waits for the reward scalar; it only writes the static gradient buffers, which
+        # nothing reads until update_policy attaches them
+        g["ev_fwd"].record()
+        g["bwd_enqueued"] = False
+        if g["bwd_graph"] is not None and self.speculative_backward:
+            g["bwd_graph"].replay()
+            g["bwd_enqueued"] = True
+        # the episode's host-visible scalars (reward sum, bad-status) leave on a side stream that waits for the
+        # forward graph only, so this read-back does not serialise behind the backward graph
+        with torch.cuda.stream(g["side"]):
+            g["side"].wait_event(g["ev_fwd"])
+            g["scal_host"].copy_(g["scal"], non_blocking=True)
+            g["ev_side"].record(g["side"])
         buf.observations.tensor, buf.values.tensor, buf.rewards.tensor = g["obs"], g["values"], g["rewards"]
         buf.actions.tensor, buf.terminals.tensor = g["actions"], g["term"]
-        buf.t = torch.full_like(buf.t, H)
+        if g.get("t_full") is None:
+            g["t_full"], g["t_zero"] = torch.full_like(buf.t, H), torch.zeros_like(buf.t)
+        buf.t = g["t_full"]
+        buf.fast_reset = self._fast_buffer_reset
         base.state = g["states"][H]
         base.steps, base._reset_pending = steps_end, pending_end
         base.last_flags, base.last_exec_action = g["flags"][H - 1], g["exec_actions"][H - 1]
@@ -412,14 +437,32 @@ class FusedRollout:
             w = self.wrapper
             w.safe_action = g["exec_actions"][H - 1]
             w._interventions = w._interventions + g["n_interv"]
+        g["ev_side"].synchronize()
+        if self.wrapper is not None:
             if w.strict:
-                if int(g["bad"]):
+                if g["scal_host"][1] != 0:
                     raise ValueError("a safeguarded step produced a non-finite action or an infeasible program "
                                      "(the reference raises here: safeguard.py:68-75 / solver error)")
             else:
                 w._status = w._status | g["bad"]
         self.last = dict(graph=True, terminal_rows=g["terminal_rows"])
-        return float(g["reward_sum"]) / base.num_envs / H
+        return float(g["scal_host"][0]) / base.num_envs / H
+
+    def _fast_buffer_reset(self) -> bool:
+        """CoupledBuffer.reset() while the buffer's tensors ARE the static graph buffers: carry the last
+        observation / value to row 0 in place (coupled_buffer.py:113-131 does the same on fresh storage; the
+        other rows are rewritten by the next collect_trajectories).  Returns False when the buffer was
+        re-bound by someone else, so the generic reset runs."""
+        g, buf = self._g, self.algo.buffer
+        if g is None or buf.observations.tensor is not g["obs"] or buf.t is not g["t_full"]:
+            buf.fast_reset = None
+            return False
+        H = g["H"]
+        g["obs"][0].copy_(g["obs"][H])
+        g["values"][0].copy_(g["values"][H])
+        buf.t = g["t_zero"]
+        g["row0_ready"] = True
+        return True
 
     def _backward_graph(self) -> Tensor:
         g, algo = self._g, self.algo
@@ -430,7 +473,9 @@ class FusedRollout:
                 raise _lib.SgbpoError("fused graph path: policy gradients must be zeroed (set_to_none) before the episode")
         if g["bwd_graph"] is None:
             g["bwd_graph"] = self._capture(self._bwd_body, g)
-        g["bwd_graph"].replay()
+        if not g.get("bwd_enqueued"):
+            g["bwd_graph"].replay()
+        g["bwd_enqueued"] = False
         return g["loss"]
 
     # ------------------------------------------------------------------------------------------------------
@@ -443,6 +488,8 @@ class FusedRollout:
         reset_at, _, _, _, pending_end, steps_end = self._schedule(H)
         if self._graphable(reset_at):
             return self._collect_graph(H, steps_end, pending_end)
+        if self._g is not None:
+            self._g["row0_ready"] = False          # this episode runs outside the static buffers
         base.cut_computation_graph()
         s0 = base.state.detach().contiguous()
         aux0 = base._aux()

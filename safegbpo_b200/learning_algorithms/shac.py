@@ -45,6 +45,7 @@ class SHAC(LearningAlgorithm):
         self._fused_engine = None
         # data-parallel hook: called between backward and clip/Adam (distributed.allreduce_policy_grads)
         self.grad_sync = None
+        self._fused_tail = None          # resolved on first use: fused clip + Adam launch when the optimizer is plain Adam on CUDA
 
     # ---- episode ---------------------------------------------------------------------------------------
     def _learn_episode(self, eps: int) -> tuple[float, float, float]:
@@ -119,8 +120,15 @@ class SHAC(LearningAlgorithm):
             loss.backward()
         if self.grad_sync is not None:
             self.grad_sync(self)
-        torch.nn.utils.clip_grad_norm_(self.policy.parameters(), self.MAX_GRAD_NORM)
-        self.policy_optim.step()
+        if self._fused_tail is None:
+            from .. import optim as sgoptim
+            self._fused_tail = sgoptim.supported(self.policy_optim)
+        if self._fused_tail:       # shac.py:148-149 as one launch (csrc/sgbpo_optim.cu)
+            from .. import optim as sgoptim
+            sgoptim.clip_adam_step(self.policy_optim, self.MAX_GRAD_NORM)
+        else:
+            torch.nn.utils.clip_grad_norm_(self.policy.parameters(), self.MAX_GRAD_NORM)
+            self.policy_optim.step()
         return float(loss)
 
     # ---- critic (next after the hot path; plain torch, vectorised over environments) -------

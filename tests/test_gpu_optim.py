@@ -1,0 +1,45 @@
+"""Fused clip_grad_norm_ + Adam launch (csrc/sgbpo_optim.cu) against torch's own implementation
+(reference: src/learning_algorithms/shac.py:148-149)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-12), (torch.float32, 2e-6)], ids=["f64", "f32"])
+@pytest.mark.parametrize("scale", [0.01, 30.0], ids=["unclipped", "clipped"])
+def test_clip_adam_matches_torch(dtype, tol, scale):
+    from safegbpo_b200 import optim as sgoptim
+    from safegbpo_b200.learning_algorithms.components.policy import Policy
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)
+    torch.set_default_device("cuda:0")
+    try:
+        torch.manual_seed(5)
+        a, b = Policy(5, 2, net_arch=[64, 64]), Policy(5, 2, net_arch=[64, 64])
+        b.load_state_dict(a.state_dict())
+        oa = torch.optim.Adam(a.parameters(), lr=3e-3, capturable=True)
+        ob = torch.optim.Adam(b.parameters(), lr=3e-3, capturable=True)
+        assert sgoptim.supported(ob)
+        for it in range(5):
+            grads = [torch.randn_like(p) * scale for p in a.parameters()]
+            for p, q, g in zip(a.parameters(), b.parameters(), grads):
+                p.grad, q.grad = g.clone(), g.clone()
+            ref_norm = torch.nn.utils.clip_grad_norm_(a.parameters(), 1.0)
+            oa.step()
+            got_norm = sgoptim.clip_adam_step(ob, 1.0)
+            np.testing.assert_allclose(float(got_norm), float(ref_norm), rtol=10 * tol)
+            for (name, p), q in zip(a.named_parameters(), b.parameters()):
+                np.testing.assert_allclose(q.grad.cpu().numpy(), p.grad.cpu().numpy(), rtol=10 * tol, atol=tol, err_msg=f"grad {name} it {it}")
+                np.testing.assert_allclose(q.detach().cpu().numpy(), p.detach().cpu().numpy(), rtol=10 * tol, atol=tol, err_msg=f"{name} it {it}")
+                sa, sb = oa.state[p], ob.state[q]
+                assert float(sa["step"]) == float(sb["step"]) == it + 1
+                np.testing.assert_allclose(sb["exp_avg_sq"].cpu().numpy(), sa["exp_avg_sq"].cpu().numpy(), rtol=10 * tol, atol=tol * tol)
+                np.testing.assert_allclose(sb["exp_avg"].cpu().numpy(), sa["exp_avg"].cpu().numpy(), rtol=10 * tol, atol=tol)
+        # the optimizer state stays loadable by torch
+        oc = torch.optim.Adam(b.parameters(), lr=3e-3, capturable=True)
+        oc.load_state_dict(ob.state_dict())
+    finally:
+        torch.set_default_device("cpu")
+        torch.set_default_dtype(prev)
