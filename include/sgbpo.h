@@ -134,14 +134,20 @@ typedef struct sgbpo_rollout {
   void* exec_actions;        /* [H][N][m] */
   void* rewards;             /* [H+2][N] */
   int32_t* flags;            /* [H][N] */
+  /* activation stash, written by sgbpo_rollout_fwd and read by sgbpo_rollout_bwd (policies with two hidden
+   * layers; all four NULL = forward only).  Recomputing the policy forward in the reverse pass would cost two
+   * of its three GEMMs; 1 KB per environment step of HBM traffic is far cheaper on this path. */
+  void* stash_h1;            /* [H][N][width]  LayerNorm output of hidden layer 1 = operand of Linear2.weight.grad */
+  void* stash_e1;            /* [H][N][width]  ELU output of hidden layer 1 */
+  void* stash_e2;            /* [H][N][width]  ELU output of hidden layer 2 */
+  void* stash_stats;         /* [H][N][4]      LayerNorm mean1, rstd1, mean2, rstd2 */
 } sgbpo_rollout;
 
 typedef struct sgbpo_rollout_grads {
   const void* grw;             /* [H]  d loss / d rewards[t] */
   const void* gobs_term;       /* [K][N][o] d(terminal value terms)/d obs rows, or NULL */
   const int32_t* term_of_row;  /* [H+2] device: -1 or k */
-  void* h1_out;                /* [H][N][width]  } operands of the hidden-hidden weight gradient */
-  void* dz2_out;               /* [H][N][width]  }   Linear.weight.grad = dz2^T h1 (one GEMM by the caller) */
+  void* dz2_out;               /* [H][N][width]  Linear2.weight.grad = dz2^T stash_h1 (one GEMM by the caller) */
   /* parameter gradients, accumulated (caller zero-fills), in torch's layouts:
    * g_w_in [width][in_dim], g_w_out [out_dim][width], g_b_hid/g_gamma/g_beta [2][width], g_b_out/g_log_std [out_dim] */
   void* g_w_in; void* g_w_out; void* g_b_hid; void* g_gamma; void* g_beta; void* g_b_out; void* g_log_std;

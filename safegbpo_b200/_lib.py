@@ -60,13 +60,14 @@ class Rollout(C.Structure):
                 ("eps", C.c_void_p), ("noise", C.c_void_p), ("dirs", C.c_void_p), ("aux0", C.c_void_p),
                 ("reset_states", C.c_void_p), ("reset_idx", C.c_void_p), ("aux_src", C.c_void_p), ("shared", C.c_void_p),
                 ("states", C.c_void_p), ("obs", C.c_void_p), ("actions", C.c_void_p), ("exec_actions", C.c_void_p),
-                ("rewards", C.c_void_p), ("flags", C.c_void_p)]
+                ("rewards", C.c_void_p), ("flags", C.c_void_p),
+                ("stash_h1", C.c_void_p), ("stash_e1", C.c_void_p), ("stash_e2", C.c_void_p), ("stash_stats", C.c_void_p)]
 
 
 class RolloutGrads(C.Structure):
     """Mirror of ``struct sgbpo_rollout_grads``."""
     _fields_ = [("grw", C.c_void_p), ("gobs_term", C.c_void_p), ("term_of_row", C.c_void_p),
-                ("h1_out", C.c_void_p), ("dz2_out", C.c_void_p), ("g_w_in", C.c_void_p), ("g_w_out", C.c_void_p),
+                ("dz2_out", C.c_void_p), ("g_w_in", C.c_void_p), ("g_w_out", C.c_void_p),
                 ("g_b_hid", C.c_void_p), ("g_gamma", C.c_void_p), ("g_beta", C.c_void_p), ("g_b_out", C.c_void_p),
                 ("g_log_std", C.c_void_p)]
 

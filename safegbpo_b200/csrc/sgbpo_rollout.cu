@@ -23,6 +23,11 @@ int sgbpo_rollout_fwd(int env_id, int dtype, const sgbpo_consts* consts, const s
   if (r->N <= 0 || r->H <= 0) return SGBPO_OK;
   if (!r->eps || !r->noise || !r->states || !r->obs || !r->actions || !r->exec_actions || !r->rewards || !r->flags)
     return fail2(SGBPO_E_ARG, "sgbpo_rollout_fwd: null buffer");
+  {
+    const int n_stash = (r->stash_h1 != nullptr) + (r->stash_e1 != nullptr) + (r->stash_e2 != nullptr) + (r->stash_stats != nullptr);
+    if (n_stash != 0 && n_stash != 4) return fail2(SGBPO_E_ARG, "sgbpo_rollout_fwd: pass all four stash buffers or none");
+    if (n_stash == 4 && policy->n_hidden != 2) return fail2(SGBPO_E_UNSUPPORTED, "activation stash: policies with two hidden layers");
+  }
   cudaStream_t st = (cudaStream_t)stream;
   ROLLOUT_DISPATCH(rollout_fwd_env, dtype, policy->width, consts, policy, r, st)
 }
@@ -31,9 +36,11 @@ int sgbpo_rollout_bwd(int env_id, int dtype, const sgbpo_consts* consts, const s
                       const sgbpo_rollout* r, const sgbpo_rollout_grads* g, void* stream) {
   if (!consts || !policy || !r || !g) return fail2(SGBPO_E_ARG, "sgbpo_rollout_bwd: null argument");
   if (r->N <= 0 || r->H <= 0) return SGBPO_OK;
-  if (!g->grw || !g->h1_out || !g->dz2_out || !g->g_w_in || !g->g_w_out || !g->g_b_hid || !g->g_gamma || !g->g_beta ||
+  if (!g->grw || !g->dz2_out || !g->g_w_in || !g->g_w_out || !g->g_b_hid || !g->g_gamma || !g->g_beta ||
       !g->g_b_out || !g->g_log_std)
     return fail2(SGBPO_E_ARG, "sgbpo_rollout_bwd: null buffer");
+  if (!r->stash_h1 || !r->stash_e1 || !r->stash_e2 || !r->stash_stats)
+    return fail2(SGBPO_E_ARG, "sgbpo_rollout_bwd: the forward pass must have been run with the activation stash buffers");
   cudaStream_t st = (cudaStream_t)stream;
   ROLLOUT_DISPATCH(rollout_bwd_env, dtype, policy->width, consts, policy, r, g, st)
 }

@@ -48,14 +48,15 @@ template <class T> struct RolloutArgs {
   T* exec_actions;        // [H][N][m]     executed (safeguarded) actions
   T* rewards;             // [H+2][N]      rows 0..H-1 written
   int32_t* flags;         // [H][N]
+  // activation stash (fwd writes, bwd reads): [H][N][W] x 3 and [H][N][4]
+  T* stash_h1; T* stash_e1; T* stash_e2; T* stash_stats;
 };
 
 template <class T> struct BackwardArgs {
   const T* grw;           // [H]   d loss / d reward[t]  (0 on rows replaced by the critic value)
   const T* gobs_term;     // [K][N][o] gradient of the terminal-value terms w.r.t. obs rows, or null
   const int* term_of_row; // [H+2]: -1 or k
-  T* h1_out;              // [H][N][W]   layer-2 input activations      } operands of dW_hid = h1^T dz2
-  T* dz2_out;             // [H][N][W]   layer-2 pre-activation grads   }
+  T* dz2_out;             // [H][N][W]   layer-2 pre-activation grads: dW_hid = dz2^T stash_h1
   // parameter gradients (accumulated with atomics, caller zero-fills)
   T* g_w_in;              // [W][o]  (torch layout of Linear.weight)
   T* g_w_out;             // [m][W]
@@ -65,6 +66,29 @@ template <class T> struct BackwardArgs {
   T* g_b_out;             // [m]
   T* g_log_std;           // [m]
 };
+
+// register tile <-> global [t][env][W]: per row, the warp touches W contiguous values (128-byte segments)
+template <class T, int W, int R>
+__device__ __forceinline__ void stream_tile(T* __restrict__ dst, int t, int64_t N, int64_t env0, int lane,
+                                            const T (&v)[R][W / 32]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (env0 + r < N) {
+#pragma unroll
+      for (int j = 0; j < W / 32; ++j) dst[((int64_t)t * N + env0 + r) * W + lane + 32 * j] = v[r][j];
+    }
+  }
+}
+template <class T, int W, int R>
+__device__ __forceinline__ void fetch_tile(const T* __restrict__ src, int t, int64_t N, int64_t env0, int lane,
+                                           T (&v)[R][W / 32]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const bool ok = env0 + r < N;
+#pragma unroll
+    for (int j = 0; j < W / 32; ++j) v[r][j] = ok ? src[((int64_t)t * N + env0 + r) * W + lane + 32 * j] : T(0);
+  }
+}
 
 // launch bounds per rows-per-warp R: fewer rows -> smaller register tiles -> more resident warps
 template <int R> struct RolloutShape {
@@ -91,7 +115,8 @@ rollout_fwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
   T* obsT = smem + off + warp * per_warp;
   T* bufA = obsT + NO * R;
   T* bufB = bufA + W * R;
-  const int64_t env = ((int64_t)blockIdx.x * nwarps + warp) * R + lane;
+  const int64_t env0 = ((int64_t)blockIdx.x * nwarps + warp) * R;       // first env of this warp
+  const int64_t env = env0 + lane;
   const bool owner = lane < R;
   const bool valid = owner && env < A.N;
   const int64_t N = A.N;
@@ -132,7 +157,29 @@ rollout_fwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
     }
     // ---- policy forward -------------------------------------------------------------------------
     T h[R][CPL];
-    net_forward<T, W, R>(net, obsT, bufA, bufB, lane, h);
+    if (A.stash_e1) {
+      // two hidden layers, activations kept for the reverse pass (ELU outputs, LayerNorm statistics, h1)
+      T ev[R][CPL], m1[R], r1[R], m2[R], r2[R];
+      tile_gemm<T, W, R>(obsT, NO, net.w_in, net.b_hid, lane, h);
+      elu_layernorm<T, W, R, true>(h, net.gamma, net.beta, lane, ev, m1, r1);
+      store_tile<T, W, R>(bufA, lane, h);
+      stream_tile<T, W, R>(A.stash_e1, t, N, env0, lane, ev);
+      stream_tile<T, W, R>(A.stash_h1, t, N, env0, lane, h);
+      __syncwarp();
+      tile_gemm<T, W, R>(bufA, W, net.w_hid, net.b_hid + W, lane, h);
+      elu_layernorm<T, W, R, true>(h, net.gamma + W, net.beta + W, lane, ev, m2, r2);
+      stream_tile<T, W, R>(A.stash_e2, t, N, env0, lane, ev);
+      if (valid) {
+        T st[4] = {T(0), T(0), T(0), T(0)};
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (lane == r) { st[0] = m1[r]; st[1] = r1[r]; st[2] = m2[r]; st[3] = r2[r]; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) A.stash_stats[((int64_t)t * N + env) * 4 + i] = st[i];
+      }
+    } else {
+      net_forward<T, W, R>(net, obsT, bufA, bufB, lane, h);
+    }
     T mu[R][NA];
     out_layer<T, W, R, NA>(h, net.w_out, net.b_out, lane, mu);
     // ---- environment step on the owner lanes ---------------------------------------------------
@@ -240,13 +287,11 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   size_t off = (size_t)(after - smem);
   off = (off + 7) & ~size_t(7);
-  // warp-private: obsT [NO][R], h1T [W][R], g2T [W][R], stash of the two ELU outputs e1S / e2S [W][R] each
-  const size_t per_warp = ((size_t)(NO + 4 * W) * R + 7) & ~size_t(7);
+  // warp-private: obsT [NO][R] and g2T [W][R] (operand of the transposed data-gradient GEMM); the forward
+  // activations come from the stash the forward kernel left in HBM, nothing is recomputed
+  const size_t per_warp = ((size_t)(NO + W) * R + 7) & ~size_t(7);
   T* obsT = smem + off + warp * per_warp;
-  T* h1T = obsT + NO * R;
-  T* g2T = h1T + W * R;
-  T* e1S = g2T + W * R;
-  T* e2S = e1S + W * R;
+  T* g2T = obsT + NO * R;
   const int64_t N = A.N;
   const int64_t env0 = ((int64_t)blockIdx.x * nwarps + warp) * R;      // first env of this warp
   const int64_t env = env0 + lane;
@@ -312,31 +357,17 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
       for (int i = 0; i < NO; ++i) obsT[i * R + lane] = valid ? A.obs[((int64_t)t * N + env) * NO + i] : T(0);
     }
     __syncwarp();
-    // ---- recompute the policy forward, stashing what the backward needs ----------------------------------
+    // ---- forward activations of this step from the stash (loads issued now, consumed after the step) ---------
     T mean1[R], rstd1[R], mean2[R], rstd2[R];
-    T mu[R][NA];
-    {
-      T z[R][CPL], ev[R][CPL];
-      tile_gemm<T, W, R>(obsT, NO, net.w_in, net.b_hid, lane, z);
-      elu_layernorm<T, W, R, true>(z, net.gamma, net.beta, lane, ev, mean1, rstd1);
-      store_tile<T, W, R>(h1T, lane, z);
-      store_tile<T, W, R>(e1S, lane, ev);
-      // stream h1 (layer-2 input) out for the dW_hid GEMM straight from the register tile:
-      // [t][env][W], 128-byte row segments per (r, j)
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        if (env0 + r < N) {
-#pragma unroll
-          for (int j = 0; j < CPL; ++j) G.h1_out[((int64_t)t * N + env0 + r) * W + lane + 32 * j] = z[r][j];
-        }
-      }
-      __syncwarp();
-      tile_gemm<T, W, R>(h1T, W, Whid, net.b_hid + W, lane, z);
-      elu_layernorm<T, W, R, true>(z, net.gamma + W, net.beta + W, lane, ev, mean2, rstd2);
-      out_layer<T, W, R, NA>(z, net.w_out, net.b_out, lane, mu);
-      store_tile<T, W, R>(e2S, lane, ev);
+    for (int r = 0; r < R; ++r) {
+      const bool ok = env0 + r < N;
+      const T* st = A.stash_stats + ((int64_t)t * N + env0 + r) * 4;
+      mean1[r] = ok ? st[0] : T(0); rstd1[r] = ok ? st[1] : T(0);
+      mean2[r] = ok ? st[2] : T(0); rstd2[r] = ok ? st[3] : T(0);
     }
-    __syncwarp();
+    T e2v[R][CPL];
+    fetch_tile<T, W, R>(A.stash_e2, t, N, env0, lane, e2v);
     // ---- step Jacobian (duals) contracted with the carried cotangents, on the owner lanes -----------------
     T ga_pre[NA];          // d loss / d (mu + sigma eps)   (after the tanh)
 #pragma unroll
@@ -346,12 +377,7 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
     for (int q = 0; q < NA; ++q) act[q] = T(0);
     if (owner) {
 #pragma unroll
-      for (int q = 0; q < NA; ++q) {
-        T m = T(0);
-#pragma unroll
-        for (int r = 0; r < R; ++r) m = (lane == r) ? mu[r][q] : m;
-        act[q] = valid ? sg_tanh(m + sigma[q] * epsv[q]) : T(0);
-      }
+      for (int q = 0; q < NA; ++q) act[q] = valid ? A.actions[((int64_t)t * N + env) * NA + q] : T(0);   // a_t = tanh(mu + sigma eps)
       D sd[NS], ad[NA], sn[NS], ae[NA], ob[NO], rew;
 #pragma unroll
       for (int i = 0; i < NS; ++i) sd[i] = D::seed(sv[i], i);
@@ -405,8 +431,7 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
     {
       // output layer: dh2 = dmu w_out^T ; dW_out += h2^T dmu (h2 = xhat2 * gamma2 + beta2)
       T xh[R][CPL], eg[R][CPL];
-      load_tile<T, W, R>(e2S, lane, eg);
-      unstash<T, W, R>(eg, mean2, rstd2, xh, eg);
+      unstash<T, W, R>(e2v, mean2, rstd2, xh, eg);
       T wo[CPL][NA], g2[CPL], b2[CPL];
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
@@ -465,11 +490,12 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
           for (int j = 0; j < CPL; ++j) G.dz2_out[((int64_t)t * N + env0 + r) * W + lane + 32 * j] = gcarry[r][j];
         }
       }
-      // dh1 = dz2 W_hid^T
+      // dh1 = dz2 W_hid^T   (the layer-1 stash is fetched first so its latency hides behind the GEMM)
+      T e1v[R][CPL];
+      fetch_tile<T, W, R>(A.stash_e1, t, N, env0, lane, e1v);
       tile_gemm_t<T, W, R>(g2T, Whid, lane, gcarry);
       // LayerNorm 1 + ELU 1 backward -> dz1
-      load_tile<T, W, R>(e1S, lane, eg);
-      unstash<T, W, R>(eg, mean1, rstd1, xh, eg);
+      unstash<T, W, R>(e1v, mean1, rstd1, xh, eg);
       T g1[CPL];
 #pragma unroll
       for (int j = 0; j < CPL; ++j) g1[j] = net.gamma[lane + 32 * j];
@@ -639,12 +665,13 @@ template <class T> RolloutArgs<T> convert_rollout(const sgbpo_rollout& r) {
   a.shared = (const StepShared<T>*)r.shared;
   a.states = (T*)r.states; a.obs = (T*)r.obs; a.actions = (T*)r.actions; a.exec_actions = (T*)r.exec_actions;
   a.rewards = (T*)r.rewards; a.flags = r.flags;
+  a.stash_h1 = (T*)r.stash_h1; a.stash_e1 = (T*)r.stash_e1; a.stash_e2 = (T*)r.stash_e2; a.stash_stats = (T*)r.stash_stats;
   return a;
 }
 template <class T> BackwardArgs<T> convert_backward(const sgbpo_rollout_grads& g) {
   BackwardArgs<T> b;
   b.grw = (const T*)g.grw; b.gobs_term = (const T*)g.gobs_term; b.term_of_row = g.term_of_row;
-  b.h1_out = (T*)g.h1_out; b.dz2_out = (T*)g.dz2_out;
+  b.dz2_out = (T*)g.dz2_out;
   b.g_w_in = (T*)g.g_w_in; b.g_w_out = (T*)g.g_w_out; b.g_b_hid = (T*)g.g_b_hid; b.g_gamma = (T*)g.g_gamma;
   b.g_beta = (T*)g.g_beta; b.g_b_out = (T*)g.g_b_out; b.g_log_std = (T*)g.g_log_std;
   return b;
@@ -690,7 +717,7 @@ template <int ENV, class T, int W> struct RolloutLaunch {
     if (pol->n_hidden < 1 || pol->n_hidden > MAX_HIDDEN) return fail2(SGBPO_E_UNSUPPORTED, "1..4 hidden layers");
     if (pol->n_hidden != 2) return fail2(SGBPO_E_UNSUPPORTED, "fused backward supports policies with two hidden layers");
     const int caps[3] = {RolloutShape<8>::MAX_WARPS, RolloutShape<4>::MAX_WARPS, RolloutShape<2>::MAX_WARPS};
-    const Shape sh = pick_shape<T>(r->N, net_bytes<T, W>(pol->in_dim, pol->n_hidden, pol->out_dim), TASK::NO, 4, W, caps);
+    const Shape sh = pick_shape<T>(r->N, net_bytes<T, W>(pol->in_dim, pol->n_hidden, pol->out_dim), TASK::NO, 1, W, caps);
     if (!sh.R) return fail2(SGBPO_E_UNSUPPORTED, "policy does not fit in shared memory (backward)");
     switch (sh.R) {
       case 8: return bwd_R<8>(sh, c, pol, r, g, st);

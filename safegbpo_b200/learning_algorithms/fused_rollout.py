@@ -280,7 +280,8 @@ class FusedRollout:
                  rewards=z(H + 2, N), values=z(H + 2, N), flags=z(H, N, dtype=torch.int32),
                  term=z(H + 2, N, dtype=torch.bool), reward_sum=z(()), n_interv=z((), dtype=torch.int64),
                  bad=z((), dtype=torch.int32), aux0=None if base._aux() is None else z(N, base._aux().shape[1]),
-                 h1=z(H, N, W), dz2=z(H, N, W), loss=z(()), fwd_graph=None, bwd_graph=None,
+                 h1=z(H, N, W), e1=z(H, N, W), e2=z(H, N, W), stats=z(H, N, 4), dz2=z(H, N, W), loss=z(()),
+                 fwd_graph=None, bwd_graph=None,
                  scal=z(2, dtype=torch.float64), scal_host=torch.zeros(2, dtype=torch.float64, device="cpu").pin_memory(),
                  side=torch.cuda.Stream(), ev_fwd=torch.cuda.Event(), ev_side=torch.cuda.Event())
         terminal_rows = [False] * (H + 2)
@@ -307,10 +308,11 @@ class FusedRollout:
         r.eps, r.noise, r.dirs, r.aux0 = p(g["eps"]), p(g["noise"]), p(g["dirs"]), p(g["aux0"])
         r.states, r.obs, r.actions, r.exec_actions = p(g["states"]), p(g["obs"]), p(g["actions"]), p(g["exec_actions"])
         r.rewards, r.flags = p(g["rewards"]), p(g["flags"])
+        r.stash_h1, r.stash_e1, r.stash_e2, r.stash_stats = p(g["h1"]), p(g["e1"]), p(g["e2"]), p(g["stats"])
         g["r"] = r
         gr = RolloutGrads()
         gr.grw, gr.gobs_term, gr.term_of_row = p(g["grw"]), p(g["gobs_term"]), p(g["term_of_row"])
-        gr.h1_out, gr.dz2_out = p(g["h1"]), p(g["dz2"])
+        gr.dz2_out = p(g["dz2"])
         (gr.g_w_in, gr.g_w_out, gr.g_b_hid, gr.g_gamma, gr.g_beta, gr.g_b_out, gr.g_log_std) = [x.data_ptr() for x in g["parts"]]
         g["gr"] = gr
         g_w_in, g_w_out, g_b_hid, g_gamma, g_beta, g_b_out, g_log_std = g["parts"]
@@ -518,6 +520,13 @@ class FusedRollout:
         r.reset_states, r.reset_idx, r.aux_src, r.shared = p(resets), p(reset_idx_t), p(aux_src_t), p(shared)
         r.states, r.obs, r.actions, r.exec_actions = states.data_ptr(), obs.data_ptr(), actions.data_ptr(), exec_actions.data_ptr()
         r.rewards, r.flags = rewards.data_ptr(), flags.data_ptr()
+        W = self.policy_pack.width
+        if self._grad_bufs is None or self._grad_bufs["h1"].shape != (H, N, W) or self._grad_bufs["h1"].dtype != dt:
+            mk = lambda *shape: torch.empty(*shape, dtype=dt, device=dev)
+            self._grad_bufs = dict(h1=mk(H, N, W), e1=mk(H, N, W), e2=mk(H, N, W), stats=mk(H, N, 4), dz2=mk(H, N, W))
+        gb = self._grad_bufs
+        r.stash_h1, r.stash_e1, r.stash_e2, r.stash_stats = (gb["h1"].data_ptr(), gb["e1"].data_ptr(), gb["e2"].data_ptr(),
+                                                               gb["stats"].data_ptr())
         lib = _lib.lib()
         self._timed("rollout_fwd", lambda: check(
             lib.sgbpo_rollout_fwd(base.env_id, dtype_code(dt), C.byref(self._consts()), C.byref(self.policy_pack.desc),
@@ -593,15 +602,13 @@ class FusedRollout:
             term_of_row[j] = kk
         gobs_term = torch.stack(gterm).contiguous()
         term_of_row_t = torch.tensor(term_of_row, dtype=torch.int32, device=dev)
-        if self._grad_bufs is None or self._grad_bufs["h1"].shape != (H, N, W):
-            self._grad_bufs = dict(h1=torch.empty(H, N, W, dtype=dt, device=dev), dz2=torch.empty(H, N, W, dtype=dt, device=dev))
         h1, dz2 = self._grad_bufs["h1"], self._grad_bufs["dz2"]
         sizes = [o * W, W * m, 2 * W, 2 * W, 2 * W, m, m]
         flat = torch.zeros(sum(sizes), dtype=dt, device=dev)
         parts = torch.split(flat, sizes)
         g = RolloutGrads()
         g.grw, g.gobs_term, g.term_of_row = grw.data_ptr(), gobs_term.data_ptr(), term_of_row_t.data_ptr()
-        g.h1_out, g.dz2_out = h1.data_ptr(), dz2.data_ptr()
+        g.dz2_out = dz2.data_ptr()
         (g.g_w_in, g.g_w_out, g.g_b_hid, g.g_gamma, g.g_beta, g.g_b_out, g.g_log_std) = [x.data_ptr() for x in parts]
         self._timed("rollout_bwd", lambda: check(
             _lib.lib().sgbpo_rollout_bwd(base.env_id, dtype_code(dt), C.byref(self._consts()),
