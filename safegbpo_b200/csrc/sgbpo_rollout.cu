@@ -3,6 +3,7 @@
 #include "sgbpo_rollout_impl.cuh"
 
 namespace sgbpo {
+int launch_rows_tc(int64_t M, const sgbpo_mlp* net, const void* x, void* out, cudaStream_t st);   // sgbpo_mlp_tc.cu
 #define ROLLOUT_DISPATCH(FN, ...)                                                       \
   switch (env_id) {                                                                     \
     case ENV_BALANCE_PENDULUM: return FN<ENV_BALANCE_PENDULUM>(__VA_ARGS__);            \
@@ -49,6 +50,11 @@ int sgbpo_mlp_rows(int dtype, int64_t M, const sgbpo_mlp* net, const void* x, vo
   if (!net || (M > 0 && (!x || !out))) return fail2(SGBPO_E_ARG, "sgbpo_mlp_rows: null argument");
   if (M <= 0) return SGBPO_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SGBPO_F32 && !(getenv("SGBPO_ROWS_TC") && getenv("SGBPO_ROWS_TC")[0] == '0')) {
+    // fp32, width 128, 2-3 hidden layers: tcgen05 tensor-core kernel (csrc/sgbpo_mlp_tc.cu); anything else: FMA tiles
+    const int rc = launch_rows_tc(M, net, x, out, st);
+    if (rc != SGBPO_E_UNSUPPORTED) return rc;
+  }
   switch (net->width) {
     case 32: return dtype ? launch_rows<double, 32>(M, net, x, out, st) : launch_rows<float, 32>(M, net, x, out, st);
     case 64: return dtype ? launch_rows<double, 64>(M, net, x, out, st) : launch_rows<float, 64>(M, net, x, out, st);
