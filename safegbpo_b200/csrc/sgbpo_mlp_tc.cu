@@ -5,9 +5,11 @@
 // Linear -> ELU -> LayerNorm per hidden layer, then Linear).  This is the one GEMM-shaped, non-sequential
 // piece of the path (262 144 rows x [o -> 128 -> 128 -> 128 -> 1] for BASELINE configs[1]).
 //
-// Mapping.  One CTA = 128 threads = one tile of 128 rows; thread t owns row t, which is also TMEM lane t:
+// Mapping.  One CTA = one tile of 128 rows at a time; 128 x NSPLIT threads: thread t owns row t % 128 (= its TMEM
+// lane) and 128 / NSPLIT of its columns (NSPLIT = 4: four warps per SM sub-partition for the issue-bound epilogue):
 //   * accumulator D[128 rows x 128 hidden] lives in TMEM (128 columns of fp32); `tcgen05.ld 32x32b` hands every
-//     thread ITS row, so bias + ELU + LayerNorm are thread-local (no shuffles, no shared-memory reductions);
+//     thread ITS row segment, so bias + ELU + LayerNorm are thread-local up to one shared-memory exchange of the
+//     NSPLIT partial row sums (no shuffles);
 //   * A = the tile's activations, B = Linear.weight [out][in] (K-major as torch stores it), both in shared
 //     memory in the no-swizzle K-major core-matrix layout [K/8][128 rows][8 halves] (16-byte units; descriptor
 //     SBO = 128 B between 8-row groups, LBO = 2048 B between K chunks).  The epilogue of layer l writes the A
@@ -25,6 +27,7 @@
 #include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/sgbpo.h"
 
@@ -112,32 +115,48 @@ __device__ __forceinline__ float elu1(float v) {                 // ATen: exp(x)
   const float en = expf(v < 0.f ? v : 0.f) - 1.0f;
   return v > 0.f ? v : en;
 }
+// 8 consecutive K values of one operand row -> fp16 hi / lo parts, one 16-byte unit each
 __device__ __forceinline__ void split_store(unsigned char* a_hi, unsigned char* a_lo, int kc, int row, const float (&h)[8]) {
   uint32_t hi[4], lo[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const __half h0 = __float2half_rn(h[2 * i]), h1 = __float2half_rn(h[2 * i + 1]);
-    const __half l0 = __float2half_rn(h[2 * i] - __half2float(h0)), l1 = __float2half_rn(h[2 * i + 1] - __half2float(h1));
-    hi[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-    lo[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    const __half2 h2 = __floats2half2_rn(h[2 * i], h[2 * i + 1]);
+    const float2 back = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn(h[2 * i] - back.x, h[2 * i + 1] - back.y);
+    hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
+    lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
   }
   const int unit = (kc * ROWS + row) * 16;
   *reinterpret_cast<uint4*>(a_hi + unit) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   *reinterpret_cast<uint4*>(a_lo + unit) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
-// LayerNorm (eps 1e-5, biased variance) of the 128 ELU outputs held by this thread, then either the next
-// layer's A operand (fp16 hi/lo parts) or the scalar output head
-__device__ __forceinline__ void normalise(float (&e)[W], float sum, const float* __restrict__ gamma,
-                                          const float* __restrict__ beta) {
-  const float mean = sum / float(W);
+// sum over the NSPLIT threads that share a row (they sit in different warps): shared-memory exchange
+template <int NSPLIT>
+__device__ __forceinline__ float row_sum(float v, float* red, int part, int row) {
+  if constexpr (NSPLIT == 1) return v;
+  red[part * ROWS + row] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int p = 0; p < NSPLIT; ++p) t += red[p * ROWS + row];
+  return t;
+}
+
+// LayerNorm (eps 1e-5, biased variance, two-pass) of the row whose CW columns [c0, c0 + CW) this thread holds
+template <int NSPLIT>
+__device__ __forceinline__ void normalise(float (&e)[W / NSPLIT], float sum, const float* __restrict__ gamma,
+                                          const float* __restrict__ beta, float* red_a, float* red_b, int part, int row) {
+  constexpr int CW = W / NSPLIT;
+  const float mean = row_sum<NSPLIT>(sum, red_a, part, row) / float(W);
   float q = 0.f;
 #pragma unroll
-  for (int c = 0; c < W; ++c) { e[c] -= mean; q += e[c] * e[c]; }
-  const float rs = rsqrtf(q / float(W) + 1e-5f);
+  for (int c = 0; c < CW; ++c) { e[c] -= mean; q += e[c] * e[c]; }
+  const float rs = rsqrtf(row_sum<NSPLIT>(q, red_b, part, row) / float(W) + 1e-5f);
 #pragma unroll
-  for (int c4 = 0; c4 < W / 4; ++c4) {
-    const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * c4), b = *reinterpret_cast<const float4*>(beta + 4 * c4);
+  for (int c4 = 0; c4 < CW / 4; ++c4) {
+    const float4 g = *reinterpret_cast<const float4*>(gamma + part * CW + 4 * c4);
+    const float4 b = *reinterpret_cast<const float4*>(beta + part * CW + 4 * c4);
     e[4 * c4 + 0] = (e[4 * c4 + 0] * rs) * g.x + b.x;
     e[4 * c4 + 1] = (e[4 * c4 + 1] * rs) * g.y + b.y;
     e[4 * c4 + 2] = (e[4 * c4 + 2] * rs) * g.z + b.z;
@@ -145,8 +164,14 @@ __device__ __forceinline__ void normalise(float (&e)[W], float sum, const float*
   }
 }
 
-__global__ void __launch_bounds__(ROWS, 1)
+// NSPLIT threads per row: thread tid owns row tid % 128 (= its TMEM lane; warps w, w+4, ... share a lane quadrant)
+// and the CW = 128 / NSPLIT columns [part * CW, (part + 1) * CW), part = tid / 128.  More threads per row = more
+// warps per SM sub-partition to interleave in the (issue-bound) epilogue.
+template <int NSPLIT>
+__global__ void __launch_bounds__(ROWS * NSPLIT, 1)
 mlp_rows_tc_kernel(int64_t M, const float* __restrict__ x, float* __restrict__ out, const __grid_constant__ Params P) {
+  constexpr int CW = W / NSPLIT, NT = ROWS * NSPLIT;
+  static_assert(CW % 32 == 0, "tcgen05.ld moves 32 columns at a time");
   extern __shared__ __align__(1024) unsigned char smem[];
   const int n_hh = P.n_hidden - 1;
   unsigned char* b_parts = smem;                                     // [n_hh][hi, lo][PART_BYTES]
@@ -155,24 +180,28 @@ mlp_rows_tc_kernel(int64_t M, const float* __restrict__ x, float* __restrict__ o
   float* w_in = reinterpret_cast<float*>(a_lo + PART_BYTES);         // [in_dim][W]
   float* vec = w_in + P.in_dim * W;                                  // per hidden layer: bias, gamma, beta; then w_out, b_out
   float* w_out = vec + 3 * P.n_hidden * W;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(w_out + W + 4);
+  float* red_a = w_out + W + 4;                                      // [NSPLIT][ROWS] exchange buffers
+  float* red_b = red_a + NSPLIT * ROWS;
+  float* red_c = red_b + NSPLIT * ROWS;                              // (three buffers: consecutive exchanges never reuse
+  uint64_t* bar = reinterpret_cast<uint64_t*>(red_c + NSPLIT * ROWS);  //  a buffer without a barrier in between)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int trow = tid % ROWS, part = tid / ROWS;
 
   // ---- one-time setup: parameters -> shared memory (weights split into fp16 hi/lo B operands) -------------
-  for (int i = tid; i < P.in_dim * W; i += ROWS) w_in[(i % P.in_dim) * W + (i / P.in_dim)] = P.w_in[i];
+  for (int i = tid; i < P.in_dim * W; i += NT) w_in[(i % P.in_dim) * W + (i / P.in_dim)] = P.w_in[i];
   for (int l = 0; l < P.n_hidden; ++l)
-    for (int i = tid; i < W; i += ROWS) {
+    for (int i = tid; i < W; i += NT) {
       vec[(3 * l + 0) * W + i] = P.b[l][i];
       vec[(3 * l + 1) * W + i] = P.gamma[l][i];
       vec[(3 * l + 2) * W + i] = P.beta[l][i];
     }
-  for (int i = tid; i < W; i += ROWS) w_out[i] = P.w_out[i];
+  for (int i = tid; i < W; i += NT) w_out[i] = P.w_out[i];
   if (tid == 0) w_out[W] = P.b_out[0];
   for (int l = 0; l < n_hh; ++l) {
     unsigned char* hi = b_parts + (size_t)l * 2 * PART_BYTES;
     unsigned char* lo = hi + PART_BYTES;
-    for (int i = tid; i < W * KCH; i += ROWS) {                      // (n, kc): 8 consecutive k of output row n
+    for (int i = tid; i < W * KCH; i += NT) {                        // (n, kc): 8 consecutive k of output row n
       const int n = i / KCH, kc = i % KCH;
       const float4 v0 = *reinterpret_cast<const float4*>(P.w_hh[l] + (size_t)n * W + kc * 8);
       const float4 v1 = *reinterpret_cast<const float4*>(P.w_hh[l] + (size_t)n * W + kc * 8 + 4);
@@ -194,45 +223,46 @@ mlp_rows_tc_kernel(int64_t M, const float* __restrict__ x, float* __restrict__ o
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);      // this warp's 32 lanes
+  // this warp's 32 lanes (quadrant warp % 4) and this thread's first column
+  const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(part * CW);
   const uint32_t bar_addr = smem_u32(bar);
   const uint32_t a_hi_addr = smem_u32(a_hi), a_lo_addr = smem_u32(a_lo);
   uint32_t phase = 0;
 
   const int64_t n_tiles = (M + ROWS - 1) / ROWS;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t row = tile * ROWS + tid;
+    const int64_t row = tile * ROWS + trow;
     const bool live = row < M;
-    float e[W];
+    float e[CW];
     float sum = 0.f;
-    // ---- layer 1 on the FMA pipe: K = in_dim (runtime), 128 accumulators in registers ------------------------
+    // ---- layer 1 on the FMA pipe: K = in_dim (runtime), CW accumulators in registers ---------------------------
 #pragma unroll
-    for (int c4 = 0; c4 < W / 4; ++c4) {
-      const float4 b4 = *reinterpret_cast<const float4*>(vec + 4 * c4);
+    for (int c4 = 0; c4 < CW / 4; ++c4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(vec + part * CW + 4 * c4);
       e[4 * c4 + 0] = b4.x; e[4 * c4 + 1] = b4.y; e[4 * c4 + 2] = b4.z; e[4 * c4 + 3] = b4.w;
     }
     for (int k = 0; k < P.in_dim; ++k) {
       const float xk = live ? x[row * P.in_dim + k] : 0.f;
-      const float* wk = w_in + k * W;
+      const float* wk = w_in + k * W + part * CW;
 #pragma unroll
-      for (int c4 = 0; c4 < W / 4; ++c4) {
+      for (int c4 = 0; c4 < CW / 4; ++c4) {
         const float4 w = *reinterpret_cast<const float4*>(wk + 4 * c4);
         e[4 * c4 + 0] = fmaf(xk, w.x, e[4 * c4 + 0]); e[4 * c4 + 1] = fmaf(xk, w.y, e[4 * c4 + 1]);
         e[4 * c4 + 2] = fmaf(xk, w.z, e[4 * c4 + 2]); e[4 * c4 + 3] = fmaf(xk, w.w, e[4 * c4 + 3]);
       }
     }
 #pragma unroll
-    for (int c = 0; c < W; ++c) { e[c] = elu1(e[c]); sum += e[c]; }
-    normalise(e, sum, vec + 1 * W, vec + 2 * W);
+    for (int c = 0; c < CW; ++c) { e[c] = elu1(e[c]); sum += e[c]; }
+    normalise<NSPLIT>(e, sum, vec + 1 * W, vec + 2 * W, red_a, red_b, part, trow);
     // ---- hidden-hidden layers on the tensor cores ---------------------------------------------------------------
     for (int l = 0; l < n_hh; ++l) {
 #pragma unroll
-      for (int kc = 0; kc < KCH; ++kc) {
+      for (int kc = 0; kc < CW / 8; ++kc) {
         const float h8[8] = {e[8 * kc], e[8 * kc + 1], e[8 * kc + 2], e[8 * kc + 3], e[8 * kc + 4], e[8 * kc + 5], e[8 * kc + 6], e[8 * kc + 7]};
-        split_store(a_hi, a_lo, kc, tid, h8);
+        split_store(a_hi, a_lo, part * (CW / 8) + kc, trow, h8);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy stores -> async proxy reads
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");    // orders the previous tile's tcgen05.ld before the next MMA
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");    // orders the previous tcgen05.ld before the next MMA
       __syncthreads();
       if (tid == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -254,30 +284,33 @@ mlp_rows_tc_kernel(int64_t M, const float* __restrict__ x, float* __restrict__ o
       mbar_wait(bar_addr, phase);
       phase ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const float* bias = vec + (3 * (l + 1) + 0) * W;
+      const float* bias = vec + (3 * (l + 1) + 0) * W + part * CW;
       sum = 0.f;
 #pragma unroll
-      for (int q = 0; q < W / 32; ++q) {
+      for (int q = 0; q < CW / 32; ++q) {
         float z[32];
         tmem_ld32(tmem_row + q * 32, z);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float v = elu1(z[i] + bias[q * 32 + i]);
-          e[q * 32 + i] = v;
-          sum += v;
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias + q * 32 + 4 * i4);
+          const float v0 = elu1(z[4 * i4 + 0] + b4.x), v1 = elu1(z[4 * i4 + 1] + b4.y);
+          const float v2 = elu1(z[4 * i4 + 2] + b4.z), v3 = elu1(z[4 * i4 + 3] + b4.w);
+          e[q * 32 + 4 * i4 + 0] = v0; e[q * 32 + 4 * i4 + 1] = v1; e[q * 32 + 4 * i4 + 2] = v2; e[q * 32 + 4 * i4 + 3] = v3;
+          sum += (v0 + v1) + (v2 + v3);
         }
       }
-      normalise(e, sum, vec + (3 * (l + 1) + 1) * W, vec + (3 * (l + 1) + 2) * W);
+      normalise<NSPLIT>(e, sum, vec + (3 * (l + 1) + 1) * W, vec + (3 * (l + 1) + 2) * W, red_a, red_b, part, trow);
     }
     // ---- output head (128 -> 1) -------------------------------------------------------------------------------
-    float o = w_out[W];
+    float o = 0.f;
 #pragma unroll
-    for (int c4 = 0; c4 < W / 4; ++c4) {
-      const float4 w = *reinterpret_cast<const float4*>(w_out + 4 * c4);
+    for (int c4 = 0; c4 < CW / 4; ++c4) {
+      const float4 w = *reinterpret_cast<const float4*>(w_out + part * CW + 4 * c4);
       o = fmaf(e[4 * c4 + 0], w.x, o); o = fmaf(e[4 * c4 + 1], w.y, o);
       o = fmaf(e[4 * c4 + 2], w.z, o); o = fmaf(e[4 * c4 + 3], w.w, o);
     }
-    if (live) out[row] = o;
+    o = row_sum<NSPLIT>(o, red_c, part, trow) + w_out[W];
+    if (live && part == 0) out[row] = o;
   }
   // ---- teardown ---------------------------------------------------------------------------------------------------
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -285,6 +318,32 @@ mlp_rows_tc_kernel(int64_t M, const float* __restrict__ x, float* __restrict__ o
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
+}
+
+template <int NSPLIT>
+static int launch_tc(int64_t M, const sgbpo_mlp* net, const Params& p, const void* x, void* out, cudaStream_t st) {
+  const size_t smem = (size_t)(net->n_hidden - 1) * 2 * PART_BYTES + 2 * PART_BYTES +
+                      sizeof(float) * ((size_t)net->in_dim * W + 3 * (size_t)net->n_hidden * W + W + 4 + 3 * NSPLIT * ROWS) + 16 + 1024;
+  if (smem > 227 * 1024) return SGBPO_E_UNSUPPORTED;
+  auto kern = mlp_rows_tc_kernel<NSPLIT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "cudaFuncSetAttribute(mlp_rows_tc): %s", cudaGetErrorString(e));
+    return SGBPO_E_CUDA;
+  }
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t tiles = (M + ROWS - 1) / ROWS;
+  // persistent CTAs, tiles dealt round-robin; an even split (e.g. 2048 tiles -> 128 CTAs x 16) beats 148 CTAs with a ragged tail
+  int64_t waves = (tiles + sms - 1) / sms;
+  const int grid = (int)((tiles + waves - 1) / waves);
+  kern<<<grid, ROWS * NSPLIT, smem, st>>>(M, (const float*)x, (float*)out, p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "mlp_rows_tc_kernel: %s", cudaGetErrorString(e));
+    return SGBPO_E_CUDA;
+  }
+  return SGBPO_OK;
 }
 
 }  // namespace tc
@@ -306,25 +365,11 @@ int launch_rows_tc(int64_t M, const sgbpo_mlp* net, const void* x, void* out, cu
     p.gamma[l] = l < net->n_hidden ? (const float*)net->ln_weight[l] : nullptr;
     p.beta[l] = l < net->n_hidden ? (const float*)net->ln_bias[l] : nullptr;
   }
-  const size_t smem = (size_t)(net->n_hidden - 1) * 2 * PART_BYTES + 2 * PART_BYTES +
-                      sizeof(float) * ((size_t)net->in_dim * W + 3 * (size_t)net->n_hidden * W + W + 4) + 16 + 1024;
-  if (smem > 227 * 1024) return SGBPO_E_UNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(mlp_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) {
-    snprintf(g_err, sizeof(g_err), "cudaFuncSetAttribute(mlp_rows_tc): %s", cudaGetErrorString(e));
-    return SGBPO_E_CUDA;
-  }
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int64_t tiles = (M + ROWS - 1) / ROWS;
-  const int grid = (int)(tiles < sms ? tiles : sms);
-  mlp_rows_tc_kernel<<<grid, ROWS, smem, st>>>(M, (const float*)x, (float*)out, p);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) {
-    snprintf(g_err, sizeof(g_err), "mlp_rows_tc_kernel: %s", cudaGetErrorString(e));
-    return SGBPO_E_CUDA;
-  }
-  return SGBPO_OK;
+  const char* v = getenv("SGBPO_ROWS_TC_SPLIT");
+  const int split = v ? atoi(v) : 4;
+  if (split == 1) return launch_tc<1>(M, net, p, x, out, st);
+  if (split == 2) return launch_tc<2>(M, net, p, x, out, st);
+  return launch_tc<4>(M, net, p, x, out, st);
 }
 
 }  // namespace sgbpo
