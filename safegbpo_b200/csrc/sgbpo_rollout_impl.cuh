@@ -278,7 +278,11 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
                    const __grid_constant__ MlpParams<T> P, const __grid_constant__ SafeConsts<T> k) {
   using TASK = Task<ENV>;
   constexpr int NS = TASK::NS, NA = TASK::NA, NO = TASK::NO, NAUX = TASK::NAUX, CPL = W / 32, KD = NS + NA;
-  using D = Dual<T, KD>;
+  // The step Jacobian is forward-mode: KD = n + m seed directions.  They are spread over the warp instead of
+  // being carried by one lane: lane = r + R * g evaluates the step of environment r with the DPL directions
+  // [g * DPL, (g + 1) * DPL) seeded, so the serial dual-number chain is (1 + DPL) wide instead of (1 + KD).
+  constexpr int GROUPS = 32 / R, DPL = (KD + GROUPS - 1) / GROUPS, GUSED = (KD + DPL - 1) / DPL;
+  using D = Dual<T, DPL>;
   extern __shared__ __align__(32) unsigned char smem_raw[];
   T* smem = reinterpret_cast<T*>(smem_raw);
   NetSmem<T, W> net;                       // same carve in every thread: pointers stay in registers
@@ -294,15 +298,17 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
   T* g2T = obsT + NO * R;
   const int64_t N = A.N;
   const int64_t env0 = ((int64_t)blockIdx.x * nwarps + warp) * R;      // first env of this warp
-  const int64_t env = env0 + lane;
+  const int row_of_lane = lane % R, group = lane / R;                   // environment and direction group of this lane
+  const int64_t env = env0 + row_of_lane;
   const bool owner = lane < R;
-  const bool valid = owner && env < N;
+  const bool stepper = group < GUSED;                                   // lanes that evaluate a slice of the step Jacobian
+  const bool valid = env < N;
 
   T sigma[NA];
 #pragma unroll
   for (int q = 0; q < NA; ++q) sigma[q] = sg_exp(P.log_std[q]);
   const T* Whid = net.w_hid;                 // single hidden-hidden layer (n_hidden == 2)
-  // carried cotangents (owner lanes)
+  // carried cotangents of this lane's environment (replicated over its direction groups)
   T gs[NS], gobs[NO];
 #pragma unroll
   for (int i = 0; i < NS; ++i) gs[i] = T(0);
@@ -323,14 +329,14 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
   for (int q = 0; q < NA; ++q) a_bout[q] = a_lstd[q] = T(0);
 
   for (int t = A.H - 1; t >= 0; --t) {
-    // ---- loads (owner lanes) ------------------------------------------------------------------------
+    // ---- loads (every lane of a direction group reads its environment's step inputs) ---------------------
     T sv[NS], epsv[NA], wv[NS], dv[NA * 2 * NA], rs[NS], aux[NAUX > 0 ? NAUX : 1];
     const int ridx = A.reset_idx ? A.reset_idx[t] : -1;
 #pragma unroll
     for (int i = 0; i < NS; ++i) { sv[i] = T(0); wv[i] = T(0); rs[i] = T(0); }
 #pragma unroll
     for (int q = 0; q < NA; ++q) epsv[q] = T(0);
-    if (valid) {
+    if (valid && stepper) {
 #pragma unroll
       for (int i = 0; i < NS; ++i) sv[i] = A.states[((int64_t)t * N + env) * NS + i];
 #pragma unroll
@@ -375,14 +381,25 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
     T act[NA];
 #pragma unroll
     for (int q = 0; q < NA; ++q) act[q] = T(0);
-    if (owner) {
+    T part[DPL];           // this lane's slice of J^T cotangent: directions group * DPL + j
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) part[j] = T(0);
+    if (stepper) {
 #pragma unroll
       for (int q = 0; q < NA; ++q) act[q] = valid ? A.actions[((int64_t)t * N + env) * NA + q] : T(0);   // a_t = tanh(mu + sigma eps)
       D sd[NS], ad[NA], sn[NS], ae[NA], ob[NO], rew;
 #pragma unroll
-      for (int i = 0; i < NS; ++i) sd[i] = D::seed(sv[i], i);
+      for (int i = 0; i < NS; ++i) {
+        sd[i] = D::lift(sv[i]);
 #pragma unroll
-      for (int q = 0; q < NA; ++q) ad[q] = D::seed(act[q], NS + q);
+        for (int j = 0; j < DPL; ++j) sd[i].d[j] = (group * DPL + j == i) ? T(1) : T(0);
+      }
+#pragma unroll
+      for (int q = 0; q < NA; ++q) {
+        ad[q] = D::lift(act[q]);
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) ad[q].d[j] = (group * DPL + j == NS + q) ? T(1) : T(0);
+      }
       int fl;
       const StepShared<T>* sh = A.shared ? A.shared + t : nullptr;
       StepShared<T> empty;
@@ -398,20 +415,28 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
         for (int i = 0; i < NO; ++i) go[i] += G.gobs_term[((int64_t)kt * N + env) * NO + i];
       }
       const T gr = G.grw[t];
+#pragma unroll
+      for (int j = 0; j < DPL; ++j) {
+        T v = gr * rew.d[j];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) v += gs[i] * sn[i].d[j];
+#pragma unroll
+        for (int i = 0; i < NO; ++i) v += go[i] * ob[i].d[j];
+        part[j] = valid ? v : T(0);
+      }
+    }
+    // gather the KD slices: direction d lives in slot d % DPL of lane row + R * (d / DPL); every lane of the
+    // environment ends up with the complete vector, so the carried cotangents stay replicated
+    {
       T acc[KD];
 #pragma unroll
-      for (int d = 0; d < KD; ++d) {
-        T v = gr * rew.d[d];
-#pragma unroll
-        for (int i = 0; i < NS; ++i) v += gs[i] * sn[i].d[d];
-#pragma unroll
-        for (int i = 0; i < NO; ++i) v += go[i] * ob[i].d[d];
-        acc[d] = valid ? v : T(0);
-      }
+      for (int d = 0; d < KD; ++d) acc[d] = __shfl_sync(0xffffffffu, part[d % DPL], row_of_lane + R * (d / DPL));
 #pragma unroll
       for (int i = 0; i < NS; ++i) gs[i] = acc[i];
+      if (owner) {
 #pragma unroll
-      for (int q = 0; q < NA; ++q) ga_pre[q] = acc[NS + q] * (T(1) - act[q] * act[q]);
+        for (int q = 0; q < NA; ++q) ga_pre[q] = acc[NS + q] * (T(1) - act[q] * act[q]);
+      }
     }
     // broadcast d mu to the whole warp: dmu[r][q] from lane r
     T dmu[R][NA];
@@ -547,13 +572,11 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
       warp_sum_rows<T, R>(p);
       T mine = T(0);
 #pragma unroll
-      for (int r = 0; r < R; ++r) mine = (lane == r) ? p[r] : mine;
+      for (int r = 0; r < R; ++r) mine = (row_of_lane == r) ? p[r] : mine;
       gobs_new[i] = mine;
     }
-    if (owner) {
 #pragma unroll
-      for (int i = 0; i < NO; ++i) gobs[i] = valid ? gobs_new[i] : T(0);
-    }
+    for (int i = 0; i < NO; ++i) gobs[i] = valid ? gobs_new[i] : T(0);
     __syncwarp();
   }
   // ---- flush the per-lane parameter gradients ----------------------------------------------------------------

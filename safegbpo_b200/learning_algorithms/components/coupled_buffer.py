@@ -41,8 +41,8 @@ class CoupledBuffer:
         return [getattr(self, n) for n in names if hasattr(self, n)]
 
     def reset(self, reset_observation: Optional[Tensor] = None, reset_value: Optional[Tensor] = None) -> None:
-        if reset_observation is None and self.fast_reset is not None and self.fast_reset():
-            return      # the fused engine owns the storage: last row -> row 0 in place, nothing re-allocated
+        if self.fast_reset is not None and self.fast_reset(reset_observation, reset_value):
+            return      # the fused engine owns the storage: row 0 is set in place, nothing re-allocated
         if reset_observation is None:
             reset_observation = self.observations[self.t].detach()
             if self.store_values:

@@ -19,4 +19,33 @@ class ValueFunction(nn.Module):
     def forward(self, x: Tensor, a: Optional[Tensor] = None) -> Tensor:
         if a is not None:
             x = torch.cat([x, a], dim=1)
+        if not torch.is_grad_enabled() and x.is_cuda and x.dim() == 2:
+            out = self._rows_kernel(x)
+            if out is not None:
+                return out
         return self.model(x)
+
+    def _rows_kernel(self, x: Tensor) -> Optional[Tensor]:
+        """Inference (no autograd) on CUDA: one launch of the batched MLP kernel (csrc/sgbpo_mlp_tc.cu on the tensor
+        cores for fp32 width-128 nets, the FMA tiles of csrc/sgbpo_rollout_impl.cuh otherwise) instead of torch's
+        ~3 launches per layer.  Returns None for layouts the kernels do not cover (torch evaluates those)."""
+        import ctypes as C
+        from ... import _lib
+        from ..fused_rollout import PackedMlp, _mlp_layout, mlp_rows_fits
+        pack = self.__dict__.get("_pack")
+        if pack is None:
+            if _mlp_layout(self.model) is None:
+                self.__dict__["_pack"] = False
+                return None
+            pack = PackedMlp(self.model)
+            self.__dict__["_pack"] = pack
+        if pack is False or x.dtype not in (torch.float32, torch.float64) or x.shape[1] != pack.in_dim:
+            return None
+        if next(self.model.parameters()).dtype != x.dtype or not mlp_rows_fits(x.dtype, pack.in_dim, pack.width, pack.n_hidden):
+            return None
+        pack.refresh()
+        x = x.contiguous()
+        out = torch.empty(x.shape[0], 1, dtype=x.dtype, device=x.device)
+        _lib.check(_lib.lib().sgbpo_mlp_rows(_lib.dtype_code(x.dtype), x.shape[0], C.byref(pack.desc), C.c_void_p(x.data_ptr()),
+                                             C.c_void_p(out.data_ptr()), _lib.stream_ptr()), "sgbpo_mlp_rows")
+        return out

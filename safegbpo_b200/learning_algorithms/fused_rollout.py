@@ -450,7 +450,7 @@ class FusedRollout:
         self.last = dict(graph=True, terminal_rows=g["terminal_rows"])
         return float(g["scal_host"][0]) / base.num_envs / H
 
-    def _fast_buffer_reset(self) -> bool:
+    def _fast_buffer_reset(self, reset_observation=None, reset_value=None) -> bool:
         """CoupledBuffer.reset() while the buffer's tensors ARE the static graph buffers: carry the last
         observation / value to row 0 in place (coupled_buffer.py:113-131 does the same on fresh storage; the
         other rows are rewritten by the next collect_trajectories).  Returns False when the buffer was
@@ -460,8 +460,14 @@ class FusedRollout:
             buf.fast_reset = None
             return False
         H = g["H"]
-        g["obs"][0].copy_(g["obs"][H])
-        g["values"][0].copy_(g["values"][H])
+        if reset_observation is None:
+            g["obs"][0].copy_(g["obs"][H])
+            g["values"][0].copy_(g["values"][H])
+        else:
+            if buf.store_values and reset_value is None:
+                return False
+            g["obs"][0].copy_(reset_observation.detach())
+            g["values"][0].copy_(reset_value.detach())
         buf.t = g["t_zero"]
         g["row0_ready"] = True
         return True
