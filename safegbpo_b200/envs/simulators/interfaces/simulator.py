@@ -61,6 +61,19 @@ class Simulator:
     def _after_reset(self):
         """Task-specific part of reset() (e.g. state = rci.sample(), goal = state[:, :2])."""
 
+    # ---- helpers of the fused engine: reset states are drawn ahead of time (batched RNG mode) ---------------
+    _RESET_ATTRS = ("state", "steps", "_reset_pending", "scheduled_reset", "goal")
+
+    def _reset_snapshot(self) -> dict:
+        return {k: getattr(self, k) for k in self._RESET_ATTRS if hasattr(self, k)}
+
+    def _reset_restore(self, snap: dict):
+        for k, v in snap.items():
+            setattr(self, k, v)
+
+    def _adopt_reset(self, state: Tensor):
+        """Side effects reset() has besides `state` for a reset that produced `state` (e.g. goal = position)."""
+
     # ---- reference API --------------------------------------------------------------------------------
     def reset(self, seed: Optional[int] = None) -> tuple[Tensor, dict[str, Any]]:
         if seed is not None:

@@ -200,6 +200,10 @@ class FusedRollout:
         terminal_rows[H] = True
         return reset_at, terminal_rows, pre_steps, post_steps, pending, steps
 
+    def _max_resets(self, H: int) -> int:
+        """Upper bound on reset-all events inside one horizon (a reset follows every num_steps steps)."""
+        return H // max(1, int(self.base.num_steps)) + 1
+
     def _draw_inputs(self, H: int):
         """Random inputs in the reference's order or, with rng_mode="batched", in three
         batched draws (same distributions, different stream order)."""
@@ -222,9 +226,16 @@ class FusedRollout:
             if want_dirs:
                 d = rng.rand(H, N, m, 2 * m).to(dt) * 2 - 1
                 dirs_t = d / torch.linalg.vector_norm(d, dim=2, keepdim=True)
-            for t in reset_at:
+            # the batched mode draws a FIXED number of reset states per episode (used or not), so the episode is the
+            # same sequence of draws whether it runs eagerly or as a replayed CUDA graph
+            snap = base._reset_snapshot()
+            for r in range(self._max_resets(H)):
                 base.reset()
-                resets.append(base.state.detach().to(dt))
+                if r < len(reset_at):
+                    resets.append(base.state.detach().to(dt))
+            base._reset_restore(snap)
+            if resets:
+                base._adopt_reset(resets[-1])
         else:
             eps, noise, dirs = [], [], []
             for t in range(H):
@@ -264,7 +275,9 @@ class FusedRollout:
     # ======================================================================================================
     def _graphable(self, reset_at) -> bool:
         base = self.base
-        return (self.use_graphs and not self.profile and rng._source is None and not reset_at
+        resets_ok = not reset_at or (self.rng_mode == "batched" and len(reset_at) <= self._max_resets(self.algo.len_trajectories)
+                                     and self._max_resets(self.algo.len_trajectories) <= 4)
+        return (self.use_graphs and not self.profile and rng._source is None and resets_ok
                 and base._shared() is None and self._episodes >= self.graph_warmup
                 and getattr(self.algo.policy_optim, "defaults", {}).get("capturable", False))
 
@@ -284,18 +297,21 @@ class FusedRollout:
                  fwd_graph=None, bwd_graph=None,
                  scal=z(2, dtype=torch.float64), scal_host=torch.zeros(2, dtype=torch.float64, device="cpu").pin_memory(),
                  side=torch.cuda.Stream(), ev_fwd=torch.cuda.Event(), ev_side=torch.cuda.Event())
-        terminal_rows = [False] * (H + 2)
-        terminal_rows[H] = True
-        disc, norm = self._weights(terminal_rows, H, N)
-        g["terminal_rows"], g["disc"], g["norm"] = terminal_rows, disc, norm
-        g["term"][H] = True
-        g["disc_t"] = torch.tensor(disc, dtype=dt, device=dev)
-        g["term_mask"] = torch.tensor(terminal_rows, dtype=torch.bool, device=dev)
-        g["grw"] = torch.tensor([0.0 if terminal_rows[t] else -disc[t] / norm for t in range(H)], dtype=dt, device=dev)
-        tor = [-1] * (H + 2)
-        tor[H] = 0
-        g["term_of_row"] = torch.tensor(tor, dtype=torch.int32, device=dev)
-        g["gobs_term"] = z(1, N, o)
+        # per-episode schedule (reset-all events of Q6, terminal rows, discounts): two small pinned host blocks
+        # copied into static device tensors before every replay, so episodes WITH resets replay the same graphs
+        RM = self._max_resets(H)
+        KM = RM + 1
+        g["RM"], g["KM"] = RM, KM
+        g["sched_i_host"] = torch.zeros(2 * H + (H + 2) + (H + 2) + KM, dtype=torch.int32, device="cpu").pin_memory()
+        g["sched_f_host"] = torch.zeros((H + 2) + H + 1 + KM, dtype=dt, device="cpu").pin_memory()
+        g["sched_i"] = z(g["sched_i_host"].numel(), dtype=torch.int32)
+        g["sched_f"] = z(g["sched_f_host"].numel())
+        si, sf = g["sched_i"], g["sched_f"]
+        g["reset_idx"], g["aux_src"] = si[0:H], si[H:2 * H]
+        g["term_of_row"], g["term_int"], g["term_rows"] = si[2 * H:3 * H + 2], si[3 * H + 2:4 * H + 4], si[4 * H + 4:]
+        g["disc_t"], g["grw"], g["norm_t"], g["term_w"] = sf[0:H + 2], sf[H + 2:2 * H + 2], sf[2 * H + 2:2 * H + 3], sf[2 * H + 3:]
+        g["reset_states"] = z(RM, N, n)
+        g["gobs_term"] = z(KM, N, o)
         sizes = [o * W, W * m, 2 * W, 2 * W, 2 * W, m, m]
         g["flat"] = z(sum(sizes))
         g["parts"] = torch.split(g["flat"], sizes)
@@ -308,6 +324,7 @@ class FusedRollout:
         r.eps, r.noise, r.dirs, r.aux0 = p(g["eps"]), p(g["noise"]), p(g["dirs"]), p(g["aux0"])
         r.states, r.obs, r.actions, r.exec_actions = p(g["states"]), p(g["obs"]), p(g["actions"]), p(g["exec_actions"])
         r.rewards, r.flags = p(g["rewards"]), p(g["flags"])
+        r.reset_states, r.reset_idx, r.aux_src = p(g["reset_states"]), p(g["reset_idx"]), p(g["aux_src"])
         r.stash_h1, r.stash_e1, r.stash_e2, r.stash_stats = p(g["h1"]), p(g["e1"]), p(g["e2"]), p(g["stats"])
         g["r"] = r
         gr = RolloutGrads()
@@ -349,6 +366,13 @@ class FusedRollout:
         torch.addcmul(g["ctr"] - g["half"], g["u"], 2.0 * g["half"], out=g["noise"])
         if g["dirs"] is not None:
             g["dirs"].div_(torch.linalg.vector_norm(g["dirs"], dim=2, keepdim=True))
+        if self.rng_mode == "batched":          # fixed number of reset-state draws per episode (see _draw_inputs)
+            snap = base._reset_snapshot()
+            for r in range(g["RM"]):
+                base.reset()
+                g["reset_states"][r].copy_(base.state)
+            base._reset_restore(snap)
+        g["term"].copy_((g["term_int"] != 0).unsqueeze(1).expand(-1, N))
         check(lib.sgbpo_rollout_fwd(base.env_id, dtype_code(dt), C.byref(self._consts()), C.byref(self.policy_pack.desc),
                                     C.byref(g["r"]), stream_ptr()), "sgbpo_rollout_fwd")
         if self.vf_native:
@@ -370,11 +394,14 @@ class FusedRollout:
         N = base.num_envs
         dt = base.state.dtype
         W = self.policy_pack.width
-        picked = torch.where(g["term_mask"].unsqueeze(1), g["values"], g["rewards"])
-        g["loss"].copy_(-(g["disc_t"].unsqueeze(1) * picked).sum() / g["norm"])
-        x = g["obs"][H].detach().clone().requires_grad_(True)
-        v = algo.target_value_function(x).sum() * (-g["disc"][H] / g["norm"])
-        g["gobs_term"][0].copy_(torch.autograd.grad(v, x)[0])
+        o = base.obs_dim
+        term_mask = g["term_int"] != 0
+        picked = torch.where(term_mask.unsqueeze(1), g["values"], g["rewards"])
+        g["loss"].copy_(-(g["disc_t"].unsqueeze(1) * picked).sum() / g["norm_t"][0])
+        # critic input-gradient on the (at most KM) terminal rows; unused slots carry weight 0
+        x = g["obs"].index_select(0, g["term_rows"]).detach().clone().requires_grad_(True)
+        v = (algo.target_value_function(x.view(-1, o)).view(g["KM"], N) * g["term_w"].unsqueeze(1)).sum()
+        g["gobs_term"].copy_(torch.autograd.grad(v, x)[0])
         g["flat"].zero_()
         check(_lib.lib().sgbpo_rollout_bwd(base.env_id, dtype_code(dt), C.byref(self._consts()),
                                            C.byref(self.policy_pack.desc), C.byref(g["r"]), C.byref(g["gr"]), stream_ptr()),
@@ -394,9 +421,37 @@ class FusedRollout:
             body(g)
         return graph
 
-    def _collect_graph(self, H: int, steps_end: int, pending_end: bool) -> float:
+    def _fill_schedule(self, g, H: int, reset_at, terminal_rows):
+        """Host side of the per-episode schedule: reset / aux indices, terminal rows, discounts (shac.py:131-139)."""
+        N = self.base.num_envs
+        disc, norm = self._weights(terminal_rows, H, N)
+        reset_idx, aux_src, cur = [-1] * H, [-1] * H, -1
+        for t in range(H):
+            if t in reset_at:
+                cur = reset_at.index(t)
+                reset_idx[t] = cur
+            aux_src[t] = cur
+        rows = [j for j in range(1, H + 1) if terminal_rows[j]]
+        term_of_row = [-1] * (H + 2)
+        for kk, j in enumerate(rows):
+            term_of_row[j] = kk
+        KM = g["KM"]
+        term_rows = rows + [H] * (KM - len(rows))
+        term_w = [-disc[j] / norm for j in rows] + [0.0] * (KM - len(rows))
+        grw = [0.0 if terminal_rows[t] else -disc[t] / norm for t in range(H)]
+        g["sched_i_host"].copy_(torch.tensor(reset_idx + aux_src + term_of_row + [int(f) for f in terminal_rows] + term_rows,
+                                             dtype=torch.int32, device="cpu"))
+        g["sched_f_host"].copy_(torch.tensor(disc + grw + [float(norm)] + term_w, dtype=g["sched_f_host"].dtype, device="cpu"))
+        g["sched_i"].copy_(g["sched_i_host"], non_blocking=True)
+        g["sched_f"].copy_(g["sched_f_host"], non_blocking=True)
+
+    def _collect_graph(self, H: int, steps_end: int, pending_end: bool, reset_at, terminal_rows) -> float:
         base, algo = self.base, self.algo
         g = self._g if self._g is not None and self._g["H"] == H else self._alloc_static(H)
+        key = (tuple(reset_at), tuple(terminal_rows))
+        if g.get("sched_key") != key:            # most episodes repeat the previous schedule: nothing to upload
+            self._fill_schedule(g, H, reset_at, terminal_rows)
+            g["sched_key"] = key
         buf = algo.buffer
         base.cut_computation_graph()
         g["s_start"].copy_(base.state)
@@ -434,6 +489,11 @@ class FusedRollout:
         buf.fast_reset = self._fast_buffer_reset
         base.state = g["states"][H]
         base.steps, base._reset_pending = steps_end, pending_end
+        if reset_at:
+            base._adopt_reset(g["reset_states"][len(reset_at) - 1].clone())
+        if g.get("sr") is None:
+            g["sr"] = (torch.zeros_like(base.scheduled_reset), torch.ones_like(base.scheduled_reset))
+        base.scheduled_reset = g["sr"][1 if pending_end else 0]
         base.last_flags, base.last_exec_action = g["flags"][H - 1], g["exec_actions"][H - 1]
         if self.wrapper is not None:
             w = self.wrapper
@@ -447,7 +507,7 @@ class FusedRollout:
                                      "(the reference raises here: safeguard.py:68-75 / solver error)")
             else:
                 w._status = w._status | g["bad"]
-        self.last = dict(graph=True, terminal_rows=g["terminal_rows"])
+        self.last = dict(graph=True, terminal_rows=terminal_rows)
         return float(g["scal_host"][0]) / base.num_envs / H
 
     def _fast_buffer_reset(self, reset_observation=None, reset_value=None) -> bool:
@@ -493,9 +553,9 @@ class FusedRollout:
         n, m, o = base.state_dim, base.action_dim, base.obs_dim
         dt, dev = base.state.dtype, base.state.device
         self._episodes += 1
-        reset_at, _, _, _, pending_end, steps_end = self._schedule(H)
+        reset_at, terminal_rows, _, _, pending_end, steps_end = self._schedule(H)
         if self._graphable(reset_at):
-            return self._collect_graph(H, steps_end, pending_end)
+            return self._collect_graph(H, steps_end, pending_end, reset_at, terminal_rows)
         if self._g is not None:
             self._g["row0_ready"] = False          # this episode runs outside the static buffers
         base.cut_computation_graph()

@@ -207,6 +207,54 @@ def test_mlp_rows_matches_torch(cuda_default):
             np.testing.assert_allclose(out.cpu().numpy(), ref.detach().cpu().numpy(), rtol=tol, atol=tol)
 
 
+@pytest.mark.parametrize("env_name", ["BalanceCartPole", "BalanceQuadrotor"])
+def test_graph_replay_with_resets_inside_the_horizon(cuda_default, env_name):
+    """Episodes whose horizon contains reset-all events (Q6; num_steps = 10 < H = 16, so every episode has one or
+    two) replay the SAME graphs: the schedule (reset / aux indices, terminal rows, discounts) is uploaded per
+    episode and the reset states are drawn inside the graph.  Must equal the eager launches of the batched RNG mode."""
+    torch.set_default_dtype(torch.float32)
+    dev = cuda_default
+    N, H = 96, 16
+    results = []
+    for use_graphs in (False, True):
+        torch.manual_seed(21)
+        sg = "bp" if env_name == "BalanceCartPole" else "none"
+        env, wrapped, algo = build(env_name, sg, {"gate": "reference"}, 64, 10, N, H, "on", dev)
+        algo.rng_order = "batched"
+        half = env.state_set.generator[0].diagonal()
+        env.state = env.state_set.center[0] + (torch.rand(N, env.state_dim) * 2 - 1) * half * 0.3
+        if hasattr(env, "goal"):
+            env.goal = env.state[:, :2].clone()
+        env.steps, env._reset_pending = 0, False
+        o0 = env.observation
+        algo.buffer.reset(o0, algo.target_value_function(o0).squeeze(1))
+        torch.manual_seed(6)
+        losses, rewards, used = [], [], 0
+        for ep in range(6):
+            algo.buffer.reset()
+            algo.policy_optim.zero_grad()
+            rewards.append(algo.collect_trajectories())
+            eng = algo._fused_engine
+            eng.use_graphs, eng.graph_warmup = use_graphs, 1
+            used += bool(eng.last.get("graph"))
+            losses.append(algo.update_policy())
+        results.append((losses, rewards, algo.buffer.observations.tensor.clone(), algo.buffer.terminals.tensor.clone(),
+                        [p.detach().clone() for p in algo.policy.parameters()], env.steps, env._reset_pending, used,
+                        env.goal.clone() if hasattr(env, "goal") else None))
+    (l0, r0, o0_, t0, p0, s0, pend0, u0, goal0), (l1, r1, o1_, t1, p1, s1, pend1, u1, goal1) = results
+    assert u0 == 0 and u1 >= 4              # graph replays really happened, with resets inside
+    assert (s0, pend0) == (s1, pend1) and torch.equal(t0, t1) and t0[1:H].any()
+    np.testing.assert_allclose(l1, l0, rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(r1, r0, rtol=2e-4, atol=1e-6)
+    # (BalanceQuadrotor: the reward's sqrt has an infinite slope at the goal = reset position, so the reference's
+    #  own gradients go non-finite there; both paths must agree on that too -> equal_nan)
+    assert torch.allclose(o0_, o1_, rtol=2e-3, atol=2e-3, equal_nan=True)
+    for a, b in zip(p0, p1):
+        assert torch.allclose(a, b, rtol=2e-3, atol=2e-5, equal_nan=True)
+    if goal0 is not None:
+        assert torch.allclose(goal0, goal1, rtol=1e-5, atol=1e-6)
+
+
 @pytest.mark.parametrize("rng_order", ["batched", "reference"])
 def test_graph_replay_equals_eager_launches(cuda_default, rng_order):
     """Four consecutive training episodes (collect + update_policy incl. Adam): the CUDA-graph replay of the
