@@ -249,8 +249,15 @@ def run_ours(args):
     t_e2e = timed(args.steps, True)
     extended = False
     t_guard = time.time()
-    while len(sampler.samples) < 3 and time.time() - t_guard < 3.0:     # very short runs: keep the same load going
-        episode(False)                                                    # (untimed) until nvidia-smi has sampled it
+    while True:                 # very short runs: keep the same load going (untimed) until nvidia-smi has sampled it
+        need = len(sampler.samples) < 3 and time.time() - t_guard < 3.0
+        if world > 1:           # episodes contain a collective: every rank must run the same number of them
+            flag = torch.tensor([1 if need else 0], device=dev, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            need = bool(int(flag))
+        if not need:
+            break
+        episode(False)
         extended = True
     sampler.stop_flag = True
     total_ms = sum(t_dev)
@@ -381,6 +388,9 @@ def step_kernel_roofline(args, base, env, dev, dtype, n_envs=None):
 
 
 if __name__ == "__main__":
+    if os.environ.get("SGBPO_BENCH_DEBUG"):          # hang diagnosis: dump every thread's python stack after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["SGBPO_BENCH_DEBUG"]), repeat=False, file=sys.stderr)
     a = parse()
     if a.impl == "reference":
         run_reference(a)
