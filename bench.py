@@ -341,10 +341,24 @@ def fused_roofline(args, engine, episode, dtype):
     achieved = per_kernel_bytes[dominant] / (ms[dominant] * 1e-3) / 1e9
     total_alg = b_alg * N * H
     all_ms = sum(v for v in ms.values() if v)
-    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic = None          # DRAM bytes per launch of the dominant kernel from the committed ncu capture of THIS workload
+    try:
+        t = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())
+        w = t["workload"]
+        if (w["env"], w["safeguard"], w["num_envs_per_gpu"], w["horizon"], w["dtype"]) == \
+                (args.env, args.safeguard, args.num_envs, args.horizon, args.dtype):
+            traffic = t["bytes_per_launch"].get(dominant)
+    except Exception:
+        pass
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "kernel": dominant, "kernel_ms": ms, "alg_bytes_per_launch": per_kernel_bytes[dominant],
             "all_kernels_achieved_gbs": total_alg / (all_ms * 1e-3) / 1e9,
-            "note": "MLP FMA-bound by construction: HBM fraction is small; see profiles/ for SM issue utilisation",
+            "note": "the per-environment chain of this workload (4096 envs x 64 sequential steps, policy MLP inside) is issue/"
+                    "latency-bound, not HBM-bound: ncu shows ~0.5 issue slots/cycle/SMSP and <3% DRAM utilisation "
+                    "(profiles/r1_ncu_full_summary.md); traffic exceeds the algorithmic bytes on purpose: the forward "
+                    "kernel stashes the policy activations (1.5 KB/env-step) so the reverse pass does not recompute two "
+                    "of its three GEMMs, and the hidden-layer weight-gradient operands are streamed for one GEMM; the "
+                    "HBM-bound regime of the same per-step kernels is reported under roofline_stress",
             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
             "launches_per_step": engine.launches_per_episode}
 

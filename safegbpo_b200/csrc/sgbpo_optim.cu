@@ -1,6 +1,6 @@
 // Policy update tail of SHAC.update_policy (reference: src/learning_algorithms/shac.py:148-149):
 //   torch.nn.utils.clip_grad_norm_(policy.parameters(), 1.0); policy_optim.step()   (torch.optim.Adam)
-// as ONE launch over all parameter tensors instead of ~30 small foreach kernels: global gradient norm,
+// as TWO small launches over all parameter tensors instead of ~30 foreach kernels: global gradient norm,
 // clip coefficient max_norm / (norm + 1e-6) clamped to 1, then the Adam update (no weight decay, no
 // amsgrad) written into torch's own optimizer state tensors (exp_avg, exp_avg_sq, step), so
 // `policy_optim.state_dict()` stays what torch would have produced.
@@ -12,7 +12,12 @@
 namespace sgbpo {
 extern thread_local char g_err[512];
 
-constexpr int OPT_THREADS = 1024;
+constexpr int OPT_THREADS = 256;
+constexpr int OPT_MAX_CTAS = 296;
+// scratch of the two-kernel update (one optimizer launch in flight at a time per device)
+__device__ unsigned int g_optim_ticket = 0;
+__device__ double g_optim_partial[OPT_MAX_CTAS];
+__device__ double g_optim_scalars[2 + 2 * SGBPO_OPT_MAX_TENSORS];      // [0] clip coefficient, then step_size / sqrt(bc2) per tensor
 
 template <class T> struct OptArgs {
   int n;
@@ -36,40 +41,65 @@ template <class T> __device__ __forceinline__ T block_sum(T v, T* scratch) {
   return t;      // every thread holds the block total
 }
 
-// single CTA: the policies on this path have 1e4..1e6 parameters, far below what would need a grid-wide reduction
+// kernel 1: sum of squares of all gradients (grid-strided partials, summed in a fixed order by whichever CTA
+// finishes last -> deterministic), clip coefficient, Adam bias corrections, step counters += 1
 template <class T, class STEP_T>
 __global__ void __launch_bounds__(OPT_THREADS)
-clip_adam_kernel(const __grid_constant__ OptArgs<T> A, double lr, double beta1, double beta2, double eps, double max_norm,
+grad_norm_kernel(const __grid_constant__ OptArgs<T> A, double lr, double beta1, double beta2, double max_norm,
                  T* __restrict__ total_norm_out) {
   __shared__ T scratch[OPT_THREADS / 32];
-  // pass 1: global L2 norm of all gradients (clip_grad_norm_: norm of the per-tensor norms == sqrt of the total sum of squares)
+  __shared__ bool s_last;
+  const int64_t stride = (int64_t)gridDim.x * OPT_THREADS;
   T acc = T(0);
   for (int i = 0; i < A.n; ++i) {
-    const T* g = A.grad[i];
-    for (int64_t j = threadIdx.x; j < A.numel[i]; j += OPT_THREADS) acc += g[j] * g[j];
+    const T* __restrict__ g = A.grad[i];
+    for (int64_t j = (int64_t)blockIdx.x * OPT_THREADS + threadIdx.x; j < A.numel[i]; j += stride) acc += g[j] * g[j];
   }
-  const T total_norm = sqrt(block_sum<T>(acc, scratch));
-  T coef = T(max_norm) / (total_norm + T(1e-6));
-  coef = coef < T(1) ? coef : T(1);
-  if (threadIdx.x == 0 && total_norm_out) *total_norm_out = total_norm;
-  // pass 2: scale the gradients in place (clip_grad_norm_ does) and apply Adam
-  for (int i = 0; i < A.n; ++i) {
-    STEP_T* sp = reinterpret_cast<STEP_T*>(A.step[i]);
+  const T part = block_sum<T>(acc, scratch);
+  if (threadIdx.x == 0) {
+    g_optim_partial[blockIdx.x] = (double)part;
+    __threadfence();
+    s_last = atomicInc(&g_optim_ticket, gridDim.x - 1) == gridDim.x - 1;      // wraps to 0 for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) {
+    T total = T(0);
+    for (unsigned b = 0; b < gridDim.x; ++b) total += (T)(*(volatile double*)&g_optim_partial[b]);
+    const T total_norm = sqrt(total);
+    T coef = T(max_norm) / (total_norm + T(1e-6));     // clip_grad_norm_: max_norm / (norm + 1e-6), clamped to 1
+    g_optim_scalars[0] = (double)(coef < T(1) ? coef : T(1));
+    if (total_norm_out) *total_norm_out = total_norm;
+  }
+  if (threadIdx.x < A.n) {
+    STEP_T* sp = reinterpret_cast<STEP_T*>(A.step[threadIdx.x]);
     const double step = (double)(*sp) + 1.0;
-    const double bc1 = 1.0 - pow(beta1, step), bc2 = 1.0 - pow(beta2, step);
-    const T step_size = T(lr / bc1), bc2_sqrt = T(sqrt(bc2));
-    T* p = A.param[i]; T* g = A.grad[i]; T* m = A.exp_avg[i]; T* v = A.exp_avg_sq[i];
-    for (int64_t j = threadIdx.x; j < A.numel[i]; j += OPT_THREADS) {
+    *sp = (STEP_T)step;
+    g_optim_scalars[2 + 2 * threadIdx.x] = lr / (1.0 - pow(beta1, step));
+    g_optim_scalars[3 + 2 * threadIdx.x] = sqrt(1.0 - pow(beta2, step));
+  }
+}
+
+// kernel 2: scale the gradients in place (clip_grad_norm_ does) and apply Adam
+template <class T>
+__global__ void __launch_bounds__(OPT_THREADS)
+adam_apply_kernel(const __grid_constant__ OptArgs<T> A, double beta1, double beta2, double eps) {
+  const T coef = (T)g_optim_scalars[0];
+  const T one_m_b1 = T(1.0 - beta1), b2 = T(beta2), one_m_b2 = T(1.0 - beta2), eps_t = T(eps);
+  const int64_t stride = (int64_t)gridDim.x * OPT_THREADS;
+  for (int i = 0; i < A.n; ++i) {
+    const T step_size = (T)g_optim_scalars[2 + 2 * i], bc2_sqrt = (T)g_optim_scalars[3 + 2 * i];
+    T* __restrict__ p = A.param[i]; T* __restrict__ g = A.grad[i]; T* __restrict__ m = A.exp_avg[i]; T* __restrict__ v = A.exp_avg_sq[i];
+    for (int64_t j = (int64_t)blockIdx.x * OPT_THREADS + threadIdx.x; j < A.numel[i]; j += stride) {
       const T gj = g[j] * coef;
+      const T mj = m[j] + (gj - m[j]) * one_m_b1;                    // exp_avg.lerp_(grad, 1 - beta1)
+      const T vj = v[j] * b2 + gj * gj * one_m_b2;                    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
       g[j] = gj;
-      const T mj = m[j] + (gj - m[j]) * T(1.0 - beta1);              // exp_avg.lerp_(grad, 1 - beta1)
-      const T vj = v[j] * T(beta2) + gj * gj * T(1.0 - beta2);        // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
       m[j] = mj;
       v[j] = vj;
-      p[j] = p[j] - step_size * (mj / (sqrt(vj) / bc2_sqrt + T(eps)));
+      p[j] = p[j] - step_size * (mj / (sqrt(vj) / bc2_sqrt + eps_t));
     }
-    __syncthreads();                 // all reads of *sp above happen before thread 0 bumps it
-    if (threadIdx.x == 0) *sp = (STEP_T)step;
   }
 }
 
@@ -82,19 +112,24 @@ template <class T>
 static int launch_clip_adam(const sgbpo_optim* o, int step_dtype, void* total_norm_out, cudaStream_t st) {
   OptArgs<T> a;
   a.n = o->n_tensors;
+  int64_t total = 0;
   for (int i = 0; i < o->n_tensors; ++i) {
     if (!o->param[i] || !o->grad[i] || !o->exp_avg[i] || !o->exp_avg_sq[i] || !o->step[i] || o->numel[i] < 0)
       return opt_fail(SGBPO_E_ARG, "sgbpo_clip_adam: null tensor pointer");
     a.param[i] = (T*)o->param[i]; a.grad[i] = (T*)o->grad[i]; a.exp_avg[i] = (T*)o->exp_avg[i];
     a.exp_avg_sq[i] = (T*)o->exp_avg_sq[i]; a.step[i] = o->step[i]; a.numel[i] = o->numel[i];
+    total += o->numel[i];
   }
+  int64_t grid = (total + 4 * OPT_THREADS - 1) / (4 * OPT_THREADS);
+  grid = grid < 1 ? 1 : (grid > OPT_MAX_CTAS ? OPT_MAX_CTAS : grid);
   if (step_dtype == SGBPO_F32)
-    clip_adam_kernel<T, float><<<1, OPT_THREADS, 0, st>>>(a, o->lr, o->beta1, o->beta2, o->eps, o->max_norm, (T*)total_norm_out);
+    grad_norm_kernel<T, float><<<(int)grid, OPT_THREADS, 0, st>>>(a, o->lr, o->beta1, o->beta2, o->max_norm, (T*)total_norm_out);
   else
-    clip_adam_kernel<T, double><<<1, OPT_THREADS, 0, st>>>(a, o->lr, o->beta1, o->beta2, o->eps, o->max_norm, (T*)total_norm_out);
+    grad_norm_kernel<T, double><<<(int)grid, OPT_THREADS, 0, st>>>(a, o->lr, o->beta1, o->beta2, o->max_norm, (T*)total_norm_out);
+  adam_apply_kernel<T><<<(int)grid, OPT_THREADS, 0, st>>>(a, o->beta1, o->beta2, o->eps);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
-    snprintf(g_err, sizeof(g_err), "clip_adam_kernel: %s", cudaGetErrorString(e));
+    snprintf(g_err, sizeof(g_err), "clip_adam kernels: %s", cudaGetErrorString(e));
     return SGBPO_E_CUDA;
   }
   return SGBPO_OK;

@@ -127,7 +127,7 @@ class FusedRollout:
         self.vf_native = mlp_rows_fits(self.base.state.dtype, vp.in_dim, vp.width, vp.n_hidden)
         self._grad_bufs = None
         self.last = None
-        self.launches_per_episode = 3          # rollout_fwd, mlp_rows, rollout_bwd (our kernels)
+        self.launches_per_episode = 5          # rollout_fwd, mlp_rows(_tc), rollout_bwd, grad_norm, adam_apply (our kernels)
         self.use_graphs = True                 # replay the episode as two CUDA graphs when its schedule allows
         self.graph_warmup = 2                  # eager episodes before capture (optimizer state, cuBLAS handles)
         self._episodes = 0
