@@ -34,7 +34,7 @@ enum { SGBPO_GATE_REFERENCE = 0, SGBPO_GATE_INTENDED = 1, SGBPO_GATE_ALWAYS = 2 
 enum {
   SGBPO_FL_PROJECTABLE = 1, SGBPO_FL_INFEASIBLE = 2, SGBPO_FL_INTERVENED = 4, SGBPO_FL_NONFINITE = 8,
   SGBPO_FL_GUARD_USED = 16, SGBPO_FL_ACTION_IN_SET = 32, SGBPO_FL_NEXT_IN_SET = 64, SGBPO_FL_CLAMPED = 128,
-  SGBPO_FL_COLLIDED = 256
+  SGBPO_FL_COLLIDED = 256, SGBPO_FL_UNREDUCED = 512
 };
 
 /* Constant set data, registered once per wrapper (replaces the numpy constants cvxpy bakes into the
@@ -42,7 +42,7 @@ enum {
 typedef struct sgbpo_consts {
   int32_t sg_kind, gate_mode;
   int32_t rm_linear, rm_zonotopic, rm_passthrough;
-  int32_t action_constrained, state_constrained, state_model; /* 0: G_s invertible, 1: polygon (n = 2) */
+  int32_t action_constrained, state_constrained, state_model; /* 0: G_s invertible, 1: polygon (n = 2), 2: unreduced (gate + raw action only) */
   int32_t disable_clamp, n_obstacles;                        /* 1: raw dynamics (no clamp); obstacles in aux (Navigate*) */
   int32_t act_set_mode, reserved1;                           /* 0: constant safe action set; 1: NavigateSeeker per-step set (P5) */
   double box_min[SGBPO_MAXN], box_max[SGBPO_MAXN];           /* feasible state box */

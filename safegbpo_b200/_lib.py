@@ -77,7 +77,7 @@ ENV_IDS = {"BalancePendulum": 0, "BalanceCartPole": 1, "SwingUpCartPole": 2, "Ba
 SG_NONE, SG_BOUNDARY_PROJECTION, SG_RAY_MASK = 0, 1, 2
 GATE = {"reference": 0, "intended": 1, "always": 2}
 FL_PROJECTABLE, FL_INFEASIBLE, FL_INTERVENED, FL_NONFINITE = 1, 2, 4, 8
-FL_GUARD_USED, FL_ACTION_IN_SET, FL_NEXT_IN_SET, FL_CLAMPED, FL_COLLIDED = 16, 32, 64, 128, 256
+FL_GUARD_USED, FL_ACTION_IN_SET, FL_NEXT_IN_SET, FL_CLAMPED, FL_COLLIDED, FL_UNREDUCED = 16, 32, 64, 128, 256, 512
 
 _VP = C.c_void_p
 _SIGNATURES = {

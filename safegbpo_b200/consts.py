@@ -208,7 +208,11 @@ def build_consts(env_name: str, sg_kind: int, *, gate_mode: int = 0, rm_linear: 
                     for j in range(3):
                         k.q_hp[r][j] = row[j]
         else:
-            raise NotImplementedError(
-                f"{env_name}: safe state set with a {G_s.shape[0]}x{G_s.shape[1]} generator needs the generic "
-                "per-environment LP/QP kernel (not built yet); see DESIGN.md 'out of scope this round'")
+            # G_s neither invertible nor 2-D (BalanceQuadrotor: 6 x 24): the feasible offsets form a 6-D polytope whose
+            # facets cannot be tabulated (beneath-beyond on it does not terminate in reasonable time) and the generic
+            # per-environment LP/QP kernel is not built yet.  Registered as "unreduced": linearisation, gate and
+            # action-set verdict run; under the shipped gate (Q1) the raw action is executed wherever the reachable
+            # box meets the feasible box (100 % of BalanceQuadrotor's RCI states), and any environment that needs
+            # the program's solution is reported (FL_UNREDUCED, NaN action -> ValueError in strict mode).
+            k.state_model = 2
     return k

@@ -27,7 +27,10 @@ constexpr int MAXROWS = 64;    // rows of a per-env action-space polytope
 
 enum SgKind : int { SG_NONE = 0, SG_BOUNDARY_PROJECTION = 1, SG_RAY_MASK = 2 };
 enum GateMode : int { GATE_REFERENCE = 0, GATE_INTENDED = 1, GATE_ALWAYS = 2 };
-enum StateModel : int { SM_INVERTIBLE = 0, SM_POLYGON = 1 };
+// SM_UNREDUCED: safe state set whose generator is neither invertible nor 2-D (BalanceQuadrotor's 6 x 24 RCI set): the
+// linearisation, the gate and the verdict on the action set run, but the program itself has no register-level
+// reduction yet -- wherever the gate asks for the safeguarded action the step reports FL_UNREDUCED (+ NaN action)
+enum StateModel : int { SM_INVERTIBLE = 0, SM_POLYGON = 1, SM_UNREDUCED = 2 };
 
 // status / verdict bits written per environment per step
 enum Flag : int {
@@ -39,7 +42,8 @@ enum Flag : int {
   FL_ACTION_IN_SET = 32,     // verdict: executed action inside the safe action set (where one exists)
   FL_NEXT_IN_SET = 64,       // verdict: linearised next-state zonotope inside the safe state set
   FL_CLAMPED = 128,          // execute_action clamped the state to the feasible box
-  FL_COLLIDED = 256          // Navigate*: the free step entered an obstacle (collision operator applied)
+  FL_COLLIDED = 256,         // Navigate*: the free step entered an obstacle (collision operator applied)
+  FL_UNREDUCED = 512         // the safeguarded action was needed but this program has no GPU reduction (SM_UNREDUCED)
 };
 
 template <class T> struct SafeConsts {
@@ -221,33 +225,65 @@ SG_HD void for_each_p2_row_m1(const S* c_f, const S (*B)[MAXM], const SafeConsts
 
 template <class TASK, class S, class T>
 SG_HD bool p2_expand_m1(const S* c_f, const S (*B)[MAXM], const SafeConsts<T>& k, S& c_out, S& L_out) {
-  // pass 1: primal rows
-  T ra[MAXROWS], rbeta[MAXROWS], rg[MAXROWS];
-  int n = 0;
+  // pass 1 on primal values: incremental 2-variable LP (Seidel).  Rows 0, 1 bound the problem (L <= 1 - |c|);
+  // every further row that cuts off the current optimum moves it onto that row's boundary, where a 1-D LP over
+  // the earlier rows finds the new optimum.  Rows are re-generated by the emitter (a few FMAs each) instead of
+  // being staged in local memory; the cost is O(n * (1 + #rows that ever cut)), not the O(n^3) of enumerating pairs.
   T cf_p[MAXN];
   T B_p[MAXN][MAXM];
 #pragma unroll
   for (int i = 0; i < TASK::NS; ++i) { cf_p[i] = primal(c_f[i]); B_p[i][0] = primal(B[i][0]); }
-  for_each_p2_row_m1<TASK, T, T>(cf_p, B_p, k, [&](T al, T be, T ga, int) {
-    if (n < MAXROWS) { ra[n] = al; rbeta[n] = be; rg[n] = ga; ++n; }
-  });
-  // vertex enumeration on primal values: maximise L
-  T best_L = T(-1), best_c = T(0);
-  int bj = -1, bk = -1;
-  for (int j = 0; j < n; ++j)
-    for (int q = j + 1; q < n; ++q) {
-      const T det = ra[j] * rbeta[q] - ra[q] * rbeta[j];
-      if (sg_abs(det) < T(1e-12)) continue;
-      const T c = (rg[j] * rbeta[q] - rg[q] * rbeta[j]) / det;
-      const T L = (ra[j] * rg[q] - ra[q] * rg[j]) / det;
-      if (!(L > best_L)) continue;
-      bool ok = true;
-      for (int r = 0; r < n && ok; ++r) {
-        const T lhs = ra[r] * c + rbeta[r] * L;
-        ok = lhs <= rg[r] + T(1e-6) * (T(1) + sg_abs(rg[r]));
-      }
-      if (ok) { best_L = L; best_c = c; bj = j; bk = q; }
+  const T vtol = sizeof(T) == 4 ? T(1e-6) : T(1e-11);
+  T best_c = T(0), best_L = T(1);
+  int bj = 0, bk = 1;
+  bool feasible = true;
+  for (int start = 2; feasible;) {
+    // first row at or after `start` violated by the current optimum
+    int vi = -1;
+    T va = T(0), vb = T(0), vg = T(0);
+    for_each_p2_row_m1<TASK, T, T>(cf_p, B_p, k, [&](T al, T be, T ga, int idx) {
+      if (vi >= 0 || idx < start) return;
+      if (al * best_c + be * best_L > ga + vtol * (T(1) + sg_abs(ga))) { vi = idx; va = al; vb = be; vg = ga; }
+    });
+    if (vi < 0) break;
+    // 1-D LP on the boundary of row vi against rows 0 .. vi-1
+    if (vb > T(0)) {
+      // L = (vg - va c) / vb ; rows r:  (al - be va / vb) c <= ga - be vg / vb
+      T lo = T(-INFINITY), hi = T(INFINITY);
+      int rlo = -1, rhi = -1;
+      for_each_p2_row_m1<TASK, T, T>(cf_p, B_p, k, [&](T al, T be, T ga, int idx) {
+        if (idx >= vi) return;
+        const T coef = al - be * va / vb, rhs = ga - be * vg / vb;
+        if (coef > T(1e-30)) { const T v = rhs / coef; if (v < hi) { hi = v; rhi = idx; } }
+        else if (coef < T(-1e-30)) { const T v = rhs / coef; if (v > lo) { lo = v; rlo = idx; } }
+        else if (rhs < -vtol * (T(1) + sg_abs(ga))) feasible = false;
+      });
+      if (!feasible || lo > hi + vtol * (T(1) + sg_abs(hi))) { feasible = false; break; }
+      // maximise L = (vg - va c) / vb:  slope -va / vb
+      const bool take_lo = va > T(0) || (va == T(0));
+      if (take_lo && rlo >= 0) { best_c = lo; bk = rlo; }
+      else if (rhi >= 0) { best_c = hi; bk = rhi; }
+      else if (rlo >= 0) { best_c = lo; bk = rlo; }
+      else { feasible = false; break; }
+      best_L = (vg - va * best_c) / vb;
+      bj = vi;
+    } else {
+      // vertical boundary c = vg / va: L is limited by the earlier rows with a positive L coefficient
+      if (sg_abs(va) < T(1e-30)) { feasible = false; break; }
+      best_c = vg / va;
+      T lim = T(INFINITY);
+      int rl = -1;
+      for_each_p2_row_m1<TASK, T, T>(cf_p, B_p, k, [&](T al, T be, T ga, int idx) {
+        if (idx >= vi) return;
+        if (be > T(0)) { const T v = (ga - al * best_c) / be; if (v < lim) { lim = v; rl = idx; } }
+        else if (al * best_c > ga + vtol * (T(1) + sg_abs(ga))) feasible = false;
+      });
+      if (!feasible || rl < 0) { feasible = false; break; }
+      best_L = lim; bj = vi; bk = rl;
     }
+    start = vi + 1;
+  }
+  if (!feasible) { bj = -1; }
   if (bj < 0 || best_L < T(0)) { c_out = C<S>(NAN); L_out = C<S>(NAN); return false; }
   // pass 2: S-typed solve on the two active rows
   Lp2Row<S> r0, r1;

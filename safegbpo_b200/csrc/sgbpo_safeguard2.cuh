@@ -241,6 +241,10 @@ template <class TASK, class S, class T>
 SG_HD bool safeguard_m2(const S* a, const S* c_f, const S (*B)[MAXM], const T* dirs, const SafeConsts<T>& k,
                         const ActRows<T>* dyn, S* out) {
   Rows2<T> R;
+  if (k.state_constrained && k.state_model == SM_UNREDUCED) {
+    out[0] = C<S>(NAN); out[1] = C<S>(NAN);
+    return false;
+  }
   if (k.sg_kind == SG_BOUNDARY_PROJECTION) return project_m2<TASK>(a, c_f, B, k, dyn, out, R);
   S center[2], safe_dist, feas_dist;
   bool feasible = true;
@@ -324,6 +328,7 @@ template <class TASK, class T>
 SG_HD bool next_state_in_set(const T* a, const T* c_f, const T (*B)[MAXM], const SafeConsts<T>& k) {
   constexpr int NS = TASK::NS, NA = TASK::NA;
   const T tol = verdict_tol<T>();
+  if (k.state_model == SM_UNREDUCED) return false;      // verdict not available for this model
   if (k.state_model == SM_INVERTIBLE) {
     for (int i = 0; i < NS; ++i) {
       T e = k.cs_hat[i];

@@ -86,6 +86,7 @@ SG_HD void safeguarded_step(const S* s, const S* a, const T* w, const T* aux, co
     if (use_guard) {
       flags |= FL_GUARD_USED;
       if (!feasible) flags |= FL_INFEASIBLE;
+      if (k.state_constrained && k.state_model == SM_UNREDUCED) flags |= FL_UNREDUCED;
       const bool straight_through = (k.sg_kind == SG_RAY_MASK) && k.rm_passthrough;   // Q11
 #pragma unroll
       for (int q = 0; q < NA; ++q) {

@@ -101,6 +101,10 @@ class Safeguard:
         if self.strict:                                # reference: host sync + ValueError every call (Q13)
             if bool(bad.any()):
                 idx = bad.nonzero().flatten()[:8].tolist()
+                if bool(((flags & _lib.FL_UNREDUCED) != 0).any()):
+                    raise NotImplementedError(
+                        f"envs {idx}: the safeguarded action is needed but this safe state set (non-invertible generator "
+                        f"with more than 2 rows) has no GPU reduction yet; see DESIGN.md section 8")
                 raise ValueError(f"Safe action are NaN / program infeasible for envs {idx} "
                                  f"(the reference raises here: safeguard.py:68-75 / solver error)")
         else:

@@ -153,3 +153,55 @@ def test_large_batch_properties():
         assert ((s_next - torch.tensor([10.0, 3.141592653589793, 10.0, 10.0], device=dev, dtype=torch.float64)) <= 1e-12).all()
         inside = feas & (((fl & _lib.FL_INTERVENED) == 0))
         assert torch.equal(a1[inside], a[inside])                                # already-safe actions pass unchanged
+
+
+def test_quadrotor_unreduced_program_follows_the_shipped_gate():
+    """BalanceQuadrotor's safe state set (6 x 24 generator) is registered as SM_UNREDUCED: linearisation, gate and
+    action-set verdict run on the GPU; under the shipped gate (Q1) every RCI state is projectable, so the executed
+    action is the raw action and states / observations / rewards / gradients must equal the oracle's (which solves
+    the lifted QP with HiGHS like the reference and then discards it).  Where the safeguarded action IS needed the
+    step must say so loudly (FL_UNREDUCED, NaN action, NotImplementedError in strict mode)."""
+    dev = torch.device("cuda:0")
+    N = 16
+    case = make_case("BalanceQuadrotor", "boundary_projection", N, seed=5, gate="reference")
+    env = case["env"]
+    env.reset(seed=5)                                    # RCI samples: feasible programs
+    case["s"] = env.state.detach().clone()
+    case["aux"] = env.goal.clone()
+    assert case["consts"].state_model == 2
+    ref = oracle_step(case)
+    # (a few RCI samples sit where the lifted program of the LINEARISED dynamics is infeasible -- the reference would
+    #  raise there although the gate discards the solution; those rows are left out of the comparison)
+    assert bool(ref["projectable"].all()) and int(ref["ok"].sum()) >= N // 2
+    okd, okc = ref["ok"].to(dev), ref["ok"].numpy()
+    s, a, (s_next, a_exec, obs, reward, flags) = run_kernel(case, "BalanceQuadrotor", torch.float64, dev)
+    fl = flags.cpu()
+    assert bool(((fl & _lib.FL_PROJECTABLE) != 0).all()) and not bool(((fl & (_lib.FL_GUARD_USED | _lib.FL_UNREDUCED)) != 0).any())
+    assert bool(((fl & _lib.FL_ACTION_IN_SET) != 0).sum() > 0)
+    cot = {k: v.to(device=dev) for k, v in case["cot"].items()}
+    ((s_next * cot["g_s_next"]).sum(1) + (a_exec * cot["g_a_exec"]).sum(1) + (obs * cot["g_obs"]).sum(1)
+     + reward * cot["g_reward"])[okd].sum().backward()
+    for got, key in ((s_next, "s_next"), (a_exec, "a_exec"), (obs, "obs"), (reward, "reward"), (s.grad, "gs"), (a.grad, "ga")):
+        np.testing.assert_allclose(got.detach().cpu().numpy()[okc], ref[key].numpy()[okc], rtol=1e-9, atol=1e-10, err_msg=key)
+    # far outside the feasible box the gate asks for the safeguarded action: reported, not silently wrong
+    far = case["s"].clone()
+    far[:, 0] = 50.0
+    t = lambda x: x.to(device=dev)
+    out = ops.safeguarded_step(t(far), t(case["a"]), t(case["w"]), ENV_IDS["BalanceQuadrotor"], case["consts"], aux=t(case["aux"]))
+    assert bool(((out[4] & _lib.FL_UNREDUCED) != 0).all()) and bool(out[1].isnan().all())
+    from safegbpo_b200.envs.balance_quadrotor import BalanceQuadrotorEnv
+    from safegbpo_b200.safeguards.boundary_projection import BoundaryProjectionSafeguard
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    torch.set_default_device(dev)
+    try:
+        qenv = BalanceQuadrotorEnv(num_envs=N, num_steps=240)
+        wrapped = BoundaryProjectionSafeguard(qenv)
+        wrapped.reset(seed=1)
+        wrapped.step(torch.zeros(N, 2))                  # RCI states: runs, raw action executed
+        qenv.state = t(far)
+        with pytest.raises(NotImplementedError):
+            wrapped.step(torch.zeros(N, 2))
+    finally:
+        torch.set_default_device("cpu")
+        torch.set_default_dtype(prev)
