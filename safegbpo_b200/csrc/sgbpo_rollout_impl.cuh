@@ -92,12 +92,14 @@ __device__ __forceinline__ void fetch_tile(const T* __restrict__ src, int t, int
 
 // launch bounds per rows-per-warp R: fewer rows -> smaller register tiles -> more resident warps
 template <int R> struct RolloutShape {
-  static constexpr int MAX_WARPS = R == 8 ? 8 : (R == 4 ? 12 : 16);
+  static constexpr int MAX_WARPS = R == 8 ? 8 : (R == 4 ? 12 : 16);      // backward kernel: 255 / 168 / 128 registers per thread
 };
+// forward kernel: <= 80 registers per thread in fp32 (16 warps fit), fp64 tiles need the full register budget
+template <class T, int R> struct FwdShape { static constexpr int MAX_WARPS = sizeof(T) == 8 ? RolloutShape<R>::MAX_WARPS : 16; };
 
 // ---------------------------------------------------------------------------------------------------------
 template <int ENV, class T, int W, int R>
-__global__ void __launch_bounds__(RolloutShape<R>::MAX_WARPS * 32)
+__global__ void __launch_bounds__(FwdShape<T, R>::MAX_WARPS * 32)
 rollout_fwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_constant__ MlpParams<T> P,
                    const __grid_constant__ SafeConsts<T> k) {
   using TASK = Task<ENV>;
@@ -725,7 +727,7 @@ template <int ENV, class T, int W> struct RolloutLaunch {
     using TASK = Task<ENV>;
     if (pol->in_dim != TASK::NO || pol->out_dim != TASK::NA) return fail2(SGBPO_E_ARG, "policy dims do not match the environment");
     if (pol->n_hidden < 1 || pol->n_hidden > MAX_HIDDEN) return fail2(SGBPO_E_UNSUPPORTED, "1..4 hidden layers");
-    const int caps[3] = {RolloutShape<8>::MAX_WARPS, RolloutShape<4>::MAX_WARPS, RolloutShape<2>::MAX_WARPS};
+    const int caps[3] = {FwdShape<T, 8>::MAX_WARPS, FwdShape<T, 4>::MAX_WARPS, FwdShape<T, 2>::MAX_WARPS};
     const Shape sh = pick_shape<T>(r->N, net_bytes<T, W>(pol->in_dim, pol->n_hidden, pol->out_dim), TASK::NO, 2, W, caps);
     if (!sh.R) return fail2(SGBPO_E_UNSUPPORTED, "policy does not fit in shared memory");
     switch (sh.R) {
