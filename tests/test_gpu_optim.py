@@ -43,3 +43,27 @@ def test_clip_adam_matches_torch(dtype, tol, scale):
     finally:
         torch.set_default_device("cpu")
         torch.set_default_dtype(prev)
+
+
+def test_value_function_inference_path_matches_torch():
+    """ValueFunction.forward under no_grad on CUDA goes through the batched MLP kernel (one launch); with autograd
+    enabled it stays the torch module.  Both must agree."""
+    from safegbpo_b200.learning_algorithms.components.value_function import ValueFunction
+    prev = torch.get_default_dtype()
+    torch.set_default_device("cuda:0")
+    try:
+        for dtype, tol in ((torch.float32, 2e-5), (torch.float64, 1e-11)):
+            torch.set_default_dtype(dtype)
+            torch.manual_seed(3)
+            for arch in ([128, 128, 128], [64, 64], [48, 48]):      # tensor-core kernel, FMA tiles, unsupported width (torch)
+                vf = ValueFunction(5, net_arch=arch)
+                x = torch.randn(777, 5) * 2
+                ref = vf(x)
+                assert ref.requires_grad
+                with torch.no_grad():
+                    got = vf(x)
+                assert got.shape == ref.shape and not got.requires_grad
+                np.testing.assert_allclose(got.cpu().numpy(), ref.detach().cpu().numpy(), rtol=tol, atol=tol)
+    finally:
+        torch.set_default_device("cpu")
+        torch.set_default_dtype(prev)
