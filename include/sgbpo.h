@@ -59,6 +59,7 @@ typedef struct sgbpo_consts {
   double k_hp[SGBPO_MAXHP][2];                               /* polygon K: hp . d <= 1 */
   double q_hp[SGBPO_MAXHP][3];                               /* polytope Q: hq . (d, L) <= 1 */
   double c_s[SGBPO_MAXN];
+  double B0hat[SGBPO_MAXN * SGBPO_MAXM];                     /* G_s^-1 B0 (signed) */
 } sgbpo_consts;
 
 /* per-step scalars shared by all environments (household series; household.py:109-113,

@@ -39,6 +39,7 @@ class Consts(C.Structure):
         ("B0hat_abs", C.c_double * (MAXN * MAXM)),
         ("n_k_hp", C.c_int32), ("n_q_hp", C.c_int32),
         ("k_hp", (C.c_double * 2) * MAXHP), ("q_hp", (C.c_double * 3) * MAXHP), ("c_s", C.c_double * MAXN),
+        ("B0hat", C.c_double * (MAXN * MAXM)),
     ]
 
 

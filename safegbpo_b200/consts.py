@@ -188,6 +188,7 @@ def build_consts(env_name: str, sg_kind: int, *, gate_mode: int = 0, rm_linear: 
                     k.Ginv[i * n + j] = Ginv[i, j]
                 for q in range(m):
                     k.B0hat_abs[i * MAXM + q] = B0h[i, q]
+                    k.B0hat[i * MAXM + q] = (Ginv @ B0)[i, q]
         elif n == 2 and m == 1:
             k.state_model = 1
             nz = G_w[:, np.abs(G_w).sum(axis=0) > 0]

@@ -128,6 +128,26 @@ template <class S, int K> struct Dual {
 
 template <class S, int K> SG_HD typename Traits<S>::base primal(const Dual<S, K>& x) { return primal(x.v); }
 
+// same dual structure over double: the iterative program P2 (m = 2) is solved in double whatever the I/O type
+template <class X> struct Widen { using type = double; };
+template <class S, int K> struct Widen<Dual<S, K>> { using type = Dual<typename Widen<S>::type, K>; };
+SG_HD double widen(float x) { return (double)x; }
+SG_HD double widen(double x) { return x; }
+template <class S, int K> SG_HD typename Widen<Dual<S, K>>::type widen(const Dual<S, K>& x) {
+  typename Widen<Dual<S, K>>::type r;
+  r.v = widen(x.v);
+#pragma unroll
+  for (int k = 0; k < K; ++k) r.d[k] = widen(x.d[k]);
+  return r;
+}
+SG_HD void narrow(double x, float& o) { o = (float)x; }
+SG_HD void narrow(double x, double& o) { o = x; }
+template <class SW, class S, int K> SG_HD void narrow(const Dual<SW, K>& x, Dual<S, K>& o) {
+  narrow(x.v, o.v);
+#pragma unroll
+  for (int k = 0; k < K; ++k) narrow(x.d[k], o.d[k]);
+}
+
 template <class S, int K> SG_HD Dual<S, K> chain(const Dual<S, K>& x, const S& fv, const S& dfdx) {
   Dual<S, K> r;
   r.v = fv;

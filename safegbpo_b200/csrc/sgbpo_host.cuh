@@ -19,7 +19,7 @@ template <class T> inline SafeConsts<T> convert_consts(const sgbpo_consts& c) {
     k.cs_hat[i] = T(c.cs_hat[i]); k.rb[i] = T(c.rb[i]); k.c_s[i] = T(c.c_s[i]);
   }
   for (int i = 0; i < MAXN * MAXN; ++i) k.Ginv[i] = T(c.Ginv[i]);
-  for (int i = 0; i < MAXN * MAXM; ++i) k.B0hat_abs[i] = T(c.B0hat_abs[i]);
+  for (int i = 0; i < MAXN * MAXM; ++i) { k.B0hat_abs[i] = T(c.B0hat_abs[i]); k.B0hat[i] = T(c.B0hat[i]); }
   for (int i = 0; i < MAXM; ++i) { k.a_lo[i] = T(c.a_lo[i]); k.a_hi[i] = T(c.a_hi[i]); k.c_a[i] = T(c.c_a[i]); }
   k.n_act_hp = c.n_act_hp; k.n_k_hp = c.n_k_hp; k.n_q_hp = c.n_q_hp;
   for (int r = 0; r < MAXHP; ++r) {

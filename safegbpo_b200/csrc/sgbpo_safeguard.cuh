@@ -69,6 +69,7 @@ template <class T> struct SafeConsts {
   T k_hp[MAXHP][2];
   T q_hp[MAXHP][3];
   T c_s[MAXN];
+  T B0hat[MAXN * MAXM];                // G_s^-1 B0 (signed), for P2 with m = 2
 };
 
 // ---- gate: AxisAlignedBox.intersects(Zonotope(c_f, B I_m))  (box.py:139-154, simulator.py:240-243) --

@@ -236,6 +236,218 @@ template <class S> SG_HD S unit_box_dist_m2(const S* c, const S* d) {   // ray_m
   return best;
 }
 
+// ================================================================================================
+// P2 for m = 2 (ray_mask.py:145-191) with an invertible safe-state generator (ManageHousehold):
+//   max geo_mean(l),  l in R^4_+,  centre c in R^2,  G = D diag(l)  (D: 2 x 4 random unit columns)
+//   rows  alpha_r . c + omega_r . l <= gamma_r,  omega_r >= 0:
+//     box    +-c_k + sum_j |D_kj| l_j <= 1                                    (ray_mask.py:157-158)
+//     state  +-(e_i - b_i . c) + sum_j |(G_s^-1 B0 D)_ij| l_j <= rb_i          (enc(Z(c+, [B0 G, G_w]) in Z(c_s, G_s)))
+// A strictly concave maximisation (sum of logs) over 6 variables and 4 + 2n rows: primal-dual interior point in
+// DOUBLE whatever the I/O type (fixed small dense algebra, 6 x 6 Cholesky in registers / local memory), then one
+// Newton step of the perturbed KKT system with the rows evaluated in the dual-number type: its derivative part is
+// the implicit-function derivative of the optimum w.r.t. (c_f, B), its primal part a last correction.
+// ================================================================================================
+constexpr int P2_NV = 6, P2_NR = 4 + 2 * MAXN;
+
+template <class W> struct P2Rows { W a[P2_NR][2]; double om[P2_NR][4]; W g[P2_NR]; int n; };
+
+template <class TASK, class SW, class S, class T>
+SG_HD void p2_rows_m2(const S* c_f, const S (*B)[MAXM], const T* dirs, const SafeConsts<T>& k, P2Rows<SW>& R) {
+  constexpr int NS = TASK::NS;
+  int r = 0;
+  for (int q = 0; q < 2; ++q)
+    for (int sgn = 0; sgn < 2; ++sgn) {
+      R.a[r][0] = SW(q == 0 ? (sgn ? -1.0 : 1.0) : 0.0);
+      R.a[r][1] = SW(q == 1 ? (sgn ? -1.0 : 1.0) : 0.0);
+      for (int j = 0; j < 4; ++j) R.om[r][j] = fabs((double)dirs[q * 4 + j]);
+      R.g[r] = SW(1.0);
+      ++r;
+    }
+  for (int i = 0; i < NS; ++i) {
+    SW e = SW((double)k.cs_hat[i]), b0 = SW(0.0), b1 = SW(0.0);
+    for (int j = 0; j < NS; ++j) {
+      const double gi = (double)k.Ginv[i * NS + j];
+      e = e - SW(gi) * widen(c_f[j]);
+      b0 = b0 + SW(gi) * widen(B[j][0]);
+      b1 = b1 + SW(gi) * widen(B[j][1]);
+    }
+    double w[4];
+    for (int j = 0; j < 4; ++j)
+      w[j] = fabs((double)k.B0hat[i * MAXM + 0] * (double)dirs[j] + (double)k.B0hat[i * MAXM + 1] * (double)dirs[4 + j]);
+    // (e - b.c) + w.l <= rb   and   -(e - b.c) + w.l <= rb
+    R.a[r][0] = -b0; R.a[r][1] = -b1; R.g[r] = SW((double)k.rb[i]) - e;
+    for (int j = 0; j < 4; ++j) R.om[r][j] = w[j];
+    ++r;
+    R.a[r][0] = b0; R.a[r][1] = b1; R.g[r] = SW((double)k.rb[i]) + e;
+    for (int j = 0; j < 4; ++j) R.om[r][j] = w[j];
+    ++r;
+  }
+  R.n = r;
+}
+
+// Cholesky of a 6 x 6 SPD matrix (lower factor in place).  A pivot that cancelled to (almost) nothing is a direction
+// the active rows leave free (the optimal centre of P2 is not unique there): it is frozen (huge pivot -> zero step)
+// instead of dividing by rounding noise.  Returns false only for NaNs.
+SG_HD bool chol6(double (*K)[P2_NV]) {
+  for (int j = 0; j < P2_NV; ++j) {
+    const double orig = K[j][j];
+    double d = orig;
+    for (int p = 0; p < j; ++p) d -= K[j][p] * K[j][p];
+    if (!(d == d)) return false;
+    // (threshold: rounding noise of the cancellation is ~1e-16 orig; genuine pivots are the log-objective curvature
+    //  1 / l^2 >= 1 against barrier entries ~1e10 at the final mu, i.e. >= ~1e-10 orig)
+    if (!(d > 1e-12 * orig)) d = 1e60;
+    d = sqrt(d);
+    K[j][j] = d;
+    for (int i = j + 1; i < P2_NV; ++i) {
+      double v = K[i][j];
+      for (int p = 0; p < j; ++p) v -= K[i][p] * K[j][p];
+      K[i][j] = v / d;
+    }
+  }
+  return true;
+}
+template <class W> SG_HD void chol6_solve(const double (*L)[P2_NV], W* x) {      // x := K^-1 x
+  for (int i = 0; i < P2_NV; ++i) {
+    W v = x[i];
+    for (int p = 0; p < i; ++p) v = v - W(L[i][p]) * x[p];
+    x[i] = v / W(L[i][i]);
+  }
+  for (int i = P2_NV - 1; i >= 0; --i) {
+    W v = x[i];
+    for (int p = i + 1; p < P2_NV; ++p) v = v - W(L[p][i]) * x[p];
+    x[i] = v / W(L[i][i]);
+  }
+}
+
+template <class TASK, class S, class T>
+SG_HD bool p2_expand_m2(const S* c_f, const S (*B)[MAXM], const T* dirs, const SafeConsts<T>& k, S* c_out, S* len_out) {
+  using SW = typename Widen<S>::type;
+  // ---- primal interior point in double ------------------------------------------------------------------
+  P2Rows<double> R;
+  {
+    T cf_p[MAXN];
+    T B_p[MAXN][MAXM];
+    for (int i = 0; i < TASK::NS; ++i) { cf_p[i] = primal(c_f[i]); B_p[i][0] = primal(B[i][0]); B_p[i][1] = primal(B[i][1]); }
+    p2_rows_m2<TASK, double, T, T>(cf_p, B_p, dirs, k, R);
+  }
+  const int nr = R.n;
+  double x[P2_NV] = {0.0, 0.0, 0.05, 0.05, 0.05, 0.05};
+  double s[P2_NR], lam[P2_NR];
+  for (int r = 0; r < nr; ++r) {
+    double ax = R.a[r][0] * x[0] + R.a[r][1] * x[1];
+    for (int j = 0; j < 4; ++j) ax += R.om[r][j] * x[2 + j];
+    s[r] = R.g[r] - ax;
+    if (s[r] < 0.1) s[r] = 0.1;
+    lam[r] = 1.0 / s[r];
+  }
+  double L[P2_NV][P2_NV];
+  double mu = 1.0;
+  bool ok = false;
+  for (int it = 0; it < 60; ++it) {
+    double rp[P2_NR], rd[P2_NV] = {0.0, 0.0, -1.0 / x[2], -1.0 / x[3], -1.0 / x[4], -1.0 / x[5]};
+    double gap = 0.0, rp_max = 0.0;
+    for (int r = 0; r < nr; ++r) {
+      double ax = R.a[r][0] * x[0] + R.a[r][1] * x[1];
+      for (int j = 0; j < 4; ++j) ax += R.om[r][j] * x[2 + j];
+      rp[r] = ax + s[r] - R.g[r];
+      rp_max = fmax(rp_max, fabs(rp[r]));
+      rd[0] += lam[r] * R.a[r][0]; rd[1] += lam[r] * R.a[r][1];
+      for (int j = 0; j < 4; ++j) rd[2 + j] += lam[r] * R.om[r][j];
+      gap += lam[r] * s[r];
+    }
+    mu = gap / nr;
+    double rd_max = 0.0;
+    for (int i = 0; i < P2_NV; ++i) rd_max = fmax(rd_max, fabs(rd[i]));
+    // converged on the central path at mu ~ 1e-10: the optimum is reached to ~1e-10 and the KKT matrix of the
+    // derivative step below is still well inside double precision (entries ~ 1 / mu)
+    if (rp_max < 1e-9 && rd_max < 1e-6 && mu < 2e-10) { ok = true; break; }
+    const double target = fmax(0.1 * mu, 5e-11);
+    // K = H + A^T diag(lam / s) A ,  rhs = -rd - A^T [(lam rp - (lam s - target)) / s]
+    double rhs[P2_NV];
+    for (int i = 0; i < P2_NV; ++i) { rhs[i] = -rd[i]; for (int j = 0; j < P2_NV; ++j) L[i][j] = 0.0; }
+    for (int j = 0; j < 4; ++j) L[2 + j][2 + j] = 1.0 / (x[2 + j] * x[2 + j]);
+    for (int r = 0; r < nr; ++r) {
+      double row[P2_NV] = {R.a[r][0], R.a[r][1], R.om[r][0], R.om[r][1], R.om[r][2], R.om[r][3]};
+      const double w = lam[r] / s[r];
+      const double t = (lam[r] * rp[r] - (lam[r] * s[r] - target)) / s[r];
+      for (int i = 0; i < P2_NV; ++i) {
+        rhs[i] -= row[i] * t;
+        for (int j = 0; j <= i; ++j) L[i][j] += w * row[i] * row[j];
+      }
+    }
+    if (!chol6(L)) break;
+    chol6_solve<double>(L, rhs);                 // rhs := dx
+    double alpha = 1.0, ds[P2_NR], dl[P2_NR];
+    for (int j = 0; j < 4; ++j)
+      if (rhs[2 + j] < 0.0) alpha = fmin(alpha, -0.995 * x[2 + j] / rhs[2 + j]);
+    for (int r = 0; r < nr; ++r) {
+      double adx = R.a[r][0] * rhs[0] + R.a[r][1] * rhs[1];
+      for (int j = 0; j < 4; ++j) adx += R.om[r][j] * rhs[2 + j];
+      ds[r] = -rp[r] - adx;
+      dl[r] = (-(lam[r] * s[r] - target) - lam[r] * ds[r]) / s[r];
+      if (ds[r] < 0.0) alpha = fmin(alpha, -0.995 * s[r] / ds[r]);
+      if (dl[r] < 0.0) alpha = fmin(alpha, -0.995 * lam[r] / dl[r]);
+    }
+    for (int i = 0; i < P2_NV; ++i) x[i] += alpha * rhs[i];
+    for (int r = 0; r < nr; ++r) { s[r] += alpha * ds[r]; lam[r] += alpha * dl[r]; }
+  }
+  if (!ok) {
+    c_out[0] = C<S>(NAN); c_out[1] = C<S>(NAN);
+    for (int j = 0; j < 4; ++j) len_out[j] = C<S>(NAN);
+    return false;
+  }
+  // ---- one Newton step of the same system with S-typed rows (implicit-function derivative + last correction) ---
+  P2Rows<SW> RS;
+  p2_rows_m2<TASK, SW, S, T>(c_f, B, dirs, k, RS);
+  SW rhs[P2_NV];
+  for (int i = 0; i < P2_NV; ++i) { rhs[i] = SW(0.0); for (int j = 0; j < P2_NV; ++j) L[i][j] = 0.0; }
+  for (int j = 0; j < 4; ++j) { rhs[2 + j] = SW(1.0 / x[2 + j]); L[2 + j][2 + j] = 1.0 / (x[2 + j] * x[2 + j]); }
+  for (int r = 0; r < nr; ++r) {
+    const SW rowS[P2_NV] = {RS.a[r][0], RS.a[r][1], SW(RS.om[r][0]), SW(RS.om[r][1]), SW(RS.om[r][2]), SW(RS.om[r][3])};
+    const double row[P2_NV] = {R.a[r][0], R.a[r][1], R.om[r][0], R.om[r][1], R.om[r][2], R.om[r][3]};
+    SW ax = rowS[0] * SW(x[0]) + rowS[1] * SW(x[1]);
+    for (int j = 0; j < 4; ++j) ax = ax + rowS[2 + j] * SW(x[2 + j]);
+    const SW rp = ax + SW(s[r]) - RS.g[r];
+    const double w = lam[r] / s[r];
+    // complementarity target of row r := its current product lam_r s_r, so that the system being differentiated is
+    // satisfied EXACTLY at the converged point (a residual lam s - mu != 0 would leak into the derivative part)
+    const SW t = (SW(lam[r]) * rp) / SW(s[r]);
+    for (int i = 0; i < P2_NV; ++i) {
+      rhs[i] = rhs[i] - rowS[i] * SW(lam[r]) - rowS[i] * t;     // -(rd + A^T t):  rd = grad g + A^T lam
+      for (int j = 0; j <= i; ++j) L[i][j] += w * row[i] * row[j];
+    }
+  }
+  if (!chol6(L)) { c_out[0] = C<S>(NAN); c_out[1] = C<S>(NAN); for (int j = 0; j < 4; ++j) len_out[j] = C<S>(NAN); return false; }
+  chol6_solve<SW>(L, rhs);
+  for (int q = 0; q < 2; ++q) narrow(SW(x[q]) + rhs[q], c_out[q]);
+  for (int j = 0; j < 4; ++j) narrow(SW(x[2 + j]) + rhs[2 + j], len_out[j]);
+  return true;
+}
+
+// P3 (ray_mask.py:215-240) on the 2-D zonotope Z(c, D diag(l)) along `dir`:  t* = min_e  h(n_e) / |n_e . dir|,
+// n_e = perp(g_e), h(n) = sum_j |n . g_j|
+template <class S, class T>
+SG_HD S ray_dist_zonotope_m2(const S* dir, const T* dirs, const S* len) {
+  S g[4][2];
+  for (int j = 0; j < 4; ++j) { g[j][0] = S(dirs[j]) * len[j]; g[j][1] = S(dirs[4 + j]) * len[j]; }
+  T best = T(INFINITY);
+  int arg = -1;
+  for (int e = 0; e < 4; ++e) {
+    const T nx = -primal(g[e][1]), ny = primal(g[e][0]);
+    const T nd = sg_abs(nx * primal(dir[0]) + ny * primal(dir[1]));
+    if (!(nd > T(1e-30))) continue;
+    T h = T(0);
+    for (int j = 0; j < 4; ++j) h += sg_abs(nx * primal(g[j][0]) + ny * primal(g[j][1]));
+    if (h / nd < best) { best = h / nd; arg = e; }
+  }
+  if (arg < 0) return C<S>(INFINITY);
+  const S nx = -g[arg][1], ny = g[arg][0];
+  S h = C<S>(0.0);
+  for (int j = 0; j < 4; ++j) h = h + sg_abs(nx * g[j][0] + ny * g[j][1]);
+  return h / sg_abs(nx * dir[0] + ny * dir[1]);
+}
+
 // safeguard(a) for m = 2.  `dirs`: the 2 x 4 random unit directions of RM-zonotopic (ray_mask.py:184-185).
 template <class TASK, class S, class T>
 SG_HD bool safeguard_m2(const S* a, const S* c_f, const S (*B)[MAXM], const T* dirs, const SafeConsts<T>& k,
@@ -249,10 +461,18 @@ SG_HD bool safeguard_m2(const S* a, const S* c_f, const S (*B)[MAXM], const T* d
   S center[2], safe_dist, feas_dist;
   bool feasible = true;
   if (k.state_constrained && k.rm_zonotopic) {
-    // P2 with four free lengths (geo-mean cone program): not reduced to closed form yet.
-    (void)dirs;
-    out[0] = C<S>(NAN); out[1] = C<S>(NAN);
-    return false;
+    // zonotopic approximation: P2 (four free lengths) then P3 along the ray from the centre (ray_mask.py:63-89)
+    if (k.state_model != SM_INVERTIBLE || k.action_constrained || !dirs) {
+      out[0] = C<S>(NAN); out[1] = C<S>(NAN);
+      return false;
+    }
+    S len[4];
+    feasible = p2_expand_m2<TASK>(c_f, B, dirs, k, center, len);
+    const S dx = a[0] - center[0], dy = a[1] - center[1];
+    const S nrm = norm2(dx, dy);
+    S dir[2] = {dx / (nrm + C<S>(1e-8)), dy / (nrm + C<S>(1e-8))};
+    safe_dist = ray_dist_zonotope_m2<S, T>(dir, dirs, len);
+    feas_dist = unit_box_dist_m2(center, dir);
   } else if (k.state_constrained) {
     S start[2];
     feasible = project_m2<TASK>(a, c_f, B, k, dyn, start, R);

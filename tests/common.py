@@ -93,3 +93,52 @@ def shared_for(env, step_index: int):
         sh.series[i] = v
     sh.load_t, sh.pv_t, sh.price_t = float(env.load[t]), float(env.pv[t]), float(env.price[t])
     return sh
+
+
+def p2_center_unique(case, tol: float = 1e-7):
+    """P2 (ray-mask expansion) fixes the lengths uniquely (strictly concave objective) but NOT always the centre:
+    when the active rows leave a direction of c free, every point of that face is optimal and solvers differ
+    (compare only the unique quantities).  For m = 2 with an invertible safe-state generator: range
+    of each centre coordinate over the rows with the oracle's optimal lengths, by LP.  Returns a bool mask."""
+    from scipy.optimize import linprog
+    import oracle.programs as P
+    sg, k, dirs = case["sg"], case["consts"], case["dirs"]
+    env = case["env"]
+    state = env.state
+    env.state = case["s"].clone()
+    const, b_mat = sg._linear()
+    env.state = state
+    n = env.state_dim
+    Ginv = np.array([k.Ginv[i * n + j] for i in range(n) for j in range(n)]).reshape(n, n)
+    cs_hat, rb = np.array(k.cs_hat[:n]), np.array(k.rb[:n])
+    B0hat = np.array([k.B0hat[i * 2 + q] for i in range(n) for q in range(2)]).reshape(n, 2)
+    mask = np.zeros(case["s"].shape[0], dtype=bool)
+    for i in range(case["s"].shape[0]):
+        sets = sg._sets(i, const, b_mat)
+        try:
+            _, ln = P.p2_expansion(dirs[i], sets, sg.B0)
+        except P.Infeasible:
+            continue
+        D, ln = dirs[i].numpy(), ln.detach().numpy()
+        cf, B = sets.c_f.detach().numpy(), sets.B.detach().numpy()
+        A, g = [], []
+        for q in range(2):
+            for sgn in (1.0, -1.0):
+                a = np.zeros(2); a[q] = sgn
+                A.append(a); g.append(1.0 - np.abs(D[q]) @ ln)
+        e, b, Wm = cs_hat - Ginv @ cf, Ginv @ B, np.abs(B0hat @ D)
+        for r in range(n):
+            A.append(-b[r]); g.append(rb[r] - e[r] - Wm[r] @ ln)
+            A.append(b[r]); g.append(rb[r] + e[r] - Wm[r] @ ln)
+        A, g = np.array(A), np.array(g) + 1e-9
+        width = 0.0
+        for q in range(2):
+            cost = np.zeros(2); cost[q] = 1.0
+            lo = linprog(cost, A_ub=A, b_ub=g, bounds=[(None, None)] * 2, method="highs")
+            hi = linprog(-cost, A_ub=A, b_ub=g, bounds=[(None, None)] * 2, method="highs")
+            if lo.status != 0 or hi.status != 0:
+                width = np.inf
+                break
+            width = max(width, -hi.fun - lo.fun)
+        mask[i] = width < tol
+    return mask

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from common import ENV_IDS, make_case, oracle_step, shared_for
+from common import ENV_IDS, make_case, oracle_step, p2_center_unique, shared_for
 from safegbpo_b200 import _lib, ops
 
 pytestmark = pytest.mark.gpu
@@ -21,6 +21,7 @@ CASES = [
     ("SwingUpCartPole", "ray_mask", {"zonotopic": True}), ("BalanceCartPole", "ray_mask", {"zonotopic": True, "linear": False}),
     ("SwingUpCartPole", "ray_mask", {"zonotopic": False, "passthrough": True}),
     ("ManageHousehold", "boundary_projection", {}), ("ManageHousehold", "ray_mask", {"zonotopic": False}),
+    ("ManageHousehold", "ray_mask", {"zonotopic": True}),
     ("BalancePendulum", "boundary_projection", {}), ("BalancePendulum", "ray_mask", {"zonotopic": False}),
     ("BalancePendulum", "ray_mask", {"zonotopic": True}), ("BalancePendulum", "ray_mask", {"zonotopic": True, "gate": "reference"}),
 ]
@@ -46,6 +47,10 @@ def test_step_fwd_bwd_vs_oracle(env_name, kind, opts, dtype):
     ref = oracle_step(case)
     s, a, (s_next, a_exec, obs, reward, flags) = run_kernel(case, env_name, dtype, dev)
     ok = ref["ok"].to(dev)
+    if env_name == "ManageHousehold" and zono:
+        # P2's optimal centre is not unique for some direction draws: only the unique ones are comparable
+        ok = ok & torch.from_numpy(p2_center_unique(case)).to(dev)
+        assert int(ok.sum()) >= 3
     flags_c = flags.cpu().numpy()
     if dtype == torch.float32:
         # fp32 may take a different branch (clamp / active row) when within rounding of a switch: compare

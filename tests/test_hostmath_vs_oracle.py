@@ -5,7 +5,7 @@ import pytest
 import torch
 
 import hostmath_util as hm
-from common import ENV_IDS, make_case, oracle_step, shared_for
+from common import p2_center_unique, ENV_IDS, make_case, oracle_step, shared_for
 from safegbpo_b200 import _lib
 
 CASES = [
@@ -18,6 +18,7 @@ CASES = [
     ("SwingUpCartPole", "ray_mask", {"zonotopic": True}), ("BalanceCartPole", "ray_mask", {"zonotopic": True, "linear": False}),
     ("SwingUpCartPole", "ray_mask", {"zonotopic": False, "passthrough": True}),
     ("ManageHousehold", "boundary_projection", {}), ("ManageHousehold", "ray_mask", {"zonotopic": False}),
+    ("ManageHousehold", "ray_mask", {"zonotopic": True}), ("ManageHousehold", "ray_mask", {"zonotopic": True, "linear": False}),
     ("BalancePendulum", "boundary_projection", {}), ("BalancePendulum", "ray_mask", {"zonotopic": False}),
     ("BalancePendulum", "ray_mask", {"zonotopic": True}), ("BalancePendulum", "ray_mask", {"zonotopic": True, "gate": "reference"}),
 ]
@@ -34,7 +35,11 @@ def test_step_matches_oracle(env_name, kind, opts):
                   dirs=None if case["dirs"] is None else case["dirs"].numpy(), shared=shared_for(env, 1),
                   cot={k: v.numpy() for k, v in case["cot"].items()})
     ok = ref["ok"].numpy()
-    assert ok.sum() >= N // 2
+    if env_name == "ManageHousehold" and kind == "ray_mask" and opts.get("zonotopic", True):
+        ok = ok & p2_center_unique(case)        # the optimal centre of P2 is not unique for some draws: not comparable
+        assert ok.sum() >= 3
+    else:
+        assert ok.sum() >= N // 2
     tol = dict(rtol=1e-5, atol=2e-6) if (kind == "ray_mask" and opts.get("zonotopic", True)) else dict(rtol=1e-10, atol=1e-11)
     for key in ("a_exec", "s_next", "obs", "reward"):
         np.testing.assert_allclose(out[key][ok], ref[key].numpy()[ok], err_msg=key, **tol)
