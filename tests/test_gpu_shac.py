@@ -128,3 +128,30 @@ def test_safeguarded_episode_vs_oracle(cuda_f64, sg_name):
     np.testing.assert_allclose(float(loss), float(ref["loss"]), rtol=1e-10)
     for (k, p), (k2, p2) in zip(algo.policy.named_parameters(), pol.named_parameters()):
         np.testing.assert_allclose(p.grad.cpu().numpy(), p2.grad.numpy(), rtol=1e-7, atol=1e-10, err_msg=k)
+
+
+def test_household_zonotopic_ray_mask_through_the_drop_in_classes(cuda_f64):
+    """ManageHouseholdEnv + RayMaskSafeguard(zonotopic): program P2 with four free lengths is solved per environment
+    inside the step kernel (interior point, csrc/sgbpo_safeguard2.cuh); the wrapper runs, differentiates, and the
+    executed actions stay inside the feasible box."""
+    from safegbpo_b200 import _lib
+    from safegbpo_b200.envs.manage_household import ManageHouseholdEnv
+    from safegbpo_b200.safeguards.ray_mask import RayMaskSafeguard
+    N = 48
+    torch.manual_seed(2)
+    env = ManageHouseholdEnv(num_envs=N, num_steps=720)
+    wrapped = RayMaskSafeguard(env, linear_projection=True, zonotopic_approximation=True, passthrough=False,
+                               gate="always", strict=False)
+    wrapped.reset(seed=4)
+    for _ in range(4):
+        action = (torch.rand(N, 2) * 2 - 1).requires_grad_(True)
+        obs, rew, term, trunc, _ = wrapped.step(action)
+        flags = env.last_flags
+        feasible = (flags & _lib.FL_INFEASIBLE) == 0
+        assert float(feasible.float().mean()) > 0.7
+        a_exec = env.last_exec_action
+        assert bool(torch.isfinite(a_exec[feasible]).all()) and bool((a_exec[feasible].abs() <= 1 + 1e-9).all())
+        assert bool(((flags & _lib.FL_NEXT_IN_SET) != 0)[feasible].float().mean() > 0.95)
+        rew[feasible].sum().backward()
+        assert bool(torch.isfinite(action.grad[feasible]).all()) and float(action.grad.abs().sum()) > 0
+        env.state = env.state.detach()
