@@ -178,6 +178,12 @@ typedef struct sgbpo_optim {
 /* one launch: global gradient norm -> clip -> Adam (no weight decay / amsgrad); total_norm_out: 1 element of dtype or NULL */
 int sgbpo_clip_adam(int dtype, int step_dtype, const sgbpo_optim* o, void* total_norm_out, void* stream);
 
+/* ---- critic targets (shac.py:187-241, calculate_estimated_values): backward TD-lambda scan per environment ----
+ * rewards / values: [H+2][N] (time-major, like CoupledBuffer); terminals: [H+2][N] bytes (torch.bool storage);
+ * est: [H][N] targets, valid: [H][N] bytes = 1 where row t of environment e is not terminal (a target exists). */
+int sgbpo_td_lambda(int dtype, int64_t N, int H, const void* rewards, const void* values, const uint8_t* terminals,
+                    double gamma, double td_weight, void* est, uint8_t* valid, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

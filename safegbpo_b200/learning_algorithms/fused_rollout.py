@@ -74,9 +74,10 @@ def rollout_fits(dtype, obs_dim: int, width: int, n_hidden: int, act_dim: int) -
 
 
 def _tall_skinny_gram(a: Tensor, b: Tensor) -> Tensor:
-    """a^T b for (M, W) operands with M >> W: a plain library GEMM, split over M so that more than a
+    """a^T b for (M, W) x (M, Wb) operands with M >> W: a plain library GEMM, split over M so that more than a
     handful of CTAs work on it (cuBLAS picks a 64x64 tile without split-K for this shape)."""
     M, W = a.shape
+    Wb = b.shape[1]
     split = 1
     for cand in (256, 128, 64, 32, 16, 8):
         if M % cand == 0 and M // cand >= 256:
@@ -84,7 +85,7 @@ def _tall_skinny_gram(a: Tensor, b: Tensor) -> Tensor:
             break
     if split == 1:
         return a.t() @ b
-    return torch.bmm(a.view(split, M // split, W).transpose(1, 2), b.view(split, M // split, W)).sum(dim=0)
+    return torch.bmm(a.view(split, M // split, W).transpose(1, 2), b.view(split, M // split, Wb)).sum(dim=0)
 
 
 class PackedMlp:

@@ -22,6 +22,7 @@ class LearningAlgorithm(ABC):
         if torch.cuda.is_available() and next(self.policy.parameters()).is_cuda:
             # device-side step counter: same arithmetic, lets the update be replayed inside a CUDA graph
             policy_optim_kwargs = {"capturable": True, **policy_optim_kwargs}
+            vf_optim_kwargs = {"capturable": True, **vf_optim_kwargs}
         self.policy_optim = torch.optim.Adam(self.policy.parameters(), **policy_optim_kwargs)
         self.value_function_optim = torch.optim.Adam(self.value_function.parameters(), **vf_optim_kwargs)
         self.regularisation_coefficient = regularisation_coefficient

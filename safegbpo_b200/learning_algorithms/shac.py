@@ -19,6 +19,43 @@ from .components.value_function import ValueFunction
 from .interfaces.learning_algorithm import LearningAlgorithm
 
 
+class _LinearSplitK(torch.autograd.Function):
+    """y = x W^T + b with the weight gradient computed by a split-K batched GEMM (tall-skinny reduction)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return torch.addmm(bias, x, weight.t())
+
+    @staticmethod
+    def backward(ctx, gy):
+        from .fused_rollout import _tall_skinny_gram
+        x, weight = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = gy @ weight if ctx.needs_input_grad[0] else None
+        return gx, _tall_skinny_gram(gy, x.contiguous()), gy.sum(dim=0)
+
+
+class _LayerNormRows(torch.autograd.Function):
+    """LayerNorm over the last dim for (rows, width) training batches.  Forward and input-gradient are ATen's own
+    kernels; the weight / bias gradients (column reductions over ~65 k rows, for which ATen's GammaBetaBackward
+    kernel takes 0.5 ms per call) are two plain column sums."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        y, mean, rstd = torch.ops.aten.native_layer_norm(x, [x.shape[-1]], weight, bias, eps)
+        ctx.save_for_backward(x, mean, rstd, weight, bias)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, mean, rstd, weight, bias = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = torch.ops.aten.native_layer_norm_backward(gy, x, [x.shape[-1]], mean, rstd, weight, bias, [True, False, False])[0]
+        xhat = (x - mean) * rstd
+        return gx, (gy * xhat).sum(dim=0), gy.sum(dim=0), None
+
+
 class SHAC(LearningAlgorithm):
     GAMMA = 0.99
     MAX_GRAD_NORM = 1.0
@@ -45,6 +82,8 @@ class SHAC(LearningAlgorithm):
         self._fused_engine = None
         # data-parallel hook: called between backward and clip/Adam (distributed.allreduce_policy_grads)
         self.grad_sync = None
+        self.vf_graphs = True            # critic fit replayed as a CUDA graph when the optimizer allows (plain Adam on CUDA)
+        self._vf_graph = None
         self._fused_tail = None          # resolved on first use: fused clip + Adam launch when the optimizer is plain Adam on CUDA
 
     # ---- episode ---------------------------------------------------------------------------------------
@@ -138,6 +177,8 @@ class SHAC(LearningAlgorithm):
         (row H-1 first, environments ascending, non-terminal rows only)."""
         H, N = self.len_trajectories, self.env.num_envs
         rewards, values, terminals = self.buffer.rewards.tensor, self.buffer.values.tensor, self.buffer.terminals.tensor
+        if rewards.is_cuda and rewards.dtype in (torch.float32, torch.float64):
+            return self._estimated_values_kernel(rewards.detach(), values.detach(), terminals)
         td = torch.ones(N)
         avg = torch.zeros(N)
         term_ret = torch.zeros(N)
@@ -166,9 +207,50 @@ class SHAC(LearningAlgorithm):
             obs = torch.cat([obs, torch.zeros(pad, self.env.obs_dim)])
         return est, obs
 
+    def _estimated_values_kernel(self, rewards: Tensor, values: Tensor, terminals: Tensor) -> tuple[Tensor, Tensor]:
+        """One launch of csrc/sgbpo_critic.cu (a thread scans one environment) + the reference's output order:
+        row H-1 first, environments ascending, non-terminal rows only, zero-padded to H * N."""
+        import ctypes as C
+        from .. import _lib
+        H, N = self.len_trajectories, self.env.num_envs
+        rewards, values = rewards.contiguous(), values.contiguous()
+        term_u8 = terminals.contiguous().view(torch.uint8)
+        est = torch.empty(H, N, dtype=rewards.dtype, device=rewards.device)
+        valid = torch.empty(H, N, dtype=torch.uint8, device=rewards.device)
+        _lib.check(_lib.lib().sgbpo_td_lambda(_lib.dtype_code(rewards.dtype), N, H, _lib.ptr(rewards), _lib.ptr(values),
+                                             _lib.ptr(term_u8), float(self.GAMMA), float(self.td_weight), _lib.ptr(est),
+                                             _lib.ptr(valid), _lib.stream_ptr()), "sgbpo_td_lambda")
+        obs = self.buffer.observations.tensor[:H].detach()
+        if self._uniform_terminals:
+            # every environment shares the terminal rows (truncation depends on the shared step counter only,
+            # simulator.py:102-106): keep whole rows, no boolean gather, no host sync
+            keep = [t for t in range(H - 1, -1, -1) if not self._terminal_rows_host[t]]
+            idx = torch.tensor(keep, dtype=torch.int64, device=est.device)
+            est_rows, obs_rows = est.index_select(0, idx).reshape(-1), obs.index_select(0, idx).reshape(-1, obs.shape[2])
+        else:
+            mask = valid.flip(0).bool()
+            est_rows, obs_rows = est.flip(0)[mask], obs.flip(0)[mask]
+        pad = H * N - est_rows.shape[0]
+        if pad:
+            est_rows = torch.cat([est_rows, est_rows.new_zeros(pad)])
+            obs_rows = torch.cat([obs_rows, obs_rows.new_zeros(pad, obs_rows.shape[1])])
+        return est_rows, obs_rows
+
+    @property
+    def _uniform_terminals(self) -> bool:
+        eng = self._fused_engine
+        return eng is not None and eng.last is not None and "terminal_rows" in eng.last and \
+            self.buffer.terminals.tensor.shape[0] == len(eng.last["terminal_rows"])
+
+    @property
+    def _terminal_rows_host(self):
+        return self._fused_engine.last["terminal_rows"]
+
     def update_value_function(self) -> float:
         with torch.no_grad():
             estimated_values, observations = self.calculate_estimated_values()
+        if self._vf_graph_ok(estimated_values):
+            return self._fit_value_function_graph(estimated_values, observations)
         batch_size = math.ceil(len(estimated_values) / self.vf_fit_num_batches)
         value_loss = torch.zeros(())
         for _ in range(self.vf_num_fits):
@@ -184,7 +266,94 @@ class SHAC(LearningAlgorithm):
                 self.value_function_optim.step()
         return float(value_loss)
 
+    # ---- critic fit as one replayed CUDA graph (shac.py:154-184) ---------------------------------------------
+    def _vf_graph_ok(self, est: Tensor) -> bool:
+        from .. import optim as sgoptim
+        # (the learning rate is a launch argument baked into the captured graph: constant schedule only)
+        return (self.vf_graphs and est.is_cuda and sgoptim.supported(self.value_function_optim)
+                and torch.is_grad_enabled() and self.VF_LEARNING_RATE_SCHEDULE == "constant")
+
+    def _fit_value_function_graph(self, est: Tensor, obs: Tensor) -> float:
+        """The vf_num_fits x vf_fit_num_batches loop (forward, MSE, backward, clip, Adam per batch) is the same
+        ~2 000 launches every episode: captured once on static input buffers and replayed.  Clip + Adam are the
+        fused launches of csrc/sgbpo_optim.cu on torch.optim.Adam's own state tensors."""
+        from .. import optim as sgoptim
+        vf, opt = self.value_function, self.value_function_optim
+        key = (tuple(est.shape), tuple(obs.shape), est.dtype, float(opt.param_groups[0]["lr"]), self.vf_num_fits,
+               self.vf_fit_num_batches)
+        g = self._vf_graph
+        if g is None or g["key"] != key:
+            g = dict(key=key, est=torch.empty_like(est), obs=torch.empty_like(obs), loss=torch.zeros((), dtype=est.dtype, device=est.device),
+                     graph=None)
+            self._vf_graph = g
+        g["est"].copy_(est)
+        g["obs"].copy_(obs)
+        if g["graph"] is None:
+            params = list(vf.parameters())
+            sgoptim._ensure_state(opt)
+            # warm-up (required before capture) runs the loop for real: snapshot and restore so the first call
+            # performs exactly one fit
+            snap_p = [p.detach().clone() for p in params]
+            snap_s = [{k: v.clone() for k, v in opt.state[p].items()} for p in params]
+            for p in params:
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._fit_body(g)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._fit_body(g)
+            with torch.no_grad():
+                for p, sp, ss in zip(params, snap_p, snap_s):
+                    p.copy_(sp)
+                    for k, v in ss.items():
+                        opt.state[p][k].copy_(v)
+            g["graph"] = graph
+        g["graph"].replay()
+        return float(g["loss"])
+
+    def _vf_forward_train(self, x: Tensor) -> Tensor:
+        """The critic's forward for training batches (tens of thousands of rows x width 128).  Same operations as the
+        nn.Sequential, but Linear's weight gradient dY^T X (a 128 x 128 result reduced over ~65 k rows, for which
+        cuBLAS launches a handful of CTAs) goes through the split-K GEMM of fused_rollout._tall_skinny_gram."""
+        from .fused_rollout import _mlp_layout
+        layout = _mlp_layout(self.value_function.model)
+        if layout is None:
+            return self.value_function(x)
+        lin, norm = layout
+        h = x
+        for l, ln in zip(lin[:-1], norm):
+            h = _LinearSplitK.apply(h, l.weight, l.bias)
+            h = torch.nn.functional.elu(h)
+            h = _LayerNormRows.apply(h, ln.weight, ln.bias, ln.eps)
+        return _LinearSplitK.apply(h, lin[-1].weight, lin[-1].bias)
+
+    def _fit_body(self, g):
+        from .. import optim as sgoptim
+        vf, opt = self.value_function, self.value_function_optim
+        est, obs = g["est"], g["obs"]
+        n = est.shape[0]
+        batch_size = math.ceil(n / self.vf_fit_num_batches)
+        grads = [p.grad for p in vf.parameters()]
+        for _ in range(self.vf_num_fits):
+            for b in range(self.vf_fit_num_batches):
+                lo, hi = b * batch_size, min((b + 1) * batch_size, n)
+                if lo >= n:
+                    break
+                torch._foreach_zero_(grads)
+                pred = self._vf_forward_train(obs[lo:hi]).squeeze(dim=1)
+                value_loss = (pred - est[lo:hi]).square().mean()
+                value_loss.backward()
+                sgoptim.clip_adam_step(opt, self.MAX_GRAD_NORM)
+        g["loss"].copy_(value_loss.detach())
+
     def update_target_value_function(self):
         with torch.no_grad():
-            for target, param in zip(self.target_value_function.parameters(), self.value_function.parameters()):
-                target.mul_(self.polyak_target).add_((1 - self.polyak_target) * param)
+            targets, params = list(self.target_value_function.parameters()), list(self.value_function.parameters())
+            torch._foreach_mul_(targets, self.polyak_target)                       # shac.py:248-251, two launches
+            torch._foreach_add_(targets, params, alpha=1 - self.polyak_target)

@@ -132,6 +132,22 @@ def shac_golden():
     out["n_draws"] = np.array(len(DRAWS) - n_init)
     np.savez_compressed(HERE / "shac_cartpole_unsafe.npz", **out)
     print("wrote shac golden: loss", float(loss), "draws", len(DRAWS) - n_init, "terminals", buf.terminals.tensor.sum().item())
+    # critic path on the SAME buffer (shac.py:154-251): TD-lambda targets, the critic fit, the Polyak update
+    crit = {"td_weight": np.array(algo.td_weight), "vf_num_fits": np.array(algo.vf_num_fits),
+            "vf_fit_num_batches": np.array(algo.vf_fit_num_batches), "polyak_target": np.array(algo.polyak_target)}
+    with torch.no_grad():
+        est, obs_rows = algo.calculate_estimated_values()
+    crit["estimated_values"], crit["estimated_observations"] = est.numpy().copy(), obs_rows.numpy().copy()
+    for k, v in algo.value_function.state_dict().items():
+        crit[f"vf0.{k}"] = v.numpy().copy()
+    crit["value_loss"] = np.array(algo.update_value_function())
+    for k, v in algo.value_function.state_dict().items():
+        crit[f"vf1.{k}"] = v.numpy().copy()
+    algo.update_target_value_function()
+    for k, v in algo.target_value_function.state_dict().items():
+        crit[f"target_vf1.{k}"] = v.numpy().copy()
+    np.savez_compressed(HERE / "shac_critic.npz", **crit)
+    print("wrote critic golden: value loss", float(crit["value_loss"]), "targets", est.shape)
 
 
 def buffer_golden():
