@@ -292,3 +292,61 @@ def test_graph_replay_equals_eager_launches(cuda_default, rng_order):
     for a, b in zip(p0, p1):
         assert torch.allclose(a, b, rtol=1e-3, atol=1e-5)
     assert i0 == i1
+
+
+def test_full_size_rollout_is_consistent_with_the_step_kernels(cuda_default):
+    """BASELINE configs[1] at full size (BalanceCartPole + boundary projection, 4096 environments, H = 64, fp32):
+    size-independent properties of the fused whole-horizon kernels -- every transition of the rollout buffer is
+    reproduced by the per-step kernel from (s_t, a_t, w_t) (same executed action, next state, observation, reward,
+    flag word), the chain is closed (row t + 1 of the state buffer is what step t produced), no feasible guarded
+    action leaves its sets, and the reverse pass is repeatable."""
+    from safegbpo_b200 import _lib, ops
+    torch.set_default_dtype(torch.float32)
+    dev = cuda_default
+    N, H = 4096, 64
+    torch.manual_seed(17)
+    env, wrapped, algo = build("BalanceCartPole", "bp", {"gate": "reference"}, 128, 240, N, H, "on", dev)
+    algo.rng_order = "batched"
+    env.reset(seed=3)
+    env.steps, env._reset_pending = 200, False                 # a reset-all falls inside the horizon (t = 40)
+    o0 = env.observation
+    algo.buffer.reset(o0, algo.target_value_function(o0).squeeze(1))
+    eng = algo._engine()
+    eng.use_graphs = False
+    algo.buffer.reset()
+    algo.policy_optim.zero_grad()
+    algo.collect_trajectories()
+    last = eng.last
+    states, obs, rewards, flags, a_exec = last["states"], last["obs"], last["rewards"], last["flags"], last["exec_actions"]
+    actions = algo.buffer.actions.tensor
+    eps, noise = last["keep"][-9], last["keep"][-8]
+    assert tuple(noise.shape) == (H, N, 4) and tuple(states.shape) == (H + 1, N, 4)
+    consts = wrapped.consts()
+    checked = 0
+    for t in (0, 1, 17, 38, 41, 63):
+        s_next, ae, ob, rw, fl = ops.safeguarded_step(states[t], actions[t], noise[t], env.env_id, consts)
+        is_reset_step = not torch.allclose(states[t + 1], s_next, rtol=1e-5, atol=1e-5)
+        assert torch.equal(fl, flags[t]), f"flag words differ at t={t}"
+        np.testing.assert_allclose(ae.cpu().numpy(), a_exec[t].cpu().numpy(), rtol=1e-6, atol=1e-7)
+        if not is_reset_step:                                  # (on the reset step the buffer holds the re-sampled state)
+            np.testing.assert_allclose(s_next.cpu().numpy(), states[t + 1].cpu().numpy(), rtol=1e-6, atol=1e-6)
+            np.testing.assert_allclose(ob.cpu().numpy(), obs[t + 1].cpu().numpy(), rtol=1e-6, atol=1e-6)
+            np.testing.assert_allclose(rw.cpu().numpy(), rewards[t].cpu().numpy(), rtol=1e-5, atol=1e-5)
+            checked += 1
+    assert checked >= 5
+    guard = (flags & _lib.FL_GUARD_USED) != 0
+    feas = (flags & _lib.FL_INFEASIBLE) == 0
+    good = guard & feas
+    assert int(good.sum()) > 1000
+    assert bool((((flags & _lib.FL_NEXT_IN_SET) != 0) | ~good).all())          # zero safety violations where feasible
+    assert bool((((flags & _lib.FL_ACTION_IN_SET) != 0) | ~good).all())
+    # the reverse pass is a pure function of the buffers and the stash: running it twice gives the same gradients
+    loss1 = eng.backward()
+    g1 = [p.grad.clone() for p in algo.policy.parameters()]
+    for p in algo.policy.parameters():
+        p.grad = None
+    loss2 = eng.backward()
+    g2 = [p.grad.clone() for p in algo.policy.parameters()]
+    for a, b in zip(g1, g2):                                   # deterministic up to the atomic accumulation order
+        assert torch.allclose(a, b, rtol=2e-3, atol=1e-6 * float(a.abs().max() + 1e-30) + 1e-9)
+    assert float(loss1) == float(loss2)
