@@ -268,6 +268,14 @@ def run_ours(args):
         total_ms, e2e_ms = float(t[0]), float(t[1])
     else:
         e2e_ms = sum(t_e2e)
+    in_sync = None
+    if world > 1:       # data parallelism check: after all the updates every rank must hold the same policy
+        flat = torch.cat([p.detach().reshape(-1).double() for p in algo.policy.parameters()])
+        probe = torch.stack([flat.sum(), flat.abs().sum(), (flat * torch.arange(flat.numel(), dtype=torch.float64)).sum()])
+        lo, hi = probe.clone(), probe.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        in_sync = bool(torch.allclose(lo, hi, rtol=1e-12, atol=0.0))
     env_steps = N * H * args.steps * world
     value = env_steps / (total_ms * 1e-3)
     e2e_value = env_steps / (e2e_ms * 1e-3)
@@ -300,6 +308,7 @@ def run_ours(args):
             "roofline": roof, "clocks": {**sampler.summary(), "n_samples": len(sampler.samples),
                                          "sampled_beyond_timed_region": extended},
             "roofline_stress": stress,
+            "replicas_in_sync": in_sync,
             "mode": "fused" if engine is not None else "eager (per-step fused safeguard+simulator kernel, torch MLP)",
         }
         if not args.no_cpu_baseline and world == 1:

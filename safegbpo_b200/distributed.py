@@ -27,6 +27,13 @@ def allreduce_policy_grads(algo):
     so the global loss over world*N environments is the mean of the per-rank losses."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return
+    engine = getattr(algo, "_fused_engine", None)
+    bufs = engine.static_grad_buffers() if engine is not None else None
+    if bufs is not None:
+        # graph path: every policy gradient is a view of two static buffers -> two in-place NCCL calls, no packing
+        for b in bufs:
+            dist.all_reduce(b, op=dist.ReduceOp.AVG)
+        return
     grads = [p.grad for p in algo.policy.parameters() if p.grad is not None]
     flat = torch.cat([g.reshape(-1) for g in grads])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)

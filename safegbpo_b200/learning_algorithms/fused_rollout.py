@@ -511,6 +511,17 @@ class FusedRollout:
         self.last = dict(graph=True, terminal_rows=terminal_rows)
         return float(g["scal_host"][0]) / base.num_envs / H
 
+    def static_grad_buffers(self):
+        """The two static tensors that hold every policy gradient of the last graph-replayed backward (all
+        `policy.*.grad` are views of them), or None when the last episode ran outside the graphs."""
+        g = self._g
+        if g is None or self.last is None or not self.last.get("graph"):
+            return None
+        for prm, buf in g["grads"].items():
+            if prm.grad is None or prm.grad.data_ptr() != buf.data_ptr():
+                return None
+        return [g["flat"], g["dw_hid"]]
+
     def _fast_buffer_reset(self, reset_observation=None, reset_value=None) -> bool:
         """CoupledBuffer.reset() while the buffer's tensors ARE the static graph buffers: carry the last
         observation / value to row 0 in place (coupled_buffer.py:113-131 does the same on fresh storage; the
