@@ -184,6 +184,14 @@ int sgbpo_clip_adam(int dtype, int step_dtype, const sgbpo_optim* o, void* total
 int sgbpo_td_lambda(int dtype, int64_t N, int H, const void* rewards, const void* values, const uint8_t* terminals,
                     double gamma, double td_weight, void* est, uint8_t* valid, void* stream);
 
+/* ---- critic fit (shac.py:154-184): hidden layer tail  h = LayerNorm(ELU(z + bias))  on (M, width) batches, one
+ * pass forward and one backward.  fwd keeps the ELU output e (M, width) and (mean, rstd) per row in stats (M, 2);
+ * bwd returns dz (gradient w.r.t. z) and ACCUMULATES the column sums d gamma, d beta, d bias (caller zero-fills). */
+int sgbpo_bias_elu_ln_fwd(int dtype, int64_t M, int width, const void* z, const void* bias, const void* gamma,
+                          const void* beta, void* h, void* e_out, void* stats, void* stream);
+int sgbpo_bias_elu_ln_bwd(int dtype, int64_t M, int width, const void* gy, const void* e, const void* stats,
+                          const void* gamma, void* dz, void* dgamma, void* dbeta, void* dbias, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

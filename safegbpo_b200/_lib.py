@@ -96,6 +96,8 @@ _SIGNATURES = {
                                     C.POINTER(RolloutGrads), _VP]),
     "sgbpo_mlp_rows": (C.c_int, [C.c_int, C.c_int64, C.POINTER(Mlp), _VP, _VP, _VP]),
     "sgbpo_clip_adam": (C.c_int, [C.c_int, C.c_int, _VP, _VP, _VP]),
+    "sgbpo_bias_elu_ln_fwd": (C.c_int, [C.c_int, C.c_int64, C.c_int] + [_VP] * 8),
+    "sgbpo_bias_elu_ln_bwd": (C.c_int, [C.c_int, C.c_int64, C.c_int] + [_VP] * 9),
     "sgbpo_td_lambda": (C.c_int, [C.c_int, C.c_int64, C.c_int, _VP, _VP, _VP, C.c_double, C.c_double, _VP, _VP, _VP]),
 }
 EXPORTED = tuple(_SIGNATURES)

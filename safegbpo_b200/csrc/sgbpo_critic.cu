@@ -44,6 +44,128 @@ td_lambda_kernel(int64_t N, int H, const T* __restrict__ rewards, const T* __res
     term_next = term_t;
   }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Critic fit (shac.py:154-184): the hidden layers are Linear -> ELU -> LayerNorm on batches of ~65 k rows.  ATen runs
+// bias add, ELU, LayerNorm and their backward as separate memory-bound passes (and its LayerNorm weight-gradient
+// kernel takes 0.5 ms for this shape); here ONE pass per direction: a warp owns a row at a time (lane l = columns
+// l, l + 32, ...: every access is one coalesced 128-byte segment; row statistics by shuffles), the column sums of the backward (d gamma, d beta, d bias) are
+// kept per lane in registers over the warp's rows and flushed with one atomicAdd per column per warp.
+// ---------------------------------------------------------------------------------------------------------------
+template <class T> __device__ __forceinline__ T wsum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float elu_neg(float x) { return expf(x) - 1.0f; }
+__device__ __forceinline__ double elu_neg(double x) { return exp(x) - 1.0; }
+__device__ __forceinline__ float rs(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double rs(double x) { return 1.0 / sqrt(x); }
+
+template <class T, int W>
+__global__ void __launch_bounds__(256)
+bias_elu_ln_fwd_kernel(int64_t M, const T* __restrict__ z, const T* __restrict__ bias, const T* __restrict__ gamma,
+                       const T* __restrict__ beta, T* __restrict__ h, T* __restrict__ e_out, T* __restrict__ stats) {
+  constexpr int CPL = W / 32;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  T b[CPL], g[CPL], be[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) { b[j] = bias[lane + 32 * j]; g[j] = gamma[lane + 32 * j]; be[j] = beta[lane + 32 * j]; }
+  for (int64_t row = warp; row < M; row += nwarps) {
+    T e[CPL], s = T(0);
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      const T v = z[row * W + lane + 32 * j] + b[j];
+      e[j] = v > T(0) ? v : elu_neg(v);
+      s += e[j];
+    }
+    const T mean = wsum(s) / T(W);
+    T q = T(0);
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) { const T d = e[j] - mean; q += d * d; }
+    const T rstd = rs(wsum(q) / T(W) + T(1e-5));
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      e_out[row * W + lane + 32 * j] = e[j];
+      h[row * W + lane + 32 * j] = ((e[j] - mean) * rstd) * g[j] + be[j];
+    }
+    if (lane == 0) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
+  }
+}
+
+template <class T, int W>
+__global__ void __launch_bounds__(256)
+bias_elu_ln_bwd_kernel(int64_t M, const T* __restrict__ gy, const T* __restrict__ e_in, const T* __restrict__ stats,
+                       const T* __restrict__ gamma, T* __restrict__ dz, T* __restrict__ dgamma, T* __restrict__ dbeta,
+                       T* __restrict__ dbias) {
+  constexpr int CPL = W / 32;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  T g[CPL], ag[CPL], ab[CPL], az[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) { g[j] = gamma[lane + 32 * j]; ag[j] = ab[j] = az[j] = T(0); }
+  for (int64_t row = warp; row < M; row += nwarps) {
+    const T mean = stats[row * 2], rstd = stats[row * 2 + 1];
+    T e[CPL], xh[CPL], dx[CPL], s1 = T(0), s2 = T(0);
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      const T gyj = gy[row * W + lane + 32 * j];
+      e[j] = e_in[row * W + lane + 32 * j];
+      xh[j] = (e[j] - mean) * rstd;
+      ag[j] += gyj * xh[j];
+      ab[j] += gyj;
+      dx[j] = gyj * g[j];
+      s1 += dx[j];
+      s2 += dx[j] * xh[j];
+    }
+    const T m1 = wsum(s1) / T(W), m2 = wsum(s2) / T(W);
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      const T de = rstd * (dx[j] - m1 - xh[j] * m2);
+      const T d = de * (e[j] > T(0) ? T(1) : e[j] + T(1));          // dELU/dz from the ELU output
+      dz[row * W + lane + 32 * j] = d;
+      az[j] += d;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    atomicAdd(dgamma + lane + 32 * j, ag[j]);
+    atomicAdd(dbeta + lane + 32 * j, ab[j]);
+    atomicAdd(dbias + lane + 32 * j, az[j]);
+  }
+}
+
+template <class T, int W>
+static int launch_eln(bool fwd, int64_t M, const void* a0, const void* a1, const void* a2, const void* a3, void* o0, void* o1,
+                      void* o2, void* o3, cudaStream_t st) {
+  int64_t blocks = (M + 7) / 8;                       // 8 warps per block, one row per warp per pass
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (fwd)
+    bias_elu_ln_fwd_kernel<T, W><<<(int)blocks, 256, 0, st>>>(M, (const T*)a0, (const T*)a1, (const T*)a2, (const T*)a3, (T*)o0,
+                                                              (T*)o1, (T*)o2);
+  else
+    bias_elu_ln_bwd_kernel<T, W><<<(int)blocks, 256, 0, st>>>(M, (const T*)a0, (const T*)a1, (const T*)a2, (const T*)a3, (T*)o0,
+                                                              (T*)o1, (T*)o2, (T*)o3);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "bias_elu_ln kernel: %s", cudaGetErrorString(e));
+    return SGBPO_E_CUDA;
+  }
+  return SGBPO_OK;
+}
+template <class T>
+static int dispatch_eln(bool fwd, int W, int64_t M, const void* a0, const void* a1, const void* a2, const void* a3, void* o0,
+                        void* o1, void* o2, void* o3, cudaStream_t st) {
+  switch (W) {
+    case 32: return launch_eln<T, 32>(fwd, M, a0, a1, a2, a3, o0, o1, o2, o3, st);
+    case 64: return launch_eln<T, 64>(fwd, M, a0, a1, a2, a3, o0, o1, o2, o3, st);
+    case 128: return launch_eln<T, 128>(fwd, M, a0, a1, a2, a3, o0, o1, o2, o3, st);
+    default:
+      snprintf(g_err, sizeof(g_err), "bias_elu_ln: widths 32, 64, 128");
+      return SGBPO_E_UNSUPPORTED;
+  }
+}
 }  // namespace sgbpo
 
 using namespace sgbpo;
@@ -69,4 +191,28 @@ extern "C" int sgbpo_td_lambda(int dtype, int64_t N, int H, const void* rewards,
     return SGBPO_E_CUDA;
   }
   return SGBPO_OK;
+}
+
+extern "C" int sgbpo_bias_elu_ln_fwd(int dtype, int64_t M, int width, const void* z, const void* bias, const void* gamma,
+                                     const void* beta, void* h, void* e_out, void* stats, void* stream) {
+  if (M <= 0) return SGBPO_OK;
+  if (!z || !bias || !gamma || !beta || !h || !e_out || !stats) {
+    snprintf(g_err, sizeof(g_err), "sgbpo_bias_elu_ln_fwd: null buffer");
+    return SGBPO_E_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  return dtype == SGBPO_F64 ? dispatch_eln<double>(true, width, M, z, bias, gamma, beta, h, e_out, stats, nullptr, st)
+                            : dispatch_eln<float>(true, width, M, z, bias, gamma, beta, h, e_out, stats, nullptr, st);
+}
+
+extern "C" int sgbpo_bias_elu_ln_bwd(int dtype, int64_t M, int width, const void* gy, const void* e, const void* stats,
+                                     const void* gamma, void* dz, void* dgamma, void* dbeta, void* dbias, void* stream) {
+  if (M <= 0) return SGBPO_OK;
+  if (!gy || !e || !stats || !gamma || !dz || !dgamma || !dbeta || !dbias) {
+    snprintf(g_err, sizeof(g_err), "sgbpo_bias_elu_ln_bwd: null buffer");
+    return SGBPO_E_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  return dtype == SGBPO_F64 ? dispatch_eln<double>(false, width, M, gy, e, stats, gamma, dz, dgamma, dbeta, dbias, st)
+                            : dispatch_eln<float>(false, width, M, gy, e, stats, gamma, dz, dgamma, dbeta, dbias, st);
 }

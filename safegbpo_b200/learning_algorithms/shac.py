@@ -36,6 +36,55 @@ class _LinearSplitK(torch.autograd.Function):
         return gx, _tall_skinny_gram(gy, x.contiguous()), gy.sum(dim=0)
 
 
+class _BiasEluLayerNormRows(torch.autograd.Function):
+    """h = LayerNorm(ELU(z + bias)) on (rows, width) training batches as ONE pass forward and ONE backward
+    (csrc/sgbpo_critic.cu); the backward also yields the three column sums d gamma, d beta, d bias."""
+
+    @staticmethod
+    def forward(ctx, z, bias, gamma, beta):
+        import ctypes as C
+        from .. import _lib
+        z = z.contiguous()
+        M, W = z.shape
+        h, e = torch.empty_like(z), torch.empty_like(z)
+        stats = torch.empty(M, 2, dtype=z.dtype, device=z.device)
+        _lib.check(_lib.lib().sgbpo_bias_elu_ln_fwd(_lib.dtype_code(z.dtype), M, W, _lib.ptr(z), _lib.ptr(bias), _lib.ptr(gamma),
+                                                   _lib.ptr(beta), _lib.ptr(h), _lib.ptr(e), _lib.ptr(stats), _lib.stream_ptr()),
+                   "sgbpo_bias_elu_ln_fwd")
+        ctx.save_for_backward(e, stats, gamma)
+        return h
+
+    @staticmethod
+    def backward(ctx, gy):
+        from .. import _lib
+        e, stats, gamma = ctx.saved_tensors
+        gy = gy.contiguous()
+        M, W = gy.shape
+        dz = torch.empty_like(gy)
+        sums = torch.zeros(3, W, dtype=gy.dtype, device=gy.device)
+        _lib.check(_lib.lib().sgbpo_bias_elu_ln_bwd(_lib.dtype_code(gy.dtype), M, W, _lib.ptr(gy), _lib.ptr(e), _lib.ptr(stats),
+                                                   _lib.ptr(gamma), _lib.ptr(dz), _lib.ptr(sums[0]), _lib.ptr(sums[1]),
+                                                   _lib.ptr(sums[2]), _lib.stream_ptr()), "sgbpo_bias_elu_ln_bwd")
+        return dz, sums[2], sums[0], sums[1]
+
+
+class _MatmulSplitK(torch.autograd.Function):
+    """z = x W^T (no bias) with the weight gradient through the split-K GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        ctx.save_for_backward(x, weight)
+        return x @ weight.t()
+
+    @staticmethod
+    def backward(ctx, gz):
+        from .fused_rollout import _tall_skinny_gram
+        x, weight = ctx.saved_tensors
+        gz = gz.contiguous()
+        gx = gz @ weight if ctx.needs_input_grad[0] else None
+        return gx, _tall_skinny_gram(gz, x.contiguous())
+
+
 class _LayerNormRows(torch.autograd.Function):
     """LayerNorm over the last dim for (rows, width) training batches.  Forward and input-gradient are ATen's own
     kernels; the weight / bias gradients (column reductions over ~65 k rows, for which ATen's GammaBetaBackward
@@ -327,10 +376,14 @@ class SHAC(LearningAlgorithm):
             return self.value_function(x)
         lin, norm = layout
         h = x
+        fusedk = x.is_cuda and x.dtype in (torch.float32, torch.float64)
         for l, ln in zip(lin[:-1], norm):
-            h = _LinearSplitK.apply(h, l.weight, l.bias)
-            h = torch.nn.functional.elu(h)
-            h = _LayerNormRows.apply(h, ln.weight, ln.bias, ln.eps)
+            if fusedk:      # GEMM, then bias + ELU + LayerNorm in one pass (widths 32 / 64 / 128 by _mlp_layout)
+                h = _BiasEluLayerNormRows.apply(_MatmulSplitK.apply(h, l.weight), l.bias, ln.weight, ln.bias)
+            else:
+                h = _LinearSplitK.apply(h, l.weight, l.bias)
+                h = torch.nn.functional.elu(h)
+                h = _LayerNormRows.apply(h, ln.weight, ln.bias, ln.eps)
         return _LinearSplitK.apply(h, lin[-1].weight, lin[-1].bias)
 
     def _fit_body(self, g):

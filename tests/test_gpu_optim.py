@@ -67,3 +67,27 @@ def test_value_function_inference_path_matches_torch():
     finally:
         torch.set_default_device("cpu")
         torch.set_default_dtype(prev)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-11), (torch.float32, 3e-5)], ids=["f64", "f32"])
+def test_bias_elu_layernorm_rows_match_torch_autograd(dtype, tol):
+    """Fused hidden-layer tail of the critic fit (csrc/sgbpo_critic.cu) against torch: h = LayerNorm(ELU(z + b)),
+    gradients w.r.t. z, bias, gamma, beta (value_function.py:38-48 / shac.py:154-184)."""
+    from safegbpo_b200.learning_algorithms.shac import _BiasEluLayerNormRows
+    dev = torch.device("cuda:0")
+    torch.manual_seed(4)
+    for W, M in ((32, 7), (64, 1000), (128, 4099)):
+        z = (torch.randn(M, W, dtype=dtype, device=dev) * 2).requires_grad_(True)
+        b = torch.randn(W, dtype=dtype, device=dev).requires_grad_(True)
+        g = (torch.rand(W, dtype=dtype, device=dev) + 0.5).requires_grad_(True)
+        be = torch.randn(W, dtype=dtype, device=dev).requires_grad_(True)
+        cot = torch.randn(M, W, dtype=dtype, device=dev)
+        ref = torch.nn.functional.layer_norm(torch.nn.functional.elu(z + b), (W,), g, be, 1e-5)
+        ref_grads = torch.autograd.grad((ref * cot).sum(), (z, b, g, be))
+        got = _BiasEluLayerNormRows.apply(z, b, g, be)
+        got_grads = torch.autograd.grad((got * cot).sum(), (z, b, g, be))
+        np.testing.assert_allclose(got.detach().cpu().numpy(), ref.detach().cpu().numpy(), rtol=tol, atol=tol)
+        for name, a, r in zip(("dz", "dbias", "dgamma", "dbeta"), got_grads, ref_grads):
+            scale = float(r.abs().max()) + 1e-30
+            np.testing.assert_allclose(a.cpu().numpy() / scale, r.cpu().numpy() / scale, rtol=10 * tol, atol=10 * tol,
+                                       err_msg=f"{name} W={W} M={M}")
