@@ -45,6 +45,8 @@ def parse():
     p.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     p.add_argument("--fused", default="auto", choices=["auto", "on", "off"])
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--policy-arch", default=None, help="comma-separated hidden widths (default 128,128)")
+    p.add_argument("--vf-arch", default=None, help="comma-separated hidden widths (default 128,128,128)")
     p.add_argument("--rng-order", default="batched", choices=["batched", "reference"],
                    help="batched: 3 RNG draws per episode (same distributions); reference: the reference's per-step order")
     return p.parse_args()
@@ -184,9 +186,14 @@ def run_ours(args):
     torch.manual_seed(1234 + rank)
     env_cls = {"BalanceCartPole": balance_cartpole.BalanceCartPoleEnv, "BalancePendulum": balance_pendulum.BalancePendulumEnv,
                "SwingUpCartPole": swingup_cartpole.SwingUpCartPoleEnv, "BalanceQuadrotor": balance_quadrotor.BalanceQuadrotorEnv,
-               "ManageHousehold": manage_household.ManageHouseholdEnv}[args.env]
+               "ManageHousehold": manage_household.ManageHouseholdEnv}.get(args.env)
     N, H = args.num_envs, args.horizon
-    env = env_cls(num_envs=N, num_steps=240)
+    if args.env == "NavigateSeeker":
+        from safegbpo_b200.envs.navigate_seeker import NavigateSeekerEnv
+        env = NavigateSeekerEnv(num_envs=N, num_steps=400, num_obstacles=1, min_radius=2.0, max_radius=4.0)
+        env.reset(seed=1)
+    else:
+        env = env_cls(num_envs=N, num_steps={"ManageHousehold": 720}.get(args.env, 240))
     if args.safeguard == "boundary_projection":
         env = BoundaryProjectionSafeguard(env, strict=False)
     elif args.safeguard == "ray_mask":
@@ -435,11 +442,20 @@ def step_kernel_roofline(args, base, env, dev, dtype, n_envs=None):
             "launches_per_step": 2 * args.horizon}
 
 
+def _apply_archs(a):
+    global POLICY_ARCH, VF_ARCH
+    if a.policy_arch:
+        POLICY_ARCH = [int(x) for x in a.policy_arch.split(",")]
+    if a.vf_arch:
+        VF_ARCH = [int(x) for x in a.vf_arch.split(",")]
+
+
 if __name__ == "__main__":
     if os.environ.get("SGBPO_BENCH_DEBUG"):          # hang diagnosis: dump every thread's python stack after N seconds
         import faulthandler
         faulthandler.dump_traceback_later(int(os.environ["SGBPO_BENCH_DEBUG"]), repeat=False, file=sys.stderr)
     a = parse()
+    _apply_archs(a)
     if a.impl == "reference":
         run_reference(a)
     else:
