@@ -119,7 +119,7 @@ def run_reference(args):
         "impl": "reference", "metric": "safeguarded env-steps/s (fwd+bwd)", "value": v, "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": len(results), "warmup": 0, "ms_per_step": 1e3 * results[-1][1],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, max(1, args.gpus)),
         "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": workers, "kind": "port",
                          "sample": f"{workers} processes x {n_w} envs x H={args.horizon} x 1 episode of the same workload "
                                    "(oracle port of the reference path: per-env HiGHS solves + torch autograd, float64)"},
