@@ -210,3 +210,56 @@ def test_quadrotor_unreduced_program_follows_the_shipped_gate():
     finally:
         torch.set_default_device("cpu")
         torch.set_default_dtype(prev)
+
+
+@pytest.mark.parametrize("env_name,kind,N", [
+    ("SwingUpCartPole", "boundary_projection", 16384), ("SwingUpCartPole", "ray_mask", 16384),
+    ("BalanceQuadrotor", "boundary_projection", 32768), ("ManageHousehold", "boundary_projection", 65536),
+    ("BalancePendulum", "ray_mask", 65536)])
+def test_baseline_config_sizes_properties(env_name, kind, N):
+    """The other BASELINE.json configurations at their full batch sizes (float64, per-step kernels through the C ABI):
+    size-independent properties -- the result does not depend on the batch an environment sits in (the first 64
+    environments of the big launch equal a 64-environment launch bit for bit), the projection is idempotent, no
+    feasible guarded action leaves its sets, already-safe actions pass unchanged, gradients are finite."""
+    dev = torch.device("cuda:0")
+    opts = {"zonotopic": False} if kind == "ray_mask" and env_name != "BalancePendulum" else {}
+    gate = "reference" if env_name == "BalanceQuadrotor" else "always"
+    case = make_case(env_name, kind, 8, seed=3, gate=gate, **opts)
+    env = case["env"]
+    g = torch.Generator().manual_seed(N)
+    c = torch.tensor(env.sim.state_center, dtype=torch.float64)
+    h = torch.tensor(env.sim.state_half, dtype=torch.float64)
+    spread = 0.08 if env_name in ("BalancePendulum", "BalanceQuadrotor") else 0.95      # RCI sets are a small part of the box
+    s = (c + (torch.rand(N, env.state_dim, generator=g, dtype=torch.float64) * 2 - 1) * h * spread).to(dev)
+    a = (torch.rand(N, env.action_dim, generator=g, dtype=torch.float64) * 2 - 1).to(dev)
+    w = torch.zeros(N, env.state_dim, dtype=torch.float64, device=dev)
+    aux = None if case["aux"] is None else s[:, :2].clone()
+    dirs = None
+    if case["dirs"] is not None:
+        d = torch.rand(N, env.action_dim, 2 * env.action_dim, generator=g, dtype=torch.float64) * 2 - 1
+        dirs = (d / torch.linalg.vector_norm(d, dim=1, keepdim=True)).to(dev)
+    eid, k, sh = ENV_IDS[env_name], case["consts"], shared_for(env, 1)
+    sr, ar = s.clone().requires_grad_(True), a.clone().requires_grad_(True)
+    s_next, a1, obs, rew, fl = ops.safeguarded_step(sr, ar, w, eid, k, aux=aux, dirs=dirs, shared=sh)
+    small = ops.safeguarded_step(s[:64], a[:64], w[:64], eid, k, aux=None if aux is None else aux[:64],
+                                 dirs=None if dirs is None else dirs[:64], shared=sh)
+    for big, sm in zip((s_next, a1, obs, rew, fl), small):
+        if big.is_floating_point():       # (infeasible programs give NaN rows in both launches)
+            assert torch.equal(torch.nan_to_num(big[:64].detach(), nan=12345.0), torch.nan_to_num(sm, nan=12345.0)), "result depends on the batch"
+        else:
+            assert torch.equal(big[:64], sm), "result depends on the batch"
+    feas = ((fl & _lib.FL_INFEASIBLE) == 0) & ((fl & _lib.FL_UNREDUCED) == 0)
+    guard = (fl & _lib.FL_GUARD_USED) != 0
+    assert float(feas.float().mean()) > 0.5
+    if kind == "boundary_projection":
+        _, a2, _, _, _ = ops.safeguarded_step(s, a1.detach(), w, eid, k, aux=aux, dirs=dirs, shared=sh)
+        assert torch.allclose(a1[feas].detach(), a2[feas], rtol=0, atol=1e-10)                       # idempotent
+        good = feas & guard
+        if env.state_constrained and k.state_model != 2:
+            assert bool((((fl & _lib.FL_NEXT_IN_SET) != 0) | ~good).all())                         # zero violations
+        if env.action_constrained:
+            assert bool((((fl & _lib.FL_ACTION_IN_SET) != 0) | ~good).all())
+        untouched = feas & ((fl & _lib.FL_INTERVENED) == 0) & ~guard
+        assert torch.equal(a1[untouched].detach(), a[untouched])
+    (rew[feas].sum() + s_next[feas].sum()).backward()
+    assert bool(torch.isfinite(sr.grad[feas]).all()) and bool(torch.isfinite(ar.grad[feas]).all())
