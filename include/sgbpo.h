@@ -163,6 +163,10 @@ int sgbpo_rollout_bwd(int env_id, int dtype, const sgbpo_consts* consts, const s
 /* batched MLP forward over M rows (target critic over the buffer's observation rows, shac.py:111) */
 int sgbpo_mlp_rows(int dtype, int64_t M, const sgbpo_mlp* net, const void* x, void* out, void* stream);
 
+/* input gradient of a scalar-output MLP over M rows: gx[row] = row_weight[row] * d net(x[row]) / d x[row]  ([M][in_dim]).
+ * The terminal-value terms of the SHAC loss (shac.py:137-147) need it as the cotangent of the terminal observation rows. */
+int sgbpo_mlp_rows_vjp(int dtype, int64_t M, const sgbpo_mlp* net, const void* x, const void* row_weight, void* gx, void* stream);
+
 /* ---- policy update tail (shac.py:148-149: clip_grad_norm_(policy, max_norm) + torch.optim.Adam.step()) ---- */
 #define SGBPO_OPT_MAX_TENSORS 24
 typedef struct sgbpo_optim {

@@ -95,6 +95,7 @@ _SIGNATURES = {
     "sgbpo_rollout_bwd": (C.c_int, [C.c_int, C.c_int, C.POINTER(Consts), C.POINTER(Mlp), C.POINTER(Rollout),
                                     C.POINTER(RolloutGrads), _VP]),
     "sgbpo_mlp_rows": (C.c_int, [C.c_int, C.c_int64, C.POINTER(Mlp), _VP, _VP, _VP]),
+    "sgbpo_mlp_rows_vjp": (C.c_int, [C.c_int, C.c_int64, C.POINTER(Mlp), _VP, _VP, _VP, _VP]),
     "sgbpo_clip_adam": (C.c_int, [C.c_int, C.c_int, _VP, _VP, _VP]),
     "sgbpo_bias_elu_ln_fwd": (C.c_int, [C.c_int, C.c_int64, C.c_int] + [_VP] * 8),
     "sgbpo_bias_elu_ln_bwd": (C.c_int, [C.c_int, C.c_int64, C.c_int] + [_VP] * 9),

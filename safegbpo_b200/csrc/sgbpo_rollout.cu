@@ -63,4 +63,16 @@ int sgbpo_mlp_rows(int dtype, int64_t M, const sgbpo_mlp* net, const void* x, vo
   }
 }
 
+int sgbpo_mlp_rows_vjp(int dtype, int64_t M, const sgbpo_mlp* net, const void* x, const void* row_weight, void* gx, void* stream) {
+  if (!net || (M > 0 && (!x || !row_weight || !gx))) return fail2(SGBPO_E_ARG, "sgbpo_mlp_rows_vjp: null argument");
+  if (M <= 0) return SGBPO_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (net->width) {
+    case 32: return dtype ? launch_vjp<double, 32>(M, net, x, row_weight, gx, st) : launch_vjp<float, 32>(M, net, x, row_weight, gx, st);
+    case 64: return dtype ? launch_vjp<double, 64>(M, net, x, row_weight, gx, st) : launch_vjp<float, 64>(M, net, x, row_weight, gx, st);
+    case 128: return dtype ? launch_vjp<double, 128>(M, net, x, row_weight, gx, st) : launch_vjp<float, 128>(M, net, x, row_weight, gx, st);
+    default: return fail2(SGBPO_E_UNSUPPORTED, "sgbpo_mlp_rows_vjp supports hidden widths 32, 64, 128");
+  }
+}
+
 }  // extern "C"

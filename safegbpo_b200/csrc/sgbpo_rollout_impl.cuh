@@ -600,6 +600,122 @@ rollout_bwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// input gradient of a scalar-output MLP over M rows:  gx[row] = w[row] * d net(x[row]) / d x[row]
+// (the critic's terminal-value terms of the SHAC loss, shac.py:137-147: d(sum_k weight_k V'(obs_k)) / d obs_k, which
+// the reverse pass of the rollout needs as a cotangent of the terminal observation rows).  Forward with the ELU
+// outputs stashed in warp-private shared memory, then the transposed pass; no parameter gradients.
+template <class T, int W, int R>
+__global__ void __launch_bounds__(R == 8 ? 256 : 512)
+mlp_rows_vjp_kernel(int64_t M, const T* __restrict__ x, const T* __restrict__ wrow, T* __restrict__ gx,
+                    const __grid_constant__ MlpParams<T> P) {
+  constexpr int CPL = W / 32;
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  T* smem = reinterpret_cast<T*>(smem_raw);
+  NetSmem<T, W> net;
+  T* after = net.load(smem, P);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int in_dim = net.in_dim, nh = net.n_hidden;
+  size_t off = (size_t)(after - smem);
+  off = (off + 7) & ~size_t(7);
+  // warp-private: inT [in_dim][R], act [W][R], stash e_l [nh][W][R]
+  const size_t per_warp = ((size_t)(in_dim + (1 + nh) * W) * R + 7) & ~size_t(7);
+  T* inT = smem + off + warp * per_warp;
+  T* act = inT + in_dim * R;
+  T* eS = act + W * R;
+  const int64_t n_blocks = (M + R - 1) / R;
+  for (int64_t blk = (int64_t)blockIdx.x * nwarps + warp; blk < n_blocks; blk += (int64_t)gridDim.x * nwarps) {
+    const int64_t row0 = blk * R;
+    const int total = in_dim * R;
+    for (int i = lane; i < total; i += 32) {
+      const int r = i / in_dim, c = i % in_dim;
+      inT[c * R + r] = (row0 + r < M) ? x[row0 * in_dim + i] : T(0);
+    }
+    __syncwarp();
+    // ---- forward, keeping the ELU outputs and the LayerNorm statistics ----------------------------------------
+    T mean[MAX_HIDDEN][R], rstd[MAX_HIDDEN][R];
+    T h[R][CPL], ev[R][CPL];
+    tile_gemm<T, W, R>(inT, in_dim, net.w_in, net.b_hid, lane, h);
+    elu_layernorm<T, W, R, true>(h, net.gamma, net.beta, lane, ev, mean[0], rstd[0]);
+    store_tile<T, W, R>(eS, lane, ev);
+#pragma unroll
+    for (int l = 1; l < MAX_HIDDEN; ++l) {
+      if (l < nh) {
+        store_tile<T, W, R>(act, lane, h);
+        __syncwarp();
+        tile_gemm<T, W, R>(act, W, net.w_hid + (size_t)(l - 1) * W * (W + 1), net.b_hid + l * W, lane, h);
+        elu_layernorm<T, W, R, true>(h, net.gamma + l * W, net.beta + l * W, lane, ev, mean[l], rstd[l]);
+        store_tile<T, W, R>(eS + (size_t)l * W * R, lane, ev);
+        __syncwarp();
+      }
+    }
+    // ---- backward w.r.t. the input -----------------------------------------------------------------------------
+    T wr[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) wr[r] = (row0 + r < M) ? wrow[row0 + r] : T(0);
+    T gc[R][CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      const T wo = net.w_out[(lane + 32 * j) * net.out_dim];
+#pragma unroll
+      for (int r = 0; r < R; ++r) gc[r][j] = wr[r] * wo;
+    }
+#pragma unroll
+    for (int l = MAX_HIDDEN - 1; l >= 0; --l) {
+      if (l < nh) {
+        T xh[R][CPL], eg[R][CPL];
+        load_tile<T, W, R>(eS + (size_t)l * W * R, lane, eg);
+        unstash<T, W, R>(eg, mean[l], rstd[l], xh, eg);
+        T s1[R], s2[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          s1[r] = T(0); s2[r] = T(0);
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) {
+            const T dx = gc[r][j] * net.gamma[l * W + lane + 32 * j];
+            gc[r][j] = dx;
+            s1[r] += dx;
+            s2[r] = fma(dx, xh[r][j], s2[r]);
+          }
+        }
+        warp_sum_rows<T, R>(s1);
+        warp_sum_rows<T, R>(s2);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const T m1 = s1[r] / T(W), m2 = s2[r] / T(W);
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) gc[r][j] = (rstd[l][r] * (gc[r][j] - m1 - xh[r][j] * m2)) * eg[r][j];
+        }
+        if (l > 0) {
+          store_tile<T, W, R>(act, lane, gc);
+          __syncwarp();
+          tile_gemm_t<T, W, R>(act, net.w_hid + (size_t)(l - 1) * W * (W + 1), lane, gc);
+          __syncwarp();
+        }
+      }
+    }
+    // input layer: gx[r][i] = sum_c dz1[r][c] w_in[i][c]
+    for (int i = 0; i < in_dim; ++i) {
+      T p[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        p[r] = T(0);
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) p[r] = fma(gc[r][j], net.w_in[i * (W + 1) + lane + 32 * j], p[r]);
+      }
+      warp_sum_rows<T, R>(p);
+      if (lane < R && row0 + lane < M) {
+        T mine = T(0);
+#pragma unroll
+        for (int r = 0; r < R; ++r) mine = (lane == r) ? p[r] : mine;
+        gx[(row0 + lane) * in_dim + i] = mine;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // launch shapes.  Shared memory per CTA = network parameters (shared by the CTA's warps) + per-warp tiles.
 constexpr size_t SMEM_CAP = 227 * 1024;
 
@@ -773,6 +889,29 @@ template <class T, int W> int launch_rows(int64_t M, const sgbpo_mlp* net, const
   return sh.R == 8 ? launch_rows_R<T, W, 8>(sh, M, net, x, out, st) : launch_rows_R<T, W, 4>(sh, M, net, x, out, st);
 }
 
+
+template <class T, int W, int R>
+int launch_vjp_R(const Shape& sh, int64_t M, const sgbpo_mlp* net, const void* x, const void* w, void* gx, cudaStream_t st) {
+  auto kern = mlp_rows_vjp_kernel<T, W, R>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
+  if (e != cudaSuccess) return cuda_fail2(e, "cudaFuncSetAttribute(mlp_rows_vjp)");
+  int64_t blocks = sh.grid;
+  const int64_t cap = (int64_t)sm_count() * (sh.smem > 110 * 1024 ? 1 : 2);
+  if (blocks > cap) blocks = cap;
+  kern<<<(int)blocks, sh.warps * 32, sh.smem, st>>>(M, (const T*)x, (const T*)w, (T*)gx, convert_mlp<T>(*net));
+  e = cudaGetLastError();
+  return e == cudaSuccess ? SGBPO_OK : cuda_fail2(e, "mlp_rows_vjp_kernel");
+}
+
+template <class T, int W> int launch_vjp(int64_t M, const sgbpo_mlp* net, const void* x, const void* w, void* gx, cudaStream_t st) {
+  if (net->n_hidden < 1 || net->n_hidden > MAX_HIDDEN) return fail2(SGBPO_E_UNSUPPORTED, "1..4 hidden layers");
+  if (net->out_dim != 1) return fail2(SGBPO_E_UNSUPPORTED, "sgbpo_mlp_rows_vjp: scalar-output networks");
+  const int caps[3] = {RowsShape<8>::MAX_WARPS, RowsShape<4>::MAX_WARPS, 0};
+  const Shape sh = pick_shape<T>(M, net_bytes<T, W>(net->in_dim, net->n_hidden, net->out_dim), net->in_dim, 1 + net->n_hidden, W,
+                                 caps, true);
+  if (!sh.R) return fail2(SGBPO_E_UNSUPPORTED, "network does not fit in shared memory");
+  return sh.R == 8 ? launch_vjp_R<T, W, 8>(sh, M, net, x, w, gx, st) : launch_vjp_R<T, W, 4>(sh, M, net, x, w, gx, st);
+}
 
 // one translation unit per (environment, dtype): SGBPO_INSTANTIATE_ROLLOUT_ENV_T(E, T, SUFFIX) in sgbpo_rollout_env<E>_<f|d>.cu
 template <int ENV, class T> int rollout_fwd_env_t(int width, const sgbpo_consts* c, const sgbpo_mlp* pol,

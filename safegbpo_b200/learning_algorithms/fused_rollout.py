@@ -67,6 +67,12 @@ def mlp_rows_fits(dtype, in_dim: int, width: int, n_hidden: int, out_dim: int = 
     return (net_smem_floats(in_dim, width, n_hidden, out_dim) + (in_dim + 2 * width) * 4 + 8) * size + 32 <= SMEM_LIMIT
 
 
+def mlp_vjp_fits(dtype, in_dim: int, width: int, n_hidden: int, out_dim: int = 1) -> bool:
+    """sgbpo_mlp_rows_vjp: one warp of 4 rows with its activation tile and n_hidden stash tiles next to the parameters."""
+    size = 4 if dtype == torch.float32 else 8
+    return (net_smem_floats(in_dim, width, n_hidden, out_dim) + (in_dim + (1 + n_hidden) * width) * 4 + 8) * size + 32 <= SMEM_LIMIT
+
+
 def rollout_fits(dtype, obs_dim: int, width: int, n_hidden: int, act_dim: int) -> bool:
     """At least one warp of 2 rows of the backward kernel (4 tiles of W + the observation tile) fits."""
     size = 4 if dtype == torch.float32 else 8
@@ -126,9 +132,10 @@ class FusedRollout:
         vp = self.vf_pack
         # critic too large for shared memory in this dtype (e.g. float64 [128]x3): evaluate it with torch
         self.vf_native = mlp_rows_fits(self.base.state.dtype, vp.in_dim, vp.width, vp.n_hidden)
+        self.vf_vjp_native = mlp_vjp_fits(self.base.state.dtype, vp.in_dim, vp.width, vp.n_hidden)
         self._grad_bufs = None
         self.last = None
-        self.launches_per_episode = 5          # rollout_fwd, mlp_rows(_tc), rollout_bwd, grad_norm, adam_apply (our kernels)
+        self.launches_per_episode = 6          # rollout_fwd, mlp_rows(_tc), mlp_rows_vjp, rollout_bwd, grad_norm, adam_apply (our kernels)
         self.use_graphs = True                 # replay the episode as two CUDA graphs when its schedule allows
         self.graph_warmup = 2                  # eager episodes before capture (optimizer state, cuBLAS handles)
         self._episodes = 0
@@ -400,9 +407,16 @@ class FusedRollout:
         picked = torch.where(term_mask.unsqueeze(1), g["values"], g["rewards"])
         g["loss"].copy_(-(g["disc_t"].unsqueeze(1) * picked).sum() / g["norm_t"][0])
         # critic input-gradient on the (at most KM) terminal rows; unused slots carry weight 0
-        x = g["obs"].index_select(0, g["term_rows"]).detach().clone().requires_grad_(True)
-        v = (algo.target_value_function(x.view(-1, o)).view(g["KM"], N) * g["term_w"].unsqueeze(1)).sum()
-        g["gobs_term"].copy_(torch.autograd.grad(v, x)[0])
+        x = g["obs"].index_select(0, g["term_rows"]).detach()
+        if self.vf_vjp_native:         # one launch: forward + transposed pass of the target critic (csrc mlp_rows_vjp_kernel)
+            roww = g["term_w"].unsqueeze(1).expand(g["KM"], N).contiguous()
+            check(_lib.lib().sgbpo_mlp_rows_vjp(dtype_code(dt), g["KM"] * N, C.byref(self.vf_pack.desc), C.c_void_p(x.data_ptr()),
+                                                C.c_void_p(roww.data_ptr()), C.c_void_p(g["gobs_term"].data_ptr()), stream_ptr()),
+                  "sgbpo_mlp_rows_vjp")
+        else:
+            x = x.clone().requires_grad_(True)
+            v = (algo.target_value_function(x.view(-1, o)).view(g["KM"], N) * g["term_w"].unsqueeze(1)).sum()
+            g["gobs_term"].copy_(torch.autograd.grad(v, x)[0])
         g["flat"].zero_()
         check(_lib.lib().sgbpo_rollout_bwd(base.env_id, dtype_code(dt), C.byref(self._consts()),
                                            C.byref(self.policy_pack.desc), C.byref(g["r"]), C.byref(g["gr"]), stream_ptr()),
@@ -672,13 +686,22 @@ class FusedRollout:
         # critic input-gradient on the terminal rows (N x o inputs each): plain autograd through the target critic
         rows = [j for j in range(1, H + 1) if terminal_rows[j]]
         term_of_row = [-1] * (H + 2)
-        gterm = []
         for kk, j in enumerate(rows):
-            x = last["obs"][j].detach().clone().requires_grad_(True)
-            v = algo.target_value_function(x).sum() * (-disc[j] / norm)
-            gterm.append(torch.autograd.grad(v, x)[0])
             term_of_row[j] = kk
-        gobs_term = torch.stack(gterm).contiguous()
+        if self.vf_vjp_native:
+            x = last["obs"][rows].detach().contiguous()                                    # [K, N, o]
+            roww = torch.tensor([-disc[j] / norm for j in rows], dtype=dt, device=dev).unsqueeze(1).expand(len(rows), N).contiguous()
+            gobs_term = torch.empty(len(rows), N, o, dtype=dt, device=dev)
+            check(_lib.lib().sgbpo_mlp_rows_vjp(dtype_code(dt), len(rows) * N, C.byref(self.vf_pack.desc), C.c_void_p(x.data_ptr()),
+                                                C.c_void_p(roww.data_ptr()), C.c_void_p(gobs_term.data_ptr()), stream_ptr()),
+                  "sgbpo_mlp_rows_vjp")
+        else:
+            gterm = []
+            for kk, j in enumerate(rows):
+                x = last["obs"][j].detach().clone().requires_grad_(True)
+                v = algo.target_value_function(x).sum() * (-disc[j] / norm)
+                gterm.append(torch.autograd.grad(v, x)[0])
+            gobs_term = torch.stack(gterm).contiguous()
         term_of_row_t = torch.tensor(term_of_row, dtype=torch.int32, device=dev)
         h1, dz2 = self._grad_bufs["h1"], self._grad_bufs["dz2"]
         sizes = [o * W, W * m, 2 * W, 2 * W, 2 * W, m, m]

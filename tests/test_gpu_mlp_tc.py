@@ -63,3 +63,41 @@ def test_tensor_core_kernel_is_tcgen05():
     target = obj if obj.exists() else _lib.LIB_PATH
     sass = subprocess.run(["cuobjdump", "-sass", str(target)], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass and "LDTM" in sass
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 2e-5)], ids=["f64", "f32"])
+def test_rows_vjp_matches_torch_autograd(dtype, tol):
+    """sgbpo_mlp_rows_vjp (input gradient of the critic on the terminal rows, shac.py:137-147) against torch autograd."""
+    from safegbpo_b200 import _lib
+    from safegbpo_b200.learning_algorithms.components.value_function import ValueFunction
+    from safegbpo_b200.learning_algorithms.fused_rollout import PackedMlp, mlp_vjp_fits
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)
+    torch.set_default_device("cuda:0")
+    try:
+        torch.manual_seed(9)
+        for in_dim, width, depth, M in ((5, 128, 3, 8192), (3, 64, 2, 77), (8, 32, 1, 5), (5, 128, 2, 4099)):
+            if not mlp_vjp_fits(dtype, in_dim, width, depth):
+                continue
+            vf = ValueFunction(in_dim, net_arch=[width] * depth)
+            with torch.no_grad():
+                for m in vf.model:
+                    if isinstance(m, torch.nn.LayerNorm):
+                        m.weight.uniform_(0.5, 2.0)
+                        m.bias.uniform_(-0.5, 0.5)
+            x = (torch.randn(M, in_dim) * 2).requires_grad_(True)
+            w = torch.randn(M)
+            ref = torch.autograd.grad((vf(x).squeeze(1) * w).sum(), x)[0]
+            pack = PackedMlp(vf.model)
+            gx = torch.empty(M, in_dim)
+            _lib.check(_lib.lib().sgbpo_mlp_rows_vjp(_lib.dtype_code(dtype), M, C.byref(pack.desc), C.c_void_p(x.detach().data_ptr()),
+                                                     C.c_void_p(w.data_ptr()), C.c_void_p(gx.data_ptr()), _lib.stream_ptr()),
+                       "sgbpo_mlp_rows_vjp")
+            torch.cuda.synchronize()
+            scale = float(ref.abs().max()) + 1e-30
+            np.testing.assert_allclose(gx.cpu().numpy() / scale, ref.cpu().numpy() / scale, rtol=10 * tol, atol=tol,
+                                       err_msg=f"in={in_dim} W={width} depth={depth} M={M}")
+    finally:
+        torch.set_default_device("cpu")
+        torch.set_default_dtype(prev)
