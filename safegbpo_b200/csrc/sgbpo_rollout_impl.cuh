@@ -627,6 +627,18 @@ mlp_rows_vjp_kernel(int64_t M, const T* __restrict__ x, const T* __restrict__ wr
   for (int64_t blk = (int64_t)blockIdx.x * nwarps + warp; blk < n_blocks; blk += (int64_t)gridDim.x * nwarps) {
     const int64_t row0 = blk * R;
     const int total = in_dim * R;
+    {
+      // rows whose weight is zero contribute nothing (unused terminal-row slots of the static episode graph): the
+      // whole tile is skipped when all of its rows are (warp-uniform test)
+      bool any = false;
+#pragma unroll
+      for (int r = 0; r < R; ++r) any = any || (row0 + r < M && wrow[row0 + r] != T(0));
+      if (!any) {
+        for (int i = lane; i < total; i += 32)
+          if (row0 * in_dim + i < M * in_dim) gx[row0 * in_dim + i] = T(0);
+        continue;
+      }
+    }
     for (int i = lane; i < total; i += 32) {
       const int r = i / in_dim, c = i % in_dim;
       inT[c * R + r] = (row0 + r < M) ? x[row0 * in_dim + i] : T(0);

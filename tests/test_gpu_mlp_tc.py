@@ -88,6 +88,7 @@ def test_rows_vjp_matches_torch_autograd(dtype, tol):
                         m.bias.uniform_(-0.5, 0.5)
             x = (torch.randn(M, in_dim) * 2).requires_grad_(True)
             w = torch.randn(M)
+            w[M // 3: 2 * M // 3] = 0.0          # zero-weight rows (unused terminal slots): skipped tiles must still write zeros
             ref = torch.autograd.grad((vf(x).squeeze(1) * w).sum(), x)[0]
             pack = PackedMlp(vf.model)
             gx = torch.empty(M, in_dim)
