@@ -1,0 +1,73 @@
+"""Configuration matrix of the reference's tests/system_tests.py (SHAC rows): every environment x safeguard combination
+the reference runs end to end must construct through the drop-in classes with the reference's constructor arguments
+(conf/envs.py, conf/safeguard.py) and complete one full SHAC learning episode (collect, policy update, critic fit,
+Polyak) with finite losses.  NavigateQuadrotor is the one environment not built yet."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ENVS = {
+    "BalancePendulum": dict(num_envs=8, num_steps=3000),
+    "BalanceCartPole": dict(num_envs=16, num_steps=240),
+    "SwingUpCartPole": dict(num_envs=32, num_steps=240),
+    "BalanceQuadrotor": dict(num_envs=16, num_steps=240),
+    "ManageHousehold": dict(num_envs=8, num_steps=720),
+    "NavigateSeeker": dict(num_envs=64, num_steps=400, num_obstacles=1, min_radius=2.0, max_radius=4.0),
+}
+SAFEGUARDS = {
+    "none": None,
+    "bp": ("BoundaryProjection", dict(regularisation_coefficient=0.1)),
+    "rm": ("RayMask", dict(regularisation_coefficient=0.1, linear_projection=True, zonotopic_approximation=True, passthrough=False)),
+    "rm_passthrough": ("RayMask", dict(regularisation_coefficient=0.1, linear_projection=True, zonotopic_approximation=True, passthrough=True)),
+    "rm_orthogonal": ("RayMask", dict(regularisation_coefficient=0.1, linear_projection=True, zonotopic_approximation=False, passthrough=False)),
+}
+# system_tests.py: SHAC x {none, BP} on Pendulum / Quadrotor, SHAC + BP on every environment, SHAC + ray mask variants on Quadrotor
+MATRIX = [("BalancePendulum", "none"), ("BalanceQuadrotor", "none")] + [(e, "bp") for e in ENVS] + \
+         [("BalanceQuadrotor", s) for s in ("rm", "rm_passthrough", "rm_orthogonal")] + \
+         [("BalancePendulum", "rm"), ("ManageHousehold", "rm"), ("SwingUpCartPole", "rm_orthogonal")]
+
+
+def _classes():
+    from safegbpo_b200.envs.balance_cartpole import BalanceCartPoleEnv
+    from safegbpo_b200.envs.balance_pendulum import BalancePendulumEnv
+    from safegbpo_b200.envs.balance_quadrotor import BalanceQuadrotorEnv
+    from safegbpo_b200.envs.manage_household import ManageHouseholdEnv
+    from safegbpo_b200.envs.navigate_seeker import NavigateSeekerEnv
+    from safegbpo_b200.envs.swingup_cartpole import SwingUpCartPoleEnv
+    from safegbpo_b200.safeguards.boundary_projection import BoundaryProjectionSafeguard
+    from safegbpo_b200.safeguards.ray_mask import RayMaskSafeguard
+    return ({"BalancePendulum": BalancePendulumEnv, "BalanceCartPole": BalanceCartPoleEnv, "SwingUpCartPole": SwingUpCartPoleEnv,
+             "BalanceQuadrotor": BalanceQuadrotorEnv, "ManageHousehold": ManageHouseholdEnv, "NavigateSeeker": NavigateSeekerEnv},
+            {"BoundaryProjection": BoundaryProjectionSafeguard, "RayMask": RayMaskSafeguard})
+
+
+@pytest.mark.parametrize("env_name,sg", MATRIX, ids=[f"{e}-{s}" for e, s in MATRIX])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_shac_learning_episode(env_name, sg, dtype):
+    from safegbpo_b200.learning_algorithms.shac import SHAC
+    envs, guards = _classes()
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)                      # main.py:14 runs float64; north_star asks for float32
+    torch.set_default_device("cuda:0")
+    try:
+        torch.manual_seed(1)
+        env = envs[env_name](**ENVS[env_name])
+        if SAFEGUARDS[sg] is not None:
+            name, kwargs = SAFEGUARDS[sg]
+            env = guards[name](env, **kwargs)           # main.py:45-47: Safeguard(env, **asdict(cfg.safeguard))
+        algo = SHAC(env=env, policy_kwargs={"net_arch": [64, 64]}, policy_optim_kwargs={"lr": 1e-3},
+                    vf_kwargs={"net_arch": [64, 64]}, vf_optim_kwargs={"lr": 1e-3}, regularisation_coefficient=0.1,
+                    len_trajectories=8, vf_num_fits=2, vf_fit_num_batches=2)
+        for eps in range(2):
+            avg_reward, policy_loss, value_loss = algo._learn_episode(eps)
+            assert math.isfinite(avg_reward) and math.isfinite(policy_loss) and math.isfinite(value_loss), \
+                (avg_reward, policy_loss, value_loss)
+        assert all(bool(torch.isfinite(p).all()) for p in algo.policy.parameters())
+        if SAFEGUARDS[sg] is not None:
+            assert isinstance(env.interventions, int)
+    finally:
+        torch.set_default_device("cpu")
+        torch.set_default_dtype(prev)
