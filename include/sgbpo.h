@@ -19,6 +19,8 @@ extern "C" {
 #define SGBPO_MAXN 6
 #define SGBPO_MAXM 2
 #define SGBPO_MAXHP 48
+#define SGBPO_MAXGEN 20
+#define SGBPO_MAXNULL 14
 
 enum { SGBPO_F32 = 0, SGBPO_F64 = 1 };
 enum { SGBPO_OK = 0, SGBPO_E_ARG = -1, SGBPO_E_CUDA = -2, SGBPO_E_UNSUPPORTED = -3 };
@@ -42,7 +44,7 @@ enum {
 typedef struct sgbpo_consts {
   int32_t sg_kind, gate_mode;
   int32_t rm_linear, rm_zonotopic, rm_passthrough;
-  int32_t action_constrained, state_constrained, state_model; /* 0: G_s invertible, 1: polygon (n = 2), 2: unreduced (gate + raw action only) */
+  int32_t action_constrained, state_constrained, state_model; /* 0: G_s invertible, 1: polygon (n = 2), 2: unreduced (gate + raw action only), 3: lifted (per-env interior point) */
   int32_t disable_clamp, n_obstacles;                        /* 1: raw dynamics (no clamp); obstacles in aux (Navigate*) */
   int32_t act_set_mode, reserved1;                           /* 0: constant safe action set; 1: NavigateSeeker per-step set (P5) */
   double box_min[SGBPO_MAXN], box_max[SGBPO_MAXN];           /* feasible state box */
@@ -60,6 +62,13 @@ typedef struct sgbpo_consts {
   double q_hp[SGBPO_MAXHP][3];                               /* polytope Q: hq . (d, L) <= 1 */
   double c_s[SGBPO_MAXN];
   double B0hat[SGBPO_MAXN * SGBPO_MAXM];                     /* G_s^-1 B0 (signed) */
+  /* state block, model 3 (G_s wide, e.g. BalanceQuadrotor 6 x 24): the containment encoding is kept in its lifted
+   * form and solved per environment (interior point).  Generators with equal direction merged, zero ones dropped:
+   * beta = Gpinv d + Nmat y,  Gamma_j = Gam_p[:, j] + Nmat z_j  parametrise  G beta = d,  G Gamma = G_w. */
+  int32_t n_gen, n_null, n_wcol, reserved2;
+  double Gpinv[SGBPO_MAXGEN][SGBPO_MAXN];                    /* pinv(G)            (n_gen x n) */
+  double Nmat[SGBPO_MAXGEN][SGBPO_MAXNULL];                  /* null space of G    (n_gen x n_null), orthonormal columns */
+  double Gam_p[SGBPO_MAXGEN][2];                             /* pinv(G) G_w        (n_gen x n_wcol) */
 } sgbpo_consts;
 
 /* per-step scalars shared by all environments (household series; household.py:109-113,

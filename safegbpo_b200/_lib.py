@@ -16,6 +16,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB_PATH = PKG / "libsgbpo.so"
 MAXN, MAXM, MAXHP = 6, 2, 48
+MAXGEN, MAXNULL = 20, 14
 
 NVCC_FLAGS = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
               "--shared", "-Xcompiler", "-fPIC"]
@@ -40,6 +41,8 @@ class Consts(C.Structure):
         ("n_k_hp", C.c_int32), ("n_q_hp", C.c_int32),
         ("k_hp", (C.c_double * 2) * MAXHP), ("q_hp", (C.c_double * 3) * MAXHP), ("c_s", C.c_double * MAXN),
         ("B0hat", C.c_double * (MAXN * MAXM)),
+        ("n_gen", C.c_int32), ("n_null", C.c_int32), ("n_wcol", C.c_int32), ("reserved2", C.c_int32),
+        ("Gpinv", (C.c_double * MAXN) * MAXGEN), ("Nmat", (C.c_double * MAXNULL) * MAXGEN), ("Gam_p", (C.c_double * 2) * MAXGEN),
     ]
 
 

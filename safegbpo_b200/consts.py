@@ -107,6 +107,26 @@ def _support_points(G_s, fixed_cols, free_col, directions):
     return np.array(pts)
 
 
+def merge_parallel_generators(G: np.ndarray, tol: float = 1e-12) -> np.ndarray:
+    """Drop zero generators and merge those of equal direction (their lengths add): same zonotope, and the same
+    containment encoding (rows with equal generators can share one budget by convexity)."""
+    cols = []
+    for j in range(G.shape[1]):
+        g = G[:, j]
+        nrm = np.linalg.norm(g)
+        if nrm < tol:
+            continue
+        for c in cols:
+            cn = np.linalg.norm(c)
+            cosang = (c @ g) / (cn * nrm)
+            if abs(abs(cosang) - 1.0) < 1e-12:
+                c += np.sign(cosang) * g
+                break
+        else:
+            cols.append(g.astype(np.float64).copy())
+    return np.stack(cols, axis=1)
+
+
 def polytope_facets(G_s: np.ndarray, fixed_cols: np.ndarray, free_col: Optional[np.ndarray] = None,
                     tol: float = 1e-10) -> np.ndarray:
     """Exact facets  h . x <= 1  of  {x = (d[, L]) : the containment encoding is feasible}.
@@ -209,11 +229,29 @@ def build_consts(env_name: str, sg_kind: int, *, gate_mode: int = 0, rm_linear: 
                     for j in range(3):
                         k.q_hp[r][j] = row[j]
         else:
-            # G_s neither invertible nor 2-D (BalanceQuadrotor: 6 x 24): the feasible offsets form a 6-D polytope whose
-            # facets cannot be tabulated (beneath-beyond on it does not terminate in reasonable time) and the generic
-            # per-environment LP/QP kernel is not built yet.  Registered as "unreduced": linearisation, gate and
-            # action-set verdict run; under the shipped gate (Q1) the raw action is executed wherever the reachable
-            # box meets the feasible box (100 % of BalanceQuadrotor's RCI states), and any environment that needs
-            # the program's solution is reported (FL_UNREDUCED, NaN action -> ValueError in strict mode).
-            k.state_model = 2
+            # G_s wide (BalanceQuadrotor: 6 x 24): the feasible offsets form a 6-D polytope whose facets cannot be
+            # tabulated (beneath-beyond on it does not terminate in reasonable time), so the containment encoding
+            # stays in its lifted form and every environment solves it (interior point, csrc/sgbpo_lifted.cuh).
+            # Generators of equal direction are merged and zero ones dropped (equivalent encoding: the merged row
+            # budget is the mean of the merged rows' budgets, convexity), which leaves 14 of the 24 columns.
+            G = merge_parallel_generators(G_s)
+            Wn = G_w[:, np.abs(G_w).sum(axis=0) > 0]
+            p, nn = G.shape[1], G.shape[1] - np.linalg.matrix_rank(G)
+            if sg_kind != _lib.SG_BOUNDARY_PROJECTION or p > _lib.MAXGEN or nn > _lib.MAXNULL or Wn.shape[1] > 2 or m != 2 \
+                    or np.linalg.matrix_rank(G) < n:
+                k.state_model = 2          # unreduced: gate + raw action only (ray-mask programs of this set: not built)
+            else:
+                k.state_model = 3
+                Gp = np.linalg.pinv(G)
+                from scipy.linalg import null_space
+                Nm = null_space(G)
+                k.n_gen, k.n_null, k.n_wcol = p, Nm.shape[1], Wn.shape[1]
+                Gam = Gp @ Wn
+                for i in range(p):
+                    for j in range(n):
+                        k.Gpinv[i][j] = Gp[i, j]
+                    for j in range(Nm.shape[1]):
+                        k.Nmat[i][j] = Nm[i, j]
+                    for j in range(Wn.shape[1]):
+                        k.Gam_p[i][j] = Gam[i, j]
     return k

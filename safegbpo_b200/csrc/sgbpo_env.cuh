@@ -107,6 +107,7 @@ template <> struct Task<ENV_BALANCE_PENDULUM> {
   using Sim = PendulumSim;
   static constexpr int NS = 2, NA = 1, NO = 3, NAUX = 0;
   static constexpr bool CLAMP = true;
+  static constexpr bool LIFTED_OK = false;   // wide safe-state generator -> per-env interior point (sgbpo_lifted.cuh)
   template <class S, class T> SG_HD static void observe(const S* s, const T*, const StepShared<T>*, S* o) {
     sg_sincos(s[0], o[0], o[1]); o[2] = s[1];
   }
@@ -119,6 +120,7 @@ template <int ENV> struct CartPoleTask {
   using Sim = CartPoleSim;
   static constexpr int NS = 4, NA = 1, NO = 5, NAUX = 0;
   static constexpr bool CLAMP = true;
+  static constexpr bool LIFTED_OK = false;   // wide safe-state generator -> per-env interior point (sgbpo_lifted.cuh)
   template <class S, class T> SG_HD static void observe(const S* s, const T*, const StepShared<T>*, S* o) {
     o[0] = s[0]; sg_sincos(s[1], o[1], o[2]); o[3] = s[2]; o[4] = s[3];
   }
@@ -134,6 +136,7 @@ template <> struct Task<ENV_BALANCE_QUADROTOR> {
   using Sim = QuadrotorSim;
   static constexpr int NS = 6, NA = 2, NO = 8, NAUX = 2;   // aux = goal (x, z)
   static constexpr bool CLAMP = true;
+  static constexpr bool LIFTED_OK = true;   // wide safe-state generator -> per-env interior point (sgbpo_lifted.cuh)
   template <class S, class T> SG_HD static void observe(const S* s, const T* aux, const StepShared<T>*, S* o) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) o[i] = s[i];
@@ -153,6 +156,7 @@ template <> struct Task<ENV_MANAGE_HOUSEHOLD> {
   using Sim = HouseholdSim;
   static constexpr int NS = 3, NA = 2, NO = 23, NAUX = 0;
   static constexpr bool CLAMP = false;   // Q7
+  static constexpr bool LIFTED_OK = false;   // wide safe-state generator -> per-env interior point (sgbpo_lifted.cuh)
   template <class S, class T> SG_HD static void observe(const S* s, const T*, const StepShared<T>* sh, S* o) {
     o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
 #pragma unroll
@@ -173,6 +177,7 @@ template <> struct Task<ENV_NAVIGATE_SEEKER> {
   // observation written by the kernel: (state, goal); the constant obstacle columns are appended by the host
   static constexpr int NS = 2, NA = 2, NO = 4, NAUX = 2 + 3 * SEEKER_MAXK;
   static constexpr bool CLAMP = true;
+  static constexpr bool LIFTED_OK = false;   // wide safe-state generator -> per-env interior point (sgbpo_lifted.cuh)
   template <class S, class T> SG_HD static void observe(const S* s, const T* aux, const StepShared<T>*, S* o) {
     o[0] = s[0]; o[1] = s[1]; o[2] = S(aux[0]); o[3] = S(aux[1]);
   }

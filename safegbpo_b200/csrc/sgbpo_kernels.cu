@@ -168,13 +168,20 @@ static int grid_for(int64_t N, int block) {
   return (int)g;
 }
 
+// Threads per CTA of the per-step kernels.  The lifted program (sgbpo_lifted.cuh) is a long serial solve per thread:
+// one warp per CTA spreads a few thousand environments over all SMs instead of packing them onto 32 of them.
+static int block_for(int64_t N, const sgbpo_consts* c) {
+  return (c->state_model == SM_LIFTED && N <= 148 * 32 * 16) ? 32 : 128;
+}
+
 template <int ENV, class T> struct Launch {
   static int fwd(int64_t N, const sgbpo_consts* c, const sgbpo_step_shared* shp, const void* s, const void* a,
                  const void* w, const void* aux, const void* dirs, const void* reset_state, void* s_next,
                  void* a_exec, void* obs, void* reward, int32_t* flags, cudaStream_t st) {
     const SafeConsts<T> k = convert_consts<T>(*c);
     const StepShared<T> sh = convert_shared<T>(shp);
-    step_fwd_kernel<ENV, T><<<grid_for(N, 128), 128, 0, st>>>(
+    const int block = block_for(N, c);
+    step_fwd_kernel<ENV, T><<<grid_for(N, block), block, 0, st>>>(
         N, k, sh, (const T*)s, (const T*)a, (const T*)w, (const T*)aux, (const T*)dirs, (const T*)reset_state,
         (T*)s_next, (T*)a_exec, (T*)obs, (T*)reward, flags);
     cudaError_t e = cudaGetLastError();
@@ -185,7 +192,8 @@ template <int ENV, class T> struct Launch {
                  const void* g_a_exec, const void* g_obs, const void* g_reward, void* gs, void* ga, cudaStream_t st) {
     const SafeConsts<T> k = convert_consts<T>(*c);
     const StepShared<T> sh = convert_shared<T>(shp);
-    step_bwd_kernel<ENV, T><<<grid_for(N, 128), 128, 0, st>>>(
+    const int block = block_for(N, c);
+    step_bwd_kernel<ENV, T><<<grid_for(N, block), block, 0, st>>>(
         N, k, sh, (const T*)s, (const T*)a, (const T*)w, (const T*)aux, (const T*)dirs, (const T*)reset_state,
         (const T*)g_s_next, (const T*)g_a_exec, (const T*)g_obs, (const T*)g_reward, (T*)gs, (T*)ga);
     cudaError_t e = cudaGetLastError();

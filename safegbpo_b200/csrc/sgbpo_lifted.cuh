@@ -1,0 +1,296 @@
+// P1 (boundary projection, boundary_projection.py:33-57) for a safe state set whose generator is WIDE (BalanceQuadrotor:
+// G_s 6 x 24, m = 2).  The containment encoding enc(Z(c_f + B a, G_w) in Z(c_s, G_s)) (zonotope.py:131-141) cannot be
+// reduced to a fixed polygon in action space (its feasible offsets form a 6-D polytope with ~10^4 facets), so the program
+// is solved per environment in its lifted form:
+//
+//   min_a 1/2 |a - a0|^2   s.t.  -1 <= a <= 1,  a in the safe action polygon,
+//        exists beta, Gamma:  G beta = c_s - c_f - B a,  G Gamma = G_w,  |beta_i| + sum_j |Gamma_ij| <= 1  for every generator i
+//
+// The equalities are eliminated with constants computed once at registration (generators of equal direction merged):
+//   beta = p - Q a + N y,   Gamma_j = Gamma_p,j + N z_j      (p = G^+ (c_s - c_f), Q = G^+ B per environment; N = null(G))
+// and every row budget becomes 2^(1+q) linear rows  s0 beta_i + s1 Gamma_i1 + s2 Gamma_i2 <= 1  (signs s = +-1).  Unknowns
+// x = (a, y, z_1, z_2): 2 + 3 (p' - n) = 38 for the quadrotor, 164 rows.  Primal-dual interior point in DOUBLE per thread
+// (dense normal equations + Cholesky in local memory), then one Newton step of the same KKT system with the environment-
+// dependent row parts (Q, p, a0) in the dual-number type: implicit-function derivative of a_s w.r.t. (a, c_f, B).
+// The solve only runs for environments whose gate asks for the safeguarded action.
+#pragma once
+#include "sgbpo_safeguard2.cuh"
+
+namespace sgbpo {
+
+constexpr int LF_MAXV = 2 + 3 * MAXNULL;
+constexpr int LF_MAXR = 4 + MAXHP + 8 * MAXGEN;
+
+// lower-triangular packed symmetric matrix helpers
+SG_HD int tri(int i, int j) { return i * (i + 1) / 2 + j; }      // i >= j
+
+SG_HD bool chol_packed(double* K, int n) {
+  for (int j = 0; j < n; ++j) {
+    const double orig = K[tri(j, j)];
+    double d = orig;
+    for (int p = 0; p < j; ++p) d -= K[tri(j, p)] * K[tri(j, p)];
+    if (!(d == d)) return false;
+    if (!(d > 1e-12 * orig)) d = 1e60;        // direction left free by the active rows: frozen (see chol6)
+    d = sqrt(d);
+    K[tri(j, j)] = d;
+    for (int i = j + 1; i < n; ++i) {
+      double v = K[tri(i, j)];
+      for (int p = 0; p < j; ++p) v -= K[tri(i, p)] * K[tri(j, p)];
+      K[tri(i, j)] = v / d;
+    }
+  }
+  return true;
+}
+template <class W> SG_HD void chol_packed_solve(const double* L, int n, W* x) {
+  for (int i = 0; i < n; ++i) {
+    W v = x[i];
+    for (int p = 0; p < i; ++p) v = v - W(L[tri(i, p)]) * x[p];
+    x[i] = v / W(L[tri(i, i)]);
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    W v = x[i];
+    for (int p = i + 1; p < n; ++p) v = v - W(L[tri(p, i)]) * x[p];
+    x[i] = v / W(L[tri(i, i)]);
+  }
+}
+
+// per-environment data of the lifted program in scalar type W
+template <class W> struct LiftedEnv {
+  W p[MAXGEN];
+  W Q[MAXGEN][2];
+  W a0[2];
+};
+
+// Row layout.  Rows 0..3: the action box; then n_act rows of the safe action polygon (coefficients on the action only);
+// then, for generator i and sign combination c = (s0, s1, s2), the budget row
+//     s0 beta_i + s1 Gamma_i1 + s2 Gamma_i2 <= 1,   beta_i = p_i - Q_i a + N_i y,   Gamma_ij = Gam_p,ij + N_i z_j .
+// Every budget row of one generator has the coefficient vector (-s0 Q_i, s0 N_i, s1 N_i, s2 N_i): the normal-equation
+// matrix  sum_r w_r coef_r coef_r^T  is a sum over generators of 4 x 4 sign-weighted sums times the outer products of
+// (Q_i, N_i) -- ~8x fewer operations than row-by-row accumulation, and the row sweeps need 4 dot products per generator.
+template <class T>
+SG_HD void lifted_small_row(int r, const SafeConsts<T>& k, const ActRows<T>* dyn, double& c0, double& c1, double& g) {
+  if (r < 4) {
+    const double sg = (r & 1) ? -1.0 : 1.0;
+    c0 = (r >> 1) ? 0.0 : sg; c1 = (r >> 1) ? sg : 0.0; g = 1.0;
+    return;
+  }
+  r -= 4;
+  if (dyn && dyn->count > 0) { c0 = (double)dyn->n[r][0]; c1 = (double)dyn->n[r][1]; g = (double)dyn->h[r]; }
+  else { c0 = (double)k.act_hp[r][0]; c1 = (double)k.act_hp[r][1]; g = (double)k.act_hp[r][2]; }
+}
+
+// (beta_i, Gamma_i1, Gamma_i2) at x; with affine = false only the part linear in x (for a step direction)
+template <class W, class T>
+SG_HD void lifted_gen_vals(int i, const LiftedEnv<W>& E, const SafeConsts<T>& k, int nn, const double* x, bool affine, W* b) {
+  double dy = 0.0, d1 = 0.0, d2 = 0.0;
+  for (int j = 0; j < nn; ++j) {
+    const double nij = (double)k.Nmat[i][j];
+    dy += nij * x[2 + j];
+    if (k.n_wcol > 0) d1 += nij * x[2 + nn + j];
+    if (k.n_wcol > 1) d2 += nij * x[2 + 2 * nn + j];
+  }
+  b[0] = W(dy) - E.Q[i][0] * W(x[0]) - E.Q[i][1] * W(x[1]);
+  b[1] = W(d1); b[2] = W(d2);
+  if (affine) {
+    b[0] = b[0] + E.p[i];
+    if (k.n_wcol > 0) b[1] = b[1] + W((double)k.Gam_p[i][0]);
+    if (k.n_wcol > 1) b[2] = b[2] + W((double)k.Gam_p[i][1]);
+  }
+}
+
+// Normal equations K (packed lower triangle, primal parts) and right-hand side of one Newton step of the perturbed KKT
+// system at (x, s, lam).  target >= 0: complementarity target of the centring step; target < 0: every row keeps its own
+// lam_r s_r (the implicit-function step after convergence).  Returns the largest primal residual.
+template <class W, class T>
+SG_HD double lifted_assemble(const LiftedEnv<W>& E, const SafeConsts<T>& k, const ActRows<T>* dyn, int n_act, int nn, int nv,
+                             const double* x, const double* s, const double* lam, double target, double* K, W* rhs) {
+  for (int q = 0; q < nv * (nv + 1) / 2; ++q) K[q] = 0.0;
+  for (int j = 0; j < nv; ++j) rhs[j] = W(0.0);
+  rhs[0] = E.a0[0] - W(x[0]); rhs[1] = E.a0[1] - W(x[1]);               // -(H x + lin)
+  double k00 = 1.0, k10 = 0.0, k11 = 1.0, rp_max = 0.0;
+  const int nsmall = 4 + n_act, combos = 1 << (1 + k.n_wcol);
+  for (int r = 0; r < nsmall; ++r) {
+    double c0, c1, g;
+    lifted_small_row<T>(r, k, dyn, c0, c1, g);
+    const double rp = c0 * x[0] + c1 * x[1] + s[r] - g;
+    rp_max = fmax(rp_max, fabs(rp));
+    const double w = lam[r] / s[r];
+    const double t = lam[r] + (lam[r] * rp - (target < 0.0 ? 0.0 : lam[r] * s[r] - target)) / s[r];
+    rhs[0] = rhs[0] - W(c0 * t); rhs[1] = rhs[1] - W(c1 * t);
+    k00 += w * c0 * c0; k10 += w * c1 * c0; k11 += w * c1 * c1;
+  }
+  const int oy = 2, o1 = 2 + nn, o2 = 2 + 2 * nn;
+  for (int i = 0; i < k.n_gen; ++i) {
+    W b[3];
+    lifted_gen_vals<W, T>(i, E, k, nn, x, true, b);
+    double sw = 0.0, m01 = 0.0, m02 = 0.0, m12 = 0.0;
+    W t0 = W(0.0), t1 = W(0.0), t2 = W(0.0);
+    for (int c = 0; c < combos; ++c) {
+      const int r = nsmall + i * combos + c;
+      const double s0 = (c & 1) ? -1.0 : 1.0, s1 = (c & 2) ? -1.0 : 1.0, s2 = (c & 4) ? -1.0 : 1.0;
+      W rp = W(s0) * b[0] + W(s[r] - 1.0);
+      if (k.n_wcol > 0) rp = rp + W(s1) * b[1];
+      if (k.n_wcol > 1) rp = rp + W(s2) * b[2];
+      rp_max = fmax(rp_max, fabs(primal(rp)));
+      const double w = lam[r] / s[r];
+      const W t = W(lam[r]) + (W(lam[r]) * rp - W(target < 0.0 ? 0.0 : lam[r] * s[r] - target)) / W(s[r]);
+      sw += w; m01 += w * s0 * s1; m02 += w * s0 * s2; m12 += w * s1 * s2;
+      t0 = t0 + W(s0) * t; t1 = t1 + W(s1) * t; t2 = t2 + W(s2) * t;
+    }
+    const double q0 = primal(E.Q[i][0]), q1 = primal(E.Q[i][1]);
+    rhs[0] = rhs[0] + E.Q[i][0] * t0; rhs[1] = rhs[1] + E.Q[i][1] * t0;
+    k00 += sw * q0 * q0; k10 += sw * q1 * q0; k11 += sw * q1 * q1;
+    for (int j = 0; j < nn; ++j) {
+      const double nj = (double)k.Nmat[i][j];
+      rhs[oy + j] = rhs[oy + j] - W(nj) * t0;
+      K[tri(oy + j, 0)] -= sw * nj * q0; K[tri(oy + j, 1)] -= sw * nj * q1;
+      const double a = sw * nj;
+      for (int l = 0; l <= j; ++l) K[tri(oy + j, oy + l)] += a * (double)k.Nmat[i][l];
+      if (k.n_wcol > 0) {
+        rhs[o1 + j] = rhs[o1 + j] - W(nj) * t1;
+        K[tri(o1 + j, 0)] -= m01 * nj * q0; K[tri(o1 + j, 1)] -= m01 * nj * q1;
+        const double a1 = m01 * nj;
+        for (int l = 0; l < nn; ++l) K[tri(o1 + j, oy + l)] += a1 * (double)k.Nmat[i][l];
+      }
+      if (k.n_wcol > 1) {
+        rhs[o2 + j] = rhs[o2 + j] - W(nj) * t2;
+        K[tri(o2 + j, 0)] -= m02 * nj * q0; K[tri(o2 + j, 1)] -= m02 * nj * q1;
+        const double a2 = m02 * nj, a12 = m12 * nj;
+        for (int l = 0; l < nn; ++l) {
+          K[tri(o2 + j, oy + l)] += a2 * (double)k.Nmat[i][l];
+          K[tri(o2 + j, o1 + l)] += a12 * (double)k.Nmat[i][l];
+        }
+      }
+    }
+  }
+  K[tri(0, 0)] = k00; K[tri(1, 0)] = k10; K[tri(1, 1)] = k11;
+  // the diagonal blocks of the three lifted groups are equal (every sign squares to one)
+  for (int j = 0; j < nn; ++j)
+    for (int l = 0; l <= j; ++l) {
+      const double v = K[tri(oy + j, oy + l)];
+      if (k.n_wcol > 0) K[tri(o1 + j, o1 + l)] = v;
+      if (k.n_wcol > 1) K[tri(o2 + j, o2 + l)] = v;
+    }
+  return rp_max;
+}
+
+template <class TASK, class W, class S, class T>
+SG_HD void lifted_env(const S* a, const S* c_f, const S (*B)[MAXM], const SafeConsts<T>& k, LiftedEnv<W>& E) {
+  constexpr int NS = TASK::NS;
+  E.a0[0] = widen(a[0]); E.a0[1] = widen(a[1]);
+  for (int i = 0; i < k.n_gen; ++i) {
+    W p = W(0.0), q0 = W(0.0), q1 = W(0.0);
+    for (int j = 0; j < NS; ++j) {
+      const W gp = W((double)k.Gpinv[i][j]);
+      p = p + gp * (W((double)k.c_s[j]) - widen(c_f[j]));
+      q0 = q0 + gp * widen(B[j][0]);
+      q1 = q1 + gp * widen(B[j][1]);
+    }
+    E.p[i] = p; E.Q[i][0] = q0; E.Q[i][1] = q1;
+  }
+}
+
+template <class TASK, class S, class T>
+SG_HD bool project_lifted_m2(const S* a, const S* c_f, const S (*B)[MAXM], const SafeConsts<T>& k, const ActRows<T>* dyn,
+                             S* out) {
+  using SW = typename Widen<S>::type;
+  const int nn = k.n_null, nv = 2 + nn * (1 + k.n_wcol);
+  const int n_act = k.action_constrained ? ((dyn && dyn->count > 0) ? dyn->count : k.n_act_hp) : 0;
+  const int nr = 4 + n_act + k.n_gen * (1 << (1 + k.n_wcol));
+  bool ok = false;
+  double x[LF_MAXV], s[LF_MAXR], lam[LF_MAXR], K[LF_MAXV * (LF_MAXV + 1) / 2], rhsv[LF_MAXV];
+  double mu = 1.0;
+  {
+    T cf_p[MAXN];
+    T B_p[MAXN][MAXM];
+    T a_p[2] = {primal(a[0]), primal(a[1])};
+    for (int i = 0; i < TASK::NS; ++i) { cf_p[i] = primal(c_f[i]); B_p[i][0] = primal(B[i][0]); B_p[i][1] = primal(B[i][1]); }
+    LiftedEnv<double> E;
+    lifted_env<TASK, double, T, T>(a_p, cf_p, B_p, k, E);
+    for (int j = 0; j < nv; ++j) x[j] = 0.0;
+    x[0] = fmin(fmax(E.a0[0], -0.9), 0.9); x[1] = fmin(fmax(E.a0[1], -0.9), 0.9);
+    const int nsmall = 4 + n_act, combos = 1 << (1 + k.n_wcol);
+    for (int r = 0; r < nsmall; ++r) {
+      double c0, c1, g;
+      lifted_small_row<T>(r, k, dyn, c0, c1, g);
+      s[r] = fmax(g - c0 * x[0] - c1 * x[1], 0.1);
+      lam[r] = 1.0 / s[r];
+    }
+    for (int i = 0; i < k.n_gen; ++i) {
+      double b[3];
+      lifted_gen_vals<double, T>(i, E, k, nn, x, true, b);
+      for (int c = 0; c < combos; ++c) {
+        const int r = nsmall + i * combos + c;
+        const double v = ((c & 1) ? -b[0] : b[0]) + ((c & 2) ? -b[1] : b[1]) + ((c & 4) ? -b[2] : b[2]);
+        s[r] = fmax(1.0 - v, 0.1);
+        lam[r] = 1.0 / s[r];
+      }
+    }
+    for (int it = 0; it < 80; ++it) {
+      double gap = 0.0;
+      for (int r = 0; r < nr; ++r) gap += lam[r] * s[r];
+      mu = gap / nr;
+      const double target = fmax(0.1 * mu, 5e-11);
+      const double rp_max = lifted_assemble<double, T>(E, k, dyn, n_act, nn, nv, x, s, lam, target, K, rhsv);
+      if (!chol_packed(K, nv)) break;
+      chol_packed_solve<double>(K, nv, rhsv);                  // rhsv := dx
+      // only the action is unique at the optimum (the lifted variables have a face of optimal values): the stopping test
+      // looks at the action part of the step
+      double alpha = 1.0;
+      const double dx_max = fmax(fabs(rhsv[0]), fabs(rhsv[1]));
+      for (int pass = 0; pass < 2; ++pass) {                  // pass 0: step length; pass 1: slack and multiplier update
+        for (int r = 0; r < nsmall; ++r) {
+          double c0, c1, g;
+          lifted_small_row<T>(r, k, dyn, c0, c1, g);
+          const double rp = c0 * x[0] + c1 * x[1] + s[r] - g;
+          const double ds = -rp - (c0 * rhsv[0] + c1 * rhsv[1]);
+          const double dl = (-(lam[r] * s[r] - target) - lam[r] * ds) / s[r];
+          if (pass == 0) {
+            if (ds < 0.0) alpha = fmin(alpha, -0.995 * s[r] / ds);
+            if (dl < 0.0) alpha = fmin(alpha, -0.995 * lam[r] / dl);
+          } else { s[r] += alpha * ds; lam[r] += alpha * dl; }
+        }
+        for (int i = 0; i < k.n_gen; ++i) {
+          double b[3], d[3];
+          lifted_gen_vals<double, T>(i, E, k, nn, x, true, b);
+          lifted_gen_vals<double, T>(i, E, k, nn, rhsv, false, d);
+          for (int c = 0; c < combos; ++c) {
+            const int r = nsmall + i * combos + c;
+            const double s0 = (c & 1) ? -1.0 : 1.0, s1 = (c & 2) ? -1.0 : 1.0, s2 = (c & 4) ? -1.0 : 1.0;
+            const double rp = s0 * b[0] + s1 * b[1] + s2 * b[2] + s[r] - 1.0;
+            const double ds = -rp - (s0 * d[0] + s1 * d[1] + s2 * d[2]);
+            const double dl = (-(lam[r] * s[r] - target) - lam[r] * ds) / s[r];
+            if (pass == 0) {
+              if (ds < 0.0) alpha = fmin(alpha, -0.995 * s[r] / ds);
+              if (dl < 0.0) alpha = fmin(alpha, -0.995 * lam[r] / dl);
+            } else { s[r] += alpha * ds; lam[r] += alpha * dl; }
+          }
+        }
+      }
+      for (int j = 0; j < nv; ++j) x[j] += alpha * rhsv[j];
+#ifdef SGBPO_LIFTED_DEBUG
+      printf("it %d mu %.3e rp %.3e alpha %.3e dx %.3e x %.6f %.6f\n", it, mu, rp_max, alpha, dx_max, x[0], x[1]);
+#endif
+      if (rp_max < 1e-9 && mu < 2e-10 && alpha * dx_max < 1e-9) { ok = true; break; }
+    }
+    // the action was already safe: the barrier centre sits ~1e-8 inside; return the action itself (identity map,
+    // identity Jacobian -- what the exact projection is there)
+    if (ok && fabs(x[0] - E.a0[0]) < 1e-7 && fabs(x[1] - E.a0[1]) < 1e-7) {
+      out[0] = a[0]; out[1] = a[1];
+      return true;
+    }
+  }
+  if (!ok) { out[0] = C<S>(NAN); out[1] = C<S>(NAN); return false; }
+  // ---- implicit-function Newton step with the environment-dependent row parts in the dual-number type -----------
+  LiftedEnv<SW> ES;
+  lifted_env<TASK, SW, S, T>(a, c_f, B, k, ES);
+  SW rhsS[LF_MAXV];
+  lifted_assemble<SW, T>(ES, k, dyn, n_act, nn, nv, x, s, lam, -1.0, K, rhsS);      // row target := lam_r s_r
+  if (!chol_packed(K, nv)) { out[0] = C<S>(NAN); out[1] = C<S>(NAN); return false; }
+  chol_packed_solve<SW>(K, nv, rhsS);
+  narrow(SW(x[0]) + rhsS[0], out[0]);
+  narrow(SW(x[1]) + rhsS[1], out[1]);
+  return true;
+}
+
+}  // namespace sgbpo

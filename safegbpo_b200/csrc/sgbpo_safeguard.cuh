@@ -24,13 +24,15 @@ namespace sgbpo {
 
 constexpr int MAXHP = 48;      // half-planes for polygon models
 constexpr int MAXROWS = 64;    // rows of a per-env action-space polytope
+constexpr int MAXGEN = 20;     // merged generators of a wide safe-state zonotope (lifted model)
+constexpr int MAXNULL = 14;    // dimension of their null space
 
 enum SgKind : int { SG_NONE = 0, SG_BOUNDARY_PROJECTION = 1, SG_RAY_MASK = 2 };
 enum GateMode : int { GATE_REFERENCE = 0, GATE_INTENDED = 1, GATE_ALWAYS = 2 };
 // SM_UNREDUCED: safe state set whose generator is neither invertible nor 2-D (BalanceQuadrotor's 6 x 24 RCI set): the
 // linearisation, the gate and the verdict on the action set run, but the program itself has no register-level
 // reduction yet -- wherever the gate asks for the safeguarded action the step reports FL_UNREDUCED (+ NaN action)
-enum StateModel : int { SM_INVERTIBLE = 0, SM_POLYGON = 1, SM_UNREDUCED = 2 };
+enum StateModel : int { SM_INVERTIBLE = 0, SM_POLYGON = 1, SM_UNREDUCED = 2, SM_LIFTED = 3 };
 
 // status / verdict bits written per environment per step
 enum Flag : int {
@@ -70,6 +72,11 @@ template <class T> struct SafeConsts {
   T q_hp[MAXHP][3];
   T c_s[MAXN];
   T B0hat[MAXN * MAXM];                // G_s^-1 B0 (signed), for P2 with m = 2
+  // state block, model 3 (lifted): beta = Gpinv d + Nmat y, Gamma_j = Gam_p[:, j] + Nmat z_j
+  int n_gen, n_null, n_wcol, reserved2;
+  T Gpinv[MAXGEN][MAXN];
+  T Nmat[MAXGEN][MAXNULL];
+  T Gam_p[MAXGEN][2];
 };
 
 // ---- gate: AxisAlignedBox.intersects(Zonotope(c_f, B I_m))  (box.py:139-154, simulator.py:240-243) --

@@ -548,7 +548,7 @@ template <class TASK, class T>
 SG_HD bool next_state_in_set(const T* a, const T* c_f, const T (*B)[MAXM], const SafeConsts<T>& k) {
   constexpr int NS = TASK::NS, NA = TASK::NA;
   const T tol = verdict_tol<T>();
-  if (k.state_model == SM_UNREDUCED) return false;      // verdict not available for this model
+  if (k.state_model == SM_UNREDUCED || k.state_model == SM_LIFTED) return false;      // verdict not available for these models
   if (k.state_model == SM_INVERTIBLE) {
     for (int i = 0; i < NS; ++i) {
       T e = k.cs_hat[i];

@@ -5,6 +5,7 @@
 #pragma once
 #include "sgbpo_safeguard.cuh"
 #include "sgbpo_safeguard2.cuh"
+#include "sgbpo_lifted.cuh"
 
 namespace sgbpo {
 
@@ -63,12 +64,29 @@ SG_HD void safeguarded_step(const S* s, const S* a, const T* w, const T* aux, co
       for (int q = 0; q < NA; ++q) Bp[i][q] = primal(B[i][q]);
     }
     const bool projectable = gate_projectable<TASK>(cfp, Bp, k);
+    const bool use_guard = k.gate_mode == GATE_REFERENCE ? !projectable
+                                                         : (k.gate_mode == GATE_INTENDED ? projectable : true);
     S g[NA];
     bool feasible;
     ActRows<T> dyn;
     dyn.count = 0;
     if constexpr (NA == 1) {
       feasible = safeguard_m1<TASK>(a[0], c_f, B, k, g[0]);
+    } else if (TASK::LIFTED_OK && k.state_constrained && k.state_model == SM_LIFTED) {
+      // wide safe-state generator: the program is an iterative per-environment solve (sgbpo_lifted.cuh), run only
+      // where the gate asks for its solution (the reference evaluates it everywhere and discards it, safeguard.py:67)
+      if (!use_guard) {
+#pragma unroll
+        for (int q = 0; q < NA; ++q) g[q] = a[q];
+        feasible = true;
+      } else if (k.sg_kind == SG_BOUNDARY_PROJECTION) {
+        if constexpr (TASK::LIFTED_OK) feasible = project_lifted_m2<TASK>(a, c_f, B, k, &dyn, g);
+        else feasible = false;
+      } else {
+#pragma unroll
+        for (int q = 0; q < NA; ++q) g[q] = C<S>(NAN);
+        feasible = false;
+      }
     } else {
       bool set_ok = true;
       if (k.act_set_mode == 1) {                 // NavigateSeeker: the safe action set is rebuilt every step (P5)
@@ -80,8 +98,6 @@ SG_HD void safeguarded_step(const S* s, const S* a, const T* w, const T* aux, co
       }
       feasible = safeguard_m2<TASK>(a, c_f, B, dirs, k, &dyn, g) && set_ok;
     }
-    const bool use_guard = k.gate_mode == GATE_REFERENCE ? !projectable
-                                                         : (k.gate_mode == GATE_INTENDED ? projectable : true);
     if (projectable) flags |= FL_PROJECTABLE;
     if (use_guard) {
       flags |= FL_GUARD_USED;

@@ -142,3 +142,37 @@ def p2_center_unique(case, tol: float = 1e-7):
             width = max(width, -hi.fun - lo.fun)
         mask[i] = width < tol
     return mask
+
+
+def containment_budget(G, W, d):
+    """Independent feasibility measure for the zonotope-in-zonotope encoding with a wide generator (n x p, p > n):
+    the smallest t with  G beta = d,  G Gamma_j = W[:, j],  |beta|_i + sum_j |Gamma_ij| <= t  (scipy HiGHS LP on the
+    UNMERGED encoding the reference states, src/safeguards/boundary_projection.py:64-84).  t <= 1 <=> the reachable
+    set  d-shifted + W  fits inside the safe set."""
+    from scipy.optimize import linprog
+    n, p = G.shape
+    q = W.shape[1]
+    nb, ng = p, q * p
+    nvar = 2 * (nb + ng) + 1
+    c = np.zeros(nvar)
+    c[-1] = 1
+    Aeq, beq = np.zeros((n * (1 + q), nvar)), np.zeros(n * (1 + q))
+    Aeq[:n, :nb], beq[:n] = G, d
+    for j in range(q):
+        Aeq[n + n * j:2 * n + n * j, nb + j * p: nb + (j + 1) * p], beq[n + n * j:2 * n + n * j] = G, W[:, j]
+    rows = []
+    for kx in range(nb + ng):
+        for sgn in (1, -1):
+            r = np.zeros(nvar)
+            r[kx], r[nb + ng + kx] = sgn, -1
+            rows.append(r)
+    for ii in range(p):
+        r = np.zeros(nvar)
+        r[nb + ng + ii] = 1
+        for j in range(q):
+            r[nb + ng + nb + j * p + ii] = 1
+        r[-1] = -1
+        rows.append(r)
+    res = linprog(c, A_ub=np.array(rows), b_ub=np.zeros(len(rows)), A_eq=Aeq, b_eq=beq, bounds=[(None, None)] * nvar,
+                  method="highs")
+    return res.fun if res.status == 0 else np.inf

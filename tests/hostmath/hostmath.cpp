@@ -21,6 +21,12 @@ template <class T> static SafeConsts<T> conv(const sgbpo_consts& c) {
   }
   for (int i = 0; i < MAXN * MAXN; ++i) k.Ginv[i] = T(c.Ginv[i]);
   for (int i = 0; i < MAXN * MAXM; ++i) { k.B0hat_abs[i] = T(c.B0hat_abs[i]); k.B0hat[i] = T(c.B0hat[i]); }
+  k.n_gen = c.n_gen; k.n_null = c.n_null; k.n_wcol = c.n_wcol;
+  for (int i = 0; i < MAXGEN; ++i) {
+    for (int j = 0; j < MAXN; ++j) k.Gpinv[i][j] = T(c.Gpinv[i][j]);
+    for (int j = 0; j < MAXNULL; ++j) k.Nmat[i][j] = T(c.Nmat[i][j]);
+    for (int j = 0; j < 2; ++j) k.Gam_p[i][j] = T(c.Gam_p[i][j]);
+  }
   for (int i = 0; i < MAXM; ++i) { k.a_lo[i] = T(c.a_lo[i]); k.a_hi[i] = T(c.a_hi[i]); k.c_a[i] = T(c.c_a[i]); }
   k.n_act_hp = c.n_act_hp; k.n_k_hp = c.n_k_hp; k.n_q_hp = c.n_q_hp;
   for (int r = 0; r < MAXHP; ++r) {

@@ -160,42 +160,64 @@ def test_large_batch_properties():
         assert torch.equal(a1[inside], a[inside])                                # already-safe actions pass unchanged
 
 
-def test_quadrotor_unreduced_program_follows_the_shipped_gate():
-    """BalanceQuadrotor's safe state set (6 x 24 generator) is registered as SM_UNREDUCED: linearisation, gate and
-    action-set verdict run on the GPU; under the shipped gate (Q1) every RCI state is projectable, so the executed
-    action is the raw action and states / observations / rewards / gradients must equal the oracle's (which solves
-    the lifted QP with HiGHS like the reference and then discards it).  Where the safeguarded action IS needed the
-    step must say so loudly (FL_UNREDUCED, NaN action, NotImplementedError in strict mode)."""
+def _quadrotor_p1_golden(golden_dir):
+    g = np.load(golden_dir / "quadrotor_p1_oracle.npz")
+    case = make_case("BalanceQuadrotor", "boundary_projection", 2, seed=7, gate="always")      # constants only
+    assert case["consts"].state_model == 3 and case["consts"].n_gen == 18 and case["consts"].n_null == 12
+    return g, case["consts"]
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_quadrotor_lifted_projection_vs_oracle_golden(golden_dir, dtype):
+    """P1 on BalanceQuadrotor's 6 x 24 safe state set (per-environment interior point, csrc/sgbpo_lifted.cuh) against the
+    oracle's lifted QP on states near the RCI boundary and actions outside the safe action set
+    (tests/golden/quadrotor_p1_oracle.npz, made by make_quadrotor_p1.py): projected action, next state, observation,
+    reward and the gradients w.r.t. state and action."""
+    dev = torch.device("cuda:0")
+    g, consts = _quadrotor_p1_golden(golden_dir)
+    t = lambda x: torch.from_numpy(x).to(device=dev, dtype=dtype)
+    s, a = t(g["s"]).requires_grad_(True), t(g["a"]).requires_grad_(True)
+    s_next, a_exec, obs, rew, fl = ops.safeguarded_step(s, a, t(g["w"]), ENV_IDS["BalanceQuadrotor"], consts, aux=t(g["aux"]))
+    ok = torch.from_numpy(g["ok"]).to(dev)
+    assert int(ok.sum()) >= 24
+    assert not bool(((fl & _lib.FL_INFEASIBLE) != 0)[ok].any())       # (the oracle's phase 1 misses a few feasible programs)
+    ((s_next * t(g["cot_g_s_next"])).sum(1) + (a_exec * t(g["cot_g_a_exec"])).sum(1) + (obs * t(g["cot_g_obs"])).sum(1)
+     + rew * t(g["cot_g_reward"]))[ok].sum().backward()
+    okc = g["ok"]
+    moved = np.abs(g["ref_a_exec"] - g["a"]).max(1) > 1e-6
+    assert int((moved & okc).sum()) >= 4                                 # the projection really binds in the fixture
+    tol, gtol = (dict(rtol=1e-6, atol=1e-7), dict(rtol=2e-5, atol=2e-5)) if dtype == torch.float64 else \
+                (dict(rtol=2e-5, atol=2e-5), dict(rtol=2e-3, atol=2e-3))
+    for got, key in ((a_exec, "a_exec"), (s_next, "s_next"), (obs, "obs"), (rew, "reward")):
+        np.testing.assert_allclose(got.detach().cpu().double().numpy()[okc], g["ref_" + key][okc], err_msg=key, **tol)
+    np.testing.assert_allclose(s.grad.cpu().double().numpy()[okc], g["ref_gs"][okc], err_msg="gs", **gtol)
+    np.testing.assert_allclose(a.grad.cpu().double().numpy()[okc], g["ref_ga"][okc], err_msg="ga", **gtol)
+    # already-safe actions pass through exactly
+    same = ~moved & okc
+    assert np.array_equal(a_exec.detach().cpu().double().numpy()[same], t(g["a"]).cpu().double().numpy()[same])
+
+
+def test_quadrotor_gate_and_unsupported_programs():
+    """Under the shipped gate (Q1) RCI states are projectable and the raw action is executed (no solve); far outside the
+    feasible box the program is infeasible and says so; the ray-mask programs of this set are not built and say so."""
     dev = torch.device("cuda:0")
     N = 16
     case = make_case("BalanceQuadrotor", "boundary_projection", N, seed=5, gate="reference")
     env = case["env"]
-    env.reset(seed=5)                                    # RCI samples: feasible programs
-    case["s"] = env.state.detach().clone()
-    case["aux"] = env.goal.clone()
-    assert case["consts"].state_model == 2
-    ref = oracle_step(case)
-    # (a few RCI samples sit where the lifted program of the LINEARISED dynamics is infeasible -- the reference would
-    #  raise there although the gate discards the solution; those rows are left out of the comparison)
-    assert bool(ref["projectable"].all()) and int(ref["ok"].sum()) >= N // 2
-    okd, okc = ref["ok"].to(dev), ref["ok"].numpy()
-    s, a, (s_next, a_exec, obs, reward, flags) = run_kernel(case, "BalanceQuadrotor", torch.float64, dev)
-    fl = flags.cpu()
-    assert bool(((fl & _lib.FL_PROJECTABLE) != 0).all()) and not bool(((fl & (_lib.FL_GUARD_USED | _lib.FL_UNREDUCED)) != 0).any())
-    assert bool(((fl & _lib.FL_ACTION_IN_SET) != 0).sum() > 0)
-    cot = {k: v.to(device=dev) for k, v in case["cot"].items()}
-    ((s_next * cot["g_s_next"]).sum(1) + (a_exec * cot["g_a_exec"]).sum(1) + (obs * cot["g_obs"]).sum(1)
-     + reward * cot["g_reward"])[okd].sum().backward()
-    for got, key in ((s_next, "s_next"), (a_exec, "a_exec"), (obs, "obs"), (reward, "reward"), (s.grad, "gs"), (a.grad, "ga")):
-        np.testing.assert_allclose(got.detach().cpu().numpy()[okc], ref[key].numpy()[okc], rtol=1e-9, atol=1e-10, err_msg=key)
-    # far outside the feasible box the gate asks for the safeguarded action: reported, not silently wrong
-    far = case["s"].clone()
+    env.reset(seed=5)
+    s0, aux = env.state.detach().clone().to(dev), env.goal.clone().to(dev)
+    a, w = case["a"].to(dev), case["w"].to(dev)
+    out = ops.safeguarded_step(s0, a, w, ENV_IDS["BalanceQuadrotor"], case["consts"], aux=aux)
+    fl = out[4]
+    assert bool(((fl & _lib.FL_PROJECTABLE) != 0).all()) and not bool(((fl & _lib.FL_GUARD_USED) != 0).any())
+    assert torch.equal(out[1], a)
+    far = s0.clone()
     far[:, 0] = 50.0
-    t = lambda x: x.to(device=dev)
-    out = ops.safeguarded_step(t(far), t(case["a"]), t(case["w"]), ENV_IDS["BalanceQuadrotor"], case["consts"], aux=t(case["aux"]))
-    assert bool(((out[4] & _lib.FL_UNREDUCED) != 0).all()) and bool(out[1].isnan().all())
+    out = ops.safeguarded_step(far, a, w, ENV_IDS["BalanceQuadrotor"], case["consts"], aux=aux)
+    assert bool(((out[4] & _lib.FL_INFEASIBLE) != 0).all()) and bool(out[1].isnan().all())
     from safegbpo_b200.envs.balance_quadrotor import BalanceQuadrotorEnv
     from safegbpo_b200.safeguards.boundary_projection import BoundaryProjectionSafeguard
+    from safegbpo_b200.safeguards.ray_mask import RayMaskSafeguard
     prev = torch.get_default_dtype()
     torch.set_default_dtype(torch.float64)
     torch.set_default_device(dev)
@@ -203,10 +225,17 @@ def test_quadrotor_unreduced_program_follows_the_shipped_gate():
         qenv = BalanceQuadrotorEnv(num_envs=N, num_steps=240)
         wrapped = BoundaryProjectionSafeguard(qenv)
         wrapped.reset(seed=1)
-        wrapped.step(torch.zeros(N, 2))                  # RCI states: runs, raw action executed
-        qenv.state = t(far)
-        with pytest.raises(NotImplementedError):
+        wrapped.step(torch.zeros(N, 2))
+        qenv.state = far
+        with pytest.raises(ValueError):
             wrapped.step(torch.zeros(N, 2))
+        qenv2 = BalanceQuadrotorEnv(num_envs=N, num_steps=240)
+        rm = RayMaskSafeguard(qenv2, linear_projection=True, zonotopic_approximation=True, passthrough=False)
+        rm.reset(seed=1)
+        assert rm.consts().state_model == 2
+        qenv2.state = far
+        with pytest.raises(NotImplementedError):
+            rm.step(torch.zeros(N, 2))
     finally:
         torch.set_default_device("cpu")
         torch.set_default_dtype(prev)
@@ -255,7 +284,7 @@ def test_baseline_config_sizes_properties(env_name, kind, N):
         _, a2, _, _, _ = ops.safeguarded_step(s, a1.detach(), w, eid, k, aux=aux, dirs=dirs, shared=sh)
         assert torch.allclose(a1[feas].detach(), a2[feas], rtol=0, atol=1e-10)                       # idempotent
         good = feas & guard
-        if env.state_constrained and k.state_model != 2:
+        if env.state_constrained and k.state_model not in (2, 3):
             assert bool((((fl & _lib.FL_NEXT_IN_SET) != 0) | ~good).all())                         # zero violations
         if env.action_constrained:
             assert bool((((fl & _lib.FL_ACTION_IN_SET) != 0) | ~good).all())

@@ -1,11 +1,13 @@
 """CPU: the device math (csrc/*.cuh compiled for the host, test-only) against the oracle.
 Values, gradients (incl. the second-order terms through B = df/da) and verdict bits."""
+from pathlib import Path
+
 import numpy as np
 import pytest
 import torch
 
 import hostmath_util as hm
-from common import p2_center_unique, ENV_IDS, make_case, oracle_step, shared_for
+from common import containment_budget, p2_center_unique, ENV_IDS, make_case, oracle_step, shared_for
 from safegbpo_b200 import _lib
 
 CASES = [
@@ -63,3 +65,36 @@ def test_float32_close_to_float64():
     assert same.mean() > 0.9
     for key in ("a_exec", "s_next", "obs", "reward"):
         np.testing.assert_allclose(o32[key][same], o64[key][same], rtol=1e-5, atol=1e-5, err_msg=key)   # fp32 tolerance
+
+
+def test_quadrotor_lifted_projection_vs_oracle_golden(golden_dir):
+    """The lifted P1 solve (csrc/sgbpo_lifted.cuh, compiled for the host) against the oracle fixture of
+    tests/golden/make_quadrotor_p1.py: projected actions, states and gradients."""
+    g = np.load(golden_dir / "quadrotor_p1_oracle.npz")
+    case = make_case("BalanceQuadrotor", "boundary_projection", 2, seed=7, gate="always")
+    assert case["consts"].state_model == 3
+    cot = {k[len("cot_"):]: g[k] for k in g.files if k.startswith("cot_")}
+    out = hm.step(ENV_IDS["BalanceQuadrotor"], case["consts"], g["s"], g["a"], g["w"], aux=g["aux"], cot=cot)
+    ok = g["ok"]
+    assert not ((out["flags"] & _lib.FL_INFEASIBLE) != 0)[ok].any()
+    for key in ("a_exec", "s_next", "obs", "reward"):
+        np.testing.assert_allclose(out[key][ok], g["ref_" + key][ok], rtol=1e-6, atol=1e-7, err_msg=key)
+    np.testing.assert_allclose(out["gs"][ok], g["ref_gs"][ok], rtol=2e-5, atol=2e-5, err_msg="gs")
+    np.testing.assert_allclose(out["ga"][ok], g["ref_ga"][ok], rtol=2e-5, atol=2e-5, err_msg="ga")
+    moved_ref = np.abs(g["ref_a_exec"] - g["a"]).max(1) > 1e-6
+    assert int(ok.sum()) >= 30 and int((moved_ref & ok).sum()) >= 4          # the projection really binds in the fixture
+    # independent of the oracle (HiGHS LP on the unmerged containment encoding, tests/common.py): every returned action
+    # is state-safe, an action is only moved when the raw one was not, and a moved one lands on the boundary
+    Gn = np.load(Path(_lib.__file__).parent / "assets" / "assets.npz")
+    Gn, cs = Gn["quadrotor_rci_generators"], Gn["quadrotor_rci_center"]
+    feas = (out["flags"] & _lib.FL_INFEASIBLE) == 0
+    for i in np.nonzero(feas)[0]:
+        mine = containment_budget(Gn, g["W"], cs - g["c_f"][i] - g["B"][i] @ out["a_exec"][i])
+        assert mine <= 1 + 1e-6, (i, mine)
+        if np.abs(out["a_exec"][i] - g["a"][i]).max() > 1e-9:
+            assert g["budget_raw"][i] > 1 - 1e-7 or np.abs(g["a"][i]).max() > 1, i
+            assert mine > 1 - 1e-5 or np.abs(out["a_exec"][i]).max() > 1 - 1e-6, (i, mine)
+    # where the oracle's SLSQP stage stopped at a slightly infeasible point (budget_ref > 1, masked out above) the
+    # solve here still returns a feasible projection
+    loose = np.isfinite(g["budget_ref"]) & (g["budget_ref"] > 1 + 1e-6)
+    assert feas[loose].all()
