@@ -237,9 +237,10 @@ def build_consts(env_name: str, sg_kind: int, *, gate_mode: int = 0, rm_linear: 
             G = merge_parallel_generators(G_s)
             Wn = G_w[:, np.abs(G_w).sum(axis=0) > 0]
             p, nn = G.shape[1], G.shape[1] - np.linalg.matrix_rank(G)
-            if sg_kind != _lib.SG_BOUNDARY_PROJECTION or p > _lib.MAXGEN or nn > _lib.MAXNULL or Wn.shape[1] > 2 or m != 2 \
+            built = sg_kind == _lib.SG_BOUNDARY_PROJECTION or (sg_kind == _lib.SG_RAY_MASK and not rm_zonotopic)
+            if not built or p > _lib.MAXGEN or nn > _lib.MAXNULL or Wn.shape[1] > 2 or m != 2 \
                     or np.linalg.matrix_rank(G) < n:
-                k.state_model = 2          # unreduced: gate + raw action only (ray-mask programs of this set: not built)
+                k.state_model = 2          # unreduced: gate + raw action only (zonotopic ray mask P2 of this set: not built)
             else:
                 k.state_model = 3
                 Gp = np.linalg.pinv(G)

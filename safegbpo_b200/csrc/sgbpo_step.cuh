@@ -82,6 +82,9 @@ SG_HD void safeguarded_step(const S* s, const S* a, const T* w, const T* aux, co
       } else if (k.sg_kind == SG_BOUNDARY_PROJECTION) {
         if constexpr (TASK::LIFTED_OK) feasible = project_lifted_m2<TASK>(a, c_f, B, k, &dyn, g);
         else feasible = false;
+      } else if (k.sg_kind == SG_RAY_MASK && !k.rm_zonotopic) {
+        if constexpr (TASK::LIFTED_OK) feasible = ray_mask_orthogonal_lifted_m2<TASK>(a, c_f, B, k, &dyn, g);
+        else feasible = false;
       } else {
 #pragma unroll
         for (int q = 0; q < NA; ++q) g[q] = C<S>(NAN);

@@ -640,6 +640,9 @@ class FusedRollout:
         base.state = states[H]
         base.scheduled_reset = torch.full_like(base.scheduled_reset, bool(base._reset_pending))
         base.last_flags, base.last_exec_action = flags[H - 1], exec_actions[H - 1]
+        self.last = dict(r=r, keep=keep + [eps, noise, states, obs, actions, exec_actions, rewards, flags, values],
+                         terminal_rows=terminal_rows, obs=obs, values=values, rewards=rewards, flags=flags,
+                         exec_actions=exec_actions, states=states)
         if self.wrapper is not None:
             w = self.wrapper
             w.safe_action = exec_actions[H - 1]
@@ -651,9 +654,6 @@ class FusedRollout:
                                      "(the reference raises here: safeguard.py:68-75 / solver error)")
             else:
                 w._status = w._status | bad.to(torch.int32)
-        self.last = dict(r=r, keep=keep + [eps, noise, states, obs, actions, exec_actions, rewards, flags, values],
-                         terminal_rows=terminal_rows, obs=obs, values=values, rewards=rewards, flags=flags,
-                         exec_actions=exec_actions, states=states)
         return float(rewards.sum()) / N / H
 
     # ------------------------------------------------------------------------------------------------------

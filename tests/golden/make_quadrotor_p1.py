@@ -2,7 +2,8 @@
 the RCI set with actions outside the safe action set, and the ORACLE's projection + gradients (oracle/programs.py:
 lifted QP, scipy SLSQP + active-set polish; ~4 s per environment, hence a committed fixture instead of a run-time call).
 
-    python tests/golden/make_quadrotor_p1.py
+    python tests/golden/make_quadrotor_p1.py            # P1 (boundary projection) -> quadrotor_p1_oracle.npz
+    python tests/golden/make_quadrotor_p1.py ray_mask   # orthogonal ray mask (P1 + P4, ray_mask.py:268-341) -> quadrotor_rm_orth_oracle.npz
 """
 import sys
 from pathlib import Path
@@ -14,8 +15,10 @@ HERE = Path(__file__).resolve().parent
 sys.path[:0] = [str(HERE.parent.parent), str(HERE.parent)]
 from common import make_case, oracle_step  # noqa: E402
 
-N = 48
-case = make_case("BalanceQuadrotor", "boundary_projection", N, seed=7, gate="always")
+RM = len(sys.argv) > 1 and sys.argv[1] == "ray_mask"
+N = 24 if RM else 48
+case = make_case("BalanceQuadrotor", "ray_mask", N, seed=7, gate="always", zonotopic=False) if RM else \
+    make_case("BalanceQuadrotor", "boundary_projection", N, seed=7, gate="always")
 env = case["env"]
 d = np.load(HERE.parent.parent / "safegbpo_b200" / "assets" / "assets.npz")
 G = torch.from_numpy(d["quadrotor_rci_generators"])
@@ -51,10 +54,11 @@ def row_budget(i, act):
 
 budget_raw = np.array([row_budget(i, case["a"][i].numpy()) for i in range(N)])
 budget_ref = np.array([row_budget(i, ref["a_exec"][i].numpy()) if bool(ref["ok"][i]) else np.inf for i in range(N)])
-ref["ok"] = ref["ok"] & torch.from_numpy(budget_ref <= 1 + 1e-6)
+if not RM:  # (the ray mask's radial map as shipped, quirk Q2, does not keep the action inside the safe set: no budget mask there)
+    ref["ok"] = ref["ok"] & torch.from_numpy(budget_ref <= 1 + 1e-6)
 out = dict(budget_raw=budget_raw, budget_ref=budget_ref, c_f=c_f, B=Bm, W=W, s=case["s"].numpy(), a=case["a"].numpy(), w=case["w"].numpy(), aux=case["aux"].numpy(), ok=ref["ok"].numpy())
 out.update({f"cot_{k}": v.numpy() for k, v in case["cot"].items()})
 out.update({f"ref_{k}": ref[k].numpy() for k in ("a_exec", "s_next", "obs", "reward", "gs", "ga")})
-np.savez_compressed(HERE / "quadrotor_p1_oracle.npz", **out)
+np.savez_compressed(HERE / ("quadrotor_rm_orth_oracle.npz" if RM else "quadrotor_p1_oracle.npz"), **out)
 moved = np.abs(out["ref_a_exec"] - out["a"]).max(1)
 print("oracle ok", int(out["ok"].sum()), "of", N, "; projected", int(((moved > 1e-6) & out["ok"]).sum()))

@@ -197,6 +197,32 @@ def test_quadrotor_lifted_projection_vs_oracle_golden(golden_dir, dtype):
     assert np.array_equal(a_exec.detach().cpu().double().numpy()[same], t(g["a"]).cpu().double().numpy()[same])
 
 
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_quadrotor_orthogonal_ray_mask_vs_oracle_golden(golden_dir, dtype):
+    """Orthogonal ray mask (P1 then P4, ray_mask.py:268-341) on BalanceQuadrotor's lifted program against the oracle
+    fixture tests/golden/quadrotor_rm_orth_oracle.npz (make_quadrotor_p1.py ray_mask)."""
+    dev = torch.device("cuda:0")
+    g = np.load(golden_dir / "quadrotor_rm_orth_oracle.npz")
+    consts = make_case("BalanceQuadrotor", "ray_mask", 2, seed=7, gate="always", zonotopic=False)["consts"]
+    assert consts.state_model == 3
+    t = lambda x: torch.from_numpy(x).to(device=dev, dtype=dtype)
+    s, a = t(g["s"]).requires_grad_(True), t(g["a"]).requires_grad_(True)
+    s_next, a_exec, obs, rew, fl = ops.safeguarded_step(s, a, t(g["w"]), ENV_IDS["BalanceQuadrotor"], consts, aux=t(g["aux"]))
+    okc = g["ok"]
+    ok = torch.from_numpy(okc).to(dev)
+    moved = np.abs(g["ref_a_exec"] - g["a"]).max(1) > 1e-6
+    assert int(okc.sum()) >= 16 and int((moved & okc).sum()) >= 5
+    assert not bool(((fl & _lib.FL_INFEASIBLE) != 0)[ok].any())
+    ((s_next * t(g["cot_g_s_next"])).sum(1) + (a_exec * t(g["cot_g_a_exec"])).sum(1) + (obs * t(g["cot_g_obs"])).sum(1)
+     + rew * t(g["cot_g_reward"]))[ok].sum().backward()
+    tol, gtol = (dict(rtol=1e-6, atol=2e-7), dict(rtol=1e-4, atol=1e-4)) if dtype == torch.float64 else \
+                (dict(rtol=5e-5, atol=5e-5), dict(rtol=5e-3, atol=5e-3))
+    for got, key in ((a_exec, "a_exec"), (s_next, "s_next"), (obs, "obs"), (rew, "reward")):
+        np.testing.assert_allclose(got.detach().cpu().double().numpy()[okc], g["ref_" + key][okc], err_msg=key, **tol)
+    np.testing.assert_allclose(s.grad.cpu().double().numpy()[okc], g["ref_gs"][okc], err_msg="gs", **gtol)
+    np.testing.assert_allclose(a.grad.cpu().double().numpy()[okc], g["ref_ga"][okc], err_msg="ga", **gtol)
+
+
 def test_quadrotor_gate_and_unsupported_programs():
     """Under the shipped gate (Q1) RCI states are projectable and the raw action is executed (no solve); far outside the
     feasible box the program is infeasible and says so; the ray-mask programs of this set are not built and say so."""

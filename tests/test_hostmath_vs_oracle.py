@@ -98,3 +98,23 @@ def test_quadrotor_lifted_projection_vs_oracle_golden(golden_dir):
     # solve here still returns a feasible projection
     loose = np.isfinite(g["budget_ref"]) & (g["budget_ref"] > 1 + 1e-6)
     assert feas[loose].all()
+
+
+def test_quadrotor_orthogonal_ray_mask_vs_oracle_golden(golden_dir):
+    """Orthogonal ray mask on the quadrotor's lifted program (P1 then P4, csrc/sgbpo_lifted.cuh) against the oracle
+    fixture (make_quadrotor_p1.py ray_mask): mapped action, next state and gradients (the radial map as shipped, quirk Q2,
+    does not keep the action inside the safe set, so there is no safety assertion here)."""
+    g = np.load(golden_dir / "quadrotor_rm_orth_oracle.npz")
+    case = make_case("BalanceQuadrotor", "ray_mask", 2, seed=7, gate="always", zonotopic=False)
+    assert case["consts"].state_model == 3
+    cot = {k[len("cot_"):]: g[k] for k in g.files if k.startswith("cot_")}
+    out = hm.step(ENV_IDS["BalanceQuadrotor"], case["consts"], g["s"], g["a"], g["w"], aux=g["aux"], cot=cot)
+    ok = g["ok"]
+    assert int(ok.sum()) >= 16
+    assert not ((out["flags"] & _lib.FL_INFEASIBLE) != 0)[ok].any()
+    for key in ("a_exec", "s_next", "obs", "reward"):
+        np.testing.assert_allclose(out[key][ok], g["ref_" + key][ok], rtol=1e-6, atol=2e-7, err_msg=key)
+    np.testing.assert_allclose(out["gs"][ok], g["ref_gs"][ok], rtol=1e-4, atol=1e-4, err_msg="gs")
+    np.testing.assert_allclose(out["ga"][ok], g["ref_ga"][ok], rtol=1e-4, atol=1e-4, err_msg="ga")
+    moved = np.abs(g["ref_a_exec"] - g["a"]).max(1) > 1e-6
+    assert int((moved & ok).sum()) >= 5                                 # P1 + P4 really run in the fixture
