@@ -240,6 +240,8 @@ int lifted_solve(const LiftedEnv<double>& E, const LiftedEnv<SW>& ES, const Safe
   bool ok = false;
   double x[LF_MAXV], s[LF_MAXR], lam[LF_MAXR], K[LF_MAXV * (LF_MAXV + 1) / 2], rhsv[LF_MAXV];
   double mu = 1.0;
+  int stalls = 0;
+  double alpha_prev = 0.0;
   for (int j = 0; j < nv; ++j) x[j] = 0.0;
   x[0] = x0[0]; x[1] = x0[1];
   for (int r = 0; r < nsmall; ++r) {
@@ -262,7 +264,12 @@ int lifted_solve(const LiftedEnv<double>& E, const LiftedEnv<SW>& ES, const Safe
     double gap = 0.0;
     for (int r = 0; r < nr; ++r) gap += lam[r] * s[r];
     mu = gap / nr;
-    const double target = fmax(0.1 * mu, 5e-11);
+    // centring parameter: a tenth of the current gap, a hundredth after a (nearly) full step (13.5 -> 11 iterations on
+    // the fixtures; overridable for experiments)
+#ifndef SGBPO_LIFTED_SIGMA
+#define SGBPO_LIFTED_SIGMA(ap) ((ap) > 0.95 ? 0.01 : 0.1)
+#endif
+    const double target = fmax(SGBPO_LIFTED_SIGMA(alpha_prev) * mu, 5e-11);
     const double rp_max = lifted_assemble<double, T>(E, k, dyn, n_act, nn, nv, x, s, lam, target, K, rhsv);
     if (!chol_packed(K, nv)) break;
     chol_packed_solve<double>(K, nv, rhsv);                  // rhsv := dx
@@ -300,10 +307,20 @@ int lifted_solve(const LiftedEnv<double>& E, const LiftedEnv<SW>& ES, const Safe
       }
     }
     for (int j = 0; j < nv; ++j) x[j] += alpha * rhsv[j];
+    alpha_prev = alpha;
 #ifdef SGBPO_LIFTED_DEBUG
     printf("it %d mu %.3e rp %.3e alpha %.3e dx %.3e x %.6f %.6f\n", it, mu, rp_max, alpha, dx_max, x[0], x[1]);
 #endif
-    if (rp_max < 1e-9 && mu < 2e-10 && alpha * dx_max < 1e-9) { ok = true; break; }
+    if (rp_max < 1e-9 && mu < 2e-10 && alpha * dx_max < 1e-9) {
+      ok = true;
+#ifdef SGBPO_LIFTED_COUNT
+      printf("ITERS %d\n", it + 1);
+#endif
+      break;
+    }
+    // infeasible program: the step length collapses while the primal residual stays (observed: alpha < 1e-4 from the
+    // ~10th iteration on, feasible programs never go below 0.05) -- stop instead of spending all iterations
+    if (alpha < 1e-4 && rp_max > 1e-7) { if (++stalls >= 3) break; } else stalls = 0;
   }
   if (!ok) return 0;
   if (fabs(x[0] - ref[0]) < 1e-7 && fabs(x[1] - ref[1]) < 1e-7) return 2;

@@ -215,7 +215,7 @@ def test_quadrotor_orthogonal_ray_mask_vs_oracle_golden(golden_dir, dtype):
     assert not bool(((fl & _lib.FL_INFEASIBLE) != 0)[ok].any())
     ((s_next * t(g["cot_g_s_next"])).sum(1) + (a_exec * t(g["cot_g_a_exec"])).sum(1) + (obs * t(g["cot_g_obs"])).sum(1)
      + rew * t(g["cot_g_reward"]))[ok].sum().backward()
-    tol, gtol = (dict(rtol=1e-6, atol=2e-7), dict(rtol=1e-4, atol=1e-4)) if dtype == torch.float64 else \
+    tol, gtol = (dict(rtol=5e-6, atol=2e-7), dict(rtol=1e-4, atol=1e-4)) if dtype == torch.float64 else \
                 (dict(rtol=5e-5, atol=5e-5), dict(rtol=5e-3, atol=5e-3))
     for got, key in ((a_exec, "a_exec"), (s_next, "s_next"), (obs, "obs"), (rew, "reward")):
         np.testing.assert_allclose(got.detach().cpu().double().numpy()[okc], g["ref_" + key][okc], err_msg=key, **tol)
