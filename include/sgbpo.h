@@ -205,6 +205,15 @@ int sgbpo_bias_elu_ln_fwd(int dtype, int64_t M, int width, const void* z, const 
 int sgbpo_bias_elu_ln_bwd(int dtype, int64_t M, int width, const void* gy, const void* e, const void* stats,
                           const void* gamma, void* dz, void* dgamma, void* dbeta, void* dbias, void* stream);
 
+/* ---- episode scalars of collect_trajectories / update_policy (shac.py:119-120, 131-142; safeguard.py:68-80), one
+ * single-CTA launch each.  stats: scal[0] = sum of the n_rewards reward entries, scal[1] = 1 if any flag word has a bit of
+ * bad_mask, *n_interv = number of flag words with a bit of interv_mask, *bad = scal[1] as int (both optional).
+ * loss: -sum_t disc[t] * sum_n (term_int[t] ? values[t][n] : rewards[t][n]) / norm[0] over `rows` buffer rows. */
+int sgbpo_episode_stats(int dtype, int64_t n_rewards, const void* rewards, int64_t n_flags, const int32_t* flags,
+                        int interv_mask, int bad_mask, double* scal, int64_t* n_interv, int32_t* bad, void* stream);
+int sgbpo_shac_loss(int dtype, int rows, int64_t N, const void* disc, const int32_t* term_int, const void* values,
+                    const void* rewards, const void* norm, void* loss, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

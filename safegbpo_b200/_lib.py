@@ -103,6 +103,8 @@ _SIGNATURES = {
     "sgbpo_bias_elu_ln_fwd": (C.c_int, [C.c_int, C.c_int64, C.c_int] + [_VP] * 8),
     "sgbpo_bias_elu_ln_bwd": (C.c_int, [C.c_int, C.c_int64, C.c_int] + [_VP] * 9),
     "sgbpo_td_lambda": (C.c_int, [C.c_int, C.c_int64, C.c_int, _VP, _VP, _VP, C.c_double, C.c_double, _VP, _VP, _VP]),
+    "sgbpo_episode_stats": (C.c_int, [C.c_int, C.c_int64, _VP, C.c_int64, _VP, C.c_int, C.c_int, _VP, _VP, _VP, _VP]),
+    "sgbpo_shac_loss": (C.c_int, [C.c_int, C.c_int, C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
 }
 EXPORTED = tuple(_SIGNATURES)
 _lib = None

@@ -166,6 +166,82 @@ static int dispatch_eln(bool fwd, int W, int64_t M, const void* a0, const void* 
       return SGBPO_E_UNSUPPORTED;
   }
 }
+
+// ---- episode scalars (fused_rollout.py graph bodies): one launch each instead of ~10 / ~7 library launches ----------
+// Grid-wide deterministic sums: every CTA reduces its grid-stride share in double (shared-memory tree), stores the partial
+// in a device-global slot, and the last CTA to finish (ticket counter) adds the partials in slot order and writes the
+// outputs.  One launch of each kernel may be in flight per device at a time (the scratch is global).
+constexpr int EP_CTAS = 128, EP_THREADS = 256, EP_VALS = 3;
+__device__ double g_ep_part[2][EP_VALS][EP_CTAS];
+__device__ unsigned int g_ep_ticket[2];
+
+template <int NV>
+__device__ inline bool grid_sum(double (&v)[NV], int which) {
+  __shared__ double sh[NV][EP_THREADS];
+  __shared__ bool last;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) sh[q][threadIdx.x] = v[q];
+  __syncthreads();
+  for (int s = EP_THREADS / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+#pragma unroll
+      for (int q = 0; q < NV; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) g_ep_part[which][q][blockIdx.x] = sh[q][0];
+    __threadfence();
+    last = atomicAdd(&g_ep_ticket[which], 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return false;
+  __threadfence();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      double a = 0.0;
+      for (unsigned int b = 0; b < gridDim.x; ++b) a += ((volatile double*)g_ep_part[which][q])[b];
+      v[q] = a;
+    }
+    g_ep_ticket[which] = 0;
+  }
+  return threadIdx.x == 0;
+}
+
+template <class T>
+__global__ void episode_stats_kernel(int64_t n_rew, const T* __restrict__ rewards, int64_t n_fl, const int32_t* __restrict__ flags,
+                                     int interv_mask, int bad_mask, double* scal, int64_t* n_interv, int32_t* bad) {
+  double v[3] = {0.0, 0.0, 0.0};
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t i = first; i < n_rew; i += stride) v[0] += (double)rewards[i];
+  for (int64_t i = first; i < n_fl; i += stride) {
+    const int32_t f = flags[i];
+    v[1] += (f & interv_mask) ? 1.0 : 0.0;
+    v[2] += (f & bad_mask) ? 1.0 : 0.0;
+  }
+  if (!grid_sum<3>(v, 0)) return;
+  scal[0] = v[0];
+  scal[1] = v[2] > 0.0 ? 1.0 : 0.0;
+  if (n_interv) *n_interv = (int64_t)v[1];
+  if (bad) *bad = v[2] > 0.0 ? 1 : 0;
+}
+
+// shac.py:131-142: loss = - sum_t disc_t * sum_n (terminal row t ? values[t][n] : rewards[t][n]) / norm
+template <class T>
+__global__ void shac_loss_kernel(int rows, int64_t N, const T* __restrict__ disc, const int32_t* __restrict__ term_int,
+                                 const T* __restrict__ values, const T* __restrict__ rewards, const T* __restrict__ norm, T* loss) {
+  double v[1] = {0.0};
+  const int64_t total = (int64_t)rows * N, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int t = (int)(e / N);
+    const double d = (double)disc[t];
+    if (d != 0.0) v[0] += d * (double)(term_int[t] != 0 ? values[e] : rewards[e]);
+  }
+  if (!grid_sum<1>(v, 1)) return;
+  *loss = (T)(-v[0] / (double)norm[0]);
+}
 }  // namespace sgbpo
 
 using namespace sgbpo;
@@ -215,4 +291,44 @@ extern "C" int sgbpo_bias_elu_ln_bwd(int dtype, int64_t M, int width, const void
   cudaStream_t st = (cudaStream_t)stream;
   return dtype == SGBPO_F64 ? dispatch_eln<double>(false, width, M, gy, e, stats, gamma, dz, dgamma, dbeta, dbias, st)
                             : dispatch_eln<float>(false, width, M, gy, e, stats, gamma, dz, dgamma, dbeta, dbias, st);
+}
+
+extern "C" int sgbpo_episode_stats(int dtype, int64_t n_rewards, const void* rewards, int64_t n_flags, const int32_t* flags,
+                                   int interv_mask, int bad_mask, double* scal, int64_t* n_interv, int32_t* bad, void* stream) {
+  if (!rewards || !scal || (n_flags > 0 && !flags)) {
+    snprintf(g_err, sizeof(g_err), "sgbpo_episode_stats: null buffer");
+    return SGBPO_E_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SGBPO_F64)
+    episode_stats_kernel<double><<<EP_CTAS, EP_THREADS, 0, st>>>(n_rewards, (const double*)rewards, n_flags, flags, interv_mask, bad_mask, scal, n_interv, bad);
+  else
+    episode_stats_kernel<float><<<EP_CTAS, EP_THREADS, 0, st>>>(n_rewards, (const float*)rewards, n_flags, flags, interv_mask, bad_mask, scal, n_interv, bad);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "episode_stats_kernel: %s", cudaGetErrorString(e));
+    return SGBPO_E_CUDA;
+  }
+  return SGBPO_OK;
+}
+
+extern "C" int sgbpo_shac_loss(int dtype, int rows, int64_t N, const void* disc, const int32_t* term_int, const void* values,
+                               const void* rewards, const void* norm, void* loss, void* stream) {
+  if (!disc || !term_int || !values || !rewards || !norm || !loss) {
+    snprintf(g_err, sizeof(g_err), "sgbpo_shac_loss: null buffer");
+    return SGBPO_E_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SGBPO_F64)
+    shac_loss_kernel<double><<<EP_CTAS, EP_THREADS, 0, st>>>(rows, N, (const double*)disc, term_int, (const double*)values, (const double*)rewards,
+                                                 (const double*)norm, (double*)loss);
+  else
+    shac_loss_kernel<float><<<EP_CTAS, EP_THREADS, 0, st>>>(rows, N, (const float*)disc, term_int, (const float*)values, (const float*)rewards,
+                                                (const float*)norm, (float*)loss);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "shac_loss_kernel: %s", cudaGetErrorString(e));
+    return SGBPO_E_CUDA;
+  }
+  return SGBPO_OK;
 }

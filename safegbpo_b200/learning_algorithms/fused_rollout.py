@@ -135,7 +135,8 @@ class FusedRollout:
         self.vf_vjp_native = mlp_vjp_fits(self.base.state.dtype, vp.in_dim, vp.width, vp.n_hidden)
         self._grad_bufs = None
         self.last = None
-        self.launches_per_episode = 6          # rollout_fwd, mlp_rows(_tc), mlp_rows_vjp, rollout_bwd, grad_norm, adam_apply (our kernels)
+        # rollout_fwd, mlp_rows(_tc), episode_stats, shac_loss, mlp_rows_vjp, rollout_bwd, grad_norm, adam_apply (our kernels)
+        self.launches_per_episode = 8
         self.use_graphs = True                 # replay the episode as two CUDA graphs when its schedule allows
         self.graph_warmup = 2                  # eager episodes before capture (optimizer state, cuBLAS handles)
         self._episodes = 0
@@ -326,6 +327,7 @@ class FusedRollout:
         g["dw_hid"] = z(W, W)
         g["ctr"] = base.noise_set.center[0].to(dt).clone()
         g["half"] = base.noise_set.generator[0].diagonal().to(dt).clone()
+        g["noise_lo"], g["noise_span"] = g["ctr"] - g["half"], 2.0 * g["half"]
         r = Rollout()
         r.N, r.H = N, H
         p = lambda t: None if t is None else t.data_ptr()
@@ -371,7 +373,7 @@ class FusedRollout:
                 if g["dirs"] is not None:
                     g["dirs"][t].uniform_(-1.0, 1.0)
                 g["u"][t].uniform_()
-        torch.addcmul(g["ctr"] - g["half"], g["u"], 2.0 * g["half"], out=g["noise"])
+        torch.addcmul(g["noise_lo"], g["u"], g["noise_span"], out=g["noise"])
         if g["dirs"] is not None:
             g["dirs"].div_(torch.linalg.vector_norm(g["dirs"], dim=2, keepdim=True))
         if self.rng_mode == "batched":          # fixed number of reset-state draws per episode (see _draw_inputs)
@@ -389,12 +391,13 @@ class FusedRollout:
         else:
             with torch.no_grad():
                 g["values"][1:H + 1] = algo.target_value_function(g["obs"][1:H + 1].reshape(H * N, o)).view(H, N)
-        g["reward_sum"].copy_(g["rewards"].sum())
-        g["scal"][0].copy_(g["reward_sum"])
-        if self.wrapper is not None:
-            g["n_interv"].copy_(((g["flags"] & _lib.FL_INTERVENED) != 0).sum())
-            g["bad"].copy_(((g["flags"] & (_lib.FL_NONFINITE | _lib.FL_INFEASIBLE)) != 0).any())
-            g["scal"][1].copy_(g["bad"])
+        # reward sum, intervention count, any non-finite / infeasible step: one launch (was ~10 library launches)
+        guarded = self.wrapper is not None
+        check(lib.sgbpo_episode_stats(dtype_code(dt), g["rewards"].numel(), C.c_void_p(g["rewards"].data_ptr()),
+                                      g["flags"].numel() if guarded else 0, C.c_void_p(g["flags"].data_ptr()),
+                                      _lib.FL_INTERVENED, _lib.FL_NONFINITE | _lib.FL_INFEASIBLE,
+                                      C.c_void_p(g["scal"].data_ptr()), C.c_void_p(g["n_interv"].data_ptr()),
+                                      C.c_void_p(g["bad"].data_ptr()), stream_ptr()), "sgbpo_episode_stats")
 
     def _bwd_body(self, g):
         """Loss, terminal-value gradient, fused reverse pass, weight-gradient GEMM (capturable)."""
@@ -403,9 +406,10 @@ class FusedRollout:
         dt = base.state.dtype
         W = self.policy_pack.width
         o = base.obs_dim
-        term_mask = g["term_int"] != 0
-        picked = torch.where(term_mask.unsqueeze(1), g["values"], g["rewards"])
-        g["loss"].copy_(-(g["disc_t"].unsqueeze(1) * picked).sum() / g["norm_t"][0])
+        check(_lib.lib().sgbpo_shac_loss(dtype_code(dt), H + 2, N, C.c_void_p(g["disc_t"].data_ptr()),
+                                         C.c_void_p(g["term_int"].data_ptr()), C.c_void_p(g["values"].data_ptr()),
+                                         C.c_void_p(g["rewards"].data_ptr()), C.c_void_p(g["norm_t"].data_ptr()),
+                                         C.c_void_p(g["loss"].data_ptr()), stream_ptr()), "sgbpo_shac_loss")
         # critic input-gradient on the (at most KM) terminal rows; unused slots carry weight 0
         x = g["obs"].index_select(0, g["term_rows"]).detach()
         if self.vf_vjp_native:         # one launch: forward + transposed pass of the target critic (csrc mlp_rows_vjp_kernel)
