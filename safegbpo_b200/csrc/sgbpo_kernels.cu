@@ -1,6 +1,7 @@
 // Per-step kernels + C ABI (include/sgbpo.h).  One thread per environment: n <= 6 states, m <= 2
 // actions, all per-env matrices (B, G_s^-1 rows, duals) live in registers; global traffic is exactly
 // the (N, n)/(N, m)/(N, o) rows, read/written as contiguous per-warp spans.  sm_100a only.
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
@@ -33,10 +34,13 @@ step_fwd_kernel(int64_t N, const __grid_constant__ SafeConsts<T> k, const __grid
                 const T* __restrict__ s, const T* __restrict__ a, const T* __restrict__ w,
                 const T* __restrict__ aux, const T* __restrict__ dirs, const T* __restrict__ reset_state,
                 T* __restrict__ s_next, T* __restrict__ a_exec, T* __restrict__ obs, T* __restrict__ reward,
-                int32_t* __restrict__ flags) {
+                int32_t* __restrict__ flags, int lanes) {
   using TASK = Task<ENV>;
   constexpr int NS = TASK::NS, NA = TASK::NA, NO = TASK::NO, NAUX = TASK::NAUX;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+  // `lanes` environments per warp (32 = one per thread; fewer for the long per-thread solves, see block_for)
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = gw * lanes + lane; lane < lanes && i < N; i += nw * lanes) {
     T sv[NS], av[NA], wv[NS], auxv[NAUX > 0 ? NAUX : 1], dv[NA * 2 * NA], rs[NS];
     load_row<NS>(s, i, sv);
     load_row<NA>(a, i, av);
@@ -66,11 +70,14 @@ step_bwd_kernel(int64_t N, const __grid_constant__ SafeConsts<T> k, const __grid
                 const T* __restrict__ s, const T* __restrict__ a, const T* __restrict__ w,
                 const T* __restrict__ aux, const T* __restrict__ dirs, const T* __restrict__ reset_state,
                 const T* __restrict__ g_s_next, const T* __restrict__ g_a_exec, const T* __restrict__ g_obs,
-                const T* __restrict__ g_reward, T* __restrict__ gs, T* __restrict__ ga) {
+                const T* __restrict__ g_reward, T* __restrict__ gs, T* __restrict__ ga, int lanes) {
   using TASK = Task<ENV>;
   constexpr int NS = TASK::NS, NA = TASK::NA, NO = TASK::NO, NAUX = TASK::NAUX, K = NS + NA;
   using D = Dual<T, K>;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+  // `lanes` environments per warp (32 = one per thread; fewer for the long per-thread solves, see block_for)
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = gw * lanes + lane; lane < lanes && i < N; i += nw * lanes) {
     T sv[NS], av[NA], wv[NS], auxv[NAUX > 0 ? NAUX : 1], dv[NA * 2 * NA], rs[NS];
     load_row<NS>(s, i, sv);
     load_row<NA>(a, i, av);
@@ -160,6 +167,12 @@ seeker_action_set_kernel(int64_t N, const __grid_constant__ SafeConsts<T> k, con
   }
 }
 
+static int env_lanes() {          // SGBPO_STEP_LANES: environments per warp of the per-step kernels (tuning)
+  const char* e = getenv("SGBPO_STEP_LANES");
+  const int v = e ? atoi(e) : 0;
+  return (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ? v : 0;
+}
+
 static int grid_for(int64_t N, int block) {
   int64_t g = (N + block - 1) / block;
   const int64_t cap = 148 * 16;      // grid-stride above 16 CTAs per SM
@@ -173,6 +186,15 @@ static int grid_for(int64_t N, int block) {
 static int block_for(int64_t N, const sgbpo_consts* c) {
   return (c->state_model == SM_LIFTED && N <= 148 * 32 * 16) ? 32 : 128;
 }
+// Environments per warp (SGBPO_STEP_LANES, tuning only).  Measured for the lifted solve at 4096 environments: 32 / 16 / 8 /
+// 4 / 2 lanes per warp = 20.6 / 42.3 / 53.7 / 74.7 / 127.8 ms per forward step -- time follows the number of warps, so
+// the dense mapping stays the default everywhere.
+static int lanes_for(const sgbpo_consts* c) {
+  const int forced = env_lanes();
+  if (forced > 0) return forced;
+  (void)c;
+  return 32;
+}
 
 template <int ENV, class T> struct Launch {
   static int fwd(int64_t N, const sgbpo_consts* c, const sgbpo_step_shared* shp, const void* s, const void* a,
@@ -180,10 +202,10 @@ template <int ENV, class T> struct Launch {
                  void* a_exec, void* obs, void* reward, int32_t* flags, cudaStream_t st) {
     const SafeConsts<T> k = convert_consts<T>(*c);
     const StepShared<T> sh = convert_shared<T>(shp);
-    const int block = block_for(N, c);
-    step_fwd_kernel<ENV, T><<<grid_for(N, block), block, 0, st>>>(
+    const int block = block_for(N, c), lanes = lanes_for(c);
+    step_fwd_kernel<ENV, T><<<grid_for(N * (32 / lanes), block), block, 0, st>>>(
         N, k, sh, (const T*)s, (const T*)a, (const T*)w, (const T*)aux, (const T*)dirs, (const T*)reset_state,
-        (T*)s_next, (T*)a_exec, (T*)obs, (T*)reward, flags);
+        (T*)s_next, (T*)a_exec, (T*)obs, (T*)reward, flags, lanes);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SGBPO_OK : cuda_fail(e, "step_fwd_kernel");
   }
@@ -192,10 +214,10 @@ template <int ENV, class T> struct Launch {
                  const void* g_a_exec, const void* g_obs, const void* g_reward, void* gs, void* ga, cudaStream_t st) {
     const SafeConsts<T> k = convert_consts<T>(*c);
     const StepShared<T> sh = convert_shared<T>(shp);
-    const int block = block_for(N, c);
-    step_bwd_kernel<ENV, T><<<grid_for(N, block), block, 0, st>>>(
+    const int block = block_for(N, c), lanes = lanes_for(c);
+    step_bwd_kernel<ENV, T><<<grid_for(N * (32 / lanes), block), block, 0, st>>>(
         N, k, sh, (const T*)s, (const T*)a, (const T*)w, (const T*)aux, (const T*)dirs, (const T*)reset_state,
-        (const T*)g_s_next, (const T*)g_a_exec, (const T*)g_obs, (const T*)g_reward, (T*)gs, (T*)ga);
+        (const T*)g_s_next, (const T*)g_a_exec, (const T*)g_obs, (const T*)g_reward, (T*)gs, (T*)ga, lanes);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SGBPO_OK : cuda_fail(e, "step_bwd_kernel");
   }
