@@ -26,31 +26,35 @@ SG_HD int tri(int i, int j) { return i * (i + 1) / 2 + j; }      // i >= j
 
 SG_HD bool chol_packed(double* K, int n) {
   for (int j = 0; j < n; ++j) {
-    const double orig = K[tri(j, j)];
+    double* Kj = K + tri(j, 0);
+    const double orig = Kj[j];
     double d = orig;
-    for (int p = 0; p < j; ++p) d -= K[tri(j, p)] * K[tri(j, p)];
+    for (int p = 0; p < j; ++p) d -= Kj[p] * Kj[p];
     if (!(d == d)) return false;
     if (!(d > 1e-12 * orig)) d = 1e60;        // direction left free by the active rows: frozen (see chol6)
     d = sqrt(d);
-    K[tri(j, j)] = d;
+    Kj[j] = d;
+    const double inv = 1.0 / d;
     for (int i = j + 1; i < n; ++i) {
-      double v = K[tri(i, j)];
-      for (int p = 0; p < j; ++p) v -= K[tri(i, p)] * K[tri(j, p)];
-      K[tri(i, j)] = v / d;
+      double* Ki = K + tri(i, 0);
+      double v = Ki[j];
+      for (int p = 0; p < j; ++p) v -= Ki[p] * Kj[p];
+      Ki[j] = v * inv;
     }
   }
   return true;
 }
 template <class W> SG_HD void chol_packed_solve(const double* L, int n, W* x) {
   for (int i = 0; i < n; ++i) {
+    const double* Li = L + tri(i, 0);
     W v = x[i];
-    for (int p = 0; p < i; ++p) v = v - W(L[tri(i, p)]) * x[p];
-    x[i] = v / W(L[tri(i, i)]);
+    for (int p = 0; p < i; ++p) v = v - W(Li[p]) * x[p];
+    x[i] = v / W(Li[i]);
   }
   for (int i = n - 1; i >= 0; --i) {
     W v = x[i];
-    for (int p = i + 1; p < n; ++p) v = v - W(L[tri(p, i)]) * x[p];
-    x[i] = v / W(L[tri(i, i)]);
+    for (int p = i + 1; p < n; ++p) v = v - W(L[tri(p, 0) + i]) * x[p];
+    x[i] = v / W(L[tri(i, 0) + i]);
   }
 }
 
@@ -153,25 +157,30 @@ SG_HD double lifted_assemble(const LiftedEnv<W>& E, const SafeConsts<T>& k, cons
     const double q0 = primal(E.Q[i][0]), q1 = primal(E.Q[i][1]);
     rhs[0] = rhs[0] + E.Q[i][0] * t0; rhs[1] = rhs[1] + E.Q[i][1] * t0;
     k00 += sw * q0 * q0; k10 += sw * q1 * q0; k11 += sw * q1 * q1;
+    double nd[MAXNULL];                       // row i of the null-space basis, converted once
+    for (int j = 0; j < nn; ++j) nd[j] = (double)k.Nmat[i][j];
     for (int j = 0; j < nn; ++j) {
-      const double nj = (double)k.Nmat[i][j];
+      const double nj = nd[j];
       rhs[oy + j] = rhs[oy + j] - W(nj) * t0;
-      K[tri(oy + j, 0)] -= sw * nj * q0; K[tri(oy + j, 1)] -= sw * nj * q1;
+      double* Ky = K + tri(oy + j, 0);
+      Ky[0] -= sw * nj * q0; Ky[1] -= sw * nj * q1;
       const double a = sw * nj;
-      for (int l = 0; l <= j; ++l) K[tri(oy + j, oy + l)] += a * (double)k.Nmat[i][l];
+      for (int l = 0; l <= j; ++l) Ky[oy + l] += a * nd[l];
       if (k.n_wcol > 0) {
         rhs[o1 + j] = rhs[o1 + j] - W(nj) * t1;
-        K[tri(o1 + j, 0)] -= m01 * nj * q0; K[tri(o1 + j, 1)] -= m01 * nj * q1;
+        double* K1 = K + tri(o1 + j, 0);
+        K1[0] -= m01 * nj * q0; K1[1] -= m01 * nj * q1;
         const double a1 = m01 * nj;
-        for (int l = 0; l < nn; ++l) K[tri(o1 + j, oy + l)] += a1 * (double)k.Nmat[i][l];
+        for (int l = 0; l < nn; ++l) K1[oy + l] += a1 * nd[l];
       }
       if (k.n_wcol > 1) {
         rhs[o2 + j] = rhs[o2 + j] - W(nj) * t2;
-        K[tri(o2 + j, 0)] -= m02 * nj * q0; K[tri(o2 + j, 1)] -= m02 * nj * q1;
+        double* K2 = K + tri(o2 + j, 0);
+        K2[0] -= m02 * nj * q0; K2[1] -= m02 * nj * q1;
         const double a2 = m02 * nj, a12 = m12 * nj;
         for (int l = 0; l < nn; ++l) {
-          K[tri(o2 + j, oy + l)] += a2 * (double)k.Nmat[i][l];
-          K[tri(o2 + j, o1 + l)] += a12 * (double)k.Nmat[i][l];
+          K2[oy + l] += a2 * nd[l];
+          K2[o1 + l] += a12 * nd[l];
         }
       }
     }
