@@ -55,54 +55,6 @@ def parse():
 # ------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path on the host cores
 # ------------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    env_name, sg_kind, n_envs, horizon, episodes, seed = args
-    import torch
-    torch.set_num_threads(1)
-    from oracle.dynamics import OracleEnv
-    from oracle.safeguard import OracleSafeguard
-    from oracle import shac as oshac
-    torch.manual_seed(seed)
-    env = OracleEnv(env_name, n_envs, 240)
-    env.reset(seed=seed)
-    # start inside the feasible box so the bounded sample does not hit infeasible programs
-    env.state = env.state_center + (torch.rand(n_envs, env.state_dim, dtype=torch.float64) * 2 - 1) * env.state_half * 0.5
-    step_fn = env
-    if sg_kind != "none":
-        step_fn = OracleSafeguard(env, sg_kind, gate="reference", strict=False)
-    obs_dim = env.observation().shape[1]
-    pol = oshac.OraclePolicy(obs_dim, env.action_dim, POLICY_ARCH).double()
-    vf = oshac.OracleValue(obs_dim, VF_ARCH).double()
-    opt = torch.optim.Adam(pol.parameters(), lr=4e-4)
-
-    def env_step(action, t):
-        obs, rew, term, trunc = step_fn.step(action)
-        return obs, rew, term | trunc
-
-    t0 = time.perf_counter()
-    for _ in range(episodes):
-        env.cut_computation_graph()
-        opt.zero_grad()
-        eps = torch.randn(horizon, n_envs, env.action_dim, dtype=torch.float64)
-        out = oshac.rollout_loss(env_step, env.observation(), pol, vf, horizon, eps)
-        out["loss"].backward()
-        torch.nn.utils.clip_grad_norm_(pol.parameters(), 1.0)
-        opt.step()
-    return time.perf_counter() - t0
-
-
-def cpu_port_throughput(env_name, sg_kind, n_envs_per_worker, horizon, episodes, workers):
-    """env-steps/s of the oracle port with `workers` processes, each owning its own environment shard."""
-    import multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    jobs = [(env_name, sg_kind, n_envs_per_worker, horizon, episodes, 100 + i) for i in range(workers)]
-    t0 = time.perf_counter()
-    with ctx.Pool(workers) as pool:
-        pool.map(_cpu_worker, jobs)
-    wall = time.perf_counter() - t0
-    return workers * n_envs_per_worker * horizon * episodes / wall, wall
-
-
 def _cpu_persistent_worker(conn, job):
     """One host process = one environment shard of the oracle port; runs one episode per "step" message."""
     env_name, sg_kind, n_envs, horizon, seed = job
@@ -146,34 +98,25 @@ def _cpu_persistent_worker(conn, job):
             conn.send("error: " + repr(exc)[:200])
 
 
-def run_reference(args):
+def cpu_port_persistent(env_name, sg_kind, horizon, steps, warmup, budget_s):
     """The reference's CPU path (oracle port: per-environment HiGHS solves + torch autograd, float64) on all host cores.
-    A step = one SHAC episode (collect + backward + clip + Adam) of a BOUNDED sample of the workload: every core owns
-    8 environments; the number of timed steps is capped so that the whole run takes about three minutes."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+    A step = one SHAC episode (collect + backward + clip + Adam) of a BOUNDED sample of the workload: every core owns 8
+    environments (process start-up and imports are outside the timed steps).  One untimed calibration step measures the
+    step time; the number of timed steps is capped so that the run fits `budget_s`.
+    Returns dict(value, steps, warmup, total_s, workers, n_w, errors)."""
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     workers = max(1, min(cores, 64))
-    # the port's cost per env-step falls with the shard size (per-step torch overhead is amortised): keep the shard at
-    # 8 environments per core -- the most favourable sample for the CPU side that still finishes -- and bound the run by
-    # the NUMBER of steps instead: ~9 s per step on the cartpole + BP workload, about 170 s in total
     n_w = 8
-    per_step_s = 9.0 * args.horizon / 64
-    budget_steps = max(2, int(170.0 / per_step_s))
-    warmup = min(args.warmup, 1)
-    steps = max(1, min(args.steps, budget_steps - warmup))
     ctx = mp.get_context("spawn")
     procs = []
     for i in range(workers):
         a, b = ctx.Pipe()
-        pr = ctx.Process(target=_cpu_persistent_worker, args=(b, (args.env, args.safeguard, n_w, args.horizon, 100 + i)), daemon=True)
+        pr = ctx.Process(target=_cpu_persistent_worker, args=(b, (env_name, sg_kind, n_w, horizon, 100 + i)), daemon=True)
         pr.start()
         procs.append((pr, a))
     for _, c in procs:
         c.recv()
-
     errors = []
 
     def step():
@@ -186,26 +129,39 @@ def run_reference(args):
                 errors.append(msg)
         return time.perf_counter() - t0
 
-    for _ in range(warmup):
+    calib = step()                                   # also the first warm-up step
+    warmup = max(1, min(warmup, 2))
+    for _ in range(warmup - 1):
         step()
+    steps = max(1, min(steps, int((budget_s - warmup * calib) / max(calib, 1e-3))))
     walls = [step() for _ in range(steps)]
     for pr, c in procs:
         c.send("stop")
     for pr, _ in procs:
         pr.join(timeout=10)
     total = sum(walls)
-    v = workers * n_w * args.horizon * steps / total
+    return dict(value=workers * n_w * horizon * steps / total, steps=steps, warmup=warmup, total_s=total, workers=workers,
+                n_w=n_w, errors=errors)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_port_persistent(args.env, args.safeguard, args.horizon, args.steps, args.warmup, budget_s=150.0)
+    v = r["value"]
     line = {
         "impl": "reference", "metric": "safeguarded env-steps/s (fwd+bwd)", "value": v, "unit": "env-steps/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "steps_requested": args.steps, "warmup_requested": args.warmup,
-        "ms_per_step": 1e3 * total / steps,
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": r["warmup"], "steps_requested": args.steps,
+        "warmup_requested": args.warmup, "ms_per_step": 1e3 * r["total_s"] / r["steps"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, max(1, args.gpus)),
-        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": workers, "kind": "port",
-                         "sample": f"each step = {workers} processes x {n_w} envs x H={args.horizon}, one SHAC episode of the same "
-                                   "workload (oracle port of the reference path: per-env HiGHS solves + torch autograd, float64)"},
+        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": r["workers"], "kind": "port",
+                         "sample": f"each step = {r['workers']} processes x {r['n_w']} envs x H={args.horizon}, one SHAC episode of the "
+                                   "same workload (oracle port of the reference path: per-env HiGHS solves + torch autograd, "
+                                   "float64); timed steps capped to a 150 s budget"},
         "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "worker_errors": {"count": len(errors), "first": errors[0] if errors else None},
+        "worker_errors": {"count": len(r["errors"]), "first": r["errors"][0] if r["errors"] else None},
     }
     print(json.dumps(line))
 
@@ -401,11 +357,10 @@ def run_ours(args):
             "mode": "fused" if engine is not None else "eager (per-step fused safeguard+simulator kernel, torch MLP)",
         }
         if not args.no_cpu_baseline and world == 1:
-            cores = os.cpu_count() or 1
-            workers = max(1, min(cores, 64))
-            v, wall = cpu_port_throughput(args.env, args.safeguard, 8, H, 1, workers)
-            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": workers, "kind": "port",
-                                    "sample": f"{workers} processes x 8 envs x H={H} x 1 episode ({wall:.1f} s wall), oracle port, float64"}
+            r = cpu_port_persistent(args.env, args.safeguard, H, 8, 1, budget_s=25.0)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "env-steps/s", "cores": r["workers"], "kind": "port",
+                                    "sample": f"{r['steps']} steps of {r['workers']} processes x {r['n_w']} envs x H={H} (one SHAC episode "
+                                              f"each, {r['total_s']:.1f} s wall), oracle port of the reference path, float64"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
