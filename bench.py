@@ -73,8 +73,11 @@ def _cpu_persistent_worker(conn, job):
     vf = oshac.OracleValue(obs_dim, VF_ARCH).double()
     opt = torch.optim.Adam(pol.parameters(), lr=4e-4)
 
+    done_steps = [0]
+
     def env_step(action, t):
         obs, rew, term, trunc = step_fn.step(action)
+        done_steps[0] += 1
         return obs, rew, term | trunc
 
     conn.send("ready")
@@ -88,6 +91,7 @@ def _cpu_persistent_worker(conn, job):
         env.cut_computation_graph()
         opt.zero_grad()
         eps = torch.randn(horizon, n_envs, env.action_dim, dtype=torch.float64)
+        done_steps[0] = 0
         try:
             out = oshac.rollout_loss(env_step, env.observation(), pol, vf, horizon, eps)
             out["loss"].backward()
@@ -95,7 +99,7 @@ def _cpu_persistent_worker(conn, job):
             opt.step()
             conn.send("done")
         except Exception as exc:        # e.g. the host LP rejecting a diverged (non-finite) state: the step still counts
-            conn.send("error: " + repr(exc)[:200])
+            conn.send(f"error after {done_steps[0]} steps: " + repr(exc)[:200])
 
 
 def cpu_port_persistent(env_name, sg_kind, horizon, steps, warmup, budget_s):
@@ -117,7 +121,7 @@ def cpu_port_persistent(env_name, sg_kind, horizon, steps, warmup, budget_s):
         procs.append((pr, a))
     for _, c in procs:
         c.recv()
-    errors = []
+    errors, lost = [], [0]
 
     def step():
         t0 = time.perf_counter()
@@ -125,8 +129,9 @@ def cpu_port_persistent(env_name, sg_kind, horizon, steps, warmup, budget_s):
             c.send("step")
         for _, c in procs:
             msg = c.recv()
-            if msg != "done":
+            if msg != "done":           # a diverged rollout stopped early: only its completed steps count as work
                 errors.append(msg)
+                lost[0] += horizon - int(msg.split()[2])
         return time.perf_counter() - t0
 
     calib = step()                                   # also the first warm-up step
@@ -134,13 +139,15 @@ def cpu_port_persistent(env_name, sg_kind, horizon, steps, warmup, budget_s):
     for _ in range(warmup - 1):
         step()
     steps = max(1, min(steps, int((budget_s - warmup * calib) / max(calib, 1e-3))))
+    errors.clear()
+    lost[0] = 0
     walls = [step() for _ in range(steps)]
     for pr, c in procs:
         c.send("stop")
     for pr, _ in procs:
         pr.join(timeout=10)
     total = sum(walls)
-    return dict(value=workers * n_w * horizon * steps / total, steps=steps, warmup=warmup, total_s=total, workers=workers,
+    return dict(value=(workers * horizon * steps - lost[0]) * n_w / total, steps=steps, warmup=warmup, total_s=total, workers=workers,
                 n_w=n_w, errors=errors)
 
 
