@@ -129,7 +129,9 @@ typedef struct sgbpo_mlp {
 /* Rollout buffers, time-major like CoupledBuffer's (T, N, .) tensors (coupled_buffer.py:79-92). */
 typedef struct sgbpo_rollout {
   int64_t N;
-  int32_t H, reserved;
+  int32_t H;
+  int32_t engine;            /* 0: FMA register tiles (float32 / float64, widths 32-128); 1: tcgen05 tensor-core kernels
+                              * (float32, policy [in -> 128 -> 128 -> m]); see sgbpo_rollout_engine_supported */
   const void* eps;           /* [H][N][m]   policy draws (Normal.rsample, policy.py:84-85) */
   const void* noise;         /* [H][N][n]   noise_set.sample() per step (simulator.py:181) */
   const void* dirs;          /* [H][N][m][2m] ray-mask directions (ray_mask.py:184-185) or NULL */
@@ -151,6 +153,10 @@ typedef struct sgbpo_rollout {
   void* stash_e1;            /* [H][N][width]  ELU output of hidden layer 1 */
   void* stash_e2;            /* [H][N][width]  ELU output of hidden layer 2 */
   void* stash_stats;         /* [H][N][4]      LayerNorm mean1, rstd1, mean2, rstd2 */
+  /* engine 1 only */
+  void* jac;                 /* [H][N][sgbpo_rollout_jac_stride(env)] step Jacobians d(s', obs', r)/d(s, a): written by
+                              * sgbpo_rollout_jac, read by sgbpo_rollout_bwd (stash_h1 is not used by engine 1) */
+  const void* reset_aux;     /* [R][N][naux] aux (goal, obstacles) in effect after reset r, or NULL: reset_states[r][:, :naux] */
 } sgbpo_rollout;
 
 typedef struct sgbpo_rollout_grads {
@@ -161,6 +167,7 @@ typedef struct sgbpo_rollout_grads {
   /* parameter gradients, accumulated (caller zero-fills), in torch's layouts:
    * g_w_in [width][in_dim], g_w_out [out_dim][width], g_b_hid/g_gamma/g_beta [2][width], g_b_out/g_log_std [out_dim] */
   void* g_w_in; void* g_w_out; void* g_b_hid; void* g_gamma; void* g_beta; void* g_b_out; void* g_log_std;
+  void* g_w_hid;               /* engine 1: [width][width] Linear2.weight.grad accumulated in-kernel (dz2_out unused) */
 } sgbpo_rollout_grads;
 
 /* forward over the whole horizon: policy MLP + safeguarded step per environment per t (one launch) */
@@ -169,6 +176,13 @@ int sgbpo_rollout_fwd(int env_id, int dtype, const sgbpo_consts* consts, const s
 /* reverse pass over the whole horizon (replaces autograd's H-long chain) */
 int sgbpo_rollout_bwd(int env_id, int dtype, const sgbpo_consts* consts, const sgbpo_mlp* policy,
                       const sgbpo_rollout* r, const sgbpo_rollout_grads* g, void* stream);
+/* engine 1, between forward and reverse pass: the dual-number Jacobian of every safeguarded step (t, environment)
+ * w.r.t. (s_t, a_t) from the stored (s_t, a_t, w_t) -- what autograd's per-step backward nodes hold, but
+ * evaluated for all H x N steps in ONE fully parallel launch instead of on the sequential reverse chain. */
+int sgbpo_rollout_jac(int env_id, int dtype, const sgbpo_consts* consts, const sgbpo_rollout* r, void* stream);
+int sgbpo_rollout_jac_stride(int env_id);     /* floats per (t, environment) record of sgbpo_rollout.jac; < 0: unknown env */
+/* 1 when engine 1 covers (env_id, dtype, policy), else 0 */
+int sgbpo_rollout_engine_supported(int env_id, int dtype, const sgbpo_mlp* policy);
 /* batched MLP forward over M rows (target critic over the buffer's observation rows, shac.py:111) */
 int sgbpo_mlp_rows(int dtype, int64_t M, const sgbpo_mlp* net, const void* x, void* out, void* stream);
 
@@ -213,6 +227,11 @@ int sgbpo_episode_stats(int dtype, int64_t n_rewards, const void* rewards, int64
                         int interv_mask, int bad_mask, double* scal, int64_t* n_interv, int32_t* bad, void* stream);
 int sgbpo_shac_loss(int dtype, int rows, int64_t N, const void* disc, const int32_t* term_int, const void* values,
                     const void* rewards, const void* norm, void* loss, void* stream);
+
+/* ---- tensor-core operand-view self-test (diagnostic; tests/test_gpu_tc_mma.py): X, Z, D are 128 x 128 float32 device
+ * matrices; mode 0: D = X Z^T, 1: D = X Z, 2: D = X^T Z, each through the fp16 hi/lo split tcgen05 path the rollout
+ * kernels use (K-major / MN-major shared-memory views of one stored operand). */
+int sgbpo_tc_selftest(int mode, const void* x, const void* z, void* d, void* stream);
 
 #ifdef __cplusplus
 }

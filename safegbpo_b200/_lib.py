@@ -60,12 +60,13 @@ class Mlp(C.Structure):
 
 class Rollout(C.Structure):
     """Mirror of ``struct sgbpo_rollout``."""
-    _fields_ = [("N", C.c_int64), ("H", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("N", C.c_int64), ("H", C.c_int32), ("engine", C.c_int32),
                 ("eps", C.c_void_p), ("noise", C.c_void_p), ("dirs", C.c_void_p), ("aux0", C.c_void_p),
                 ("reset_states", C.c_void_p), ("reset_idx", C.c_void_p), ("aux_src", C.c_void_p), ("shared", C.c_void_p),
                 ("states", C.c_void_p), ("obs", C.c_void_p), ("actions", C.c_void_p), ("exec_actions", C.c_void_p),
                 ("rewards", C.c_void_p), ("flags", C.c_void_p),
-                ("stash_h1", C.c_void_p), ("stash_e1", C.c_void_p), ("stash_e2", C.c_void_p), ("stash_stats", C.c_void_p)]
+                ("stash_h1", C.c_void_p), ("stash_e1", C.c_void_p), ("stash_e2", C.c_void_p), ("stash_stats", C.c_void_p),
+                ("jac", C.c_void_p), ("reset_aux", C.c_void_p)]
 
 
 class RolloutGrads(C.Structure):
@@ -73,7 +74,7 @@ class RolloutGrads(C.Structure):
     _fields_ = [("grw", C.c_void_p), ("gobs_term", C.c_void_p), ("term_of_row", C.c_void_p),
                 ("dz2_out", C.c_void_p), ("g_w_in", C.c_void_p), ("g_w_out", C.c_void_p),
                 ("g_b_hid", C.c_void_p), ("g_gamma", C.c_void_p), ("g_beta", C.c_void_p), ("g_b_out", C.c_void_p),
-                ("g_log_std", C.c_void_p)]
+                ("g_log_std", C.c_void_p), ("g_w_hid", C.c_void_p)]
 
 
 ENV_IDS = {"BalancePendulum": 0, "BalanceCartPole": 1, "SwingUpCartPole": 2, "BalanceQuadrotor": 3,
@@ -97,6 +98,9 @@ _SIGNATURES = {
     "sgbpo_rollout_fwd": (C.c_int, [C.c_int, C.c_int, C.POINTER(Consts), C.POINTER(Mlp), C.POINTER(Rollout), _VP]),
     "sgbpo_rollout_bwd": (C.c_int, [C.c_int, C.c_int, C.POINTER(Consts), C.POINTER(Mlp), C.POINTER(Rollout),
                                     C.POINTER(RolloutGrads), _VP]),
+    "sgbpo_rollout_jac": (C.c_int, [C.c_int, C.c_int, C.POINTER(Consts), C.POINTER(Rollout), _VP]),
+    "sgbpo_rollout_jac_stride": (C.c_int, [C.c_int]),
+    "sgbpo_rollout_engine_supported": (C.c_int, [C.c_int, C.c_int, C.POINTER(Mlp)]),
     "sgbpo_mlp_rows": (C.c_int, [C.c_int, C.c_int64, C.POINTER(Mlp), _VP, _VP, _VP]),
     "sgbpo_mlp_rows_vjp": (C.c_int, [C.c_int, C.c_int64, C.POINTER(Mlp), _VP, _VP, _VP, _VP]),
     "sgbpo_clip_adam": (C.c_int, [C.c_int, C.c_int, _VP, _VP, _VP]),
@@ -105,6 +109,7 @@ _SIGNATURES = {
     "sgbpo_td_lambda": (C.c_int, [C.c_int, C.c_int64, C.c_int, _VP, _VP, _VP, C.c_double, C.c_double, _VP, _VP, _VP]),
     "sgbpo_episode_stats": (C.c_int, [C.c_int, C.c_int64, _VP, C.c_int64, _VP, C.c_int, C.c_int, _VP, _VP, _VP, _VP]),
     "sgbpo_shac_loss": (C.c_int, [C.c_int, C.c_int, C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "sgbpo_tc_selftest": (C.c_int, [C.c_int, _VP, _VP, _VP, _VP]),
 }
 EXPORTED = tuple(_SIGNATURES)
 _lib = None
@@ -120,8 +125,27 @@ def build(verbose: bool = False) -> Path:
     from concurrent.futures import ThreadPoolExecutor
     srcs = sources()
     import hashlib
-    headers = sorted(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "sgbpo.h"]
-    hdr_hash = hashlib.sha1(b"".join(p.read_bytes() for p in headers)).hexdigest()
+    import re
+
+    inc_re = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
+    dep_cache: dict[Path, tuple[Path, ...]] = {}
+
+    def deps(path: Path) -> tuple[Path, ...]:
+        """Transitive closure of the quoted includes of `path` (resolved relative to the including file)."""
+        path = path.resolve()
+        if path in dep_cache:
+            return dep_cache[path]
+        dep_cache[path] = ()
+        found: list[Path] = []
+        for rel in inc_re.findall(path.read_text()):
+            inc = (path.parent / rel).resolve()
+            if inc.exists():
+                found.append(inc)
+                found.extend(deps(inc))
+        dep_cache[path] = tuple(sorted(set(found)))
+        return dep_cache[path]
+
+    hdr_hashes = {src: hashlib.sha1(b"".join(p.read_bytes() for p in deps(src))).hexdigest() for src in srcs}   # (sequential: deps() memoises)
     objdir = PKG / "build"
     objdir.mkdir(exist_ok=True)
     compile_flags = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
@@ -130,9 +154,9 @@ def build(verbose: bool = False) -> Path:
     def compile_one(src: Path):
         obj = objdir / (src.stem + ".o")
         stamp = objdir / (src.stem + ".sha1")
-        # content hash of the unit and every header (mtimes are not trusted: a concurrent or interrupted build
+        # content hash of the unit and every header it includes, transitively (mtimes are not trusted: a concurrent or interrupted build
         # could leave a newer object compiled from older headers)
-        want = hashlib.sha1((hdr_hash + hashlib.sha1(src.read_bytes()).hexdigest() + " ".join(compile_flags)).encode()).hexdigest()
+        want = hashlib.sha1((hdr_hashes[src] + hashlib.sha1(src.read_bytes()).hexdigest() + " ".join(compile_flags)).encode()).hexdigest()
         if obj.exists() and stamp.exists() and stamp.read_text() == want:
             return obj, ""
         stamp.unlink(missing_ok=True)

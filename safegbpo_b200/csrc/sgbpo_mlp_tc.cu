@@ -30,17 +30,13 @@
 #include <cstdlib>
 
 #include "../../include/sgbpo.h"
+#include "sgbpo_tc.cuh"
 
 namespace sgbpo {
 extern thread_local char g_err[512];
 
 namespace tc {
 
-constexpr int ROWS = 128;            // rows per tile = threads per CTA = TMEM lanes
-constexpr int W = 128;               // hidden width
-constexpr int KCH = W / 8;           // 16-byte K chunks per row
-constexpr int PART_BYTES = ROWS * W * 2;          // one fp16 part of a 128 x 128 operand: 32 KB
-constexpr uint32_t SBO = 128, LBO = ROWS * 16;    // bytes: next 8-row group / next K chunk
 constexpr int MAX_HH = 2;            // hidden-hidden layers kept in shared memory
 constexpr int MAX_IN = 64;
 constexpr uint32_t TMEM_COLS = 128;
@@ -51,85 +47,6 @@ struct Params {
   const float* b[MAX_HH + 1];  const float* gamma[MAX_HH + 1];  const float* beta[MAX_HH + 1];
   const float* b_out;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// shared-memory matrix descriptor: K-major, no swizzle (cute::UMMA::SmemDescriptor, version 1)
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((LBO >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((SBO >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B fp16, both K-major, N = 128, M = 128
-constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(W >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
-
-__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  for (uint32_t spin = 0; !done; ++spin) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (spin > (1u << 26)) __trap();      // never hang the GPU: a lost arrival becomes a launch failure
-  }
-}
-// 32 consecutive fp32 columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ float elu1(float v) {                 // ATen: exp(x) - 1 on the negative side
-  const float en = expf(v < 0.f ? v : 0.f) - 1.0f;
-  return v > 0.f ? v : en;
-}
-// 8 consecutive K values of one operand row -> fp16 hi / lo parts, one 16-byte unit each
-__device__ __forceinline__ void split_store(unsigned char* a_hi, unsigned char* a_lo, int kc, int row, const float (&h)[8]) {
-  uint32_t hi[4], lo[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const __half2 h2 = __floats2half2_rn(h[2 * i], h[2 * i + 1]);
-    const float2 back = __half22float2(h2);
-    const __half2 l2 = __floats2half2_rn(h[2 * i] - back.x, h[2 * i + 1] - back.y);
-    hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
-    lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
-  }
-  const int unit = (kc * ROWS + row) * 16;
-  *reinterpret_cast<uint4*>(a_hi + unit) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<uint4*>(a_lo + unit) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-}
 
 // sum over the NSPLIT threads that share a row (they sit in different warps): shared-memory exchange
 template <int NSPLIT>
@@ -346,6 +263,59 @@ static int launch_tc(int64_t M, const sgbpo_mlp* net, const Params& p, const voi
   return SGBPO_OK;
 }
 
+
+// ---- operand-view self-test: D = X Z^T (mode 0), X Z (mode 1: B as MN-major view), X^T Z (mode 2: both MN-major) ----
+// One CTA, thread r owns row r of X and Z (128 x 128 fp32 each); tests/test_gpu_tc_mma.py compares with float64 torch.
+__global__ void __launch_bounds__(ROWS, 1)
+tc_selftest_kernel(int mode, const float* __restrict__ X, const float* __restrict__ Z, float* __restrict__ D) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* x_hi = smem;
+  unsigned char* x_lo = x_hi + PART_BYTES;
+  unsigned char* z_hi = x_lo + PART_BYTES;
+  unsigned char* z_lo = z_hi + PART_BYTES;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(z_lo + PART_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int kc = 0; kc < KCH; ++kc) {
+    float h[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = X[tid * W + kc * 8 + i];
+    split_store(x_hi, x_lo, kc, tid, h);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = Z[tid * W + kc * 8 + i];
+    split_store(z_hi, z_lo, kc, tid, h);
+  }
+  if (tid == 0) {
+    mbar_init(smem_u32(bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) {
+    const uint32_t xh = smem_u32(x_hi), xl = smem_u32(x_lo), zh = smem_u32(z_hi), zl = smem_u32(z_lo);
+    if (mode == 0) mma_split3<false, false>(tmem_base, xh, xl, zh, zl, 0);
+    else if (mode == 1) mma_split3<false, true>(tmem_base, xh, xl, zh, zl, 0);
+    else mma_split3<true, true>(tmem_base, xh, xl, zh, zl, 0);
+    mma_commit(smem_u32(bar));
+  }
+  mbar_wait(smem_u32(bar), 0);
+  tc_fence_after();
+#pragma unroll
+  for (int q = 0; q < W / 32; ++q) {
+    float z[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + q * 32, z);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) D[tid * W + q * 32 + i] = z[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
 }  // namespace tc
 
 // returns SGBPO_E_UNSUPPORTED (no error text) when the network is outside what the tensor-core kernel covers
@@ -373,3 +343,17 @@ int launch_rows_tc(int64_t M, const sgbpo_mlp* net, const void* x, void* out, cu
 }
 
 }  // namespace sgbpo
+
+extern "C" int sgbpo_tc_selftest(int mode, const void* x, const void* z, void* d, void* stream) {
+  using namespace sgbpo;
+  using namespace sgbpo::tc;
+  if (!x || !z || !d || mode < 0 || mode > 2) { snprintf(g_err, sizeof(g_err), "sgbpo_tc_selftest: bad argument"); return SGBPO_E_ARG; }
+  const size_t smem = 4 * (size_t)PART_BYTES + 64;
+  cudaError_t e = cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) {
+    tc_selftest_kernel<<<1, ROWS, smem, (cudaStream_t)stream>>>(mode, (const float*)x, (const float*)z, (float*)d);
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "tc_selftest_kernel: %s", cudaGetErrorString(e)); return SGBPO_E_CUDA; }
+  return SGBPO_OK;
+}

@@ -131,6 +131,8 @@ class SHAC(LearningAlgorithm):
         self._fused_engine = None
         # data-parallel hook: called between backward and clip/Adam (distributed.allreduce_policy_grads)
         self.grad_sync = None
+        # same for the critic: called after every critic batch's backward, before clip + Adam (distributed.allreduce_critic_grads)
+        self.vf_grad_sync = None
         self.vf_graphs = True            # critic fit replayed as a CUDA graph when the optimizer allows (plain Adam on CUDA)
         self._vf_graph = None
         self._fused_tail = None          # resolved on first use: fused clip + Adam launch when the optimizer is plain Adam on CUDA
@@ -311,6 +313,8 @@ class SHAC(LearningAlgorithm):
                 pred = self.value_function(observations[lo:hi]).squeeze(dim=1)
                 value_loss = (pred - estimated_values[lo:hi]).square().mean()
                 value_loss.backward()
+                if self.vf_grad_sync is not None:
+                    self.vf_grad_sync(self)
                 torch.nn.utils.clip_grad_norm_(self.value_function.parameters(), self.MAX_GRAD_NORM)
                 self.value_function_optim.step()
         return float(value_loss)
@@ -319,7 +323,9 @@ class SHAC(LearningAlgorithm):
     def _vf_graph_ok(self, est: Tensor) -> bool:
         from .. import optim as sgoptim
         # (the learning rate is a launch argument baked into the captured graph: constant schedule only)
-        return (self.vf_graphs and est.is_cuda and sgoptim.supported(self.value_function_optim)
+        # a collective per batch inside the captured loop needs a capture-safe backend: opt in with vf_graphs = "collective"
+        sync_ok = self.vf_grad_sync is None or self.vf_graphs == "collective"
+        return (bool(self.vf_graphs) and sync_ok and est.is_cuda and sgoptim.supported(self.value_function_optim)
                 and torch.is_grad_enabled() and self.VF_LEARNING_RATE_SCHEDULE == "constant")
 
     def _fit_value_function_graph(self, est: Tensor, obs: Tensor) -> float:
@@ -392,16 +398,17 @@ class SHAC(LearningAlgorithm):
         est, obs = g["est"], g["obs"]
         n = est.shape[0]
         batch_size = math.ceil(n / self.vf_fit_num_batches)
-        grads = [p.grad for p in vf.parameters()]
         for _ in range(self.vf_num_fits):
             for b in range(self.vf_fit_num_batches):
                 lo, hi = b * batch_size, min((b + 1) * batch_size, n)
                 if lo >= n:
                     break
-                torch._foreach_zero_(grads)
+                torch._foreach_zero_([p.grad for p in vf.parameters()])     # (vf_grad_sync may re-bind .grad to flat views)
                 pred = self._vf_forward_train(obs[lo:hi]).squeeze(dim=1)
                 value_loss = (pred - est[lo:hi]).square().mean()
                 value_loss.backward()
+                if self.vf_grad_sync is not None:
+                    self.vf_grad_sync(self)
                 sgoptim.clip_adam_step(opt, self.MAX_GRAD_NORM)
         g["loss"].copy_(value_loss.detach())
 
