@@ -130,8 +130,11 @@ typedef struct sgbpo_mlp {
 typedef struct sgbpo_rollout {
   int64_t N;
   int32_t H;
-  int32_t engine;            /* 0: FMA register tiles (float32 / float64, widths 32-128); 1: tcgen05 tensor-core kernels
-                              * (float32, policy [in -> 128 -> 128 -> m]); see sgbpo_rollout_engine_supported */
+  int32_t engine;            /* bit 0, forward: 0 = FMA register tiles (float32 / float64, widths 32-128), 1 = tcgen05 kernel;
+                              * bit 1, reverse pass: 0 = sequential FMA kernel, 1 = parallel tensor-core reverse pass
+                              * (row-batched policy backward + per-environment scan).  The tensor-core engines cover float32
+                              * policies [in -> 128 -> 128 -> m]: sgbpo_rollout_engine_supported.  Both forward engines
+                              * write the same activation stash, so any combination is valid. */
   const void* eps;           /* [H][N][m]   policy draws (Normal.rsample, policy.py:84-85) */
   const void* noise;         /* [H][N][n]   noise_set.sample() per step (simulator.py:181) */
   const void* dirs;          /* [H][N][m][2m] ray-mask directions (ray_mask.py:184-185) or NULL */
@@ -153,10 +156,13 @@ typedef struct sgbpo_rollout {
   void* stash_e1;            /* [H][N][width]  ELU output of hidden layer 1 */
   void* stash_e2;            /* [H][N][width]  ELU output of hidden layer 2 */
   void* stash_stats;         /* [H][N][4]      LayerNorm mean1, rstd1, mean2, rstd2 */
-  /* engine 1 only */
+  const void* reset_aux;     /* [R][N][naux] aux (goal, obstacles) in effect after reset r, or NULL: reset_states[r][:, :naux]
+                              * (forward engine 1 and sgbpo_rollout_jac) */
+  /* reverse engine 1 only (stash_h1 is not used by it and may be NULL) */
   void* jac;                 /* [H][N][sgbpo_rollout_jac_stride(env)] step Jacobians d(s', obs', r)/d(s, a): written by
-                              * sgbpo_rollout_jac, read by sgbpo_rollout_bwd (stash_h1 is not used by engine 1) */
-  const void* reset_aux;     /* [R][N][naux] aux (goal, obstacles) in effect after reset r, or NULL: reset_states[r][:, :naux] */
+                              * sgbpo_rollout_jac, read by sgbpo_rollout_bwd */
+  void* pol_jac;             /* [H][N][sgbpo_rollout_pol_jac_stride(env)] scratch: policy Jacobians d mu / d obs per row */
+  void* dmu;                 /* [H][N][m] scratch: d loss / d mu_t from the scan */
 } sgbpo_rollout;
 
 typedef struct sgbpo_rollout_grads {
@@ -167,7 +173,7 @@ typedef struct sgbpo_rollout_grads {
   /* parameter gradients, accumulated (caller zero-fills), in torch's layouts:
    * g_w_in [width][in_dim], g_w_out [out_dim][width], g_b_hid/g_gamma/g_beta [2][width], g_b_out/g_log_std [out_dim] */
   void* g_w_in; void* g_w_out; void* g_b_hid; void* g_gamma; void* g_beta; void* g_b_out; void* g_log_std;
-  void* g_w_hid;               /* engine 1: [width][width] Linear2.weight.grad accumulated in-kernel (dz2_out unused) */
+  void* g_w_hid;               /* reverse engine 1: [width][width] Linear2.weight.grad accumulated in-kernel (dz2_out unused) */
 } sgbpo_rollout_grads;
 
 /* forward over the whole horizon: policy MLP + safeguarded step per environment per t (one launch) */
@@ -181,6 +187,7 @@ int sgbpo_rollout_bwd(int env_id, int dtype, const sgbpo_consts* consts, const s
  * evaluated for all H x N steps in ONE fully parallel launch instead of on the sequential reverse chain. */
 int sgbpo_rollout_jac(int env_id, int dtype, const sgbpo_consts* consts, const sgbpo_rollout* r, void* stream);
 int sgbpo_rollout_jac_stride(int env_id);     /* floats per (t, environment) record of sgbpo_rollout.jac; < 0: unknown env */
+int sgbpo_rollout_pol_jac_stride(int env_id); /* same for sgbpo_rollout.pol_jac */
 /* 1 when engine 1 covers (env_id, dtype, policy), else 0 */
 int sgbpo_rollout_engine_supported(int env_id, int dtype, const sgbpo_mlp* policy);
 /* batched MLP forward over M rows (target critic over the buffer's observation rows, shac.py:111) */

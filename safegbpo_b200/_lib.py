@@ -66,7 +66,7 @@ class Rollout(C.Structure):
                 ("states", C.c_void_p), ("obs", C.c_void_p), ("actions", C.c_void_p), ("exec_actions", C.c_void_p),
                 ("rewards", C.c_void_p), ("flags", C.c_void_p),
                 ("stash_h1", C.c_void_p), ("stash_e1", C.c_void_p), ("stash_e2", C.c_void_p), ("stash_stats", C.c_void_p),
-                ("jac", C.c_void_p), ("reset_aux", C.c_void_p)]
+                ("reset_aux", C.c_void_p), ("jac", C.c_void_p), ("pol_jac", C.c_void_p), ("dmu", C.c_void_p)]
 
 
 class RolloutGrads(C.Structure):
@@ -100,6 +100,7 @@ _SIGNATURES = {
                                     C.POINTER(RolloutGrads), _VP]),
     "sgbpo_rollout_jac": (C.c_int, [C.c_int, C.c_int, C.POINTER(Consts), C.POINTER(Rollout), _VP]),
     "sgbpo_rollout_jac_stride": (C.c_int, [C.c_int]),
+    "sgbpo_rollout_pol_jac_stride": (C.c_int, [C.c_int]),
     "sgbpo_rollout_engine_supported": (C.c_int, [C.c_int, C.c_int, C.POINTER(Mlp)]),
     "sgbpo_mlp_rows": (C.c_int, [C.c_int, C.c_int64, C.POINTER(Mlp), _VP, _VP, _VP]),
     "sgbpo_mlp_rows_vjp": (C.c_int, [C.c_int, C.c_int64, C.POINTER(Mlp), _VP, _VP, _VP, _VP]),

@@ -32,6 +32,17 @@ static int tc_jac_dispatch(int env_id, const sgbpo_consts* c, const sgbpo_rollou
 static int tc_bwd_dispatch(int env_id, const sgbpo_mlp* pol, const sgbpo_rollout* r, const sgbpo_rollout_grads* g, cudaStream_t st) {
   ROLLOUT_TC_DISPATCH(rollout_tc_bwd_env, pol, r, g, st)
 }
+static int tc_pol_jac_stride(int env_id) {
+  switch (env_id) {
+    case ENV_BALANCE_PENDULUM: return tcr::pol_jac_stride_of<ENV_BALANCE_PENDULUM>();
+    case ENV_BALANCE_CARTPOLE: return tcr::pol_jac_stride_of<ENV_BALANCE_CARTPOLE>();
+    case ENV_SWINGUP_CARTPOLE: return tcr::pol_jac_stride_of<ENV_SWINGUP_CARTPOLE>();
+    case ENV_BALANCE_QUADROTOR: return tcr::pol_jac_stride_of<ENV_BALANCE_QUADROTOR>();
+    case ENV_MANAGE_HOUSEHOLD: return tcr::pol_jac_stride_of<ENV_MANAGE_HOUSEHOLD>();
+    case ENV_NAVIGATE_SEEKER: return tcr::pol_jac_stride_of<ENV_NAVIGATE_SEEKER>();
+    default: return -1;
+  }
+}
 static int tc_jac_stride(int env_id) {
   switch (env_id) {
     case ENV_BALANCE_PENDULUM: return tcr::JacShape<ENV_BALANCE_PENDULUM>::STRIDE;
@@ -55,18 +66,19 @@ int sgbpo_rollout_fwd(int env_id, int dtype, const sgbpo_consts* consts, const s
   if (r->N <= 0 || r->H <= 0) return SGBPO_OK;
   if (!r->eps || !r->noise || !r->states || !r->obs || !r->actions || !r->exec_actions || !r->rewards || !r->flags)
     return fail2(SGBPO_E_ARG, "sgbpo_rollout_fwd: null buffer");
-  if (r->engine == 0) {
+  const int fwd_engine = r->engine & 1;
+  if (fwd_engine == 0) {
     const int n_stash = (r->stash_h1 != nullptr) + (r->stash_e1 != nullptr) + (r->stash_e2 != nullptr) + (r->stash_stats != nullptr);
-    if (n_stash != 0 && n_stash != 4) return fail2(SGBPO_E_ARG, "sgbpo_rollout_fwd: pass all four stash buffers or none");
-    if (n_stash == 4 && policy->n_hidden != 2) return fail2(SGBPO_E_UNSUPPORTED, "activation stash: policies with two hidden layers");
+    if (n_stash != 0 && n_stash != 4 && !(n_stash == 3 && !r->stash_h1))
+      return fail2(SGBPO_E_ARG, "sgbpo_rollout_fwd: pass the stash buffers (h1 optional) or none");
+    if (n_stash != 0 && policy->n_hidden != 2) return fail2(SGBPO_E_UNSUPPORTED, "activation stash: policies with two hidden layers");
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (r->engine == 1) {
+  if (r->engine < 0 || r->engine > 3) return fail2(SGBPO_E_ARG, "sgbpo_rollout_fwd: unknown engine");
+  if (fwd_engine == 1) {
     if (dtype != SGBPO_F32) return fail2(SGBPO_E_UNSUPPORTED, "tensor-core rollout: float32 only");
-    if (r->stash_e1 && !r->jac) return fail2(SGBPO_E_ARG, "sgbpo_rollout_fwd (engine 1): the Jacobian buffer is required with the stash");
     return tc_fwd_dispatch(env_id, consts, policy, r, st);
   }
-  if (r->engine != 0) return fail2(SGBPO_E_ARG, "sgbpo_rollout_fwd: unknown engine");
   ROLLOUT_DISPATCH(rollout_fwd_env, dtype, policy->width, consts, policy, r, st)
 }
 
@@ -79,6 +91,7 @@ int sgbpo_rollout_jac(int env_id, int dtype, const sgbpo_consts* consts, const s
 }
 
 int sgbpo_rollout_jac_stride(int env_id) { return tc_jac_stride(env_id); }
+int sgbpo_rollout_pol_jac_stride(int env_id) { return tc_pol_jac_stride(env_id); }
 
 int sgbpo_rollout_engine_supported(int env_id, int dtype, const sgbpo_mlp* policy) {
   if (!policy || dtype != SGBPO_F32 || tc_jac_stride(env_id) < 0) return 0;
@@ -90,12 +103,12 @@ int sgbpo_rollout_bwd(int env_id, int dtype, const sgbpo_consts* consts, const s
                       const sgbpo_rollout* r, const sgbpo_rollout_grads* g, void* stream) {
   if (!consts || !policy || !r || !g) return fail2(SGBPO_E_ARG, "sgbpo_rollout_bwd: null argument");
   if (r->N <= 0 || r->H <= 0) return SGBPO_OK;
-  if (r->engine == 1) {
+  if ((r->engine >> 1) & 1) {
     if (dtype != SGBPO_F32) return fail2(SGBPO_E_UNSUPPORTED, "tensor-core rollout: float32 only");
     if (!g->grw || !g->g_w_hid || !g->g_w_in || !g->g_w_out || !g->g_b_hid || !g->g_gamma || !g->g_beta || !g->g_b_out || !g->g_log_std)
       return fail2(SGBPO_E_ARG, "sgbpo_rollout_bwd: null buffer");
     if (!r->stash_e1 || !r->stash_e2 || !r->stash_stats || !r->jac)
-      return fail2(SGBPO_E_ARG, "sgbpo_rollout_bwd (engine 1): forward stash and sgbpo_rollout_jac output are required");
+      return fail2(SGBPO_E_ARG, "sgbpo_rollout_bwd (reverse engine 1): forward stash and sgbpo_rollout_jac output are required");
     return tc_bwd_dispatch(env_id, policy, r, g, (cudaStream_t)stream);
   }
   if (!g->grw || !g->dz2_out || !g->g_w_in || !g->g_w_out || !g->g_b_hid || !g->g_gamma || !g->g_beta ||

@@ -166,7 +166,7 @@ rollout_fwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
       elu_layernorm<T, W, R, true>(h, net.gamma, net.beta, lane, ev, m1, r1);
       store_tile<T, W, R>(bufA, lane, h);
       stream_tile<T, W, R>(A.stash_e1, t, N, env0, lane, ev);
-      stream_tile<T, W, R>(A.stash_h1, t, N, env0, lane, h);
+      if (A.stash_h1) stream_tile<T, W, R>(A.stash_h1, t, N, env0, lane, h);
       __syncwarp();
       tile_gemm<T, W, R>(bufA, W, net.w_hid, net.b_hid + W, lane, h);
       elu_layernorm<T, W, R, true>(h, net.gamma + W, net.beta + W, lane, ev, m2, r2);

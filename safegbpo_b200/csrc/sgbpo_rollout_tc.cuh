@@ -16,10 +16,13 @@
 //   rollout_jac_kernel      one thread per (t, environment): the dual-number Jacobian of the safeguarded step w.r.t.
 //                           (s_t, a_t).  It depends only on stored (s_t, a_t, w_t), so it leaves the sequential chain
 //                           and runs at full occupancy over all H x N steps.
-//   rollout_tc_bwd_kernel   t = H-1..0: contracts the stored Jacobian with the carried cotangents, policy backward with
-//                           dh1 = dz2 W_hid and dW_hid += dz2^T h1 on the tensor cores.  Both read the SAME stored
-//                           operands through K-major / MN-major descriptor views (sgbpo_tc.cuh); dW_hid accumulates in
-//                           TMEM over the whole horizon under a power-of-two scale that keeps dz2 inside fp16 range.
+//   policy_rows_bwd_kernel  the policy backward over ALL H x N rows as 128-row tiles (no time loop): dh1 = dz2 W_hid and
+//                           dW_hid += dz2^T h1 on the tensor cores, both reading the SAME stored operands through
+//                           K-major / MN-major descriptor views (sgbpo_tc.cuh); dW_hid accumulates in TMEM over all tiles of
+//                           a CTA under a power-of-two scale that keeps dz2 inside fp16 range.  Run twice: Jacobian mode
+//                           (d mu / d obs per row) before, gradient mode (parameter gradients) after
+//   rollout_scan_kernel     the only sequential part of the reverse pass: a linear recursion of (n + o + m)-vectors per
+//                           environment over t = H-1..0 (see the section comment below).
 #pragma once
 #include <cuda_runtime.h>
 #include <cmath>
@@ -44,7 +47,7 @@ struct PolicyTc {                         // device pointers to the torch parame
 };
 
 struct TcExtra {
-  float* jac;                // [H][N][jac_stride]  step Jacobians (rollout_jac_kernel -> rollout_tc_bwd_kernel)
+  float* jac;                // [H][N][jac_stride]  step Jacobians (rollout_jac_kernel -> rollout_scan_kernel)
   const float* reset_aux;    // [R][N][NAUX] aux in effect after reset r, or null (then reset_states[r][:, :NAUX])
   float* g_w_hid;            // [W][W] Linear2.weight.grad, accumulated with atomics (caller zero-fills)
 };
@@ -202,11 +205,13 @@ rollout_tc_fwd_kernel(const __grid_constant__ RolloutArgs<float> A, const __grid
       for (int i = 0; i < IN; ++i) S.obsS[i * ROWS + trow] = valid ? A.obs[env * IN + i] : 0.f;
     }
     bar_sync(qbar, 128);
+    int ridx_next = A.reset_idx ? A.reset_idx[0] : -1;
 
     for (int t = 0; t < A.H; ++t) {
       // this step's streaming inputs (owner threads), issued before the MLP so their latency hides behind it
       float epsv[NA], wv[NS], dv[NA * 2 * NA], rs[NS];
-      const int ridx = A.reset_idx ? A.reset_idx[t] : -1;
+      const int ridx = ridx_next;
+      ridx_next = (A.reset_idx && t + 1 < A.H) ? A.reset_idx[t + 1] : -1;
       if (owner) {
 #pragma unroll
         for (int q = 0; q < NA; ++q) epsv[q] = valid ? A.eps[((int64_t)t * N + env) * NA + q] : 0.f;
@@ -241,7 +246,7 @@ rollout_tc_fwd_kernel(const __grid_constant__ RolloutArgs<float> A, const __grid
       }
       float sum = 0.f;
 #pragma unroll
-      for (int c = 0; c < CW; ++c) { e[c] = elu1(e[c]); sum += e[c]; }
+      for (int c = 0; c < CW; ++c) { e[c] = elu1_fast(e[c]); sum += e[c]; }
       if (A.stash_e1 && valid) store_cols(A.stash_e1 + stash_off, e);
       float st[4];
       normalise4(e, sum, S.g1, S.be1, S.red_a, S.red_b, part, trow, qbar, st[0], st[1]);
@@ -265,8 +270,8 @@ rollout_tc_fwd_kernel(const __grid_constant__ RolloutArgs<float> A, const __grid
 #pragma unroll
         for (int c4 = 0; c4 < CW / 4; ++c4) {
           const float4 b4 = *reinterpret_cast<const float4*>(S.b2 + part * CW + 4 * c4);
-          e[4 * c4 + 0] = elu1(z[4 * c4 + 0] + b4.x); e[4 * c4 + 1] = elu1(z[4 * c4 + 1] + b4.y);
-          e[4 * c4 + 2] = elu1(z[4 * c4 + 2] + b4.z); e[4 * c4 + 3] = elu1(z[4 * c4 + 3] + b4.w);
+          e[4 * c4 + 0] = elu1_fast(z[4 * c4 + 0] + b4.x); e[4 * c4 + 1] = elu1_fast(z[4 * c4 + 1] + b4.y);
+          e[4 * c4 + 2] = elu1_fast(z[4 * c4 + 2] + b4.z); e[4 * c4 + 3] = elu1_fast(z[4 * c4 + 3] + b4.w);
           sum += (e[4 * c4 + 0] + e[4 * c4 + 1]) + (e[4 * c4 + 2] + e[4 * c4 + 3]);
         }
       }
@@ -402,30 +407,40 @@ rollout_jac_kernel(const __grid_constant__ RolloutArgs<float> A, const __grid_co
 }
 
 // ======================================================================================================================
-// backward
+// reverse pass.  The reverse-mode recursion of the rollout is LINEAR in the cotangents, and its only sequential part is
+//     (gs_{t+1}, gobs_{t+1})  ->  v = J_t^T (gs_{t+1}, gobs_{t+1} + terminal term, grw_t)  ->  gs_t = v[:n],  dmu_t = v[n:] (1 - a_t^2)
+//                             ->  gobs_t = M_t^T dmu_t
+// with J_t the step Jacobian (rollout_jac_kernel) and M_t = d mu_t / d obs_t the policy's input-output Jacobian.  Both
+// depend only on stored forward data, so they are evaluated for ALL H x N rows in parallel (policy_rows_bwd_kernel in
+// Jacobian mode: tensor cores over 128-row tiles), the recursion shrinks to a scan of (n + o + m)-vectors per environment
+// (rollout_scan_kernel), and the parameter gradients become ONE batched pass over the H x N rows with the now-known
+// cotangents dmu_t (policy_rows_bwd_kernel in gradient mode: dW_hid accumulates in TMEM over all rows of a CTA).
 // ======================================================================================================================
-struct BwdSmem {
+// NSP = threads per row (4 or 8: 512 or 1024 threads per CTA, 32 or 16 hidden columns per thread).  The kernel is a chain of
+// short dependent phases separated by barriers, so the 8-way split (twice the warps, half the registers per thread) hides
+// more latency; the 4-way split remains for wide policy inputs whose exchange buffers would not fit.
+template <int NSP> struct BwdSmem {
   unsigned char *w_hi, *w_lo, *a_hi, *a_lo, *h_hi, *h_lo;
-  float *w_in, *g1, *g2, *be1, *w_out, *misc, *obsS, *dmuS, *red_a, *red_b, *db2S;
+  float *w_in, *g1, *g2, *be1, *w_out, *obsS, *dmuS, *red_a, *red_b, *db2S;
   uint32_t* maxS;
   uint64_t* bar;
   uint32_t* tmem_slot;
   __host__ __device__ static int nop(int no) { return (no + 3) & ~3; }
-  __host__ __device__ static size_t bytes(int in_dim, int no, int out_dim) {
-    return 6 * (size_t)PART_BYTES + sizeof(float) * ((size_t)in_dim * W + 3 * W + (size_t)out_dim * W + 8 + (size_t)ROWS * nop(no) +
-                                                       (size_t)out_dim * ROWS + 4 * NSPLIT * ROWS + W) + 8 + 32;
+  __host__ __device__ static size_t bytes(int in_dim, int no, int out_dim, bool grad) {
+    return (grad ? 6 : 4) * (size_t)PART_BYTES + sizeof(float) * ((size_t)in_dim * W + 3 * W + (size_t)out_dim * W + (size_t)ROWS * nop(no) +
+                                                                     (size_t)out_dim * ROWS + 4 * NSP * ROWS + W) + 8 + 32;
   }
-  __device__ void carve(unsigned char* smem, int in_dim, int no, int out_dim) {
-    w_hi = smem; w_lo = w_hi + PART_BYTES; a_hi = w_lo + PART_BYTES; a_lo = a_hi + PART_BYTES; h_hi = a_lo + PART_BYTES; h_lo = h_hi + PART_BYTES;
-    float* f = reinterpret_cast<float*>(h_lo + PART_BYTES);
+  __device__ void carve(unsigned char* smem, int in_dim, int no, int out_dim, bool grad) {
+    w_hi = smem; w_lo = w_hi + PART_BYTES; a_hi = w_lo + PART_BYTES; a_lo = a_hi + PART_BYTES;
+    h_hi = a_lo + PART_BYTES; h_lo = h_hi + PART_BYTES;            // (gradient mode only)
+    float* f = reinterpret_cast<float*>(grad ? h_lo + PART_BYTES : h_hi);
     w_in = f; f += in_dim * W;                 // [i][W]
     g1 = f; f += W; g2 = f; f += W; be1 = f; f += W;
     w_out = f; f += out_dim * W;               // [q][W]
-    misc = f; f += 8;                          // sigma[0..2)
-    obsS = f; f += ROWS * nop(no);             // [row][NOP] observation of the step being differentiated
+    obsS = f; f += ROWS * nop(no);             // [row][NOP] policy input of the tile's rows (gradient mode)
     dmuS = f; f += out_dim * ROWS;             // [q][row]
-    red_a = f; f += 2 * NSPLIT * ROWS;         // float2 per (part, row)
-    red_b = f; f += 2 * NSPLIT * ROWS;
+    red_a = f; f += 2 * NSP * ROWS;            // float2 per (part, row)
+    red_b = f; f += 2 * NSP * ROWS;
     db2S = f; f += W;
     maxS = reinterpret_cast<uint32_t*>(f);     // two alternating slots
     bar = reinterpret_cast<uint64_t*>(maxS + 2);
@@ -433,49 +448,108 @@ struct BwdSmem {
   }
 };
 
-// pair of row sums over the NSPLIT threads of a row
-__device__ __forceinline__ float2 row_sum4_pair(float a, float b, float* red, int part, int row, int bar_id) {
+// pair of row sums over the NSP threads of a row
+template <int NSP>
+__device__ __forceinline__ float2 row_sum_pair(float a, float b, float* red, int part, int row, int bar_id) {
   reinterpret_cast<float2*>(red)[part * ROWS + row] = make_float2(a, b);
-  bar_sync(bar_id, 128);
+  bar_sync(bar_id, 32 * NSP);
   const float2* r = reinterpret_cast<const float2*>(red);
-  const float2 v0 = r[row], v1 = r[ROWS + row], v2 = r[2 * ROWS + row], v3 = r[3 * ROWS + row];
-  return make_float2((v0.x + v1.x) + (v2.x + v3.x), (v0.y + v1.y) + (v2.y + v3.y));
-}
-
-// Column sums over the 32 rows of a warp through a warp-private 32 x 32 scratch tile (XOR-swizzled: conflict-free both ways).
-// write: lane = row stores its CW values; read: lane = column.
-__device__ __forceinline__ void scratch_put(float* scratch, int lane, const float (&v)[CW]) {
+  float2 t = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int c = 0; c < CW; ++c) scratch[c * 32 + (lane ^ c)] = v[c];
+  for (int p = 0; p < NSP; ++p) { const float2 v = r[p * ROWS + row]; t.x += v.x; t.y += v.y; }
+  return t;
 }
-__device__ __forceinline__ float scratch_get(const float* scratch, int lane, int r) { return scratch[lane * 32 + (r ^ lane)]; }
 
-template <int ENV>
-__global__ void __launch_bounds__(NT, 1)
-rollout_tc_bwd_kernel(const __grid_constant__ RolloutArgs<float> A, const __grid_constant__ BackwardArgs<float> G,
-                      const __grid_constant__ PolicyTc P, const __grid_constant__ TcExtra X) {
-  using TASK = Task<ENV>;
-  using JS = JacShape<ENV>;
-  constexpr int NS = TASK::NS, NA = TASK::NA, NO = TASK::NO, KD = JS::KD;
-  constexpr int NOP = (NO + 3) & ~3;
-  constexpr uint32_t TMEM_COLS = 256;            // [0, 128): dh1 of the step, [128, 256): dW_hid accumulated over the horizon
+template <int C> __device__ __forceinline__ void load_cols_n(const float* __restrict__ src, float (&e)[C]) {
+#pragma unroll
+  for (int c4 = 0; c4 < C / 4; ++c4) {
+    const float4 v = *reinterpret_cast<const float4*>(src + 4 * c4);
+    e[4 * c4] = v.x; e[4 * c4 + 1] = v.y; e[4 * c4 + 2] = v.z; e[4 * c4 + 3] = v.w;
+  }
+}
+template <int C> __device__ __forceinline__ void split_store_cols_n(unsigned char* hi, unsigned char* lo, int col0, int row, const float (&e)[C]) {
+#pragma unroll
+  for (int kc = 0; kc < C / 8; ++kc) {
+    const float h8[8] = {e[8 * kc], e[8 * kc + 1], e[8 * kc + 2], e[8 * kc + 3], e[8 * kc + 4], e[8 * kc + 5], e[8 * kc + 6], e[8 * kc + 7]};
+    split_store(hi, lo, col0 / 8 + kc, row, h8);
+  }
+}
+template <int C> __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[C]);
+template <> __device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
+template <> __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Column sums over the 32 rows of a warp through a warp-private C x 32 scratch tile, XOR-swizzled so that both the write
+// (lane = row stores its C values) and the read (lane = column lane % C, rows [(lane / C) * C, +C)) are conflict-free.
+// With C = 16 the two half-warps sum disjoint row halves of the same 16 columns; the partial sums are only ever ADDED
+// (register accumulators flushed with atomics), so they are never combined explicitly.
+template <int C> __device__ __forceinline__ void scratch_put_n(float* scratch, int lane, const float (&v)[C]) {
+#pragma unroll
+  for (int c = 0; c < C; ++c) scratch[c * 32 + (lane ^ c)] = v[c];
+}
+template <int C> __device__ __forceinline__ float scratch_get_n(const float* scratch, int lane, int j) {
+  const int col = lane % C, row = (lane / C) * C + j;
+  return scratch[col * 32 + (row ^ col)];
+}
+template <int C> __device__ __forceinline__ float scratch_colsum_n(const float* scratch, int lane) {      // four independent chains
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < C; ++j) a[j & 3] += scratch_get_n<C>(scratch, lane, j);
+  return (a[0] + a[1]) + (a[2] + a[3]);
+}
+
+struct RowsBwdArgs {
+  int64_t M;                 // rows = H * N, row = t * N + env
+  const float* e1;  const float* e2;  const float* stats;      // forward stash [M][W], [M][W], [M][4]
+  const float* obs;          // [M (+ N)][in_dim] policy inputs (rollout buffer rows 0..H-1)       (gradient mode)
+  const float* dmu;          // [M][out_dim] d loss / d mu                                         (gradient mode)
+  float* pol_jac;            // [M][out_dim][NOP] d mu_q / d obs                                   (Jacobian mode)
+  float* g_w_hid;  float* g_w_in;  float* g_w_out;  float* g_b_hid;  float* g_gamma;  float* g_beta;     // accumulated (atomics)
+};
+
+// GRAD = false: policy input-output Jacobian of every row (cotangent e_q per output q).  GRAD = true: parameter gradients of
+// the batched policy for the row cotangents dmu.  NA = policy outputs, NO = differentiated inputs (the first NO of in_dim).
+template <int NA, int NO, bool GRAD, int NSP>
+__global__ void __launch_bounds__(ROWS * NSP, 1)
+policy_rows_bwd_kernel(const __grid_constant__ RowsBwdArgs R, const __grid_constant__ PolicyTc P) {
+  constexpr int NOP = (NO + 3) & ~3, C = W / NSP, NTK = ROWS * NSP;
+  constexpr uint32_t TMEM_COLS = GRAD ? 256 : 128;       // [0, 128): dh1 of the tile; [128, 256): dW_hid over all tiles of this CTA
   extern __shared__ __align__(1024) unsigned char smem[];
-  BwdSmem S;
+  BwdSmem<NSP> S;
   const int IN = P.in_dim;
-  S.carve(smem, IN, NO, NA);
+  S.carve(smem, IN, NO, NA, GRAD);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int trow = tid % ROWS, part = tid / ROWS, qbar = quad_barrier_id(warp);
   const bool owner = part == 0;
-  float* scratch = reinterpret_cast<float*>(S.a_hi) + warp * 1024;     // warp-private 4 KB inside the (idle) dz2 operand buffer
-  float* exch = reinterpret_cast<float*>(S.a_hi);                      // [part][row][NOP] exchange of the input-gradient partials
+  float* scratch = reinterpret_cast<float*>(S.a_hi) + warp * (C * 32);   // warp-private tile inside the (idle) dz2 operand buffer
+  float* exch = reinterpret_cast<float*>(S.a_hi);                        // [part][row][NOP] exchange of the input-gradient partials
+  static_assert(!GRAD || true, "");
+  // this lane's column and row subset in the column-sum phases
+  const int cs_col = part * C + lane % C, cs_row0 = (warp & 3) * 32 + (lane / C) * C;
 
   // ---- one-time setup ---------------------------------------------------------------------------------------------
-  for (int i = tid; i < IN * W; i += NT) S.w_in[(i % IN) * W + (i / IN)] = P.w_in[i];
-  for (int i = tid; i < W; i += NT) { S.g1[i] = P.gamma1[i]; S.g2[i] = P.gamma2[i]; S.be1[i] = P.beta1[i]; S.db2S[i] = 0.f; }
-  for (int i = tid; i < NA * W; i += NT) S.w_out[i] = P.w_out[i];
-  if (tid < NA) S.misc[tid] = expf(P.log_std[tid]);
+  for (int i = tid; i < IN * W; i += NTK) S.w_in[(i % IN) * W + (i / IN)] = P.w_in[i];
+  for (int i = tid; i < W; i += NTK) { S.g1[i] = P.gamma1[i]; S.g2[i] = P.gamma2[i]; S.be1[i] = P.beta1[i]; S.db2S[i] = 0.f; }
+  for (int i = tid; i < NA * W; i += NTK) S.w_out[i] = P.w_out[i];
   if (tid < 2) S.maxS[tid] = 0u;
-  load_weight_parts(S.w_hi, S.w_lo, P.w_hid, tid);
+  for (int i = tid; i < W * KCH; i += NTK) {
+    const int n = i / KCH, kc = i % KCH;
+    const float4 v0 = *reinterpret_cast<const float4*>(P.w_hid + (size_t)n * W + kc * 8);
+    const float4 v1 = *reinterpret_cast<const float4*>(P.w_hid + (size_t)n * W + kc * 8 + 4);
+    const float h[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    split_store(S.w_hi, S.w_lo, kc, n, h);
+  }
   if (tid == 0) {
     mbar_init(smem_u32(S.bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -486,348 +560,384 @@ rollout_tc_bwd_kernel(const __grid_constant__ RolloutArgs<float> A, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *S.tmem_slot;
-  const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(part * CW);
+  const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(part * C);
   const uint32_t bar_addr = smem_u32(S.bar);
   const uint32_t a_hi_addr = smem_u32(S.a_hi), a_lo_addr = smem_u32(S.a_lo), w_hi_addr = smem_u32(S.w_hi), w_lo_addr = smem_u32(S.w_lo);
   const uint32_t h_hi_addr = smem_u32(S.h_hi), h_lo_addr = smem_u32(S.h_lo);
   uint32_t phase = 0;
-  const int64_t N = A.N;
-  const int64_t n_tiles = (N + ROWS - 1) / ROWS;
+  const int64_t n_tiles = (R.M + ROWS - 1) / ROWS;
 
-  // per-lane column accumulators (column part * 32 + lane, summed over this warp's 32 rows, all steps and tiles)
-  float acc_b2 = 0.f, acc_b1 = 0.f, acc_g1 = 0.f, acc_S[NA], acc_win[NO], acc_B[NA], acc_lstd[NA];
+  // per-lane column accumulators (column cs_col, summed over this lane's row subset and all tiles of this CTA)
+  float acc_b2 = 0.f, acc_b1 = 0.f, acc_g1 = 0.f, acc_S[NA], acc_win[NO], acc_B[NA];
 #pragma unroll
-  for (int q = 0; q < NA; ++q) { acc_S[q] = 0.f; acc_B[q] = 0.f; acc_lstd[q] = 0.f; }
+  for (int q = 0; q < NA; ++q) { acc_S[q] = 0.f; acc_B[q] = 0.f; }
 #pragma unroll
   for (int i = 0; i < NO; ++i) acc_win[i] = 0.f;
-  uint32_t it = 0;              // steps processed by this CTA (selects the alternating max slot)
+  uint32_t it = 0;              // (tile, cotangent) passes processed by this CTA (selects the alternating max slot)
   float scale = 1.f;            // power of two: the dz2 operand holds scale * dz2, the TMEM accumulator scale * dW_hid
   bool acc_live = false;        // the dW_hid accumulator holds data (CTA-uniform)
 
-  // flush of the TMEM dW_hid accumulator into global memory (thread = output row c_out, its 32 input columns)
-  auto flush_dw = [&](float inv_scale) {
+  auto flush_dw = [&](float inv_scale) {      // TMEM dW_hid accumulator -> global (thread = output row c_out, its C input columns)
     tc_fence_after();
-    float z[32];
-    tmem_ld32(tmem_row + 128, z);
-    float* dst = X.g_w_hid + (size_t)trow * W + part * CW;
+    float z[C];
+    tmem_ld_cols<C>(tmem_row + 128, z);
+    float* dst = R.g_w_hid + (size_t)trow * W + part * C;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) atomicAdd(dst + i, z[i] * inv_scale);
+    for (int i = 0; i < C; ++i) atomicAdd(dst + i, z[i] * inv_scale);
     tc_fence_before();
   };
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t env = tile * ROWS + trow;
-    const bool valid = env < N;
-    float gs[NS], gobs[NO];
+    const int64_t row = tile * ROWS + trow;
+    const bool valid = row < R.M;
+    const size_t row_off = valid ? (size_t)row : 0;
+    float4 st = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) st = *reinterpret_cast<const float4*>(R.stats + row_off * 4);
+    const float mean1 = st.x, rstd1 = st.y, mean2 = st.z, rstd2 = st.w;
+    float e2[C];
 #pragma unroll
-    for (int i = 0; i < NS; ++i) gs[i] = 0.f;
-#pragma unroll
-    for (int i = 0; i < NO; ++i) gobs[i] = 0.f;
-
-    for (int t = A.H - 1; t >= 0; --t) {
-      const size_t row_off = (size_t)t * N + (valid ? env : 0);
-      // ---- loads of this step (latency overlaps the Jacobian contraction) -----------------------------------------------
-      float e2[CW], e1[CW];
-      if (valid) { load_cols(A.stash_e2 + row_off * W + part * CW, e2); load_cols(A.stash_e1 + row_off * W + part * CW, e1); }
-      else {
-#pragma unroll
-        for (int c = 0; c < CW; ++c) { e2[c] = 0.f; e1[c] = 0.f; }
-      }
-      float4 st = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid) st = *reinterpret_cast<const float4*>(A.stash_stats + row_off * 4);
-      // ---- owner: contract the step Jacobian with the carried cotangents ------------------------------------------------
+    for (int c = 0; c < C; ++c) e2[c] = 0.f;
+    if (valid) load_cols_n<C>(R.e2 + row_off * W + part * C, e2);
+    if (GRAD) {
       if (owner) {
-        float act[NA], epsv[NA], v[KD];
 #pragma unroll
-        for (int d = 0; d < KD; ++d) v[d] = 0.f;
-        if (valid) {
-          float rec[JS::STRIDE];
-          const float4* src = reinterpret_cast<const float4*>(X.jac + row_off * JS::STRIDE);
+        for (int i = 0; i < NO; ++i) S.obsS[trow * NOP + i] = valid ? R.obs[row_off * IN + i] : 0.f;
 #pragma unroll
-          for (int i = 0; i < JS::STRIDE / 4; ++i) { const float4 x4 = src[i]; rec[4 * i] = x4.x; rec[4 * i + 1] = x4.y; rec[4 * i + 2] = x4.z; rec[4 * i + 3] = x4.w; }
-          float go[NO];
-#pragma unroll
-          for (int i = 0; i < NO; ++i) go[i] = gobs[i];
-          const int kt = G.term_of_row ? G.term_of_row[t + 1] : -1;
-          if (kt >= 0) {
-#pragma unroll
-            for (int i = 0; i < NO; ++i) go[i] += G.gobs_term[((int64_t)kt * N + env) * IN + i];
-          }
-          const float gr = G.grw[t];
-#pragma unroll
-          for (int d = 0; d < KD; ++d) {
-            float x = gr * rec[(NS + NO) * KD + d];
-#pragma unroll
-            for (int i = 0; i < NS; ++i) x = fmaf(gs[i], rec[i * KD + d], x);
-#pragma unroll
-            for (int i = 0; i < NO; ++i) x = fmaf(go[i], rec[(NS + i) * KD + d], x);
-            v[d] = x;
-          }
-#pragma unroll
-          for (int q = 0; q < NA; ++q) { act[q] = A.actions[row_off * NA + q]; epsv[q] = A.eps[row_off * NA + q]; }
-#pragma unroll
-          for (int i = 0; i < NO; ++i) S.obsS[trow * NOP + i] = A.obs[row_off * IN + i];
-        } else {
-#pragma unroll
-          for (int q = 0; q < NA; ++q) { act[q] = 0.f; epsv[q] = 0.f; }
-#pragma unroll
-          for (int i = 0; i < NO; ++i) S.obsS[trow * NOP + i] = 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < NS; ++i) gs[i] = v[i];
-#pragma unroll
-        for (int q = 0; q < NA; ++q) {
-          const float ga_pre = v[NS + q] * (1.f - act[q] * act[q]);      // d loss / d (mu + sigma eps)
-          S.dmuS[q * ROWS + trow] = ga_pre;
-          acc_lstd[q] += ga_pre * epsv[q] * S.misc[q];
-        }
+        for (int q = 0; q < NA; ++q) S.dmuS[q * ROWS + trow] = valid ? R.dmu[row_off * NA + q] : 0.f;
       }
-      bar_sync(qbar, 128);
+      // h1 (the B operand of dW_hid) re-derived from the stash with the forward's own operations
+      float h1[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) h1[c] = 0.f;
+      if (valid) load_cols_n<C>(R.e1 + row_off * W + part * C, h1);
+#pragma unroll
+      for (int c4 = 0; c4 < C / 4; ++c4) {
+        const float4 g = *reinterpret_cast<const float4*>(S.g1 + part * C + 4 * c4);
+        const float4 b = *reinterpret_cast<const float4*>(S.be1 + part * C + 4 * c4);
+        h1[4 * c4 + 0] = valid ? ((h1[4 * c4 + 0] - mean1) * rstd1) * g.x + b.x : 0.f;
+        h1[4 * c4 + 1] = valid ? ((h1[4 * c4 + 1] - mean1) * rstd1) * g.y + b.y : 0.f;
+        h1[4 * c4 + 2] = valid ? ((h1[4 * c4 + 2] - mean1) * rstd1) * g.z + b.z : 0.f;
+        h1[4 * c4 + 3] = valid ? ((h1[4 * c4 + 3] - mean1) * rstd1) * g.w + b.w : 0.f;
+      }
+      split_store_cols_n<C>(S.h_hi, S.h_lo, part * C, trow, h1);
+      bar_sync(qbar, 32 * NSP);
+    }
+    constexpr int PASSES = GRAD ? 1 : NA;
+#pragma unroll 1
+    for (int pass = 0; pass < PASSES; ++pass) {
       float dmu[NA];
 #pragma unroll
-      for (int q = 0; q < NA; ++q) dmu[q] = S.dmuS[q * ROWS + trow];
-      const float mean1 = st.x, rstd1 = st.y, mean2 = st.z, rstd2 = st.w;
-      // ---- h1 (the B operand of dW_hid) re-derived from the stash with the forward's own operations ---------------------
-      {
-        float h1[CW];
+      for (int q = 0; q < NA; ++q) dmu[q] = GRAD ? S.dmuS[q * ROWS + trow] : (q == pass ? 1.f : 0.f);
+      if (GRAD) {
+        // ---- S_q[c] = sum_rows dmu_q xhat2[c] column sums.  The scratch aliases the dz2 operand, which is idle here: the
+        //      previous tile's MMAs have completed and this tile's dz2 is stored after the next CTA barrier
 #pragma unroll
-        for (int c4 = 0; c4 < CW / 4; ++c4) {
-          const float4 g = *reinterpret_cast<const float4*>(S.g1 + part * CW + 4 * c4);
-          const float4 b = *reinterpret_cast<const float4*>(S.be1 + part * CW + 4 * c4);
-          h1[4 * c4 + 0] = ((e1[4 * c4 + 0] - mean1) * rstd1) * g.x + b.x;
-          h1[4 * c4 + 1] = ((e1[4 * c4 + 1] - mean1) * rstd1) * g.y + b.y;
-          h1[4 * c4 + 2] = ((e1[4 * c4 + 2] - mean1) * rstd1) * g.z + b.z;
-          h1[4 * c4 + 3] = ((e1[4 * c4 + 3] - mean1) * rstd1) * g.w + b.w;
-        }
-        if (!valid) {
+        for (int q = 0; q < NA; ++q) {
 #pragma unroll
-          for (int c = 0; c < CW; ++c) h1[c] = 0.f;
+          for (int c = 0; c < C; ++c) scratch[c * 32 + (lane ^ c)] = dmu[q] * ((e2[c] - mean2) * rstd2);
+          __syncwarp();
+          float b = 0.f;
+#pragma unroll
+          for (int r4 = 0; r4 < C / 4; ++r4) {
+            const float4 d4 = *reinterpret_cast<const float4*>(S.dmuS + q * ROWS + cs_row0 + 4 * r4);
+            b += (d4.x + d4.y) + (d4.z + d4.w);
+          }
+          acc_S[q] += scratch_colsum_n<C>(scratch, lane);
+          acc_B[q] += b;
+          __syncwarp();
         }
-        split_store_cols(S.h_hi, S.h_lo, part, trow, h1);
       }
-      // ---- output layer + LayerNorm 2 + ELU 2 backward -> dz2 ---------------------------------------------------------------
-      float gc[CW];           // gradient tile of this thread
-      float xs[CW];           // dmu_q * xhat2 products for the column sums S_q (q = 0 first)
+      // ---- output layer + LayerNorm 2 + ELU 2 backward -> dz2 -----------------------------------------------------------
+      float gc[C];
       {
-        float s1 = 0.f, s2 = 0.f;
+        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int c = 0; c < CW; ++c) {
-          float dh = 0.f;
+        for (int c4 = 0; c4 < C / 4; ++c4) {
+          const float4 g4 = *reinterpret_cast<const float4*>(S.g2 + part * C + 4 * c4);
+          float dh[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int q = 0; q < NA; ++q) dh = fmaf(dmu[q], S.w_out[q * W + part * CW + c], dh);
-          const float xh = (e2[c] - mean2) * rstd2;
-          const float dx = dh * S.g2[part * CW + c];
-          gc[c] = dx;
-          s1 += dx;
-          s2 = fmaf(dx, xh, s2);
+          for (int q = 0; q < NA; ++q) {
+            const float4 w4 = *reinterpret_cast<const float4*>(S.w_out + q * W + part * C + 4 * c4);
+            dh[0] = fmaf(dmu[q], w4.x, dh[0]); dh[1] = fmaf(dmu[q], w4.y, dh[1]);
+            dh[2] = fmaf(dmu[q], w4.z, dh[2]); dh[3] = fmaf(dmu[q], w4.w, dh[3]);
+          }
+          const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float xh = (e2[4 * c4 + j] - mean2) * rstd2;
+            const float dx = dh[j] * gg[j];
+            gc[4 * c4 + j] = dx;
+            s1[j] += dx;
+            s2[j] = fmaf(dx, xh, s2[j]);
+          }
         }
-        const float2 tot = row_sum4_pair(s1, s2, S.red_a, part, trow, qbar);
+        const float2 tot = row_sum_pair<NSP>((s1[0] + s1[1]) + (s1[2] + s1[3]), (s2[0] + s2[1]) + (s2[2] + s2[3]), S.red_a, part, trow, qbar);
         const float m1 = tot.x / float(W), m2 = tot.y / float(W);
 #pragma unroll
-        for (int c = 0; c < CW; ++c) {
+        for (int c = 0; c < C; ++c) {
           const float xh = (e2[c] - mean2) * rstd2;
           const float de = rstd2 * (gc[c] - m1 - xh * m2);
-          gc[c] = de * (e2[c] > 0.f ? 1.f : e2[c] + 1.f);
+          gc[c] = valid ? de * (e2[c] > 0.f ? 1.f : e2[c] + 1.f) : 0.f;
         }
       }
-      // ---- power-of-two scale that keeps dz2 inside fp16 range (CTA-uniform) -------------------------------------------------
+      if (GRAD) {                // db2 column sums (the scratch is still idle)
+        scratch_put_n<C>(scratch, lane, gc);
+        __syncwarp();
+        acc_b2 += scratch_colsum_n<C>(scratch, lane);
+      }
+      // ---- power-of-two scale that keeps dz2 inside fp16 range (CTA-uniform) ---------------------------------------------
       {
-        float mx = 0.f;
+        float mx[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int c = 0; c < CW; ++c) mx = fmaxf(mx, fabsf(gc[c]));
+        for (int c4 = 0; c4 < C / 4; ++c4) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          for (int j = 0; j < 4; ++j) mx[j] = fmaxf(mx[j], fabsf(gc[4 * c4 + j]));
+        }
+        float mxx = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
         uint32_t* slot = S.maxS + (it & 1);
-        if (lane == 0) atomicMax(slot, __float_as_uint(mx));
-        tc_fence_before();
-        __syncthreads();
+        if (lane == 0) atomicMax(slot, __float_as_uint(mxx));
+        __syncthreads();           // (also: every warp is done reading its scratch tile before dz2 is stored over it)
         const float m = __uint_as_float(*slot);
         if (tid == 0) S.maxS[(it + 1) & 1] = 0u;         // the other slot is next used two barriers from now
         ++it;
         const float prod = m * scale;
         if (m > 0.f && !(prod >= 0.25f && prod <= 8192.f)) {
-          if (acc_live) flush_dw(1.f / scale);
+          if (GRAD && acc_live) flush_dw(1.f / scale);
           acc_live = false;
           int ex;
           frexpf(m, &ex);                                 // m = f * 2^ex, f in [0.5, 1)
           scale = (m - m == 0.f) ? ldexpf(1.f, 7 - ex) : 1.f;      // m * scale in [64, 128)
         }
       }
-      {
-        float sc[CW];
 #pragma unroll
-        for (int c = 0; c < CW; ++c) sc[c] = gc[c] * scale;
-        split_store_cols(S.a_hi, S.a_lo, part, trow, sc);
-      }
+      for (int c = 0; c < C; ++c) gc[c] *= scale;
+      split_store_cols_n<C>(S.a_hi, S.a_lo, part * C, trow, gc);
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
       if (tid == 0) {
         tc_fence_after();
-        // dh1[env][c_in] = sum_c_out dz2[env][c_out] W_hid[c_out][c_in]: A K-major, B = the forward weight operand viewed MN-major
+        // dh1[row][c_in] = sum_c_out dz2[row][c_out] W_hid[c_out][c_in]: A K-major, B = the forward weight operand viewed MN-major
         mma_split3<false, true>(tmem_base, a_hi_addr, a_lo_addr, w_hi_addr, w_lo_addr, 0);
-        // dW_hid[c_out][c_in] += sum_env dz2[env][c_out] h1[env][c_in]: both operands viewed MN-major
-        mma_split3<true, true>(tmem_base + 128, a_hi_addr, a_lo_addr, h_hi_addr, h_lo_addr, acc_live ? 1u : 0u);
+        if (GRAD)   // dW_hid[c_out][c_in] += sum_rows dz2[row][c_out] h1[row][c_in]: both operands viewed MN-major
+          mma_split3<true, true>(tmem_base + 128, a_hi_addr, a_lo_addr, h_hi_addr, h_lo_addr, acc_live ? 1u : 0u);
         mma_commit(bar_addr);
       }
-      acc_live = true;
-      // column sums that do not need dh1 run while the MMAs execute: S_q (needs xhat2, dmu) cannot use the scratch yet (it
-      // aliases the dz2 operand), so they are formed after the wait
+      if (GRAD) acc_live = true;
+      float e1[C];              // (loaded while the MMAs execute)
+#pragma unroll
+      for (int c = 0; c < C; ++c) e1[c] = 0.f;
+      if (valid) load_cols_n<C>(R.e1 + row_off * W + part * C, e1);
       mbar_wait(bar_addr, phase);
       phase ^= 1;
       tc_fence_after();
-      // ---- db2 and S_q column sums (scratch is free now: both MMAs have read the dz2 operand) --------------------------------
-      scratch_put(scratch, lane, gc);
-      __syncwarp();
+      // ---- dh1 from TMEM, LayerNorm 1 + ELU 1 backward -> dz1 (in place) ---------------------------------------------------
+      tmem_ld_cols<C>(tmem_row, gc);
       {
-        float a = 0.f;
-#pragma unroll
-        for (int r = 0; r < 32; ++r) a += scratch_get(scratch, lane, r);
-        acc_b2 += a;
-      }
-      __syncwarp();
-#pragma unroll
-      for (int q = 0; q < NA; ++q) {
-#pragma unroll
-        for (int c = 0; c < CW; ++c) xs[c] = dmu[q] * ((e2[c] - mean2) * rstd2);
-        scratch_put(scratch, lane, xs);
-        __syncwarp();
-        float a = 0.f, b = 0.f;
-#pragma unroll
-        for (int r = 0; r < 32; ++r) { a += scratch_get(scratch, lane, r); b += S.dmuS[q * ROWS + (warp & 3) * 32 + r]; }
-        acc_S[q] += a;
-        acc_B[q] += b;
-        __syncwarp();
-      }
-      // ---- dh1 from TMEM, LayerNorm 1 + ELU 1 backward -> dz1 ----------------------------------------------------------------
-      {
-        float z[32];
-        tmem_ld32(tmem_row, z);
         const float inv = 1.f / scale;
-        float s1 = 0.f, s2 = 0.f;
+        if (GRAD) {              // d gamma1[c] = sum_rows dh1 xhat1 (the scratch is free again: both MMAs have read the dz2 operand)
 #pragma unroll
-        for (int c = 0; c < CW; ++c) {
-          const float dh = z[c] * inv;
-          const float xh = (e1[c] - mean1) * rstd1;
-          xs[c] = dh * xh;                               // d gamma1 contribution
-          const float dx = dh * S.g1[part * CW + c];
-          gc[c] = dx;
-          s1 += dx;
-          s2 = fmaf(dx, xh, s2);
+          for (int c = 0; c < C; ++c) scratch[c * 32 + (lane ^ c)] = (gc[c] * inv) * ((e1[c] - mean1) * rstd1);
+          __syncwarp();
+          acc_g1 += scratch_colsum_n<C>(scratch, lane);
+          __syncwarp();
         }
-        const float2 tot = row_sum4_pair(s1, s2, S.red_b, part, trow, qbar);
+        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c4 = 0; c4 < C / 4; ++c4) {
+          const float4 g4 = *reinterpret_cast<const float4*>(S.g1 + part * C + 4 * c4);
+          const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float xh = (e1[4 * c4 + j] - mean1) * rstd1;
+            const float dx = (gc[4 * c4 + j] * inv) * gg[j];
+            gc[4 * c4 + j] = dx;
+            s1[j] += dx;
+            s2[j] = fmaf(dx, xh, s2[j]);
+          }
+        }
+        const float2 tot = row_sum_pair<NSP>((s1[0] + s1[1]) + (s1[2] + s1[3]), (s2[0] + s2[1]) + (s2[2] + s2[3]), S.red_b, part, trow, qbar);
         const float m1 = tot.x / float(W), m2 = tot.y / float(W);
 #pragma unroll
-        for (int c = 0; c < CW; ++c) {
+        for (int c = 0; c < C; ++c) {
           const float xh = (e1[c] - mean1) * rstd1;
           const float de = rstd1 * (gc[c] - m1 - xh * m2);
-          gc[c] = de * (e1[c] > 0.f ? 1.f : e1[c] + 1.f);     // dz1
+          gc[c] = valid ? de * (e1[c] > 0.f ? 1.f : e1[c] + 1.f) : 0.f;     // dz1
         }
       }
-      // ---- d gamma1, db1, dW_in column sums ------------------------------------------------------------------------------------
-      scratch_put(scratch, lane, xs);
-      __syncwarp();
-      {
-        float a = 0.f;
-#pragma unroll
-        for (int r = 0; r < 32; ++r) a += scratch_get(scratch, lane, r);
-        acc_g1 += a;
-      }
-      __syncwarp();
-      scratch_put(scratch, lane, gc);
-      __syncwarp();
-      {
-        float a = 0.f;
-        const float* ob = S.obsS + (size_t)((warp & 3) * 32) * NOP;
+      if (GRAD) {
+        // ---- db1, dW_in column sums ------------------------------------------------------------------------------------------
+        scratch_put_n<C>(scratch, lane, gc);
+        __syncwarp();
+        {
+          float a[2] = {0.f, 0.f};
+          const float* ob = S.obsS + (size_t)cs_row0 * NOP;
 #pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-          const float x = scratch_get(scratch, lane, r);
-          a += x;
-          float orow[NOP];
+          for (int j = 0; j < C; ++j) {
+            const float x = scratch_get_n<C>(scratch, lane, j);
+            a[j & 1] += x;
+            float orow[NOP];
 #pragma unroll
-          for (int i4 = 0; i4 < NOP / 4; ++i4) {
-            const float4 o4 = *reinterpret_cast<const float4*>(ob + r * NOP + 4 * i4);
-            orow[4 * i4] = o4.x; orow[4 * i4 + 1] = o4.y; orow[4 * i4 + 2] = o4.z; orow[4 * i4 + 3] = o4.w;
+            for (int i4 = 0; i4 < NOP / 4; ++i4) {
+              const float4 o4 = *reinterpret_cast<const float4*>(ob + j * NOP + 4 * i4);
+              orow[4 * i4] = o4.x; orow[4 * i4 + 1] = o4.y; orow[4 * i4 + 2] = o4.z; orow[4 * i4 + 3] = o4.w;
+            }
+#pragma unroll
+            for (int i = 0; i < NO; ++i) acc_win[i] = fmaf(x, orow[i], acc_win[i]);
           }
-#pragma unroll
-          for (int i = 0; i < NO; ++i) acc_win[i] = fmaf(x, orow[i], acc_win[i]);
+          acc_b1 += a[0] + a[1];
         }
-        acc_b1 += a;
-      }
-      // ---- input layer: d obs_t = dz1 W_in (partials over this thread's columns, summed by the owner) --------------------------
-      bar_sync(qbar, 128);          // every warp of the quadrant is done with its scratch before the exchange overwrites the region
-      {
+      } else {
+        // ---- input layer: d mu_q / d obs = dz1 W_in (partials over this thread's columns, summed by the owner) ----------------
         float p[NO];
 #pragma unroll
         for (int i = 0; i < NO; ++i) {
-          float a = 0.f;
+          float a[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int c4 = 0; c4 < CW / 4; ++c4) {
-            const float4 w = *reinterpret_cast<const float4*>(S.w_in + i * W + part * CW + 4 * c4);
-            a = fmaf(gc[4 * c4 + 0], w.x, a); a = fmaf(gc[4 * c4 + 1], w.y, a);
-            a = fmaf(gc[4 * c4 + 2], w.z, a); a = fmaf(gc[4 * c4 + 3], w.w, a);
+          for (int c4 = 0; c4 < C / 4; ++c4) {
+            const float4 w = *reinterpret_cast<const float4*>(S.w_in + i * W + part * C + 4 * c4);
+            a[0] = fmaf(gc[4 * c4 + 0], w.x, a[0]); a[1] = fmaf(gc[4 * c4 + 1], w.y, a[1]);
+            a[2] = fmaf(gc[4 * c4 + 2], w.z, a[2]); a[3] = fmaf(gc[4 * c4 + 3], w.w, a[3]);
           }
-          p[i] = a;
+          p[i] = (a[0] + a[1]) + (a[2] + a[3]);
         }
-        // the exchange region [part][row][NOP] overlaps OTHER quadrants' scratch tiles, so the whole CTA must have left the
-        // column-sum phase
-        __syncthreads();
+        // (the exchange region aliases the dz2 operand: the MMA that read it has completed)
 #pragma unroll
         for (int i = 0; i < NO; ++i) exch[((size_t)part * ROWS + trow) * NOP + i] = p[i];
-        bar_sync(qbar, 128);
-        if (owner) {
+        bar_sync(qbar, 32 * NSP);
+        if (owner && valid) {
+          float* dst = R.pol_jac + ((size_t)row * NA + pass) * NOP;
 #pragma unroll
-          for (int i = 0; i < NO; ++i) {
+          for (int i = 0; i < NOP; ++i) {
             float a = 0.f;
+            if (i < NO) {
 #pragma unroll
-            for (int pp = 0; pp < NSPLIT; ++pp) a += exch[((size_t)pp * ROWS + trow) * NOP + i];
-            gobs[i] = valid ? a : 0.f;
+              for (int pp = 0; pp < NSP; ++pp) a += exch[((size_t)pp * ROWS + trow) * NOP + i];
+            }
+            dst[i] = a;
           }
         }
       }
-      // the next step's stores into the dz2 operand / observation tile wait for every reader of this step
+      // the next pass / tile stores into the dz2 operand, the observation tile and the exchange region
       __syncthreads();
     }
   }
   // ---- flush ------------------------------------------------------------------------------------------------------------------
-  if (acc_live) flush_dw(1.f / scale);
-  {
-    const int c = part * CW + lane;
-    atomicAdd(G.g_b_hid + c, acc_b1);
-    atomicAdd(G.g_b_hid + W + c, acc_b2);
-    atomicAdd(G.g_gamma + c, acc_g1);
+  if (GRAD) {
+    if (acc_live) flush_dw(1.f / scale);
+    const int c = cs_col;
+    atomicAdd(R.g_b_hid + c, acc_b1);
+    atomicAdd(R.g_b_hid + W + c, acc_b2);
+    atomicAdd(R.g_gamma + c, acc_g1);
     atomicAdd(S.db2S + c, acc_b2);
     float dg2 = 0.f, db2 = 0.f;
 #pragma unroll
     for (int q = 0; q < NA; ++q) {
       const float wo = S.w_out[q * W + c];
-      atomicAdd(G.g_w_out + q * W + c, P.gamma2[c] * acc_S[q] + P.beta2[c] * acc_B[q]);
+      atomicAdd(R.g_w_out + q * W + c, P.gamma2[c] * acc_S[q] + P.beta2[c] * acc_B[q]);
       dg2 = fmaf(wo, acc_S[q], dg2);
       db2 = fmaf(wo, acc_B[q], db2);
     }
-    atomicAdd(G.g_gamma + W + c, dg2);
-    atomicAdd(G.g_beta + W + c, db2);
+    atomicAdd(R.g_gamma + W + c, dg2);
+    atomicAdd(R.g_beta + W + c, db2);
 #pragma unroll
-    for (int i = 0; i < NO; ++i) atomicAdd(G.g_w_in + (size_t)c * IN + i, acc_win[i]);
-    if (owner) {
-#pragma unroll
-      for (int q = 0; q < NA; ++q) {
-        float l = acc_lstd[q];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
-        if (lane == 0) { atomicAdd(G.g_log_std + q, l); atomicAdd(G.g_b_out + q, acc_B[q]); }
-      }
-    }
+    for (int i = 0; i < NO; ++i) atomicAdd(R.g_w_in + (size_t)c * IN + i, acc_win[i]);
   }
   tc_fence_before();
   __syncthreads();
-  // d beta1 = sum_rows dh1 = W_hid^T (sum_rows dz2): one matrix-vector product per CTA
-  if (tid < W) {
+  if (GRAD && tid < W) {      // d beta1 = sum_rows dh1 = W_hid^T (sum_rows dz2): one matrix-vector product per CTA
     float a = 0.f;
     for (int kk = 0; kk < W; ++kk) a = fmaf(P.w_hid[(size_t)kk * W + tid], S.db2S[kk], a);
-    atomicAdd(G.g_beta + tid, a);
+    atomicAdd(R.g_beta + tid, a);
   }
   if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---- the sequential part: one thread per environment, a scan of (n + o + m)-vectors over t = H-1 .. 0 ------------------------
+struct ScanArgs {
+  int64_t N;
+  int H, in_dim;
+  const float* jac;          // [H][N][STRIDE]
+  const float* pol_jac;      // [H][N][NA][NOP]
+  const float* actions;      // [H][N][NA]   a_t = tanh(mu + sigma eps)
+  const float* eps;          // [H][N][NA]
+  const float* grw;          // [H]
+  const float* gobs_term;    // [K][N][in_dim] or null
+  const int* term_of_row;    // [H+2] or null
+  const float* log_std;      // [NA]
+  float* dmu;                // [H][N][NA]   out: d loss / d mu_t
+  float* g_b_out;  float* g_log_std;       // [NA] accumulated (atomics)
+};
+
+template <int ENV>
+__global__ void __launch_bounds__(128)
+rollout_scan_kernel(const __grid_constant__ ScanArgs A) {
+  using TASK = Task<ENV>;
+  using JS = JacShape<ENV>;
+  constexpr int NS = TASK::NS, NA = TASK::NA, NO = TASK::NO, KD = JS::KD, NOP = (NO + 3) & ~3;
+  const int64_t env = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const bool valid = env < A.N;
+  const int64_t e = valid ? env : 0;
+  float gs[NS], gobs[NO], sb[NA], sl[NA], sigma[NA];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) gs[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < NO; ++i) gobs[i] = 0.f;
+#pragma unroll
+  for (int q = 0; q < NA; ++q) { sb[q] = 0.f; sl[q] = 0.f; sigma[q] = expf(A.log_std[q]); }
+  for (int t = A.H - 1; t >= 0; --t) {
+    const size_t row = (size_t)t * A.N + e;
+    float rec[JS::STRIDE], pj[NA * NOP], act[NA], epsv[NA];
+    const float4* src = reinterpret_cast<const float4*>(A.jac + row * JS::STRIDE);
+#pragma unroll
+    for (int i = 0; i < JS::STRIDE / 4; ++i) { const float4 x = src[i]; rec[4 * i] = x.x; rec[4 * i + 1] = x.y; rec[4 * i + 2] = x.z; rec[4 * i + 3] = x.w; }
+    const float4* ps = reinterpret_cast<const float4*>(A.pol_jac + row * (NA * NOP));
+#pragma unroll
+    for (int i = 0; i < NA * NOP / 4; ++i) { const float4 x = ps[i]; pj[4 * i] = x.x; pj[4 * i + 1] = x.y; pj[4 * i + 2] = x.z; pj[4 * i + 3] = x.w; }
+#pragma unroll
+    for (int q = 0; q < NA; ++q) { act[q] = A.actions[row * NA + q]; epsv[q] = A.eps[row * NA + q]; }
+    float go[NO];
+#pragma unroll
+    for (int i = 0; i < NO; ++i) go[i] = gobs[i];
+    const int kt = A.term_of_row ? A.term_of_row[t + 1] : -1;
+    if (kt >= 0) {
+#pragma unroll
+      for (int i = 0; i < NO; ++i) go[i] += A.gobs_term[((size_t)kt * A.N + e) * A.in_dim + i];
+    }
+    const float gr = A.grw[t];
+    float v[KD];
+#pragma unroll
+    for (int d = 0; d < KD; ++d) {
+      float x = gr * rec[(NS + NO) * KD + d];
+#pragma unroll
+      for (int i = 0; i < NS; ++i) x = fmaf(gs[i], rec[i * KD + d], x);
+#pragma unroll
+      for (int i = 0; i < NO; ++i) x = fmaf(go[i], rec[(NS + i) * KD + d], x);
+      v[d] = x;
+    }
+#pragma unroll
+    for (int i = 0; i < NS; ++i) gs[i] = v[i];
+#pragma unroll
+    for (int i = 0; i < NO; ++i) gobs[i] = 0.f;
+#pragma unroll
+    for (int q = 0; q < NA; ++q) {
+      const float ga_pre = valid ? v[NS + q] * (1.f - act[q] * act[q]) : 0.f;      // d loss / d (mu + sigma eps)
+      if (valid) A.dmu[row * NA + q] = ga_pre;
+      sb[q] += ga_pre;
+      sl[q] += ga_pre * epsv[q] * sigma[q];
+#pragma unroll
+      for (int i = 0; i < NO; ++i) gobs[i] = fmaf(pj[q * NOP + i], ga_pre, gobs[i]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NA; ++q) {
+    float b = sb[q], l = sl[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { b += __shfl_xor_sync(0xffffffffu, b, o); l += __shfl_xor_sync(0xffffffffu, l, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(A.g_b_out + q, b); atomicAdd(A.g_log_std + q, l); }
+  }
 }
 
 // ======================================================================================================================
@@ -884,20 +994,61 @@ template <int ENV> int rollout_jac(const sgbpo_consts* c, const sgbpo_rollout* r
   return e == cudaSuccess ? SGBPO_OK : cuda_fail2(e, "rollout_jac_kernel");
 }
 
+template <int NA, int NO, bool GRAD, int NSP>
+int launch_rows_bwd(const RowsBwdArgs& R, const PolicyTc& p, int in_dim, cudaStream_t st) {
+  const size_t smem = BwdSmem<NSP>::bytes(in_dim, NO, NA, GRAD);
+  if (smem > SMEM_CAP) return fail2(SGBPO_E_UNSUPPORTED, "tensor-core reverse pass: policy input too wide for shared memory");
+  auto kern = policy_rows_bwd_kernel<NA, NO, GRAD, NSP>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail2(e, "cudaFuncSetAttribute(policy_rows_bwd)");
+  kern<<<tc_grid(R.M), ROWS * NSP, smem, st>>>(R, p);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? SGBPO_OK : cuda_fail2(e, "policy_rows_bwd_kernel");
+}
+
 template <int ENV> int rollout_tc_bwd(const sgbpo_mlp* pol, const sgbpo_rollout* r, const sgbpo_rollout_grads* g, cudaStream_t st) {
   using TASK = Task<ENV>;
+  using JS = JacShape<ENV>;
+  constexpr int NA = TASK::NA, NO = TASK::NO, NOP = (NO + 3) & ~3;
   PolicyTc p;
-  if (!tc_policy(pol, p) || pol->out_dim != TASK::NA) return fail2(SGBPO_E_UNSUPPORTED, "tensor-core rollout: float32 policy [in -> 128 -> 128 -> m]");
-  if (!r->jac || !g->g_w_hid) return fail2(SGBPO_E_ARG, "tensor-core reverse pass: jac and g_w_hid buffers are required");
-  const size_t smem = BwdSmem::bytes(pol->in_dim, TASK::NO, TASK::NA);
-  if (smem > SMEM_CAP) return fail2(SGBPO_E_UNSUPPORTED, "tensor-core reverse pass: policy input too wide for shared memory");
-  auto kern = rollout_tc_bwd_kernel<ENV>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return cuda_fail2(e, "cudaFuncSetAttribute(rollout_tc_bwd)");
-  kern<<<tc_grid(r->N), NT, smem, st>>>(convert_rollout<float>(*r), convert_backward<float>(*g), p, tc_extra(r, g));
-  e = cudaGetLastError();
-  return e == cudaSuccess ? SGBPO_OK : cuda_fail2(e, "rollout_tc_bwd_kernel");
+  if (!tc_policy(pol, p) || pol->out_dim != NA) return fail2(SGBPO_E_UNSUPPORTED, "tensor-core reverse pass: float32 policy [in -> 128 -> 128 -> m]");
+  if (!r->jac || !r->pol_jac || !r->dmu || !g->g_w_hid) return fail2(SGBPO_E_ARG, "tensor-core reverse pass: jac, pol_jac, dmu and g_w_hid buffers are required");
+  RowsBwdArgs R;
+  R.M = r->N * (int64_t)r->H;
+  R.e1 = (const float*)r->stash_e1; R.e2 = (const float*)r->stash_e2; R.stats = (const float*)r->stash_stats;
+  R.obs = (const float*)r->obs; R.dmu = (const float*)r->dmu; R.pol_jac = (float*)r->pol_jac;
+  R.g_w_hid = (float*)g->g_w_hid; R.g_w_in = (float*)g->g_w_in; R.g_w_out = (float*)g->g_w_out; R.g_b_hid = (float*)g->g_b_hid;
+  R.g_gamma = (float*)g->g_gamma; R.g_beta = (float*)g->g_beta;
+  // threads per row: 8 unless the Jacobian-mode exchange [8][128][NOP] would overflow the 64 KB operand buffer it aliases
+  const int forced = env_int("SGBPO_ROWS_BWD_SPLIT");
+  const bool split8 = forced ? forced == 8 : NOP <= 16;
+  // 1. policy input-output Jacobians of all H x N rows
+  {
+    const int rc = split8 ? launch_rows_bwd<NA, NO, false, 8>(R, p, pol->in_dim, st) : launch_rows_bwd<NA, NO, false, 4>(R, p, pol->in_dim, st);
+    if (rc != SGBPO_OK) return rc;
+  }
+  // 2. the sequential recursion: a scan per environment
+  {
+    ScanArgs S;
+    S.N = r->N; S.H = r->H; S.in_dim = pol->in_dim;
+    S.jac = (const float*)r->jac; S.pol_jac = (const float*)r->pol_jac; S.actions = (const float*)r->actions; S.eps = (const float*)r->eps;
+    S.grw = (const float*)g->grw; S.gobs_term = (const float*)g->gobs_term; S.term_of_row = g->term_of_row;
+    S.log_std = p.log_std; S.dmu = (float*)r->dmu; S.g_b_out = (float*)g->g_b_out; S.g_log_std = (float*)g->g_log_std;
+    const int block = r->N >= 148 * 128 ? 128 : 32;
+    rollout_scan_kernel<ENV><<<(int)((r->N + block - 1) / block), block, 0, st>>>(S);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail2(e, "rollout_scan_kernel");
+  }
+  // 3. parameter gradients of the batched policy for the row cotangents
+  {
+    const int rc = split8 ? launch_rows_bwd<NA, NO, true, 8>(R, p, pol->in_dim, st) : launch_rows_bwd<NA, NO, true, 4>(R, p, pol->in_dim, st);
+    if (rc != SGBPO_OK) return rc;
+  }
+  (void)JS::STRIDE; (void)NOP;
+  return SGBPO_OK;
 }
+
+template <int ENV> int pol_jac_stride_of() { return Task<ENV>::NA * ((Task<ENV>::NO + 3) & ~3); }
 
 // one translation unit per environment: SGBPO_INSTANTIATE_ROLLOUT_TC(E) in sgbpo_rollout_tc_env<E>.cu
 template <int ENV> int rollout_tc_fwd_env(const sgbpo_consts* c, const sgbpo_mlp* pol, const sgbpo_rollout* r, cudaStream_t st);

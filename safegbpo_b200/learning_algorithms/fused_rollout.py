@@ -136,12 +136,18 @@ class FusedRollout:
         self.vf_vjp_native = mlp_vjp_fits(self.base.state.dtype, vp.in_dim, vp.width, vp.n_hidden)
         self._grad_bufs = None
         self.last = None
-        # engine 1: tcgen05 tensor-core kernels (float32, policy [o -> 128 -> 128 -> m]); engine 0: FMA register tiles.
-        # SGBPO_ROLLOUT_ENGINE=0 forces the FMA tiles (A/B measurements, tests).
-        self.engine = self.pick_engine(self.base, self.policy_pack)
-        self.jac_stride = _lib.lib().sgbpo_rollout_jac_stride(self.base.env_id) if self.engine == 1 else 0
+        # Engines (include/sgbpo.h, sgbpo_rollout.engine): forward 0 = FMA register tiles, 1 = tcgen05 kernel (one CTA per 128
+        # environments: wins once there are more 128-environment tiles than SMs can hide latency for); reverse 0 = sequential
+        # FMA kernel, 1 = parallel tensor-core reverse pass.  SGBPO_ROLLOUT_ENGINE = 0 | 1 | 2 forces (fwd, reverse) =
+        # (0, 0) | (1, 1) | (0, 1) for A/B measurements and tests.
+        self.engine_fwd, self.engine_bwd = self.pick_engine(self.base, self.policy_pack)
+        self.engine = self.engine_fwd | (self.engine_bwd << 1)
+        lib = _lib.lib()
+        self.jac_stride = lib.sgbpo_rollout_jac_stride(self.base.env_id) if self.engine_bwd else 0
+        self.pol_jac_stride = lib.sgbpo_rollout_pol_jac_stride(self.base.env_id) if self.engine_bwd else 0
         # rollout_fwd, mlp_rows(_tc), episode_stats, shac_loss, mlp_rows_vjp, [rollout_jac,] rollout_bwd, grad_norm, adam_apply
-        self.launches_per_episode = 9 if self.engine == 1 else 8
+        # (reverse engine 1: rollout_jac, policy_rows_bwd<jac>, rollout_scan, policy_rows_bwd<grad> instead of rollout_bwd)
+        self.launches_per_episode = 11 if self.engine_bwd else 8
         self.use_graphs = True                 # replay the episode as two CUDA graphs when its schedule allows
         self.graph_warmup = 2                  # eager episodes before capture (optimizer state, cuBLAS handles)
         self._episodes = 0
@@ -150,11 +156,20 @@ class FusedRollout:
         self.speculative_backward = True       # graph path: enqueue the backward graph right behind the forward graph
         self.kernel_ms = {"rollout_fwd": [], "mlp_rows": [], "rollout_jac": [], "rollout_bwd": []}
 
+    TC_FORWARD_MIN_ENVS = 12288       # measured cross-over of the two forward kernels on one B200 (profiles/r2_engines.md)
+
     @staticmethod
-    def pick_engine(base, pack: "PackedMlp") -> int:
-        if base.state.dtype != torch.float32 or os.environ.get("SGBPO_ROLLOUT_ENGINE", "1") == "0":
-            return 0
-        return int(_lib.lib().sgbpo_rollout_engine_supported(base.env_id, 0, C.byref(pack.desc)))
+    def pick_engine(base, pack: "PackedMlp") -> tuple[int, int]:
+        force = os.environ.get("SGBPO_ROLLOUT_ENGINE", "")
+        if base.state.dtype != torch.float32 or force == "0":
+            return 0, 0
+        if not _lib.lib().sgbpo_rollout_engine_supported(base.env_id, 0, C.byref(pack.desc)):
+            return 0, 0
+        if force == "1":
+            return 1, 1
+        if force == "2":
+            return 0, 1
+        return (1 if base.num_envs >= FusedRollout.TC_FORWARD_MIN_ENVS else 0), 1
 
     def _timed(self, name, fn):
         if not self.profile:
@@ -313,8 +328,9 @@ class FusedRollout:
                  rewards=z(H + 2, N), values=z(H + 2, N), flags=z(H, N, dtype=torch.int32),
                  term=z(H + 2, N, dtype=torch.bool), reward_sum=z(()), n_interv=z((), dtype=torch.int64),
                  bad=z((), dtype=torch.int32), aux0=None if base._aux() is None else z(N, base._aux().shape[1]),
-                 h1=None if self.engine == 1 else z(H, N, W), e1=z(H, N, W), e2=z(H, N, W), stats=z(H, N, 4),
-                 dz2=None if self.engine == 1 else z(H, N, W), jac=z(H, N, self.jac_stride) if self.engine == 1 else None, loss=z(()),
+                 h1=None if self.engine_bwd else z(H, N, W), e1=z(H, N, W), e2=z(H, N, W), stats=z(H, N, 4),
+                 dz2=None if self.engine_bwd else z(H, N, W), jac=z(H, N, self.jac_stride) if self.engine_bwd else None,
+                 pol_jac=z(H, N, self.pol_jac_stride) if self.engine_bwd else None, dmu=z(H, N, m) if self.engine_bwd else None, loss=z(()),
                  fwd_graph=None, bwd_graph=None,
                  scal=z(2, dtype=torch.float64), scal_host=torch.zeros(2, dtype=torch.float64, device="cpu").pin_memory(),
                  side=torch.cuda.Stream(), ev_fwd=torch.cuda.Event(), ev_side=torch.cuda.Event())
@@ -333,10 +349,10 @@ class FusedRollout:
         g["disc_t"], g["grw"], g["norm_t"], g["term_w"] = sf[0:H + 2], sf[H + 2:2 * H + 2], sf[2 * H + 2:2 * H + 3], sf[2 * H + 3:]
         g["reset_states"] = z(RM, N, n)
         g["gobs_term"] = z(KM, N, o)
-        sizes = [o * W, W * m, 2 * W, 2 * W, 2 * W, m, m] + ([W * W] if self.engine == 1 else [])
+        sizes = [o * W, W * m, 2 * W, 2 * W, 2 * W, m, m] + ([W * W] if self.engine_bwd else [])
         g["flat"] = z(sum(sizes))
         g["parts"] = torch.split(g["flat"], sizes)
-        g["dw_hid"] = g["parts"][7].view(W, W) if self.engine == 1 else z(W, W)
+        g["dw_hid"] = g["parts"][7].view(W, W) if self.engine_bwd else z(W, W)
         g["ctr"] = base.noise_set.center[0].to(dt).clone()
         g["half"] = base.noise_set.generator[0].diagonal().to(dt).clone()
         g["noise_lo"], g["noise_span"] = g["ctr"] - g["half"], 2.0 * g["half"]
@@ -348,13 +364,13 @@ class FusedRollout:
         r.rewards, r.flags = p(g["rewards"]), p(g["flags"])
         r.reset_states, r.reset_idx, r.aux_src = p(g["reset_states"]), p(g["reset_idx"]), p(g["aux_src"])
         r.stash_h1, r.stash_e1, r.stash_e2, r.stash_stats = p(g["h1"]), p(g["e1"]), p(g["e2"]), p(g["stats"])
-        r.engine, r.jac = self.engine, p(g["jac"])
+        r.engine, r.jac, r.pol_jac, r.dmu = self.engine, p(g["jac"]), p(g["pol_jac"]), p(g["dmu"])
         g["r"] = r
         gr = RolloutGrads()
         gr.grw, gr.gobs_term, gr.term_of_row = p(g["grw"]), p(g["gobs_term"]), p(g["term_of_row"])
         gr.dz2_out = p(g["dz2"])
         (gr.g_w_in, gr.g_w_out, gr.g_b_hid, gr.g_gamma, gr.g_beta, gr.g_b_out, gr.g_log_std) = [x.data_ptr() for x in g["parts"][:7]]
-        gr.g_w_hid = p(g["dw_hid"]) if self.engine == 1 else None
+        gr.g_w_hid = p(g["dw_hid"]) if self.engine_bwd else None
         g["gr"] = gr
         g_w_in, g_w_out, g_b_hid, g_gamma, g_beta, g_b_out, g_log_std = g["parts"][:7]
         pack = self.policy_pack
@@ -436,13 +452,13 @@ class FusedRollout:
             v = (algo.target_value_function(x.view(-1, o)).view(g["KM"], N) * g["term_w"].unsqueeze(1)).sum()
             g["gobs_term"].copy_(torch.autograd.grad(v, x)[0])
         g["flat"].zero_()
-        if self.engine == 1:           # step Jacobians of all H x N steps in one parallel launch, then the sequential reverse pass
+        if self.engine_bwd:            # step Jacobians of all H x N steps in one parallel launch, then the parallel reverse pass
             check(_lib.lib().sgbpo_rollout_jac(base.env_id, dtype_code(dt), C.byref(self._consts()), C.byref(g["r"]), stream_ptr()),
                   "sgbpo_rollout_jac")
         check(_lib.lib().sgbpo_rollout_bwd(base.env_id, dtype_code(dt), C.byref(self._consts()),
                                            C.byref(self.policy_pack.desc), C.byref(g["r"]), C.byref(g["gr"]), stream_ptr()),
               "sgbpo_rollout_bwd")
-        if self.engine == 0:
+        if not self.engine_bwd:
             g["dw_hid"].copy_(_tall_skinny_gram(g["dz2"].view(H * N, W), g["h1"].view(H * N, W)))
 
     def _capture(self, body, g):
@@ -556,7 +572,7 @@ class FusedRollout:
         for prm, buf in g["grads"].items():
             if prm.grad is None or prm.grad.data_ptr() != buf.data_ptr():
                 return None
-        return [g["flat"]] if self.engine == 1 else [g["flat"], g["dw_hid"]]
+        return [g["flat"]] if self.engine_bwd else [g["flat"], g["dw_hid"]]
 
     def _fast_buffer_reset(self, reset_observation=None, reset_value=None) -> bool:
         """CoupledBuffer.reset() while the buffer's tensors ARE the static graph buffers: carry the last
@@ -638,14 +654,15 @@ class FusedRollout:
         if self._grad_bufs is None or self._grad_bufs["e1"].shape != (H, N, W) or self._grad_bufs["e1"].dtype != dt:
             mk = lambda *shape: torch.empty(*shape, dtype=dt, device=dev)
             self._grad_bufs = dict(e1=mk(H, N, W), e2=mk(H, N, W), stats=mk(H, N, 4))
-            if self.engine == 1:
-                self._grad_bufs.update(jac=mk(H, N, self.jac_stride))
+            if self.engine_bwd:
+                self._grad_bufs.update(jac=mk(H, N, self.jac_stride), pol_jac=mk(H, N, self.pol_jac_stride), dmu=mk(H, N, m))
             else:
                 self._grad_bufs.update(h1=mk(H, N, W), dz2=mk(H, N, W))
         gb = self._grad_bufs
         r.stash_e1, r.stash_e2, r.stash_stats = gb["e1"].data_ptr(), gb["e2"].data_ptr(), gb["stats"].data_ptr()
-        if self.engine == 1:
-            r.engine, r.jac = 1, gb["jac"].data_ptr()
+        r.engine = self.engine
+        if self.engine_bwd:
+            r.jac, r.pol_jac, r.dmu = gb["jac"].data_ptr(), gb["pol_jac"].data_ptr(), gb["dmu"].data_ptr()
         else:
             r.stash_h1 = gb["h1"].data_ptr()
         lib = _lib.lib()
@@ -732,7 +749,7 @@ class FusedRollout:
                 gterm.append(torch.autograd.grad(v, x)[0])
             gobs_term = torch.stack(gterm).contiguous()
         term_of_row_t = torch.tensor(term_of_row, dtype=torch.int32, device=dev)
-        tc = self.engine == 1
+        tc = bool(self.engine_bwd)
         sizes = [o * W, W * m, 2 * W, 2 * W, 2 * W, m, m] + ([W * W] if tc else [])
         flat = torch.zeros(sum(sizes), dtype=dt, device=dev)
         parts = torch.split(flat, sizes)

@@ -50,7 +50,8 @@ def _episode(env_name, sg, opts, N, H, num_steps, dtype, engine, dev, state, wei
         algo.policy_optim.zero_grad()
         algo.collect_trajectories()
         eng = algo._fused_engine
-        assert eng is not None and eng.engine == (engine if dtype == torch.float32 else 0)
+        want = {0: (0, 0), 1: (1, 1), 2: (0, 1)}[engine] if dtype == torch.float32 else (0, 0)
+        assert eng is not None and (eng.engine_fwd, eng.engine_bwd) == want
         loss = eng.backward()
         torch.cuda.synchronize()
         if draws is None:
@@ -86,23 +87,24 @@ def test_tensor_core_engine_vs_float64(cuda_default, env_name, sg, opts, N, H, n
     dev = cuda_default
     ref, state, weights, draws = _episode(env_name, sg, opts, N, H, num_steps, torch.float64, 0, dev, None, None, None, spread)
     fma, *_ = _episode(env_name, sg, opts, N, H, num_steps, torch.float32, 0, dev, state, weights, draws, spread)
-    tc, *_ = _episode(env_name, sg, opts, N, H, num_steps, torch.float32, 1, dev, state, weights, draws, spread)
-    fin = torch.isfinite(ref["obs"]).all(dim=2).all(dim=0) & torch.isfinite(fma["obs"]).all(dim=2).all(dim=0) \
-        & torch.isfinite(tc["obs"]).all(dim=2).all(dim=0)
-    assert fin.float().mean() > 0.9
-    for key in ("obs", "actions", "rewards"):
-        r = ref[key][:, fin]
-        e_fma, e_tc = _rel(fma[key][:, fin], r), _rel(tc[key][:, fin], r)
-        assert e_tc <= max(3.0 * e_fma, 2e-4), f"{key}: tensor-core {e_tc:.2e} vs FMA {e_fma:.2e}"
-    if bool(fin.all()) and all(bool(torch.isfinite(g).all()) for g in ref["grads"].values()):
-        assert abs(tc["loss"] - ref["loss"]) <= max(3.0 * abs(fma["loss"] - ref["loss"]), 2e-4 * abs(ref["loss"]))
-        for k, g in ref["grads"].items():
-            e_fma, e_tc = _rel(fma["grads"][k], g), _rel(tc["grads"][k], g)
-            assert e_tc <= max(3.0 * e_fma, 5e-4), f"grad {k}: tensor-core {e_tc:.2e} vs FMA {e_fma:.2e}"
+    for engine in (1, 2):        # tensor-core forward + parallel reverse pass; FMA forward + parallel reverse pass
+        tc, *_ = _episode(env_name, sg, opts, N, H, num_steps, torch.float32, engine, dev, state, weights, draws, spread)
+        fin = torch.isfinite(ref["obs"]).all(dim=2).all(dim=0) & torch.isfinite(fma["obs"]).all(dim=2).all(dim=0) \
+            & torch.isfinite(tc["obs"]).all(dim=2).all(dim=0)
+        assert fin.float().mean() > 0.9
+        for key in ("obs", "actions", "rewards"):
+            r = ref[key][:, fin]
+            e_fma, e_tc = _rel(fma[key][:, fin], r), _rel(tc[key][:, fin], r)
+            assert e_tc <= max(3.0 * e_fma, 2e-4), f"engine {engine} {key}: tensor-core {e_tc:.2e} vs FMA {e_fma:.2e}"
+        if bool(fin.all()) and all(bool(torch.isfinite(g).all()) for g in ref["grads"].values()):
+            assert abs(tc["loss"] - ref["loss"]) <= max(3.0 * abs(fma["loss"] - ref["loss"]), 2e-4 * abs(ref["loss"]))
+            for k, g in ref["grads"].items():
+                e_fma, e_tc = _rel(fma["grads"][k], g), _rel(tc["grads"][k], g)
+                assert e_tc <= max(3.0 * e_fma, 5e-4), f"engine {engine} grad {k}: tensor-core {e_tc:.2e} vs FMA {e_fma:.2e}"
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("engine,r_rows", [(1, None), (0, 4), (0, 8)], ids=["tcgen05", "fma-R4", "fma-R8"])
+@pytest.mark.parametrize("engine,r_rows", [(1, None), (2, 4), (0, 4), (0, 8)], ids=["tcgen05", "fma-fwd+tc-reverse", "fma-R4", "fma-R8"])
 def test_headline_instantiations_gradients_vs_float64(cuda_default, engine, r_rows):
     """BASELINE configs[1] shapes (BalanceCartPole + boundary projection, policy [128, 128], H = 64, N = 1024): the
     policy gradients of the instantiations the benchmark times -- rollout_tc_bwd_kernel and
@@ -129,7 +131,7 @@ def test_tensor_core_kernels_are_tcgen05():
     if not obj.exists():
         pytest.skip("object files are not shipped to the GPU box (the CPU run checks them)")
     sass = subprocess.run(["cuobjdump", "-sass", str(obj)], capture_output=True, text=True).stdout
-    for kernel in ("rollout_tc_fwd_kernel", "rollout_tc_bwd_kernel"):
+    for kernel in ("rollout_tc_fwd_kernel", "policy_rows_bwd_kernel"):
         body = sass[sass.index(kernel):]
         body = body[:body.index("Function :", 10)] if "Function :" in body[10:] else body
         assert "UTCHMMA" in body and "LDTM" in body, kernel
