@@ -47,6 +47,10 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--policy-arch", default=None, help="comma-separated hidden widths (default 128,128)")
     p.add_argument("--vf-arch", default=None, help="comma-separated hidden widths (default 128,128,128)")
+    p.add_argument("--gate", default="intended", choices=["reference", "intended", "always"],
+                   help="intended: the guard acts where the linearised reachable set meets the feasible box (safeguard.py:63-67 as the "
+                        "paper describes it); reference: the shipped inverted where() (Q1), under which the guard fires only where the "
+                        "program is infeasible -- the reference itself raises there, so it is not a benchmarkable steady state")
     p.add_argument("--rng-order", default="batched", choices=["batched", "reference"],
                    help="batched: 3 RNG draws per episode (same distributions); reference: the reference's per-step order")
     return p.parse_args()
@@ -55,9 +59,13 @@ def parse():
 # ------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path on the host cores
 # ------------------------------------------------------------------------------------------------------
+CPU_ENVS_PER_WORKER = 64          # per-process N in {64, 256, 1024}; the CPU path is linear in N
+STATE_SPREAD = 0.9                # both arms: initial states uniform in 0.9 x the feasible state box
+
+
 def _cpu_persistent_worker(conn, job):
     """One host process = one environment shard of the oracle port; runs one episode per "step" message."""
-    env_name, sg_kind, n_envs, horizon, seed = job
+    env_name, sg_kind, n_envs, horizon, seed, gate = job
     import torch
     torch.set_num_threads(1)
     from oracle.dynamics import OracleEnv
@@ -66,62 +74,65 @@ def _cpu_persistent_worker(conn, job):
     torch.manual_seed(seed)
     env = OracleEnv(env_name, n_envs, 240)
     env.reset(seed=seed)
-    env.state = env.state_center + (torch.rand(n_envs, env.state_dim, dtype=torch.float64) * 2 - 1) * env.state_half * 0.5
-    step_fn = env if sg_kind == "none" else OracleSafeguard(env, sg_kind, gate="reference", strict=False)
+    # the safeguard bakes in the linearisation of environment 0 at CONSTRUCTION (Q4, safeguard.py:54).  The reference constructs
+    # it on an un-reset environment (torch.empty state); both arms here construct it at the zero state
+    env.state = torch.zeros_like(env.state)
+    step_fn = env if sg_kind == "none" else OracleSafeguard(env, sg_kind, gate=gate, strict=False)
     obs_dim = env.observation().shape[1]
     pol = oshac.OraclePolicy(obs_dim, env.action_dim, POLICY_ARCH).double()
     vf = oshac.OracleValue(obs_dim, VF_ARCH).double()
     opt = torch.optim.Adam(pol.parameters(), lr=4e-4)
-
-    done_steps = [0]
+    counts = {"infeasible": 0, "nonfinite": 0}
 
     def env_step(action, t):
         obs, rew, term, trunc = step_fn.step(action)
-        done_steps[0] += 1
+        if step_fn is not env:              # infeasible programs whose solution the gate actually uses
+            used = {"reference": ~step_fn.projectable, "intended": step_fn.projectable}.get(gate, torch.ones_like(step_fn.projectable))
+            counts["infeasible"] += int((step_fn.infeasible & used).sum())
+        counts["nonfinite"] += int((~torch.isfinite(obs).all(dim=1)).sum())
         return obs, rew, term | trunc
 
     conn.send("ready")
     k = 0
     while conn.recv() == "step":
-        # every step starts from a fresh bounded sample inside the feasible box (the untrained float64 rollout of the
-        # port diverges after a few hundred steps and the host LP then rejects non-finite data)
+        # every step (= one SHAC episode) starts from a fresh sample of the same initial-state distribution as the GPU arm
         k += 1
         env.reset(seed=seed + 1000 * k)
-        env.state = env.state_center + (torch.rand(n_envs, env.state_dim, dtype=torch.float64) * 2 - 1) * env.state_half * 0.5
+        env.state = env.state_center + (torch.rand(n_envs, env.state_dim, dtype=torch.float64) * 2 - 1) * env.state_half * STATE_SPREAD
         env.cut_computation_graph()
         opt.zero_grad()
         eps = torch.randn(horizon, n_envs, env.action_dim, dtype=torch.float64)
-        done_steps[0] = 0
+        counts["infeasible"] = counts["nonfinite"] = 0
         try:
             out = oshac.rollout_loss(env_step, env.observation(), pol, vf, horizon, eps)
             out["loss"].backward()
-            torch.nn.utils.clip_grad_norm_(pol.parameters(), 1.0)
-            opt.step()
-            conn.send("done")
-        except Exception as exc:        # e.g. the host LP rejecting a diverged (non-finite) state: the step still counts
-            conn.send(f"error after {done_steps[0]} steps: " + repr(exc)[:200])
+            if bool(torch.isfinite(out["loss"])):        # (a non-finite episode is counted below and must not poison the weights)
+                torch.nn.utils.clip_grad_norm_(pol.parameters(), 1.0)
+                opt.step()
+            conn.send(("done", counts["infeasible"], counts["nonfinite"]))
+        except Exception as exc:        # a failed worker-episode is REPORTED (worker_errors) and its work is not counted
+            conn.send(("error", repr(exc)[:200]))
 
 
-def cpu_port_persistent(env_name, sg_kind, horizon, steps, warmup, budget_s):
+def cpu_port_persistent(env_name, sg_kind, horizon, steps, warmup, budget_s, n_w=CPU_ENVS_PER_WORKER, gate="intended"):
     """The reference's CPU path (oracle port: per-environment HiGHS solves + torch autograd, float64) on all host cores.
-    A step = one SHAC episode (collect + backward + clip + Adam) of a BOUNDED sample of the workload: every core owns 8
-    environments (process start-up and imports are outside the timed steps).  One untimed calibration step measures the
-    step time; the number of timed steps is capped so that the run fits `budget_s`.
-    Returns dict(value, steps, warmup, total_s, workers, n_w, errors)."""
+    A step = one SHAC episode (collect + backward + clip + Adam) of a BOUNDED sample of the workload: every core owns
+    `n_w` environments (process start-up and imports are outside the timed steps).  The first warm-up step also
+    calibrates the step time; warm-up and timed steps are capped so that the run fits `budget_s`.
+    Returns dict(value, steps, warmup, total_s, workers, n_w, errors, infeasible_env_steps, nonfinite_env_steps)."""
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     workers = max(1, min(cores, 64))
-    n_w = 8
     ctx = mp.get_context("spawn")
     procs = []
     for i in range(workers):
         a, b = ctx.Pipe()
-        pr = ctx.Process(target=_cpu_persistent_worker, args=(b, (env_name, sg_kind, n_w, horizon, 100 + i)), daemon=True)
+        pr = ctx.Process(target=_cpu_persistent_worker, args=(b, (env_name, sg_kind, n_w, horizon, 100 + i, gate)), daemon=True)
         pr.start()
         procs.append((pr, a))
     for _, c in procs:
         c.recv()
-    errors, lost = [], [0]
+    errors, tally = [], {"failed_workers": 0, "infeasible": 0, "nonfinite": 0}
 
     def step():
         t0 = time.perf_counter()
@@ -129,46 +140,70 @@ def cpu_port_persistent(env_name, sg_kind, horizon, steps, warmup, budget_s):
             c.send("step")
         for _, c in procs:
             msg = c.recv()
-            if msg != "done":           # a diverged rollout stopped early: only its completed steps count as work
-                errors.append(msg)
-                lost[0] += horizon - int(msg.split()[2])
+            if msg[0] == "done":
+                tally["infeasible"] += msg[1]
+                tally["nonfinite"] += msg[2]
+            else:
+                errors.append(msg[1])
+                tally["failed_workers"] += 1
         return time.perf_counter() - t0
 
-    calib = step()                                   # also the first warm-up step
-    warmup = max(1, min(warmup, 2))
+    calib = step()                                   # the first warm-up step
+    warmup = max(1, min(warmup, int(0.35 * budget_s / max(calib, 1e-3))))
     for _ in range(warmup - 1):
         step()
     steps = max(1, min(steps, int((budget_s - warmup * calib) / max(calib, 1e-3))))
     errors.clear()
-    lost[0] = 0
+    for key in tally:
+        tally[key] = 0
     walls = [step() for _ in range(steps)]
     for pr, c in procs:
         c.send("stop")
     for pr, _ in procs:
         pr.join(timeout=10)
     total = sum(walls)
-    return dict(value=(workers * horizon * steps - lost[0]) * n_w / total, steps=steps, warmup=warmup, total_s=total, workers=workers,
-                n_w=n_w, errors=errors)
+    done_env_steps = (workers * steps - tally["failed_workers"]) * horizon * n_w
+    return dict(value=done_env_steps / total, steps=steps, warmup=warmup, total_s=total, workers=workers, n_w=n_w, errors=errors,
+                infeasible_env_steps=tally["infeasible"], nonfinite_env_steps=tally["nonfinite"],
+                ms_per_env_step_per_core=1e3 * total * workers / max(done_env_steps, 1))
+
+
+def _cpu_config(args, r):
+    """What the CPU arm actually ran (the GPU arm's config keys + the documented differences)."""
+    cfg = workload_config(args, max(1, args.gpus))
+    cfg.update({"num_envs_cpu": r["workers"] * r["n_w"], "envs_per_worker": r["n_w"], "cpu_workers": r["workers"],
+                "cpu_note": "the CPU path is linear in the number of environments (BASELINE.md section 3): the arm runs "
+                            f"{r['workers']} processes x {r['n_w']} environments and the GPU/CPU ratio is per env-step; float64 like the reference",
+                "initial_states": f"uniform in {STATE_SPREAD} x feasible state box, fresh sample every step (both arms)"})
+    return cfg
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_port_persistent(args.env, args.safeguard, args.horizon, args.steps, args.warmup, budget_s=150.0)
+    r = cpu_port_persistent(args.env, args.safeguard, args.horizon, args.steps, max(3, args.warmup), budget_s=200.0, gate=args.gate)
     v = r["value"]
+    per_n = {str(r["n_w"]): {"env_steps_per_s": v, "ms_per_env_step_per_core": r["ms_per_env_step_per_core"]}}
+    if os.environ.get("SGBPO_REF_SWEEP"):            # optional: the other per-process sizes of BASELINE.md section 3 (slow)
+        for n_w in (256,):
+            q = cpu_port_persistent(args.env, args.safeguard, args.horizon, 1, 1, budget_s=1.0, n_w=n_w, gate=args.gate)
+            per_n[str(n_w)] = {"env_steps_per_s": q["value"], "ms_per_env_step_per_core": q["ms_per_env_step_per_core"]}
     line = {
         "impl": "reference", "metric": "safeguarded env-steps/s (fwd+bwd)", "value": v, "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": r["steps"], "warmup": r["warmup"], "steps_requested": args.steps,
         "warmup_requested": args.warmup, "ms_per_step": 1e3 * r["total_s"] / r["steps"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, max(1, args.gpus)),
+        "config": _cpu_config(args, r),
         "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": r["workers"], "kind": "port",
                          "sample": f"each step = {r['workers']} processes x {r['n_w']} envs x H={args.horizon}, one SHAC episode of the "
                                    "same workload (oracle port of the reference path: per-env HiGHS solves + torch autograd, "
-                                   "float64); timed steps capped to a 150 s budget"},
+                                   "float64); warm-up and timed steps capped to a 200 s budget",
+                         "ms_per_env_step_per_core": r["ms_per_env_step_per_core"], "per_envs_per_worker": per_n},
         "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "worker_errors": {"count": len(r["errors"]), "first": r["errors"][0] if r["errors"] else None},
+        "gates": {"infeasible_env_steps": r["infeasible_env_steps"], "nonfinite_env_steps": r["nonfinite_env_steps"],
+                  "env_steps": r["workers"] * r["n_w"] * args.horizon * r["steps"]},
     }
     print(json.dumps(line))
 
@@ -177,7 +212,8 @@ def workload_config(args, world):
     return {"workload": f"{args.env}+{args.safeguard}, {args.num_envs} envs/GPU x {world} GPU, H={args.horizon}, "
                         f"policy {POLICY_ARCH}, critic {VF_ARCH}, SHAC collect_trajectories+update_policy",
             "env": args.env, "safeguard": args.safeguard, "num_envs_per_gpu": args.num_envs, "horizon": args.horizon,
-            "gate": "reference (Q1 as shipped)", "rng_order": args.rng_order, "l2_policy": "working set per episode > L2 not guaranteed; "
+            "gate": args.gate, "rng_order": args.rng_order,
+            "initial_states": f"uniform in {STATE_SPREAD} x feasible state box, fresh sample every step (both arms)", "l2_policy": "working set per episode > L2 not guaranteed; "
             "a 256 MiB buffer is written between timed episodes to flush L2"}
 
 
@@ -240,23 +276,22 @@ def run_ours(args):
     else:
         env = env_cls(num_envs=N, num_steps={"ManageHousehold": 720}.get(args.env, 240))
     if args.safeguard == "boundary_projection":
-        env = BoundaryProjectionSafeguard(env, strict=False)
+        env = BoundaryProjectionSafeguard(env, gate=args.gate, strict=False)
     elif args.safeguard == "ray_mask":
-        env = RayMaskSafeguard(env, linear_projection=True, zonotopic_approximation=True, passthrough=False, strict=False)
+        env = RayMaskSafeguard(env, linear_projection=True, zonotopic_approximation=True, passthrough=False, gate=args.gate, strict=False)
     algo = SHAC(env=env, policy_kwargs={"net_arch": POLICY_ARCH}, policy_optim_kwargs={"lr": 4e-4},
                 vf_kwargs={"net_arch": VF_ARCH}, vf_optim_kwargs={"lr": 2e-3}, regularisation_coefficient=0.1,
                 len_trajectories=H, fused=args.fused, rng_order=args.rng_order)
     if world > 1:      # replicated networks: broadcast rank 0's parameters; gradients are summed over ranks
         from safegbpo_b200 import distributed as sgdist
-        sgdist.broadcast_parameters(algo)
-        algo.grad_sync = sgdist.allreduce_policy_grads
+        sgdist.attach(algo)          # broadcast + policy AND critic gradient all-reduce hooks
     base = env.env if hasattr(env, "env") else env
     n = base.state_dim
     # synthetic batched initial states, pinned on the host (e2e leg copies them in every step)
     gen = torch.Generator(device="cpu").manual_seed(99 + rank)
     half = base.state_set.generator[0].diagonal().cpu()
     ctr = base.state_set.center[0].cpu()
-    s0_host = (ctr + (torch.rand(N, n, generator=gen, device="cpu", dtype=dtype) * 2 - 1) * half * 0.9).pin_memory()
+    s0_host = (ctr + (torch.rand(N, n, generator=gen, device="cpu", dtype=dtype) * 2 - 1) * half * STATE_SPREAD).pin_memory()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     launches = {"n": 0}
 
@@ -321,13 +356,12 @@ def run_ours(args):
     else:
         e2e_ms = sum(t_e2e)
     in_sync = None
-    if world > 1:       # data parallelism check: after all the updates every rank must hold the same policy
-        flat = torch.cat([p.detach().reshape(-1).double() for p in algo.policy.parameters()])
-        probe = torch.stack([flat.sum(), flat.abs().sum(), (flat * torch.arange(flat.numel(), dtype=torch.float64)).sum()])
-        lo, hi = probe.clone(), probe.clone()
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        in_sync = bool(torch.allclose(lo, hi, rtol=1e-12, atol=0.0))
+    if world > 1:
+        # data parallelism check: one FULL SHAC iteration (untimed: collect, policy update, critic fit with its per-batch gradient
+        # all-reduce, Polyak) on every rank, after which policy, critic and target critic must be bit-identical everywhere
+        from safegbpo_b200 import distributed as sgdist
+        algo._learn_episode(0)
+        in_sync = sgdist.replicas_in_sync(algo)
     env_steps = N * H * args.steps * world
     value = env_steps / (total_ms * 1e-3)
     e2e_value = env_steps / (e2e_ms * 1e-3)
@@ -336,6 +370,11 @@ def run_ours(args):
         roof = fused_roofline(args, engine, episode, dtype)
     else:
         roof = step_kernel_roofline(args, base, env, dev, dtype)
+    gates = correctness_gates(args, algo, env, base, episode, dtype, dev) if rank == 0 else None
+    if world > 1:           # the gate episodes contain the gradient all-reduce: every rank runs them
+        if rank != 0:
+            for _ in range(3):
+                episode(True)
     stress = None
     if rank == 0:
         try:
@@ -361,16 +400,112 @@ def run_ours(args):
                                          "sampled_beyond_timed_region": extended},
             "roofline_stress": stress,
             "replicas_in_sync": in_sync,
+            "gates": gates,
             "mode": "fused" if engine is not None else "eager (per-step fused safeguard+simulator kernel, torch MLP)",
         }
         if not args.no_cpu_baseline and world == 1:
-            r = cpu_port_persistent(args.env, args.safeguard, H, 8, 1, budget_s=25.0)
+            r = cpu_port_persistent(args.env, args.safeguard, H, 1, 1, budget_s=30.0, gate=args.gate)
             line["cpu_baseline"] = {"value": r["value"], "unit": "env-steps/s", "cores": r["workers"], "kind": "port",
-                                    "sample": f"{r['steps']} steps of {r['workers']} processes x {r['n_w']} envs x H={H} (one SHAC episode "
-                                              f"each, {r['total_s']:.1f} s wall), oracle port of the reference path, float64"}
+                                    "sample": f"{r['steps']} step(s) of {r['workers']} processes x {r['n_w']} envs x H={H} (one SHAC episode "
+                                              f"each, {r['total_s']:.1f} s wall, after one warm-up step), oracle port of the reference path, float64",
+                                    "ms_per_env_step_per_core": r["ms_per_env_step_per_core"], "envs_per_worker": r["n_w"],
+                                    "num_envs_cpu": r["workers"] * r["n_w"], "worker_errors": len(r["errors"]),
+                                    "infeasible_env_steps": r["infeasible_env_steps"], "nonfinite_env_steps": r["nonfinite_env_steps"]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def correctness_gates(args, algo, env, base, episode, dtype, dev):
+    """Correctness beside the throughput: flag-word statistics of extra untimed episodes (infeasible
+    fraction, non-finite actions, interventions, safety violations among feasible guarded steps) and a 64-environment slice of
+    one safeguarded step, forward + backward, against the float64 oracle (max relative errors, verdict mismatches)."""
+    import torch
+    from safegbpo_b200 import _lib, ops
+    out = {}
+    engine = algo._fused_engine
+    if engine is not None:
+        tot = {"env_steps": 0, "guard_used": 0, "infeasible": 0, "nonfinite": 0, "intervened": 0, "safety_violations": 0}
+        k = env.consts() if hasattr(env, "consts") else None
+        for _ in range(3):
+            episode(True)
+            torch.cuda.synchronize()
+            fl = engine._g["flags"] if (engine.last or {}).get("graph") else engine.last["flags"]
+            guard = (fl & _lib.FL_GUARD_USED) != 0
+            infeas = (fl & _lib.FL_INFEASIBLE) != 0
+            ok = guard & ~infeas
+            viol = torch.zeros_like(ok)
+            if k is not None and k.state_constrained:
+                viol |= ok & ((fl & _lib.FL_NEXT_IN_SET) == 0)
+            if k is not None and k.action_constrained:
+                viol |= ok & ((fl & _lib.FL_ACTION_IN_SET) == 0)
+            tot["env_steps"] += fl.numel()
+            tot["guard_used"] += int(guard.sum())
+            tot["infeasible"] += int((guard & infeas).sum())
+            tot["nonfinite"] += int(((fl & _lib.FL_NONFINITE) != 0).sum())
+            tot["intervened"] += int(((fl & _lib.FL_INTERVENED) != 0).sum())
+            tot["safety_violations"] += int(viol.sum())
+        tot["infeasible_fraction_of_guarded"] = tot["infeasible"] / max(tot["guard_used"], 1)
+        out["episodes"] = tot
+    try:
+        out["oracle_slice"] = oracle_slice_check(args, env, base, dtype, dev)
+    except Exception as exc:             # the oracle leg is a checker: its absence is reported, never hidden
+        out["oracle_slice"] = {"skipped": repr(exc)[:200]}
+    ep = out.get("episodes", {})
+    sl = out.get("oracle_slice", {})
+    out["pass"] = bool(ep.get("nonfinite", 0) == 0 and ep.get("safety_violations", 0) == 0
+                       and sl.get("verdict_mismatches", 0) == 0 and sl.get("max_rel_err", 0.0) <= sl.get("tolerance", 1.0))
+    return out
+
+
+def oracle_slice_check(args, env, base, dtype, dev, n=64):
+    """One safeguarded step of `n` environments, forward + backward, on the GPU kernels (the benchmark's dtype and constants)
+    against the float64 oracle port on the CPU; the gate is forced on for the slice so that every program is solved."""
+    import copy
+    import torch
+    from safegbpo_b200 import _lib, ops
+    from oracle.dynamics import OracleEnv
+    from oracle.safeguard import OracleSafeguard
+    if args.safeguard == "none" or args.env not in ("BalanceCartPole", "SwingUpCartPole", "BalancePendulum"):
+        return {"skipped": "slice check covers the pendulum / cartpole safeguards (the other oracles take minutes per batch)"}
+    f64 = torch.float64
+    gcpu = torch.Generator(device="cpu").manual_seed(7)
+    oenv = OracleEnv(args.env, n, 240)
+    oenv.reset(seed=0)
+    spread = 0.1 if args.env == "BalancePendulum" else STATE_SPREAD
+    st = oenv.state_center + (torch.rand(n, oenv.state_dim, dtype=f64, generator=gcpu, device="cpu") * 2 - 1) * oenv.state_half * spread
+    a = torch.rand(n, oenv.action_dim, dtype=f64, generator=gcpu, device="cpu") * 2 - 1
+    kind = {"boundary_projection": "boundary_projection", "ray_mask": "ray_mask"}[args.safeguard]
+    sg = OracleSafeguard(oenv, kind, gate="always", strict=False)
+    dirs = sg.draw_directions() if kind == "ray_mask" and oenv.state_constrained else None
+    w = oenv.noise_sample()
+    s_o, a_o = st.clone().requires_grad_(True), a.clone().requires_grad_(True)
+    oenv.state = s_o
+    obs, rew, _, _ = sg.step(a_o, directions=dirs, noise=w)
+    ok = ~sg.infeasible & torch.isfinite(obs).all(dim=1)
+    (rew[ok].sum() + obs[ok].sum()).backward()
+    k = copy.copy(env.consts())
+    k.gate_mode = _lib.GATE["always"]
+    s_d = st.to(dev, dtype).requires_grad_(True)
+    a_d = a.to(dev, dtype).requires_grad_(True)
+    s_next, a_exec, obs_d, rew_d, flags = ops.safeguarded_step(s_d, a_d, w.to(dev, dtype), base.env_id, k,
+                                                               dirs=None if dirs is None else dirs.to(dev, dtype))
+    okd = ok.to(dev)
+    (rew_d[okd].sum() + obs_d[okd].sum()).backward()
+    torch.cuda.synchronize()
+
+    def rel(x, y):
+        x, y = x.detach().double().cpu()[ok], y.detach().double()[ok]
+        return float((x - y).abs().max() / (y.abs().max() + 1e-30))
+
+    infeasible_d = ((flags & _lib.FL_INFEASIBLE) != 0).cpu()
+    errs = {"safe_action": rel(a_exec, sg.safe_action), "next_state": rel(s_next, oenv.state), "obs": rel(obs_d, obs),
+            "grad_state": rel(s_d.grad, s_o.grad), "grad_action": rel(a_d.grad, a_o.grad)}
+    tol = 1e-5 if dtype == torch.float32 else 1e-9
+    if kind == "ray_mask" and dtype == torch.float32:
+        tol = 2e-4          # the ray-mask maps divide by a chord length (tests/test_gpu_step_parity.py)
+    return {"n_envs": n, "feasible": int(ok.sum()), "verdict_mismatches": int((infeasible_d != sg.infeasible).sum()),
+            "rel_err": errs, "max_rel_err": max(errs.values()), "tolerance": tol, "gate": "always (every program solved)"}
 
 
 def _peaks():

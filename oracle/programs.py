@@ -492,6 +492,9 @@ class _IntervalFn(torch.autograd.Function):
         glo, ghi = np.zeros_like(th), np.zeros_like(th)
         infeasible = np.zeros(N, dtype=bool)
         for i in range(N):
+            if not np.isfinite(th[i]).all():       # a diverged environment: the reference's solver raises on non-finite
+                infeasible[i] = True               # parameters; under strict=False the row is reported infeasible (NaN action)
+                continue
             try:
                 lo[i], hi[i], glo[i], ghi[i] = prog.bounds(th[i])
             except Infeasible:

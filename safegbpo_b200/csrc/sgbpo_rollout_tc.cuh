@@ -887,30 +887,38 @@ rollout_scan_kernel(const __grid_constant__ ScanArgs A) {
   for (int i = 0; i < NO; ++i) gobs[i] = 0.f;
 #pragma unroll
   for (int q = 0; q < NA; ++q) { sb[q] = 0.f; sl[q] = 0.f; sigma[q] = expf(A.log_std[q]); }
-  for (int t = A.H - 1; t >= 0; --t) {
+  // the loads of step t - 1 do not depend on the recursion: they are issued before step t's arithmetic (two register buffers,
+  // the time loop unrolled by two so that both are statically indexed)
+  struct StepIn { float4 rec[JS::STRIDE / 4]; float4 pj[NA * NOP / 4]; float act[NA], eps[NA], term[NO], gr; };
+  auto fetch = [&](int t, StepIn& in) {
     const size_t row = (size_t)t * A.N + e;
-    float rec[JS::STRIDE], pj[NA * NOP], act[NA], epsv[NA];
     const float4* src = reinterpret_cast<const float4*>(A.jac + row * JS::STRIDE);
 #pragma unroll
-    for (int i = 0; i < JS::STRIDE / 4; ++i) { const float4 x = src[i]; rec[4 * i] = x.x; rec[4 * i + 1] = x.y; rec[4 * i + 2] = x.z; rec[4 * i + 3] = x.w; }
+    for (int i = 0; i < JS::STRIDE / 4; ++i) in.rec[i] = src[i];
     const float4* ps = reinterpret_cast<const float4*>(A.pol_jac + row * (NA * NOP));
 #pragma unroll
-    for (int i = 0; i < NA * NOP / 4; ++i) { const float4 x = ps[i]; pj[4 * i] = x.x; pj[4 * i + 1] = x.y; pj[4 * i + 2] = x.z; pj[4 * i + 3] = x.w; }
+    for (int i = 0; i < NA * NOP / 4; ++i) in.pj[i] = ps[i];
 #pragma unroll
-    for (int q = 0; q < NA; ++q) { act[q] = A.actions[row * NA + q]; epsv[q] = A.eps[row * NA + q]; }
+    for (int q = 0; q < NA; ++q) { in.act[q] = A.actions[row * NA + q]; in.eps[q] = A.eps[row * NA + q]; }
+    const int kt = A.term_of_row ? A.term_of_row[t + 1] : -1;
+#pragma unroll
+    for (int i = 0; i < NO; ++i) in.term[i] = kt >= 0 ? A.gobs_term[((size_t)kt * A.N + e) * A.in_dim + i] : 0.f;
+    in.gr = A.grw[t];
+  };
+  auto step = [&](int t, const StepIn& in) {
+    const size_t row = (size_t)t * A.N + e;
+    float rec[JS::STRIDE], pj[NA * NOP];
+#pragma unroll
+    for (int i = 0; i < JS::STRIDE / 4; ++i) { rec[4 * i] = in.rec[i].x; rec[4 * i + 1] = in.rec[i].y; rec[4 * i + 2] = in.rec[i].z; rec[4 * i + 3] = in.rec[i].w; }
+#pragma unroll
+    for (int i = 0; i < NA * NOP / 4; ++i) { pj[4 * i] = in.pj[i].x; pj[4 * i + 1] = in.pj[i].y; pj[4 * i + 2] = in.pj[i].z; pj[4 * i + 3] = in.pj[i].w; }
     float go[NO];
 #pragma unroll
-    for (int i = 0; i < NO; ++i) go[i] = gobs[i];
-    const int kt = A.term_of_row ? A.term_of_row[t + 1] : -1;
-    if (kt >= 0) {
-#pragma unroll
-      for (int i = 0; i < NO; ++i) go[i] += A.gobs_term[((size_t)kt * A.N + e) * A.in_dim + i];
-    }
-    const float gr = A.grw[t];
+    for (int i = 0; i < NO; ++i) go[i] = gobs[i] + in.term[i];
     float v[KD];
 #pragma unroll
     for (int d = 0; d < KD; ++d) {
-      float x = gr * rec[(NS + NO) * KD + d];
+      float x = in.gr * rec[(NS + NO) * KD + d];
 #pragma unroll
       for (int i = 0; i < NS; ++i) x = fmaf(gs[i], rec[i * KD + d], x);
 #pragma unroll
@@ -923,12 +931,22 @@ rollout_scan_kernel(const __grid_constant__ ScanArgs A) {
     for (int i = 0; i < NO; ++i) gobs[i] = 0.f;
 #pragma unroll
     for (int q = 0; q < NA; ++q) {
-      const float ga_pre = valid ? v[NS + q] * (1.f - act[q] * act[q]) : 0.f;      // d loss / d (mu + sigma eps)
+      const float ga_pre = valid ? v[NS + q] * (1.f - in.act[q] * in.act[q]) : 0.f;      // d loss / d (mu + sigma eps)
       if (valid) A.dmu[row * NA + q] = ga_pre;
       sb[q] += ga_pre;
-      sl[q] += ga_pre * epsv[q] * sigma[q];
+      sl[q] += ga_pre * in.eps[q] * sigma[q];
 #pragma unroll
       for (int i = 0; i < NO; ++i) gobs[i] = fmaf(pj[q * NOP + i], ga_pre, gobs[i]);
+    }
+  };
+  StepIn bufa, bufb;
+  fetch(A.H - 1, bufa);
+  for (int t = A.H - 1; t >= 0; t -= 2) {
+    if (t > 0) fetch(t - 1, bufb);
+    step(t, bufa);
+    if (t > 0) {
+      if (t > 1) fetch(t - 2, bufa);
+      step(t - 1, bufb);
     }
   }
 #pragma unroll
@@ -1021,7 +1039,7 @@ template <int ENV> int rollout_tc_bwd(const sgbpo_mlp* pol, const sgbpo_rollout*
   R.g_gamma = (float*)g->g_gamma; R.g_beta = (float*)g->g_beta;
   // threads per row: 8 unless the Jacobian-mode exchange [8][128][NOP] would overflow the 64 KB operand buffer it aliases
   const int forced = env_int("SGBPO_ROWS_BWD_SPLIT");
-  const bool split8 = forced ? forced == 8 : NOP <= 16;
+  const bool split8 = forced == 8;      // (measured: the 4-way split is faster at 4096 and 65536 environments, profiles/r2_engines.md)
   // 1. policy input-output Jacobians of all H x N rows
   {
     const int rc = split8 ? launch_rows_bwd<NA, NO, false, 8>(R, p, pol->in_dim, st) : launch_rows_bwd<NA, NO, false, 4>(R, p, pol->in_dim, st);

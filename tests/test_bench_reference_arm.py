@@ -27,6 +27,11 @@ def test_reference_arm_line():
     assert d["e2e"] == {"value": d["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("BalanceCartPole+boundary_projection")
     assert d["worker_errors"]["count"] == 0
+    # the arm states what it actually ran (the label said 4096 environments, the run had 128)
+    cfg = d["config"]
+    assert cfg["envs_per_worker"] == 64 and cfg["num_envs_cpu"] == 64 * cfg["cpu_workers"] == 64 * d["cpu_baseline"]["cores"]
+    assert d["gates"]["nonfinite_env_steps"] == 0 and d["gates"]["env_steps"] == cfg["num_envs_cpu"] * 4 * d["steps"]
+    assert d["cpu_baseline"]["ms_per_env_step_per_core"] > 0
 
 
 def test_reference_arm_other_ranks_do_nothing():
