@@ -430,7 +430,7 @@ def correctness_gates(args, algo, env, base, episode, dtype, dev):
         for _ in range(3):
             episode(True)
             torch.cuda.synchronize()
-            fl = engine._g["flags"] if (engine.last or {}).get("graph") else engine.last["flags"]
+            fl = engine.last["flags"]
             guard = (fl & _lib.FL_GUARD_USED) != 0
             infeas = (fl & _lib.FL_INFEASIBLE) != 0
             ok = guard & ~infeas
@@ -469,21 +469,29 @@ def oracle_slice_check(args, env, base, dtype, dev, n=64):
     if args.safeguard == "none" or args.env not in ("BalanceCartPole", "SwingUpCartPole", "BalancePendulum"):
         return {"skipped": "slice check covers the pendulum / cartpole safeguards (the other oracles take minutes per batch)"}
     f64 = torch.float64
-    gcpu = torch.Generator(device="cpu").manual_seed(7)
-    oenv = OracleEnv(args.env, n, 240)
-    oenv.reset(seed=0)
-    spread = 0.1 if args.env == "BalancePendulum" else STATE_SPREAD
-    st = oenv.state_center + (torch.rand(n, oenv.state_dim, dtype=f64, generator=gcpu, device="cpu") * 2 - 1) * oenv.state_half * spread
-    a = torch.rand(n, oenv.action_dim, dtype=f64, generator=gcpu, device="cpu") * 2 - 1
-    kind = {"boundary_projection": "boundary_projection", "ray_mask": "ray_mask"}[args.safeguard]
-    sg = OracleSafeguard(oenv, kind, gate="always", strict=False)
-    dirs = sg.draw_directions() if kind == "ray_mask" and oenv.state_constrained else None
-    w = oenv.noise_sample()
-    s_o, a_o = st.clone().requires_grad_(True), a.clone().requires_grad_(True)
-    oenv.state = s_o
-    obs, rew, _, _ = sg.step(a_o, directions=dirs, noise=w)
-    ok = ~sg.infeasible & torch.isfinite(obs).all(dim=1)
-    (rew[ok].sum() + obs[ok].sum()).backward()
+    prev_dtype = torch.get_default_dtype()
+    torch.set_default_dtype(f64)
+    try:
+        with torch.device("cpu"):          # the oracle is a CPU program; the bench's default device is the GPU
+            gcpu = torch.Generator(device="cpu").manual_seed(7)
+            oenv = OracleEnv(args.env, n, 240)
+            oenv.reset(seed=0)
+            spread = 0.1 if args.env == "BalancePendulum" else STATE_SPREAD
+            st = oenv.state_center + (torch.rand(n, oenv.state_dim, dtype=f64, generator=gcpu, device="cpu") * 2 - 1) * oenv.state_half * spread
+            a = torch.rand(n, oenv.action_dim, dtype=f64, generator=gcpu, device="cpu") * 2 - 1
+            kind = {"boundary_projection": "boundary_projection", "ray_mask": "ray_mask"}[args.safeguard]
+            oenv.state = torch.zeros_like(st)        # Q4: both sides bake in the linearisation at the zero (pre-reset) state
+            sg = OracleSafeguard(oenv, kind, gate="always", strict=False)
+            oenv.state = st.clone()
+            dirs = sg.draw_directions() if kind == "ray_mask" and oenv.state_constrained else None
+            w = oenv.noise_sample()
+            s_o, a_o = st.clone().requires_grad_(True), a.clone().requires_grad_(True)
+            oenv.state = s_o
+            obs, rew, _, _ = sg.step(a_o, directions=dirs, noise=w)
+            ok = ~sg.infeasible & torch.isfinite(obs).all(dim=1)
+            (rew[ok].sum() + obs[ok].sum()).backward()
+    finally:
+        torch.set_default_dtype(prev_dtype)
     k = copy.copy(env.consts())
     k.gate_mode = _lib.GATE["always"]
     s_d = st.to(dev, dtype).requires_grad_(True)

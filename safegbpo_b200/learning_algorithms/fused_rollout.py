@@ -553,6 +553,7 @@ class FusedRollout:
             w.safe_action = g["exec_actions"][H - 1]
             w._interventions = w._interventions + g["n_interv"]
         g["ev_side"].synchronize()
+        self.last = dict(graph=True, terminal_rows=terminal_rows, flags=g["flags"], states=g["states"], exec_actions=g["exec_actions"])
         if self.wrapper is not None:
             if w.strict:
                 if g["scal_host"][1] != 0:
@@ -560,7 +561,6 @@ class FusedRollout:
                                      "(the reference raises here: safeguard.py:68-75 / solver error)")
             else:
                 w._status = w._status | g["bad"]
-        self.last = dict(graph=True, terminal_rows=terminal_rows)
         return float(g["scal_host"][0]) / base.num_envs / H
 
     def static_grad_buffers(self):

@@ -176,3 +176,43 @@ def containment_budget(G, W, d):
     res = linprog(c, A_ub=np.array(rows), b_ub=np.zeros(len(rows)), A_eq=Aeq, b_eq=beq, bounds=[(None, None)] * nvar,
                   method="highs")
     return res.fun if res.status == 0 else np.inf
+
+
+def p1_feasibility_budget(G, W, c_s, c_f, B, act_rows=None):
+    """Independent feasibility verdict of program P1 for ONE environment (scipy HiGHS LP on the UNMERGED containment
+    encoding, src/safeguards/interfaces/safeguard.py:98-197): the smallest t for which some action a in [-1, 1]^m
+    (and inside the safe action polytope `act_rows`: rows (n_x, n_y, h) with n . a <= h) has
+        G beta = c_s - c_f - B a,   G Gamma_j = W[:, j],   |beta|_i + sum_j |Gamma_ij| <= t.
+    t <= 1  <=>  the program is feasible.  G: safe-state generator (n x p), W: noise generator (n x q)."""
+    from scipy.optimize import linprog
+    n, p = G.shape
+    q, m = W.shape[1], B.shape[1]
+    nb, ng = p, q * p
+    nx = nb + ng
+    nvar = m + 2 * nx + 1                      # a | beta, Gamma | their absolute values | t
+    c = np.zeros(nvar)
+    c[-1] = 1
+    Aeq, beq = np.zeros((n * (1 + q), nvar)), np.zeros(n * (1 + q))
+    Aeq[:n, :m], Aeq[:n, m:m + nb], beq[:n] = B, G, c_s - c_f
+    for j in range(q):
+        Aeq[n + n * j:2 * n + n * j, m + nb + j * p: m + nb + (j + 1) * p], beq[n + n * j:2 * n + n * j] = G, W[:, j]
+    rows, rhs = [], []
+    for kx in range(nx):
+        for sgn in (1, -1):
+            r = np.zeros(nvar)
+            r[m + kx], r[m + nx + kx] = sgn, -1
+            rows.append(r); rhs.append(0.0)
+    for ii in range(p):
+        r = np.zeros(nvar)
+        r[m + nx + ii] = 1
+        for j in range(q):
+            r[m + nx + nb + j * p + ii] = 1
+        r[-1] = -1
+        rows.append(r); rhs.append(0.0)
+    for row in (act_rows if act_rows is not None else []):
+        r = np.zeros(nvar)
+        r[:m] = row[:m]
+        rows.append(r); rhs.append(row[m])
+    bounds = [(-1.0, 1.0)] * m + [(None, None)] * (nvar - m)
+    res = linprog(c, A_ub=np.array(rows), b_ub=np.array(rhs), A_eq=Aeq, b_eq=beq, bounds=bounds, method="highs")
+    return res.fun if res.status == 0 else np.inf
