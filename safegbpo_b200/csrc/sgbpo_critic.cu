@@ -9,6 +9,7 @@
 #include <cstdio>
 
 #include "../../include/sgbpo.h"
+#include "sgbpo_slots.cuh"
 
 namespace sgbpo {
 extern thread_local char g_err[512];
@@ -170,13 +171,13 @@ static int dispatch_eln(bool fwd, int W, int64_t M, const void* a0, const void* 
 // ---- episode scalars (fused_rollout.py graph bodies): one launch each instead of ~10 / ~7 library launches ----------
 // Grid-wide deterministic sums: every CTA reduces its grid-stride share in double (shared-memory tree), stores the partial
 // in a device-global slot, and the last CTA to finish (ticket counter) adds the partials in slot order and writes the
-// outputs.  One launch of each kernel may be in flight per device at a time (the scratch is global).
+// outputs.  The scratch is one slot per calling stream (sgbpo_slots.cuh).
 constexpr int EP_CTAS = 128, EP_THREADS = 256, EP_VALS = 3;
-__device__ double g_ep_part[2][EP_VALS][EP_CTAS];
-__device__ unsigned int g_ep_ticket[2];
+__device__ double g_ep_part[2 * N_SLOTS][EP_VALS][EP_CTAS];
+__device__ unsigned int g_ep_ticket[2 * N_SLOTS];
 
 template <int NV>
-__device__ inline bool grid_sum(double (&v)[NV], int which) {
+__device__ inline bool grid_sum(double (&v)[NV], int which) {      // which = 2 * slot + kernel
   __shared__ double sh[NV][EP_THREADS];
   __shared__ bool last;
 #pragma unroll
@@ -212,7 +213,7 @@ __device__ inline bool grid_sum(double (&v)[NV], int which) {
 
 template <class T>
 __global__ void episode_stats_kernel(int64_t n_rew, const T* __restrict__ rewards, int64_t n_fl, const int32_t* __restrict__ flags,
-                                     int interv_mask, int bad_mask, double* scal, int64_t* n_interv, int32_t* bad) {
+                                     int interv_mask, int bad_mask, double* scal, int64_t* n_interv, int32_t* bad, int slot) {
   double v[3] = {0.0, 0.0, 0.0};
   const int64_t stride = (int64_t)gridDim.x * blockDim.x, first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (int64_t i = first; i < n_rew; i += stride) v[0] += (double)rewards[i];
@@ -221,7 +222,7 @@ __global__ void episode_stats_kernel(int64_t n_rew, const T* __restrict__ reward
     v[1] += (f & interv_mask) ? 1.0 : 0.0;
     v[2] += (f & bad_mask) ? 1.0 : 0.0;
   }
-  if (!grid_sum<3>(v, 0)) return;
+  if (!grid_sum<3>(v, 2 * slot)) return;
   scal[0] = v[0];
   scal[1] = v[2] > 0.0 ? 1.0 : 0.0;
   if (n_interv) *n_interv = (int64_t)v[1];
@@ -231,7 +232,7 @@ __global__ void episode_stats_kernel(int64_t n_rew, const T* __restrict__ reward
 // shac.py:131-142: loss = - sum_t disc_t * sum_n (terminal row t ? values[t][n] : rewards[t][n]) / norm
 template <class T>
 __global__ void shac_loss_kernel(int rows, int64_t N, const T* __restrict__ disc, const int32_t* __restrict__ term_int,
-                                 const T* __restrict__ values, const T* __restrict__ rewards, const T* __restrict__ norm, T* loss) {
+                                 const T* __restrict__ values, const T* __restrict__ rewards, const T* __restrict__ norm, T* loss, int slot) {
   double v[1] = {0.0};
   const int64_t total = (int64_t)rows * N, stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
@@ -239,7 +240,7 @@ __global__ void shac_loss_kernel(int rows, int64_t N, const T* __restrict__ disc
     const double d = (double)disc[t];
     if (d != 0.0) v[0] += d * (double)(term_int[t] != 0 ? values[e] : rewards[e]);
   }
-  if (!grid_sum<1>(v, 1)) return;
+  if (!grid_sum<1>(v, 2 * slot + 1)) return;
   *loss = (T)(-v[0] / (double)norm[0]);
 }
 }  // namespace sgbpo
@@ -301,9 +302,9 @@ extern "C" int sgbpo_episode_stats(int dtype, int64_t n_rewards, const void* rew
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == SGBPO_F64)
-    episode_stats_kernel<double><<<EP_CTAS, EP_THREADS, 0, st>>>(n_rewards, (const double*)rewards, n_flags, flags, interv_mask, bad_mask, scal, n_interv, bad);
+    episode_stats_kernel<double><<<EP_CTAS, EP_THREADS, 0, st>>>(n_rewards, (const double*)rewards, n_flags, flags, interv_mask, bad_mask, scal, n_interv, bad, stream_slot(st));
   else
-    episode_stats_kernel<float><<<EP_CTAS, EP_THREADS, 0, st>>>(n_rewards, (const float*)rewards, n_flags, flags, interv_mask, bad_mask, scal, n_interv, bad);
+    episode_stats_kernel<float><<<EP_CTAS, EP_THREADS, 0, st>>>(n_rewards, (const float*)rewards, n_flags, flags, interv_mask, bad_mask, scal, n_interv, bad, stream_slot(st));
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(g_err, sizeof(g_err), "episode_stats_kernel: %s", cudaGetErrorString(e));
@@ -321,10 +322,10 @@ extern "C" int sgbpo_shac_loss(int dtype, int rows, int64_t N, const void* disc,
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == SGBPO_F64)
     shac_loss_kernel<double><<<EP_CTAS, EP_THREADS, 0, st>>>(rows, N, (const double*)disc, term_int, (const double*)values, (const double*)rewards,
-                                                 (const double*)norm, (double*)loss);
+                                                 (const double*)norm, (double*)loss, stream_slot(st));
   else
     shac_loss_kernel<float><<<EP_CTAS, EP_THREADS, 0, st>>>(rows, N, (const float*)disc, term_int, (const float*)values, (const float*)rewards,
-                                                (const float*)norm, (float*)loss);
+                                                (const float*)norm, (float*)loss, stream_slot(st));
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(g_err, sizeof(g_err), "shac_loss_kernel: %s", cudaGetErrorString(e));

@@ -7,17 +7,32 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "../../include/sgbpo.h"
+#include "sgbpo_slots.cuh"
 
 namespace sgbpo {
 extern thread_local char g_err[512];
 
+int stream_slot(cudaStream_t st) {
+  static std::mutex mu;
+  static std::unordered_map<cudaStream_t, int> slots;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = slots.find(st);
+  if (it != slots.end()) return it->second;
+  const int slot = (int)(slots.size() % N_SLOTS);
+  slots.emplace(st, slot);
+  return slot;
+}
+
 constexpr int OPT_THREADS = 256;
 constexpr int OPT_MAX_CTAS = 296;
-// scratch of the two-kernel update (one optimizer launch in flight at a time per device)
-__device__ unsigned int g_optim_ticket = 0;
-__device__ double g_optim_partial[OPT_MAX_CTAS];
-__device__ double g_optim_scalars[2 + 2 * SGBPO_OPT_MAX_TENSORS];      // [0] clip coefficient, then step_size / sqrt(bc2) per tensor
+// scratch of the two-kernel update, one slot per calling stream (sgbpo_slots.cuh)
+__device__ unsigned int g_optim_ticket[N_SLOTS];
+__device__ double g_optim_partial[N_SLOTS][OPT_MAX_CTAS];
+__device__ double g_optim_scalars[N_SLOTS][2 + 2 * SGBPO_OPT_MAX_TENSORS];      // [0] clip coefficient, then step_size / sqrt(bc2) per tensor
 
 template <class T> struct OptArgs {
   int n;
@@ -46,7 +61,7 @@ template <class T> __device__ __forceinline__ T block_sum(T v, T* scratch) {
 template <class T, class STEP_T>
 __global__ void __launch_bounds__(OPT_THREADS)
 grad_norm_kernel(const __grid_constant__ OptArgs<T> A, double lr, double beta1, double beta2, double max_norm,
-                 T* __restrict__ total_norm_out) {
+                 T* __restrict__ total_norm_out, int slot) {
   __shared__ T scratch[OPT_THREADS / 32];
   __shared__ bool s_last;
   const int64_t stride = (int64_t)gridDim.x * OPT_THREADS;
@@ -57,39 +72,39 @@ grad_norm_kernel(const __grid_constant__ OptArgs<T> A, double lr, double beta1, 
   }
   const T part = block_sum<T>(acc, scratch);
   if (threadIdx.x == 0) {
-    g_optim_partial[blockIdx.x] = (double)part;
+    g_optim_partial[slot][blockIdx.x] = (double)part;
     __threadfence();
-    s_last = atomicInc(&g_optim_ticket, gridDim.x - 1) == gridDim.x - 1;      // wraps to 0 for the next launch
+    s_last = atomicInc(&g_optim_ticket[slot], gridDim.x - 1) == gridDim.x - 1;      // wraps to 0 for the next launch
   }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
   if (threadIdx.x == 0) {
     T total = T(0);
-    for (unsigned b = 0; b < gridDim.x; ++b) total += (T)(*(volatile double*)&g_optim_partial[b]);
+    for (unsigned b = 0; b < gridDim.x; ++b) total += (T)(*(volatile double*)&g_optim_partial[slot][b]);
     const T total_norm = sqrt(total);
     T coef = T(max_norm) / (total_norm + T(1e-6));     // clip_grad_norm_: max_norm / (norm + 1e-6), clamped to 1
-    g_optim_scalars[0] = (double)(coef < T(1) ? coef : T(1));
+    g_optim_scalars[slot][0] = (double)((coef < T(1) || coef != coef) ? coef : T(1));      // torch.clamp(max=1) keeps a NaN norm NaN
     if (total_norm_out) *total_norm_out = total_norm;
   }
   if (threadIdx.x < A.n) {
     STEP_T* sp = reinterpret_cast<STEP_T*>(A.step[threadIdx.x]);
     const double step = (double)(*sp) + 1.0;
     *sp = (STEP_T)step;
-    g_optim_scalars[2 + 2 * threadIdx.x] = lr / (1.0 - pow(beta1, step));
-    g_optim_scalars[3 + 2 * threadIdx.x] = sqrt(1.0 - pow(beta2, step));
+    g_optim_scalars[slot][2 + 2 * threadIdx.x] = lr / (1.0 - pow(beta1, step));
+    g_optim_scalars[slot][3 + 2 * threadIdx.x] = sqrt(1.0 - pow(beta2, step));
   }
 }
 
 // kernel 2: scale the gradients in place (clip_grad_norm_ does) and apply Adam
 template <class T>
 __global__ void __launch_bounds__(OPT_THREADS)
-adam_apply_kernel(const __grid_constant__ OptArgs<T> A, double beta1, double beta2, double eps) {
-  const T coef = (T)g_optim_scalars[0];
+adam_apply_kernel(const __grid_constant__ OptArgs<T> A, double beta1, double beta2, double eps, int slot) {
+  const T coef = (T)g_optim_scalars[slot][0];
   const T one_m_b1 = T(1.0 - beta1), b2 = T(beta2), one_m_b2 = T(1.0 - beta2), eps_t = T(eps);
   const int64_t stride = (int64_t)gridDim.x * OPT_THREADS;
   for (int i = 0; i < A.n; ++i) {
-    const T step_size = (T)g_optim_scalars[2 + 2 * i], bc2_sqrt = (T)g_optim_scalars[3 + 2 * i];
+    const T step_size = (T)g_optim_scalars[slot][2 + 2 * i], bc2_sqrt = (T)g_optim_scalars[slot][3 + 2 * i];
     T* __restrict__ p = A.param[i]; T* __restrict__ g = A.grad[i]; T* __restrict__ m = A.exp_avg[i]; T* __restrict__ v = A.exp_avg_sq[i];
     for (int64_t j = (int64_t)blockIdx.x * OPT_THREADS + threadIdx.x; j < A.numel[i]; j += stride) {
       const T gj = g[j] * coef;
@@ -122,11 +137,12 @@ static int launch_clip_adam(const sgbpo_optim* o, int step_dtype, void* total_no
   }
   int64_t grid = (total + 4 * OPT_THREADS - 1) / (4 * OPT_THREADS);
   grid = grid < 1 ? 1 : (grid > OPT_MAX_CTAS ? OPT_MAX_CTAS : grid);
+  const int slot = stream_slot(st);
   if (step_dtype == SGBPO_F32)
-    grad_norm_kernel<T, float><<<(int)grid, OPT_THREADS, 0, st>>>(a, o->lr, o->beta1, o->beta2, o->max_norm, (T*)total_norm_out);
+    grad_norm_kernel<T, float><<<(int)grid, OPT_THREADS, 0, st>>>(a, o->lr, o->beta1, o->beta2, o->max_norm, (T*)total_norm_out, slot);
   else
-    grad_norm_kernel<T, double><<<(int)grid, OPT_THREADS, 0, st>>>(a, o->lr, o->beta1, o->beta2, o->max_norm, (T*)total_norm_out);
-  adam_apply_kernel<T><<<(int)grid, OPT_THREADS, 0, st>>>(a, o->beta1, o->beta2, o->eps);
+    grad_norm_kernel<T, double><<<(int)grid, OPT_THREADS, 0, st>>>(a, o->lr, o->beta1, o->beta2, o->max_norm, (T*)total_norm_out, slot);
+  adam_apply_kernel<T><<<(int)grid, OPT_THREADS, 0, st>>>(a, o->beta1, o->beta2, o->eps, slot);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(g_err, sizeof(g_err), "clip_adam kernels: %s", cudaGetErrorString(e));

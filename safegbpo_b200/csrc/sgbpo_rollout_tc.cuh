@@ -428,7 +428,7 @@ template <int NSP> struct BwdSmem {
   __host__ __device__ static int nop(int no) { return (no + 3) & ~3; }
   __host__ __device__ static size_t bytes(int in_dim, int no, int out_dim, bool grad) {
     return (grad ? 6 : 4) * (size_t)PART_BYTES + sizeof(float) * ((size_t)in_dim * W + 3 * W + (size_t)out_dim * W + (size_t)ROWS * nop(no) +
-                                                                     (size_t)out_dim * ROWS + 4 * NSP * ROWS + W) + 8 + 32;
+                                                                     (size_t)out_dim * ROWS + 2 * NSP * ROWS + W) + 8 + 32;
   }
   __device__ void carve(unsigned char* smem, int in_dim, int no, int out_dim, bool grad) {
     w_hi = smem; w_lo = w_hi + PART_BYTES; a_hi = w_lo + PART_BYTES; a_lo = a_hi + PART_BYTES;
@@ -439,8 +439,8 @@ template <int NSP> struct BwdSmem {
     w_out = f; f += out_dim * W;               // [q][W]
     obsS = f; f += ROWS * nop(no);             // [row][NOP] policy input of the tile's rows (gradient mode)
     dmuS = f; f += out_dim * ROWS;             // [q][row]
-    red_a = f; f += 2 * NSP * ROWS;            // float2 per (part, row)
-    red_b = f; f += 2 * NSP * ROWS;
+    red_a = f; f += 2 * NSP * ROWS;            // float2 per (part, row); the two row-sum exchanges of a pass are separated by
+    red_b = red_a;                             // CTA barriers, so they share the buffer
     db2S = f; f += W;
     maxS = reinterpret_cast<uint32_t*>(f);     // two alternating slots
     bar = reinterpret_cast<uint64_t*>(maxS + 2);
@@ -520,15 +520,17 @@ struct RowsBwdArgs {
 
 // GRAD = false: policy input-output Jacobian of every row (cotangent e_q per output q).  GRAD = true: parameter gradients of
 // the batched policy for the row cotangents dmu.  NA = policy outputs, NO = differentiated inputs (the first NO of in_dim).
-template <int NA, int NO, bool GRAD, int NSP>
+// NIN >= in_dim: compile-time bound on the policy input width (NavigateSeeker appends constant obstacle columns to the NO
+// differentiated observations; they carry no input gradient but they do enter Linear1.weight.grad).
+template <int NA, int NO, int NIN, bool GRAD, int NSP>
 __global__ void __launch_bounds__(ROWS * NSP, 1)
 policy_rows_bwd_kernel(const __grid_constant__ RowsBwdArgs R, const __grid_constant__ PolicyTc P) {
-  constexpr int NOP = (NO + 3) & ~3, C = W / NSP, NTK = ROWS * NSP;
+  constexpr int NOP = (NO + 3) & ~3, NIP = (NIN + 3) & ~3, C = W / NSP, NTK = ROWS * NSP;
   constexpr uint32_t TMEM_COLS = GRAD ? 256 : 128;       // [0, 128): dh1 of the tile; [128, 256): dW_hid over all tiles of this CTA
   extern __shared__ __align__(1024) unsigned char smem[];
   BwdSmem<NSP> S;
   const int IN = P.in_dim;
-  S.carve(smem, IN, NO, NA, GRAD);
+  S.carve(smem, IN, NIN, NA, GRAD);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int trow = tid % ROWS, part = tid / ROWS, qbar = quad_barrier_id(warp);
   const bool owner = part == 0;
@@ -568,11 +570,11 @@ policy_rows_bwd_kernel(const __grid_constant__ RowsBwdArgs R, const __grid_const
   const int64_t n_tiles = (R.M + ROWS - 1) / ROWS;
 
   // per-lane column accumulators (column cs_col, summed over this lane's row subset and all tiles of this CTA)
-  float acc_b2 = 0.f, acc_b1 = 0.f, acc_g1 = 0.f, acc_S[NA], acc_win[NO], acc_B[NA];
+  float acc_b2 = 0.f, acc_b1 = 0.f, acc_g1 = 0.f, acc_S[NA], acc_win[NIN], acc_B[NA];
 #pragma unroll
   for (int q = 0; q < NA; ++q) { acc_S[q] = 0.f; acc_B[q] = 0.f; }
 #pragma unroll
-  for (int i = 0; i < NO; ++i) acc_win[i] = 0.f;
+  for (int i = 0; i < NIN; ++i) acc_win[i] = 0.f;
   uint32_t it = 0;              // (tile, cotangent) passes processed by this CTA (selects the alternating max slot)
   float scale = 1.f;            // power of two: the dz2 operand holds scale * dz2, the TMEM accumulator scale * dW_hid
   bool acc_live = false;        // the dW_hid accumulator holds data (CTA-uniform)
@@ -601,7 +603,7 @@ policy_rows_bwd_kernel(const __grid_constant__ RowsBwdArgs R, const __grid_const
     if (GRAD) {
       if (owner) {
 #pragma unroll
-        for (int i = 0; i < NO; ++i) S.obsS[trow * NOP + i] = valid ? R.obs[row_off * IN + i] : 0.f;
+        for (int i = 0; i < NIN; ++i) S.obsS[trow * NIP + i] = (valid && i < IN) ? R.obs[row_off * IN + i] : 0.f;
 #pragma unroll
         for (int q = 0; q < NA; ++q) S.dmuS[q * ROWS + trow] = valid ? R.dmu[row_off * NA + q] : 0.f;
       }
@@ -773,19 +775,19 @@ policy_rows_bwd_kernel(const __grid_constant__ RowsBwdArgs R, const __grid_const
         __syncwarp();
         {
           float a[2] = {0.f, 0.f};
-          const float* ob = S.obsS + (size_t)cs_row0 * NOP;
+          const float* ob = S.obsS + (size_t)cs_row0 * NIP;
 #pragma unroll 4
           for (int j = 0; j < C; ++j) {
             const float x = scratch_get_n<C>(scratch, lane, j);
             a[j & 1] += x;
-            float orow[NOP];
+            float orow[NIP];
 #pragma unroll
-            for (int i4 = 0; i4 < NOP / 4; ++i4) {
-              const float4 o4 = *reinterpret_cast<const float4*>(ob + j * NOP + 4 * i4);
+            for (int i4 = 0; i4 < NIP / 4; ++i4) {
+              const float4 o4 = *reinterpret_cast<const float4*>(ob + j * NIP + 4 * i4);
               orow[4 * i4] = o4.x; orow[4 * i4 + 1] = o4.y; orow[4 * i4 + 2] = o4.z; orow[4 * i4 + 3] = o4.w;
             }
 #pragma unroll
-            for (int i = 0; i < NO; ++i) acc_win[i] = fmaf(x, orow[i], acc_win[i]);
+            for (int i = 0; i < NIN; ++i) acc_win[i] = fmaf(x, orow[i], acc_win[i]);
           }
           acc_b1 += a[0] + a[1];
         }
@@ -843,7 +845,8 @@ policy_rows_bwd_kernel(const __grid_constant__ RowsBwdArgs R, const __grid_const
     atomicAdd(R.g_gamma + W + c, dg2);
     atomicAdd(R.g_beta + W + c, db2);
 #pragma unroll
-    for (int i = 0; i < NO; ++i) atomicAdd(R.g_w_in + (size_t)c * IN + i, acc_win[i]);
+    for (int i = 0; i < NIN; ++i)
+      if (i < IN) atomicAdd(R.g_w_in + (size_t)c * IN + i, acc_win[i]);
   }
   tc_fence_before();
   __syncthreads();
@@ -1012,11 +1015,12 @@ template <int ENV> int rollout_jac(const sgbpo_consts* c, const sgbpo_rollout* r
   return e == cudaSuccess ? SGBPO_OK : cuda_fail2(e, "rollout_jac_kernel");
 }
 
-template <int NA, int NO, bool GRAD, int NSP>
+template <int NA, int NO, int NIN, bool GRAD, int NSP>
 int launch_rows_bwd(const RowsBwdArgs& R, const PolicyTc& p, int in_dim, cudaStream_t st) {
-  const size_t smem = BwdSmem<NSP>::bytes(in_dim, NO, NA, GRAD);
+  if (in_dim > NIN) return fail2(SGBPO_E_ARG, "tensor-core reverse pass: policy input wider than the environment's observation");
+  const size_t smem = BwdSmem<NSP>::bytes(in_dim, NIN, NA, GRAD);
   if (smem > SMEM_CAP) return fail2(SGBPO_E_UNSUPPORTED, "tensor-core reverse pass: policy input too wide for shared memory");
-  auto kern = policy_rows_bwd_kernel<NA, NO, GRAD, NSP>;
+  auto kern = policy_rows_bwd_kernel<NA, NO, NIN, GRAD, NSP>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail2(e, "cudaFuncSetAttribute(policy_rows_bwd)");
   kern<<<tc_grid(R.M), ROWS * NSP, smem, st>>>(R, p);
@@ -1028,6 +1032,7 @@ template <int ENV> int rollout_tc_bwd(const sgbpo_mlp* pol, const sgbpo_rollout*
   using TASK = Task<ENV>;
   using JS = JacShape<ENV>;
   constexpr int NA = TASK::NA, NO = TASK::NO, NOP = (NO + 3) & ~3;
+  constexpr int NIN = TASK::NAUX > 2 ? NO + (TASK::NAUX - 2) : NO;       // constant observation columns appended from aux (NavigateSeeker)
   PolicyTc p;
   if (!tc_policy(pol, p) || pol->out_dim != NA) return fail2(SGBPO_E_UNSUPPORTED, "tensor-core reverse pass: float32 policy [in -> 128 -> 128 -> m]");
   if (!r->jac || !r->pol_jac || !r->dmu || !g->g_w_hid) return fail2(SGBPO_E_ARG, "tensor-core reverse pass: jac, pol_jac, dmu and g_w_hid buffers are required");
@@ -1042,7 +1047,7 @@ template <int ENV> int rollout_tc_bwd(const sgbpo_mlp* pol, const sgbpo_rollout*
   const bool split8 = forced == 8;      // (measured: the 4-way split is faster at 4096 and 65536 environments, profiles/r2_engines.md)
   // 1. policy input-output Jacobians of all H x N rows
   {
-    const int rc = split8 ? launch_rows_bwd<NA, NO, false, 8>(R, p, pol->in_dim, st) : launch_rows_bwd<NA, NO, false, 4>(R, p, pol->in_dim, st);
+    const int rc = split8 ? launch_rows_bwd<NA, NO, NIN, false, 8>(R, p, pol->in_dim, st) : launch_rows_bwd<NA, NO, NIN, false, 4>(R, p, pol->in_dim, st);
     if (rc != SGBPO_OK) return rc;
   }
   // 2. the sequential recursion: a scan per environment
@@ -1059,7 +1064,7 @@ template <int ENV> int rollout_tc_bwd(const sgbpo_mlp* pol, const sgbpo_rollout*
   }
   // 3. parameter gradients of the batched policy for the row cotangents
   {
-    const int rc = split8 ? launch_rows_bwd<NA, NO, true, 8>(R, p, pol->in_dim, st) : launch_rows_bwd<NA, NO, true, 4>(R, p, pol->in_dim, st);
+    const int rc = split8 ? launch_rows_bwd<NA, NO, NIN, true, 8>(R, p, pol->in_dim, st) : launch_rows_bwd<NA, NO, NIN, true, 4>(R, p, pol->in_dim, st);
     if (rc != SGBPO_OK) return rc;
   }
   (void)JS::STRIDE; (void)NOP;

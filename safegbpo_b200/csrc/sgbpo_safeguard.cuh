@@ -321,7 +321,9 @@ SG_HD bool safeguard_m1(const S& a, const S* c_f, const S (*B)[MAXM], const Safe
                              ? safe_interval_m1<TASK>(c_f, B, k)
                              : Interval<S>{C<S>(0.0), C<S>(0.0), true};
   if (k.sg_kind == SG_BOUNDARY_PROJECTION) {
-    out = project_interval(a, iv);
+    // an empty interval has no projection: NaN like the m = 2 path (and like the reference's solver failure), never a
+    // finite action that violates a constraint
+    out = iv.feasible ? project_interval(a, iv) : C<S>(NAN);
     return iv.feasible;
   }
   // ---- ray mask ----

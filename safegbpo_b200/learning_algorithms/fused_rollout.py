@@ -24,7 +24,10 @@ from torch import Tensor
 from .. import _lib, rng
 from .._lib import Mlp, Rollout, RolloutGrads, check, dtype_code, stream_ptr
 
-FUSED_ENVS = {"BalancePendulum", "BalanceCartPole", "SwingUpCartPole", "BalanceQuadrotor"}
+FUSED_ENVS = {"BalancePendulum", "BalanceCartPole", "SwingUpCartPole", "BalanceQuadrotor", "ManageHousehold", "NavigateSeeker"}
+# environments whose whole-horizon path exists only on the tensor-core engines (float32, policy [o -> 128 -> 128 -> m]): the
+# household's per-step series and the seeker's obstacle columns / per-reset goal + obstacles are handled by rollout_tc_fwd_kernel
+TC_ONLY_ENVS = {"ManageHousehold", "NavigateSeeker"}
 WIDTHS = (32, 64, 128)
 
 
@@ -161,11 +164,11 @@ class FusedRollout:
     @staticmethod
     def pick_engine(base, pack: "PackedMlp") -> tuple[int, int]:
         force = os.environ.get("SGBPO_ROLLOUT_ENGINE", "")
-        if base.state.dtype != torch.float32 or force == "0":
+        if base.state.dtype != torch.float32 or (force == "0" and base.ENV_NAME not in TC_ONLY_ENVS):
             return 0, 0
         if not _lib.lib().sgbpo_rollout_engine_supported(base.env_id, 0, C.byref(pack.desc)):
             return 0, 0
-        if force == "1":
+        if force == "1" or base.ENV_NAME in TC_ONLY_ENVS:
             return 1, 1
         if force == "2":
             return 0, 1
@@ -204,7 +207,10 @@ class FusedRollout:
         if algo.buffer.store_safe_actions:
             return None
         pw = _mlp_layout(pol.model)[0][0].out_features
-        if not rollout_fits(base.state.dtype, base.obs_dim, pw, 2, base.action_dim):
+        if base.ENV_NAME in TC_ONLY_ENVS:
+            if FusedRollout.pick_engine(base, PackedMlp(pol.model, pol.log_std)) != (1, 1):
+                return None
+        elif not rollout_fits(base.state.dtype, base.obs_dim, pw, 2, base.action_dim):
             return None
         if hasattr(env, "consts"):
             try:
@@ -249,8 +255,9 @@ class FusedRollout:
                      and getattr(wrapper, "zonotopic_approximation", False) and wrapper.state_constrained)
         reset_at, terminal_rows, pre_steps, post_steps, pending_end, steps_end = self._schedule(H)
         reset_idx, aux_src = [-1] * H, [-1] * H
-        resets = []
+        resets, reset_aux = [], []
         household = base._shared() is not None
+        per_reset_aux = hasattr(base, "obstacles")          # NavigateSeeker: reset() re-samples goal and obstacles on the host
         if self.rng_mode == "batched":
             eps_t = rng.randn(H, N, m).to(dt)
             u = rng.rand(H, N, n).to(dt)
@@ -263,14 +270,20 @@ class FusedRollout:
                 dirs_t = d / torch.linalg.vector_norm(d, dim=2, keepdim=True)
             # the batched mode draws a FIXED number of reset states per episode (used or not), so the episode is the
             # same sequence of draws whether it runs eagerly or as a replayed CUDA graph
-            snap = base._reset_snapshot()
-            for r in range(self._max_resets(H)):
-                base.reset()
-                if r < len(reset_at):
+            if per_reset_aux:           # (never graph-replayed: the resets are drawn when they happen, with their goal / obstacles)
+                for _ in reset_at:
+                    base.reset()
                     resets.append(base.state.detach().to(dt))
-            base._reset_restore(snap)
-            if resets:
-                base._adopt_reset(resets[-1])
+                    reset_aux.append(base._aux().to(dt))
+            else:
+                snap = base._reset_snapshot()
+                for r in range(self._max_resets(H)):
+                    base.reset()
+                    if r < len(reset_at):
+                        resets.append(base.state.detach().to(dt))
+                base._reset_restore(snap)
+                if resets:
+                    base._adopt_reset(resets[-1])
         else:
             eps, noise, dirs = [], [], []
             for t in range(H):
@@ -281,6 +294,8 @@ class FusedRollout:
                 if t in reset_at:
                     base.reset()                  # draws in the reference's position of the stream
                     resets.append(base.state.detach().to(dt))
+                    if per_reset_aux:
+                        reset_aux.append(base._aux().to(dt))
             eps_t, noise_t = torch.stack(eps), torch.stack(noise)
             dirs_t = torch.stack(dirs) if dirs else None
         cur = -1
@@ -301,6 +316,7 @@ class FusedRollout:
             shared_t = torch.tensor(np.stack(rows), dtype=dt, device=dev)
         base.steps, base._reset_pending = steps_end, pending_end
         resets_t = torch.stack(resets) if resets else None
+        self._reset_aux_t = torch.stack(reset_aux).contiguous() if reset_aux else None
         return eps_t, noise_t, dirs_t, resets_t, reset_idx, aux_src, terminal_rows, shared_t
 
 
@@ -313,7 +329,7 @@ class FusedRollout:
         resets_ok = not reset_at or (self.rng_mode == "batched" and len(reset_at) <= self._max_resets(self.algo.len_trajectories)
                                      and self._max_resets(self.algo.len_trajectories) <= 4)
         return (self.use_graphs and not self.profile and rng._source is None and resets_ok
-                and base._shared() is None and self._episodes >= self.graph_warmup
+                and base._shared() is None and not hasattr(base, "obstacles") and self._episodes >= self.graph_warmup
                 and getattr(self.algo.policy_optim, "defaults", {}).get("capturable", False))
 
     def _alloc_static(self, H: int):
@@ -643,7 +659,8 @@ class FusedRollout:
         reset_idx_t, aux_src_t = sched[0], sched[1]
         r = Rollout()
         r.N, r.H = N, H
-        keep = [eps, noise, dirs, aux0, resets, reset_idx_t, aux_src_t, shared]
+        keep = [eps, noise, dirs, aux0, resets, reset_idx_t, aux_src_t, shared, self._reset_aux_t]
+        r.reset_aux = None if self._reset_aux_t is None else self._reset_aux_t.data_ptr()
         p = lambda t: None if t is None else t.contiguous().data_ptr()
         eps, noise = eps.contiguous(), noise.contiguous()
         r.eps, r.noise, r.dirs, r.aux0 = p(eps), p(noise), p(dirs), p(aux0)

@@ -334,8 +334,13 @@ class SHAC(LearningAlgorithm):
         fused launches of csrc/sgbpo_optim.cu on torch.optim.Adam's own state tensors."""
         from .. import optim as sgoptim
         vf, opt = self.value_function, self.value_function_optim
+        sgoptim._ensure_state(opt)
+        # the captured graph bakes in the parameter and optimizer-state storage: a load_state_dict() / checkpoint resume that
+        # replaces them must trigger a re-capture
+        ptrs = tuple((p.data_ptr(), opt.state[p]["exp_avg"].data_ptr(), opt.state[p]["exp_avg_sq"].data_ptr(),
+                      opt.state[p]["step"].data_ptr()) for p in vf.parameters())
         key = (tuple(est.shape), tuple(obs.shape), est.dtype, float(opt.param_groups[0]["lr"]), self.vf_num_fits,
-               self.vf_fit_num_batches)
+               self.vf_fit_num_batches, ptrs)
         g = self._vf_graph
         if g is None or g["key"] != key:
             g = dict(key=key, est=torch.empty_like(est), obs=torch.empty_like(obs), loss=torch.zeros((), dtype=est.dtype, device=est.device),

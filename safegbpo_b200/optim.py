@@ -50,13 +50,17 @@ def _ensure_state(optim: torch.optim.Adam):
 def clip_adam_step(optim: torch.optim.Adam, max_norm: float) -> torch.Tensor:
     """clip_grad_norm_ + Adam.step in one launch; returns the total gradient norm (0-dim device tensor).
     Parameters without a gradient are skipped, as torch does.  The argument block is cached while the
-    gradient tensors stay the same storage (the fused engine re-attaches its static buffers every episode)."""
+    gradient, parameter and optimizer-state tensors stay the same storage (the fused engine re-attaches its static
+    gradient buffers every episode)."""
     g = optim.param_groups[0]
     ps = [p for p in g["params"] if p.grad is not None]
-    key = tuple(p.grad.data_ptr() for p in ps)
+    _ensure_state(optim)
+    # every pointer the argument block bakes in: gradients, parameters AND the optimizer's state tensors (load_state_dict(),
+    # .to() or a checkpoint resume replace them without touching the gradients)
+    key = tuple((p.grad.data_ptr(), p.data_ptr(), optim.state[p]["exp_avg"].data_ptr(), optim.state[p]["exp_avg_sq"].data_ptr(),
+                 optim.state[p]["step"].data_ptr()) for p in ps)
     cache = getattr(optim, "_sgbpo_cache", None)
     if cache is None or cache[0] != key:
-        _ensure_state(optim)
         o = Optim()
         o.n_tensors = len(ps)
         step_dtype = None

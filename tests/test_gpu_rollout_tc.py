@@ -135,3 +135,91 @@ def test_tensor_core_kernels_are_tcgen05():
         body = sass[sass.index(kernel):]
         body = body[:body.index("Function :", 10)] if "Function :" in body[10:] else body
         assert "UTCHMMA" in body and "LDTM" in body, kernel
+
+
+def _build_any(env_name, N, H, num_steps, fused, dev):
+    from safegbpo_b200.envs.manage_household import ManageHouseholdEnv
+    from safegbpo_b200.envs.navigate_seeker import NavigateSeekerEnv
+    from safegbpo_b200.safeguards.boundary_projection import BoundaryProjectionSafeguard
+    from safegbpo_b200.learning_algorithms.shac import SHAC
+    if env_name == "ManageHousehold":
+        env = ManageHouseholdEnv(num_envs=N, num_steps=num_steps)
+    else:
+        env = NavigateSeekerEnv(num_envs=N, num_steps=num_steps, num_obstacles=1, min_radius=2.0, max_radius=4.0)
+    wrapped = BoundaryProjectionSafeguard(env, gate="always", strict=False)
+    algo = SHAC(env=wrapped, policy_kwargs={"net_arch": [128, 128]}, policy_optim_kwargs={"lr": 1e-3},
+                vf_kwargs={"net_arch": [128, 128, 128]}, vf_optim_kwargs={"lr": 1e-3}, regularisation_coefficient=0.1,
+                len_trajectories=H, fused=fused)
+    return env, wrapped, algo
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_name,num_steps", [("ManageHousehold", 720), ("NavigateSeeker", 400), ("NavigateSeeker", 5)],
+                         ids=["household", "seeker", "seeker-resets"])
+def test_household_and_seeker_fused_vs_eager(cuda_default, env_name, num_steps):
+    """ManageHousehold (per-step shared series, 23 observations) and NavigateSeeker (obstacle columns of the observation,
+    per-step safe action set P5, collision operator, goal + obstacles re-sampled at every reset) through the tensor-core
+    whole-horizon engine against the eager per-step path (torch autograd over the per-step kernels) on replayed draws:
+    float64 eager = truth, float32 eager = the float32 noise floor, float32 fused must stay within 3x of it."""
+    from safegbpo_b200 import rng
+    dev = cuda_default
+    N, H = 200, 10
+    out = {}
+    draws = state = weights = aux = None
+    for tag, dtype, fused in (("ref", torch.float64, "off"), ("eager32", torch.float32, "off"), ("fused32", torch.float32, "on")):
+        torch.set_default_dtype(dtype)
+        torch.manual_seed(5)
+        env, wrapped, algo = _build_any(env_name, N, H, num_steps, fused, dev)
+        if weights is None:
+            weights = ({k: v.double() for k, v in algo.policy.state_dict().items()},
+                       {k: v.double() for k, v in algo.target_value_function.state_dict().items()})
+            half = env.state_set.generator[0].diagonal().double()
+            state = env.state_set.center[0].double() + (torch.rand(N, env.state_dim, dtype=torch.float64) * 2 - 1) * half * 0.5
+            if env_name == "NavigateSeeker":
+                env.state = state.clone()
+                env._after_reset()                  # goal + obstacles for these states (host rejection sampling)
+                aux = (env.goal.double().clone(), [(b.center.double().clone(), b.radius.double().clone()) for b in env.obstacles])
+        algo.policy.load_state_dict({k: v.to(dtype) for k, v in weights[0].items()})
+        algo.target_value_function.load_state_dict({k: v.to(dtype) for k, v in weights[1].items()})
+        env.state, env.steps, env._reset_pending = state.to(dtype).clone(), 2, False
+        if aux is not None:
+            env.goal = aux[0].to(dtype).clone()
+            for b, (c, r) in zip(env.obstacles, aux[1]):
+                b.center, b.radius = c.to(dtype).clone(), r.to(dtype).clone()
+        o0 = env.observation
+        algo.buffer.reset(o0, algo.target_value_function(o0).squeeze(1))
+        if draws is None:
+            rec = Recorder()
+            rng.set_source(rec)
+        else:
+            rng.set_source(Replay([(k, d.to(dtype)) for k, d in draws], dev))
+        algo.buffer.reset()
+        algo.policy_optim.zero_grad()
+        algo.collect_trajectories()
+        if fused == "on":
+            eng = algo._fused_engine
+            assert eng is not None and (eng.engine_fwd, eng.engine_bwd) == (1, 1)
+            loss = eng.backward()
+        else:
+            loss = algo.policy_loss()
+            loss.backward()
+        torch.cuda.synchronize()
+        rng.set_source(None)
+        if draws is None:
+            draws = [(k, d.double()) for k, d in rec.draws]
+        out[tag] = dict(obs=algo.buffer.observations.tensor.detach().double().cpu(), rewards=algo.buffer.rewards.tensor.detach().double().cpu(),
+                        actions=algo.buffer.actions.tensor.detach().double().cpu(), loss=float(loss),
+                        grads={k: p.grad.double().cpu() for k, p in algo.policy.named_parameters()})
+    ref, e32, f32 = out["ref"], out["eager32"], out["fused32"]
+    fin = torch.isfinite(ref["obs"]).all(dim=2).all(dim=0) & torch.isfinite(e32["obs"]).all(dim=2).all(dim=0) \
+        & torch.isfinite(f32["obs"]).all(dim=2).all(dim=0)
+    assert fin.float().mean() > 0.9
+    for key in ("obs", "actions", "rewards"):
+        r = ref[key][:, fin]
+        a, b = _rel(e32[key][:, fin], r), _rel(f32[key][:, fin], r)
+        assert b <= max(3.0 * a, 2e-4), f"{key}: fused {b:.2e} vs eager float32 {a:.2e}"
+    if bool(fin.all()):
+        assert abs(f32["loss"] - ref["loss"]) <= max(3.0 * abs(e32["loss"] - ref["loss"]), 2e-4 * abs(ref["loss"]))
+        for k, g in ref["grads"].items():
+            a, b = _rel(e32["grads"][k], g), _rel(f32["grads"][k], g)
+            assert b <= max(3.0 * a, 1e-3), f"grad {k}: fused {b:.2e} vs eager float32 {a:.2e}"
