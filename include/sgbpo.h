@@ -46,7 +46,10 @@ typedef struct sgbpo_consts {
   int32_t rm_linear, rm_zonotopic, rm_passthrough;
   int32_t action_constrained, state_constrained, state_model; /* 0: G_s invertible, 1: polygon (n = 2), 2: unreduced (gate + raw action only), 3: lifted (per-env interior point) */
   int32_t disable_clamp, n_obstacles;                        /* 1: raw dynamics (no clamp); obstacles in aux (Navigate*) */
-  int32_t act_set_mode, reserved1;                           /* 0: constant safe action set; 1: NavigateSeeker per-step set (P5) */
+  int32_t act_set_mode;                                      /* 0: constant safe action set; 1: NavigateSeeker per-step set (P5) */
+  int32_t infeasible_raw;                                    /* action executed where the guarded program is infeasible (always flagged
+                                                              * FL_INFEASIBLE): 0 = NaN (the reference's solver raises there), 1 = the raw
+                                                              * policy action, identity gradient (non-strict rollouts stay finite) */
   double box_min[SGBPO_MAXN], box_max[SGBPO_MAXN];           /* feasible state box */
   double noise_center[SGBPO_MAXN];
   double a_lo[SGBPO_MAXM], a_hi[SGBPO_MAXM];                 /* m = 1 safe action interval */

@@ -32,7 +32,7 @@ class Consts(C.Structure):
         ("sg_kind", C.c_int32), ("gate_mode", C.c_int32),
         ("rm_linear", C.c_int32), ("rm_zonotopic", C.c_int32), ("rm_passthrough", C.c_int32),
         ("action_constrained", C.c_int32), ("state_constrained", C.c_int32), ("state_model", C.c_int32),
-        ("disable_clamp", C.c_int32), ("n_obstacles", C.c_int32), ("act_set_mode", C.c_int32), ("reserved1", C.c_int32),
+        ("disable_clamp", C.c_int32), ("n_obstacles", C.c_int32), ("act_set_mode", C.c_int32), ("infeasible_raw", C.c_int32),
         ("box_min", C.c_double * MAXN), ("box_max", C.c_double * MAXN), ("noise_center", C.c_double * MAXN),
         ("a_lo", C.c_double * MAXM), ("a_hi", C.c_double * MAXM),
         ("n_act_hp", C.c_int32), ("act_hp", (C.c_double * 3) * MAXHP), ("c_a", C.c_double * MAXM),

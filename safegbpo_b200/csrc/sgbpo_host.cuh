@@ -13,7 +13,7 @@ template <class T> inline SafeConsts<T> convert_consts(const sgbpo_consts& c) {
   k.rm_linear = c.rm_linear; k.rm_zonotopic = c.rm_zonotopic; k.rm_passthrough = c.rm_passthrough;
   k.action_constrained = c.action_constrained; k.state_constrained = c.state_constrained;
   k.state_model = c.state_model; k.disable_clamp = c.disable_clamp;
-  k.n_obstacles = c.n_obstacles; k.act_set_mode = c.act_set_mode;
+  k.n_obstacles = c.n_obstacles; k.act_set_mode = c.act_set_mode; k.infeasible_raw = c.infeasible_raw;
   for (int i = 0; i < MAXN; ++i) {
     k.box_min[i] = T(c.box_min[i]); k.box_max[i] = T(c.box_max[i]); k.noise_center[i] = T(c.noise_center[i]);
     k.cs_hat[i] = T(c.cs_hat[i]); k.rb[i] = T(c.rb[i]); k.c_s[i] = T(c.c_s[i]);

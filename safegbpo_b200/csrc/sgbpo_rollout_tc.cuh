@@ -424,11 +424,15 @@ template <int NSP> struct BwdSmem {
   float *w_in, *g1, *g2, *be1, *w_out, *obsS, *dmuS, *red_a, *red_b, *db2S;
   uint32_t* maxS;
   uint64_t* bar;
+  uint64_t* tma_bar;
   uint32_t* tmem_slot;
+  float* stage;              // (Jacobian mode) the NEXT tile's e2 rows, landed by TMA bulk copies while this tile computes
+  static constexpr int STAGE_PITCH = W + 4;           // floats per staged row: 528 B, conflict-free 16-byte reads down a column of rows
   __host__ __device__ static int nop(int no) { return (no + 3) & ~3; }
   __host__ __device__ static size_t bytes(int in_dim, int no, int out_dim, bool grad) {
     return (grad ? 6 : 4) * (size_t)PART_BYTES + sizeof(float) * ((size_t)in_dim * W + 3 * W + (size_t)out_dim * W + (size_t)ROWS * nop(no) +
-                                                                     (size_t)out_dim * ROWS + 2 * NSP * ROWS + W) + 8 + 32;
+                                                                     (size_t)out_dim * ROWS + 2 * NSP * ROWS + W) + 8 + 48 +
+           (grad ? 0 : sizeof(float) * (size_t)ROWS * STAGE_PITCH);
   }
   __device__ void carve(unsigned char* smem, int in_dim, int no, int out_dim, bool grad) {
     w_hi = smem; w_lo = w_hi + PART_BYTES; a_hi = w_lo + PART_BYTES; a_lo = a_hi + PART_BYTES;
@@ -444,7 +448,9 @@ template <int NSP> struct BwdSmem {
     db2S = f; f += W;
     maxS = reinterpret_cast<uint32_t*>(f);     // two alternating slots
     bar = reinterpret_cast<uint64_t*>(maxS + 2);
-    tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    tma_bar = bar + 1;
+    tmem_slot = reinterpret_cast<uint32_t*>(tma_bar + 1);
+    stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~uintptr_t(15));    // bulk-copy destination: 16-byte aligned
   }
 };
 
@@ -554,6 +560,7 @@ policy_rows_bwd_kernel(const __grid_constant__ RowsBwdArgs R, const __grid_const
   }
   if (tid == 0) {
     mbar_init(smem_u32(S.bar), 1);
+    mbar_init(smem_u32(S.tma_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc<TMEM_COLS>(smem_u32(S.tmem_slot));
@@ -563,11 +570,23 @@ policy_rows_bwd_kernel(const __grid_constant__ RowsBwdArgs R, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *S.tmem_slot;
   const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(part * C);
-  const uint32_t bar_addr = smem_u32(S.bar);
+  const uint32_t bar_addr = smem_u32(S.bar), tma_bar_addr = smem_u32(S.tma_bar);
   const uint32_t a_hi_addr = smem_u32(S.a_hi), a_lo_addr = smem_u32(S.a_lo), w_hi_addr = smem_u32(S.w_hi), w_lo_addr = smem_u32(S.w_lo);
   const uint32_t h_hi_addr = smem_u32(S.h_hi), h_lo_addr = smem_u32(S.h_lo);
-  uint32_t phase = 0;
+  uint32_t phase = 0, tma_phase = 0;
   const int64_t n_tiles = (R.M + ROWS - 1) / ROWS;
+  // TMA staging (Jacobian mode): the owner thread of a row issues one bulk copy of its 512-byte e2 row into the padded stage;
+  // thread 0 arms the transaction barrier with the tile's byte count.  Issued for tile i + 1 as soon as every thread holds
+  // tile i's e2 in registers, so the copy runs under tile i's arithmetic and MMA.
+  auto stage_tile = [&](int64_t tile) {
+    if (!owner) return;
+    const int64_t row0 = tile * ROWS;
+    const int64_t rows_here = R.M - row0 < ROWS ? R.M - row0 : ROWS;
+    if (tid == 0) mbar_expect_tx(tma_bar_addr, (uint32_t)rows_here * W * 4);
+    if (trow < rows_here)
+      bulk_g2s(smem_u32(S.stage + trow * BwdSmem<NSP>::STAGE_PITCH), R.e2 + (size_t)(row0 + trow) * W, W * 4, tma_bar_addr);
+  };
+  if (!GRAD && (int64_t)blockIdx.x < n_tiles) stage_tile(blockIdx.x);
 
   // per-lane column accumulators (column cs_col, summed over this lane's row subset and all tiles of this CTA)
   float acc_b2 = 0.f, acc_b1 = 0.f, acc_g1 = 0.f, acc_S[NA], acc_win[NIN], acc_B[NA];
@@ -599,7 +618,16 @@ policy_rows_bwd_kernel(const __grid_constant__ RowsBwdArgs R, const __grid_const
     float e2[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) e2[c] = 0.f;
-    if (valid) load_cols_n<C>(R.e2 + row_off * W + part * C, e2);
+    if (GRAD) {
+      if (valid) load_cols_n<C>(R.e2 + row_off * W + part * C, e2);
+    } else {
+      mbar_wait(tma_bar_addr, tma_phase);            // this tile's rows have landed in the stage
+      tma_phase ^= 1;
+      if (valid) load_cols_n<C>(S.stage + trow * BwdSmem<NSP>::STAGE_PITCH + part * C, e2);
+      fence_async_smem();                            // generic-proxy reads of the stage before the async-proxy refill
+      __syncthreads();
+      if (tile + gridDim.x < n_tiles) stage_tile(tile + gridDim.x);
+    }
     if (GRAD) {
       if (owner) {
 #pragma unroll

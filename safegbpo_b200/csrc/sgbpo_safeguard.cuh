@@ -53,7 +53,7 @@ template <class T> struct SafeConsts {
   int rm_linear, rm_zonotopic, rm_passthrough;
   int action_constrained, state_constrained, state_model;
   int disable_clamp, n_obstacles;
-  int act_set_mode, reserved1;
+  int act_set_mode, infeasible_raw;
   T box_min[MAXN], box_max[MAXN];      // feasible state box: gate (box.py:139-154) and clamp
   T noise_center[MAXN];
   // action block

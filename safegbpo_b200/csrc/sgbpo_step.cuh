@@ -107,10 +107,12 @@ SG_HD void safeguarded_step(const S* s, const S* a, const T* w, const T* aux, co
       if (!feasible) flags |= FL_INFEASIBLE;
       if (k.state_constrained && k.state_model == SM_UNREDUCED) flags |= FL_UNREDUCED;
       const bool straight_through = (k.sg_kind == SG_RAY_MASK) && k.rm_passthrough;   // Q11
+      if (feasible || !k.infeasible_raw) {       // (infeasible_raw: the raw action stays in place where no safe action exists)
 #pragma unroll
-      for (int q = 0; q < NA; ++q) {
-        if (straight_through) a_exec[q] = a[q] + S(primal(g[q]) - primal(a[q]));
-        else a_exec[q] = g[q];
+        for (int q = 0; q < NA; ++q) {
+          if (straight_through) a_exec[q] = a[q] + S(primal(g[q]) - primal(a[q]));
+          else a_exec[q] = g[q];
+        }
       }
     }
     int differ = 0;

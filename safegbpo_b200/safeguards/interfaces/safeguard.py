@@ -59,6 +59,9 @@ class Safeguard:
             self._consts = build_consts(env.ENV_NAME, self.SG_KIND, gate_mode=_lib.GATE[self.gate], safe_action=sa,
                                         safe_state=ss, G_w=G_w, B0=f64(self.action_mat[0]), dynamic_action_set=dynamic,
                                         n_obstacles=int(getattr(env, "num_obstacles", 0)), **self._rm_flags())
+            # strict (the reference's behaviour): an infeasible program yields NaN and raises; non-strict: the raw action is
+            # executed there, flagged FL_INFEASIBLE, so that long rollouts and the weights stay finite
+            self._consts.infeasible_raw = 0 if self.strict else 1
         return self._consts
 
     def _directions(self) -> Optional[Tensor]:

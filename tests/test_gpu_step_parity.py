@@ -155,7 +155,9 @@ def test_large_batch_properties():
         assert torch.allclose(a1[feas], a2[feas], rtol=0, atol=1e-12)            # projection is idempotent
         assert (((fl & _lib.FL_NEXT_IN_SET) != 0) | ~feas).all()                 # zero violations where feasible
         assert (a1[feas].abs() <= 1 + 1e-12).all()
-        assert ((s_next - torch.tensor([10.0, 3.141592653589793, 10.0, 10.0], device=dev, dtype=torch.float64)) <= 1e-12).all()
+        # (an empty safe interval has no projection: NaN action and next state, flagged FL_INFEASIBLE, like the m = 2 path)
+        assert ((s_next[feas] - torch.tensor([10.0, 3.141592653589793, 10.0, 10.0], device=dev, dtype=torch.float64)) <= 1e-12).all()
+        assert bool(a1[~feas].isnan().all())
         inside = feas & (((fl & _lib.FL_INTERVENED) == 0))
         assert torch.equal(a1[inside], a[inside])                                # already-safe actions pass unchanged
 
