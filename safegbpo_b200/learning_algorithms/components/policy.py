@@ -47,3 +47,24 @@ class Policy(nn.Module):
 
     def predict(self, x: Tensor, deterministic: bool = True) -> Tensor:
         return torch.tanh(self.model(x)) if deterministic else self.forward(x)
+
+    # ---- what the model-free consumers (PPO / SAC) ask of the policy: reference policy.py:112-158 ------------------------
+    def _dist(self, x: Tensor) -> torch.distributions.Normal:
+        return torch.distributions.Normal(self.model(x), torch.exp(self.log_std))
+
+    def log_prob(self, action: Tensor, x: Tensor) -> Tensor:
+        """Log-density of a tanh-squashed Gaussian action: change of variables inside (-1, 1), the Gaussian tail mass at the
+        saturated values +-1 (policy.py:112-141)."""
+        dist = self._dist(x)
+        tiny = torch.finfo(action.dtype).eps
+        clamped = action.clamp(min=-1.0 + tiny, max=1.0 - tiny)
+        pre = 0.5 * (clamped.log1p() - (-clamped).log1p())                 # atanh
+        inside = dist.log_prob(pre) - torch.log(1 - clamped ** 2)
+        at_bound = torch.where(action > 0, torch.log(1 - dist.cdf(pre) + tiny), torch.log(dist.cdf(-pre) + tiny))
+        saturated = torch.isclose(action.abs(), torch.ones_like(action))
+        return torch.where(saturated, at_bound, inside).sum(dim=1)
+
+    def entropy(self, x: Tensor) -> Tensor:
+        """Entropy of the un-squashed Gaussian (the reference's stated approximation, policy.py:143-158)."""
+        return self._dist(x).entropy().sum(dim=1)
+

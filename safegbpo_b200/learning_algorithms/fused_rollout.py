@@ -157,6 +157,7 @@ class FusedRollout:
         self._g = None                         # static buffers + captured graphs
         self.profile = False                   # record CUDA events around each of our kernels
         self.speculative_backward = True       # graph path: enqueue the backward graph right behind the forward graph
+        self.forward_only = False              # model-free consumers (consumers.RolloutCollector): no activation stash, no reverse pass
         self.kernel_ms = {"rollout_fwd": [], "mlp_rows": [], "rollout_jac": [], "rollout_bwd": []}
 
     TC_FORWARD_MIN_ENVS = 12288       # measured cross-over of the two forward kernels on one B200 (profiles/r2_engines.md)
@@ -668,7 +669,8 @@ class FusedRollout:
         r.states, r.obs, r.actions, r.exec_actions = states.data_ptr(), obs.data_ptr(), actions.data_ptr(), exec_actions.data_ptr()
         r.rewards, r.flags = rewards.data_ptr(), flags.data_ptr()
         W = self.policy_pack.width
-        if self._grad_bufs is None or self._grad_bufs["e1"].shape != (H, N, W) or self._grad_bufs["e1"].dtype != dt:
+        if not self.forward_only and (self._grad_bufs is None or self._grad_bufs["e1"].shape != (H, N, W)
+                                      or self._grad_bufs["e1"].dtype != dt):
             mk = lambda *shape: torch.empty(*shape, dtype=dt, device=dev)
             self._grad_bufs = dict(e1=mk(H, N, W), e2=mk(H, N, W), stats=mk(H, N, 4))
             if self.engine_bwd:
@@ -676,11 +678,14 @@ class FusedRollout:
             else:
                 self._grad_bufs.update(h1=mk(H, N, W), dz2=mk(H, N, W))
         gb = self._grad_bufs
-        r.stash_e1, r.stash_e2, r.stash_stats = gb["e1"].data_ptr(), gb["e2"].data_ptr(), gb["stats"].data_ptr()
+        if not self.forward_only:
+            r.stash_e1, r.stash_e2, r.stash_stats = gb["e1"].data_ptr(), gb["e2"].data_ptr(), gb["stats"].data_ptr()
         r.engine = self.engine
-        if self.engine_bwd:
+        if self.forward_only:
+            pass
+        elif self.engine_bwd:
             r.jac, r.pol_jac, r.dmu = gb["jac"].data_ptr(), gb["pol_jac"].data_ptr(), gb["dmu"].data_ptr()
-        else:
+        elif not self.forward_only:
             r.stash_h1 = gb["h1"].data_ptr()
         lib = _lib.lib()
         self._timed("rollout_fwd", lambda: check(
