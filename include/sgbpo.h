@@ -28,7 +28,8 @@ enum { SGBPO_OK = 0, SGBPO_E_ARG = -1, SGBPO_E_CUDA = -2, SGBPO_E_UNSUPPORTED = 
 /* environment ids (envs/*.py) */
 enum {
   SGBPO_ENV_BALANCE_PENDULUM = 0, SGBPO_ENV_BALANCE_CARTPOLE = 1, SGBPO_ENV_SWINGUP_CARTPOLE = 2,
-  SGBPO_ENV_BALANCE_QUADROTOR = 3, SGBPO_ENV_MANAGE_HOUSEHOLD = 4, SGBPO_ENV_NAVIGATE_SEEKER = 5
+  SGBPO_ENV_BALANCE_QUADROTOR = 3, SGBPO_ENV_MANAGE_HOUSEHOLD = 4, SGBPO_ENV_NAVIGATE_SEEKER = 5,
+  SGBPO_ENV_NAVIGATE_QUADROTOR = 6
 };
 /* safeguard kinds (safeguards/*.py), gate modes (safeguard.py:63-67) and per-env flag bits */
 enum { SGBPO_SG_NONE = 0, SGBPO_SG_BOUNDARY_PROJECTION = 1, SGBPO_SG_RAY_MASK = 2 };
@@ -36,7 +37,7 @@ enum { SGBPO_GATE_REFERENCE = 0, SGBPO_GATE_INTENDED = 1, SGBPO_GATE_ALWAYS = 2 
 enum {
   SGBPO_FL_PROJECTABLE = 1, SGBPO_FL_INFEASIBLE = 2, SGBPO_FL_INTERVENED = 4, SGBPO_FL_NONFINITE = 8,
   SGBPO_FL_GUARD_USED = 16, SGBPO_FL_ACTION_IN_SET = 32, SGBPO_FL_NEXT_IN_SET = 64, SGBPO_FL_CLAMPED = 128,
-  SGBPO_FL_COLLIDED = 256, SGBPO_FL_UNREDUCED = 512
+  SGBPO_FL_COLLIDED = 256, SGBPO_FL_UNREDUCED = 512, SGBPO_FL_REACHED = 1024
 };
 
 /* Constant set data, registered once per wrapper (replaces the numpy constants cvxpy bakes into the
@@ -44,7 +45,7 @@ enum {
 typedef struct sgbpo_consts {
   int32_t sg_kind, gate_mode;
   int32_t rm_linear, rm_zonotopic, rm_passthrough;
-  int32_t action_constrained, state_constrained, state_model; /* 0: G_s invertible, 1: polygon (n = 2), 2: unreduced (gate + raw action only), 3: lifted (per-env interior point) */
+  int32_t action_constrained, state_constrained, state_model; /* 0: G_s invertible, 1: polygon (n = 2), 2: unreduced (gate + raw action only), 3: lifted (per-env interior point), 4: rebuilt per step (NavigateQuadrotor; G_w in Gam_p) */
   int32_t disable_clamp, n_obstacles;                        /* 1: raw dynamics (no clamp); obstacles in aux (Navigate*) */
   int32_t act_set_mode;                                      /* 0: constant safe action set; 1: NavigateSeeker per-step set (P5) */
   int32_t infeasible_raw;                                    /* action executed where the guarded program is infeasible (always flagged
@@ -113,6 +114,13 @@ int sgbpo_linearise(int env_id, int dtype, int64_t N, const sgbpo_consts* consts
  * goal then (cx, cy, r) per obstacle; status (N) int32: 0 ok, 1 degenerate/infeasible. */
 int sgbpo_seeker_action_set(int dtype, int64_t N, const sgbpo_consts* consts, const void* s, const void* aux,
                             void* generator, int32_t* status, void* stream);
+
+/* NavigateQuadrotorEnv.safe_state_set (envs/navigate_quadrotor.py:436-779, programs P6-P8, no_grad): the per-environment
+ * safe state zonotope of the CURRENT state: center (N,6), generator (N,6,6) = [position | velocity | roll] blocks;
+ * aux (N, 2 + 3*3 + 2): goal, (cx, cz, r) per obstacle, initial goal distance, reached flag; status (N) int32: 0 ok,
+ * 1 degenerate (the reference's all-rows fallback blocks / an infeasible support-point program). */
+int sgbpo_navquad_safe_state_set(int dtype, int64_t N, const sgbpo_consts* consts, const void* s, const void* aux,
+                                 void* center, void* generator, int32_t* status, void* stream);
 
 /* ---- whole-horizon fused rollout (SHAC.collect_trajectories + reverse pass, shac.py:96-151) ------------ */
 

@@ -78,11 +78,12 @@ class RolloutGrads(C.Structure):
 
 
 ENV_IDS = {"BalancePendulum": 0, "BalanceCartPole": 1, "SwingUpCartPole": 2, "BalanceQuadrotor": 3,
-           "ManageHousehold": 4, "NavigateSeeker": 5}
+           "ManageHousehold": 4, "NavigateSeeker": 5, "NavigateQuadrotor": 6}
 SG_NONE, SG_BOUNDARY_PROJECTION, SG_RAY_MASK = 0, 1, 2
 GATE = {"reference": 0, "intended": 1, "always": 2}
 FL_PROJECTABLE, FL_INFEASIBLE, FL_INTERVENED, FL_NONFINITE = 1, 2, 4, 8
 FL_GUARD_USED, FL_ACTION_IN_SET, FL_NEXT_IN_SET, FL_CLAMPED, FL_COLLIDED, FL_UNREDUCED = 16, 32, 64, 128, 256, 512
+FL_REACHED = 1024
 
 _VP = C.c_void_p
 _SIGNATURES = {
@@ -95,6 +96,7 @@ _SIGNATURES = {
                        + [_VP] * 6 + [_VP] * 4 + [_VP, _VP, _VP]),
     "sgbpo_linearise": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.POINTER(Consts)] + [_VP] * 5 + [_VP]),
     "sgbpo_seeker_action_set": (C.c_int, [C.c_int, C.c_int64, C.POINTER(Consts)] + [_VP] * 5),
+    "sgbpo_navquad_safe_state_set": (C.c_int, [C.c_int, C.c_int64, C.POINTER(Consts)] + [_VP] * 6),
     "sgbpo_rollout_fwd": (C.c_int, [C.c_int, C.c_int, C.POINTER(Consts), C.POINTER(Mlp), C.POINTER(Rollout), _VP]),
     "sgbpo_rollout_bwd": (C.c_int, [C.c_int, C.c_int, C.POINTER(Consts), C.POINTER(Mlp), C.POINTER(Rollout),
                                     C.POINTER(RolloutGrads), _VP]),

@@ -28,7 +28,8 @@ BOXES = {   # feasible state box (centre, half) and noise centre per simulator; 
     "household": ([5.0, 21.0, 55.0], [5.0, 3.0, 45.0], [0.0, 15.0, 0.0], [0.0, 25.0, 0.0]),
 }
 ENV_SIM = {"BalancePendulum": "pendulum", "BalanceCartPole": "cartpole", "SwingUpCartPole": "cartpole",
-           "BalanceQuadrotor": "quadrotor", "ManageHousehold": "household", "NavigateSeeker": "seeker"}
+           "BalanceQuadrotor": "quadrotor", "ManageHousehold": "household", "NavigateSeeker": "seeker",
+           "NavigateQuadrotor": "quadrotor"}
 
 
 def zonotope_polygon_rows(center: np.ndarray, gen: np.ndarray) -> np.ndarray:
@@ -161,7 +162,7 @@ def build_consts(env_name: str, sg_kind: int, *, gate_mode: int = 0, rm_linear: 
                  rm_zonotopic: bool = True, rm_passthrough: bool = False,
                  safe_action: Optional[tuple] = None, safe_state: Optional[tuple] = None,
                  G_w: Optional[np.ndarray] = None, B0: Optional[np.ndarray] = None,
-                 dynamic_action_set: bool = False, n_obstacles: int = 0) -> Consts:
+                 dynamic_action_set: bool = False, n_obstacles: int = 0, dynamic_state_set: bool = False) -> Consts:
     """Fill ``struct sgbpo_consts``.  safe_action / safe_state: (center, generator) numpy float64 or None."""
     sim = ENV_SIM[env_name]
     bc, bh, nc, _ = (np.asarray(x, dtype=np.float64) for x in BOXES[sim])
@@ -174,7 +175,19 @@ def build_consts(env_name: str, sg_kind: int, *, gate_mode: int = 0, rm_linear: 
     k.action_constrained = int(safe_action is not None or dynamic_action_set)
     k.n_obstacles = int(n_obstacles)
     k.act_set_mode = int(dynamic_action_set)
-    k.state_constrained = int(safe_state is not None)
+    k.state_constrained = int(safe_state is not None or dynamic_state_set)
+    if dynamic_state_set:
+        # NavigateQuadrotor: the safe state set is rebuilt per environment every step (csrc/sgbpo_navquad.cuh, P6-P8); the only
+        # registered constant is the noise generator G_w = E_0 G_noise of the init-time linearisation (Q4), stored in Gam_p
+        k.state_model = 4
+        Gw = np.zeros((n, n)) if G_w is None else np.asarray(G_w, dtype=np.float64)
+        Wn = Gw[:, np.abs(Gw).sum(axis=0) > 0]
+        if Wn.shape[1] > 2:
+            raise ValueError("NavigateQuadrotor: at most two noise generators")
+        k.n_wcol = Wn.shape[1]
+        for i in range(n):
+            for j in range(Wn.shape[1]):
+                k.Gam_p[i][j] = Wn[i, j]
     if safe_action is not None:
         c_a, G_a = (np.asarray(x, dtype=np.float64) for x in safe_action)
         m = c_a.shape[0]

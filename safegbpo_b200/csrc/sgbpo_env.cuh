@@ -27,7 +27,8 @@ enum EnvId : int {
   ENV_BALANCE_QUADROTOR = 3,
   ENV_MANAGE_HOUSEHOLD = 4,
   ENV_NAVIGATE_SEEKER = 5,
-  ENV_COUNT = 6
+  ENV_NAVIGATE_QUADROTOR = 6,
+  ENV_COUNT = 7
 };
 
 // ---- simulators --------------------------------------------------------------------------------
@@ -186,6 +187,32 @@ template <> struct Task<ENV_NAVIGATE_SEEKER> {
     const S q = dx * dx + dz * dz;
     if (primal(q) == T(0)) return C<S>(0.0);
     return -(C<S>(2.0) * sg_sqrt(q));
+  }
+};
+
+// NavigateQuadrotor (envs/navigate_quadrotor.py): quadrotor dynamics, goal + up to SEEKER_MAXK circular obstacles.
+// aux = goal (2), (cx, cz, r) per obstacle (9), initial goal distance (1), reached flag 0/1 (1).  The reward is stateful in
+// the reference (`reached`, navigate_quadrotor.py:229-231): the kernel reads the flag from aux and reports a fresh arrival
+// through the flag word (FL_REACHED), the host keeps the flag.
+constexpr int NAVQUAD_NAUX = 2 + 3 * SEEKER_MAXK + 2;
+template <> struct Task<ENV_NAVIGATE_QUADROTOR> {
+  using Sim = QuadrotorSim;
+  static constexpr int NS = 6, NA = 2, NO = 8, NAUX = NAVQUAD_NAUX;
+  static constexpr bool CLAMP = true;
+  static constexpr bool LIFTED_OK = false;
+  template <class S, class T> SG_HD static void observe(const S* s, const T* aux, const StepShared<T>*, S* o) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) o[i] = s[i];
+    o[6] = S(aux[0]); o[7] = S(aux[1]);
+  }
+  // GOAL_REWARD * just_reached - goal_distance / initial_goal_distance  (the collision penalty is added by the step, which
+  // knows whether the free step entered an obstacle: navigate_quadrotor.py:218-236)
+  template <class S, class T> SG_HD static S reward(const S* s, const S*, const T* aux, const StepShared<T>*) {
+    const S dx = S(aux[0]) - s[0], dz = S(aux[1]) - s[1];
+    const S q = dx * dx + dz * dz;
+    const S dist = primal(q) == T(0) ? C<S>(0.0) : sg_sqrt(q);
+    const bool just_reached = aux[NAVQUAD_NAUX - 1] == T(0) && primal(dist) < T(0.1);
+    return (just_reached ? C<S>(100.0) : C<S>(0.0)) - dist / S(aux[NAVQUAD_NAUX - 2]);
   }
 };
 

@@ -167,6 +167,26 @@ seeker_action_set_kernel(int64_t N, const __grid_constant__ SafeConsts<T> k, con
   }
 }
 
+template <class T>
+__global__ void __launch_bounds__(128)
+navquad_state_set_kernel(int64_t N, const __grid_constant__ SafeConsts<T> k, const T* __restrict__ s, const T* __restrict__ aux,
+                         T* __restrict__ center, T* __restrict__ gen, int32_t* __restrict__ status) {
+  using TASK = Task<ENV_NAVIGATE_QUADROTOR>;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    T sv[6], av[NAVQUAD_NAUX], cf[6], B[6][MAXM];
+    load_row<6>(s, i, sv);
+    load_row<NAVQUAD_NAUX>(aux, i, av);
+    linearise_cB<TASK, T, T>(sv, k.noise_center, cf, B);
+    StateDyn<T> sd;
+    navquad_safe_state_set<T>(cf, B, av, k, sd);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) center[i * 6 + q] = sd.center[q];
+#pragma unroll
+    for (int q = 0; q < 36; ++q) gen[i * 36 + q] = sd.gen[q];
+    status[i] = sd.degenerate ? 1 : 0;
+  }
+}
+
 static int env_lanes() {          // SGBPO_STEP_LANES: environments per warp of the per-step kernels (tuning)
   const char* e = getenv("SGBPO_STEP_LANES");
   const int v = e ? atoi(e) : 0;
@@ -237,6 +257,7 @@ template <int ENV, class T> struct Launch {
     case ENV_BALANCE_QUADROTOR: return dtype ? Launch<ENV_BALANCE_QUADROTOR, double>::CALL : Launch<ENV_BALANCE_QUADROTOR, float>::CALL; \
     case ENV_MANAGE_HOUSEHOLD: return dtype ? Launch<ENV_MANAGE_HOUSEHOLD, double>::CALL : Launch<ENV_MANAGE_HOUSEHOLD, float>::CALL; \
     case ENV_NAVIGATE_SEEKER: return dtype ? Launch<ENV_NAVIGATE_SEEKER, double>::CALL : Launch<ENV_NAVIGATE_SEEKER, float>::CALL; \
+    case ENV_NAVIGATE_QUADROTOR: return dtype ? Launch<ENV_NAVIGATE_QUADROTOR, double>::CALL : Launch<ENV_NAVIGATE_QUADROTOR, float>::CALL; \
     default: return fail(SGBPO_E_ARG, "unknown env_id");                                         \
   }
 
@@ -253,7 +274,7 @@ int sgbpo_env_dims(int env_id, int* n, int* m, int* o, int* naux) {
 #define DIMS(E) case E: *n = Task<E>::NS; *m = Task<E>::NA; *o = Task<E>::NO; *naux = Task<E>::NAUX; return SGBPO_OK;
   switch (env_id) {
     DIMS(ENV_BALANCE_PENDULUM) DIMS(ENV_BALANCE_CARTPOLE) DIMS(ENV_SWINGUP_CARTPOLE)
-    DIMS(ENV_BALANCE_QUADROTOR) DIMS(ENV_MANAGE_HOUSEHOLD) DIMS(ENV_NAVIGATE_SEEKER)
+    DIMS(ENV_BALANCE_QUADROTOR) DIMS(ENV_MANAGE_HOUSEHOLD) DIMS(ENV_NAVIGATE_SEEKER) DIMS(ENV_NAVIGATE_QUADROTOR)
     default: return fail(SGBPO_E_ARG, "unknown env_id");
   }
 #undef DIMS
@@ -294,6 +315,22 @@ int sgbpo_seeker_action_set(int dtype, int64_t N, const sgbpo_consts* consts, co
   }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? SGBPO_OK : cuda_fail(e, "seeker_action_set_kernel");
+}
+
+int sgbpo_navquad_safe_state_set(int dtype, int64_t N, const sgbpo_consts* consts, const void* s, const void* aux,
+                                 void* center, void* generator, int32_t* status, void* stream) {
+  if (N == 0) return SGBPO_OK;
+  if (!consts || !s || !aux || !center || !generator || !status || N < 0) return fail(SGBPO_E_ARG, "sgbpo_navquad_safe_state_set: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype) {
+    navquad_state_set_kernel<double><<<grid_for(N, 128), 128, 0, st>>>(N, convert_consts<double>(*consts), (const double*)s,
+                                                                      (const double*)aux, (double*)center, (double*)generator, status);
+  } else {
+    navquad_state_set_kernel<float><<<grid_for(N, 128), 128, 0, st>>>(N, convert_consts<float>(*consts), (const float*)s,
+                                                                     (const float*)aux, (float*)center, (float*)generator, status);
+  }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? SGBPO_OK : cuda_fail(e, "navquad_state_set_kernel");
 }
 
 int sgbpo_linearise(int env_id, int dtype, int64_t N, const sgbpo_consts* consts, const void* s, void* c, void* A,

@@ -32,7 +32,9 @@ enum GateMode : int { GATE_REFERENCE = 0, GATE_INTENDED = 1, GATE_ALWAYS = 2 };
 // SM_UNREDUCED: safe state set whose generator is neither invertible nor 2-D (BalanceQuadrotor's 6 x 24 RCI set): the
 // linearisation, the gate and the verdict on the action set run, but the program itself has no register-level
 // reduction yet -- wherever the gate asks for the safeguarded action the step reports FL_UNREDUCED (+ NaN action)
-enum StateModel : int { SM_INVERTIBLE = 0, SM_POLYGON = 1, SM_UNREDUCED = 2, SM_LIFTED = 3 };
+// SM_DYNAMIC: the safe state set is rebuilt every step per environment (NavigateQuadrotor, sgbpo_navquad.cuh); its generator is
+// block-invertible, so the rows are those of SM_INVERTIBLE with per-environment constants
+enum StateModel : int { SM_INVERTIBLE = 0, SM_POLYGON = 1, SM_UNREDUCED = 2, SM_LIFTED = 3, SM_DYNAMIC = 4 };
 
 // status / verdict bits written per environment per step
 enum Flag : int {
@@ -45,7 +47,8 @@ enum Flag : int {
   FL_NEXT_IN_SET = 64,       // verdict: linearised next-state zonotope inside the safe state set
   FL_CLAMPED = 128,          // execute_action clamped the state to the feasible box
   FL_COLLIDED = 256,         // Navigate*: the free step entered an obstacle (collision operator applied)
-  FL_UNREDUCED = 512         // the safeguarded action was needed but this program has no GPU reduction (SM_UNREDUCED)
+  FL_UNREDUCED = 512,        // the safeguarded action was needed but this program has no GPU reduction (SM_UNREDUCED)
+  FL_REACHED = 1024          // NavigateQuadrotor: the goal was reached at this step for the first time (reward bonus paid)
 };
 
 template <class T> struct SafeConsts {

@@ -10,10 +10,21 @@
 
 namespace sgbpo {
 
+// per-environment safe state set of this step in the form the m = 2 row builder consumes
+template <class T> struct StateDyn {
+  T Ginv[MAXN * MAXN];   // G_s^-1 (row-major n x n)
+  T cs_hat[MAXN];        // G_s^-1 c_s
+  T rb[MAXN];            // 1 - row sums of |G_s^-1 G_w|
+  T center[MAXN];        // c_s
+  T gen[MAXN * MAXN];    // G_s (row-major), for the public safe_state_set() accessor
+  bool degenerate;       // the reference's fallback blocks (or an infeasible support-point program): no usable set
+};
+
 // per-environment safe action set computed this step (NavigateSeeker, P5): rows n . a <= h, constants for autograd
 template <class T> struct ActRows {
   T n[4][2], h[4];
-  int count;        // 0: use the registered constant set
+  int count = 0;                          // 0: use the registered constant set
+  const StateDyn<T>* sdyn = nullptr;      // per-environment safe STATE set of this step (NavigateQuadrotor, P6-P8; state model SM_DYNAMIC)
 };
 
 // P5, envs/navigate_seeker.py:415-477: largest (geo-mean) rectangle Z(0, U diag(len)) of actions whose one-step
@@ -100,19 +111,24 @@ SG_HD void for_each_row_m2(const S* c_f, const S (*B)[MAXM], const SafeConsts<T>
       for (int r = 0; r < k.n_act_hp; ++r) emit(S(k.act_hp[r][0]), S(k.act_hp[r][1]), S(k.act_hp[r][2]), idx++);
     }
   }
-  if (k.state_constrained && k.state_model == SM_INVERTIBLE) {
+  const bool dynamic_state = k.state_model == SM_DYNAMIC && dyn && dyn->sdyn;
+  if (k.state_constrained && (k.state_model == SM_INVERTIBLE || dynamic_state)) {
+    // constants registered once, or this step's per-environment set (built under no_grad in the reference: constants for autograd)
+    const T* Ginv = dynamic_state ? dyn->sdyn->Ginv : k.Ginv;
+    const T* cs_hat = dynamic_state ? dyn->sdyn->cs_hat : k.cs_hat;
+    const T* rb = dynamic_state ? dyn->sdyn->rb : k.rb;
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
-      S e = S(k.cs_hat[i]), b0 = S(T(0)), b1 = S(T(0));
+      S e = S(cs_hat[i]), b0 = S(T(0)), b1 = S(T(0));
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
-        const S gi = S(k.Ginv[i * NS + j]);
+        const S gi = S(Ginv[i * NS + j]);
         e = e - gi * c_f[j];
         b0 = b0 + gi * B[j][0];
         b1 = b1 + gi * B[j][1];
       }
-      emit(-b0, -b1, S(k.rb[i]) - e, idx++);
-      emit(b0, b1, S(k.rb[i]) + e, idx++);
+      emit(-b0, -b1, S(rb[i]) - e, idx++);
+      emit(b0, b1, S(rb[i]) + e, idx++);
     }
   }
 }
@@ -462,7 +478,7 @@ SG_HD bool safeguard_m2(const S* a, const S* c_f, const S (*B)[MAXM], const T* d
   bool feasible = true;
   if (k.state_constrained && k.rm_zonotopic) {
     // zonotopic approximation: P2 (four free lengths) then P3 along the ray from the centre (ray_mask.py:63-89)
-    if (k.state_model != SM_INVERTIBLE || k.action_constrained || !dirs) {
+    if (k.state_model != SM_INVERTIBLE || k.action_constrained || !dirs) {      // (incl. SM_DYNAMIC: P2 on a per-step set is not built)
       out[0] = C<S>(NAN); out[1] = C<S>(NAN);
       return false;
     }
@@ -545,19 +561,24 @@ template <class TASK, class T> SG_HD bool action_in_set(const T* a, const SafeCo
 }
 
 template <class TASK, class T>
-SG_HD bool next_state_in_set(const T* a, const T* c_f, const T (*B)[MAXM], const SafeConsts<T>& k) {
+SG_HD bool next_state_in_set(const T* a, const T* c_f, const T (*B)[MAXM], const SafeConsts<T>& k, const ActRows<T>* dyn = nullptr) {
   constexpr int NS = TASK::NS, NA = TASK::NA;
   const T tol = verdict_tol<T>();
   if (k.state_model == SM_UNREDUCED || k.state_model == SM_LIFTED) return false;      // verdict not available for these models
-  if (k.state_model == SM_INVERTIBLE) {
+  const bool dynamic_state = k.state_model == SM_DYNAMIC && dyn && dyn->sdyn;
+  if (k.state_model == SM_DYNAMIC && (!dynamic_state || dyn->sdyn->degenerate)) return false;
+  if (k.state_model == SM_INVERTIBLE || dynamic_state) {
+    const T* Ginv = dynamic_state ? dyn->sdyn->Ginv : k.Ginv;
+    const T* cs_hat = dynamic_state ? dyn->sdyn->cs_hat : k.cs_hat;
+    const T* rb = dynamic_state ? dyn->sdyn->rb : k.rb;
     for (int i = 0; i < NS; ++i) {
-      T e = k.cs_hat[i];
+      T e = cs_hat[i];
       for (int j = 0; j < NS; ++j) {
         T nx = c_f[j];
         for (int q = 0; q < NA; ++q) nx += B[j][q] * a[q];
-        e -= k.Ginv[i * NS + j] * nx;
+        e -= Ginv[i * NS + j] * nx;
       }
-      if (sg_abs(e) > k.rb[i] + tol * (T(1) + sg_abs(k.rb[i]))) return false;
+      if (sg_abs(e) > rb[i] + tol * (T(1) + sg_abs(rb[i]))) return false;
     }
     return true;
   }

@@ -6,6 +6,7 @@
 #include "sgbpo_safeguard.cuh"
 #include "sgbpo_safeguard2.cuh"
 #include "sgbpo_lifted.cuh"
+#include "sgbpo_navquad.cuh"
 
 namespace sgbpo {
 
@@ -43,6 +44,33 @@ SG_HD void collision_operator(const S* s_prev, S* s_next, const T* aux, const Sa
   s_next[1] = iy + ry * rem;
 }
 
+// NavigateQuadrotor: elastic collision of the free step with the (last) obstacle it entered (navigate_quadrotor.py:275-328).
+// Position and velocity are reflected; roll and roll rate of the collided environments keep their PRE-step values, as shipped.
+template <class S, class T>
+SG_HD void collision_operator_quad(const S* s_prev, S* s_next, const T* aux, int hit) {
+  const S cx = S(aux[2 + 3 * hit]), cy = S(aux[3 + 3 * hit]), rad = S(aux[4 + 3 * hit]);
+  const S tx = s_prev[0] - cx, ty = s_prev[1] - cy;
+  const S fvx = s_next[3], fvy = s_next[4];
+  const S vx = fvx * C<S>(0.05), vy = fvy * C<S>(0.05);
+  const S qa = vx * vx + vy * vy;
+  const S qb = C<S>(2.0) * (tx * vx + ty * vy);
+  const S qc = tx * tx + ty * ty - rad * rad;
+  const S t = (-qb - sg_sqrt(qb * qb - C<S>(4.0) * qa * qc)) / (C<S>(2.0) * qa);
+  const S ix = s_prev[0] + t * vx, iy = s_prev[1] + t * vy;
+  S nx = ix - cx, ny = iy - cy;
+  const S nn = sg_sqrt(nx * nx + ny * ny);
+  nx = nx / nn; ny = ny / nn;
+  const S vdn = fvx * nx + fvy * ny;
+  const S rx = fvx - C<S>(2.0) * vdn * nx, ry = fvy - C<S>(2.0) * vdn * ny;
+  const S rem = (C<S>(1.0) - t) * C<S>(0.05);
+  s_next[0] = ix + rx * rem;
+  s_next[1] = iy + ry * rem;
+  s_next[2] = s_prev[2];
+  s_next[3] = rx;
+  s_next[4] = ry;
+  s_next[5] = s_prev[5];
+}
+
 template <class TASK, class S, class T>
 SG_HD void safeguarded_step(const S* s, const S* a, const T* w, const T* aux, const T* dirs,
                             const StepShared<T>* sh, const SafeConsts<T>& k, bool reset_now,
@@ -70,6 +98,13 @@ SG_HD void safeguarded_step(const S* s, const S* a, const T* w, const T* aux, co
     bool feasible;
     ActRows<T> dyn;
     dyn.count = 0;
+    StateDyn<T> sdyn;                             // (only NavigateQuadrotor touches it)
+    if constexpr (TASK::NAUX == NAVQUAD_NAUX) {
+      if (k.state_constrained && k.state_model == SM_DYNAMIC) {      // this step's safe state set (P6-P8, no_grad in the reference)
+        navquad_safe_state_set<T>(cfp, Bp, aux, k, sdyn);
+        dyn.sdyn = &sdyn;
+      }
+    }
     if constexpr (NA == 1) {
       feasible = safeguard_m1<TASK>(a[0], c_f, B, k, g[0]);
     } else if (TASK::LIFTED_OK && k.state_constrained && k.state_model == SM_LIFTED) {
@@ -99,7 +134,13 @@ SG_HD void safeguarded_step(const S* s, const S* a, const T* w, const T* aux, co
         set_ok = seeker_action_set<T>(sp, aux, k, U, len);
         seeker_rows<T>(U, len, dyn);
       }
-      feasible = safeguard_m2<TASK>(a, c_f, B, dirs, k, &dyn, g) && set_ok;
+      if (dyn.sdyn && dyn.sdyn->degenerate) {      // no usable safe state set at this step: nothing to project onto
+        feasible = false;
+#pragma unroll
+        for (int q = 0; q < NA; ++q) g[q] = C<S>(NAN);
+      } else {
+        feasible = safeguard_m2<TASK>(a, c_f, B, dirs, k, &dyn, g) && set_ok;
+      }
     }
     if (projectable) flags |= FL_PROJECTABLE;
     if (use_guard) {
@@ -129,13 +170,20 @@ SG_HD void safeguarded_step(const S* s, const S* a, const T* w, const T* aux, co
 #pragma unroll
     for (int q = 0; q < NA; ++q) ap[q] = primal(a_exec[q]);
     if (k.action_constrained && action_in_set<TASK>(ap, k, &dyn)) flags |= FL_ACTION_IN_SET;
-    if (k.state_constrained && next_state_in_set<TASK>(ap, cfp, Bp, k)) flags |= FL_NEXT_IN_SET;
+    if (k.state_constrained && next_state_in_set<TASK>(ap, cfp, Bp, k, &dyn)) flags |= FL_NEXT_IN_SET;
   }
   S wS[NS];
 #pragma unroll
   for (int i = 0; i < NS; ++i) wS[i] = S(w[i]);
   TASK::Sim::f(s, a_exec, wS, s_next);
-  if constexpr (TASK::NAUX > 2) {
+  bool quad_hit = false;
+  if constexpr (TASK::NAUX == NAVQUAD_NAUX) {
+    if (k.n_obstacles > 0) {
+      T fp[2] = {primal(s_next[0]), primal(s_next[1])};
+      const int hit = navquad_last_hit<T>(fp, aux, k);
+      if (hit >= 0) { quad_hit = true; flags |= FL_COLLIDED; collision_operator_quad<S, T>(s, s_next, aux, hit); }
+    }
+  } else if constexpr (TASK::NAUX > 2) {
     if (k.n_obstacles > 0) collision_operator<TASK>(s, s_next, aux, k, flags);
   }
   if (TASK::CLAMP && !k.disable_clamp) {
@@ -152,6 +200,11 @@ SG_HD void safeguarded_step(const S* s, const S* a, const T* w, const T* aux, co
   }
   TASK::observe(s_next, aux, sh, obs);
   reward = TASK::reward(s_next, a_exec, aux, sh);
+  if constexpr (TASK::NAUX == NAVQUAD_NAUX) {
+    if (quad_hit) reward = reward - C<S>(10.0);                   // COLLISION_PENALTY * collided.any() (navigate_quadrotor.py:236)
+    const T dx = aux[0] - primal(s_next[0]), dz = aux[1] - primal(s_next[1]);
+    if (aux[NAVQUAD_NAUX - 1] == T(0) && sg_sqrt(dx * dx + dz * dz) < T(0.1)) flags |= FL_REACHED;
+  }
 }
 
 }  // namespace sgbpo

@@ -13,13 +13,14 @@ from torch import Tensor
 
 from .. import _lib, ops, rng, sets
 from ..consts import build_consts
+from .interfaces.obstacle_course import ObstacleCourse
 from .interfaces.safe_action_env import SafeActionEnv
 from .simulators.seeker import SeekerEnv
 
 MAXK = 3      # obstacles the kernels carry per environment (csrc/sgbpo_env.cuh: SEEKER_MAXK)
 
 
-class NavigateSeekerEnv(SeekerEnv, SafeActionEnv):
+class NavigateSeekerEnv(ObstacleCourse, SeekerEnv, SafeActionEnv):
     ENV_NAME = "NavigateSeeker"
     EVAL_ENVS: int = 6
     DISTANCE_PENALTY: float = 2.0
@@ -30,10 +31,7 @@ class NavigateSeekerEnv(SeekerEnv, SafeActionEnv):
         if num_obstacles > MAXK:
             raise NotImplementedError(f"the kernels carry at most {MAXK} obstacles per environment")
         SafeActionEnv.__init__(self, num_action_gens=2)
-        mid = min_radius + (max_radius - min_radius) / 2
-        self.additional_observation_set = sets.AxisAlignedBox(
-            torch.tensor([0.0, 0.0, mid] * num_obstacles).unsqueeze(0).repeat(num_envs, 1),
-            torch.diag_embed(torch.tensor([8.0, 8.0, (max_radius - min_radius) / 2] * num_obstacles).repeat(num_envs, 1)))
+        self._init_obstacles(num_envs, num_obstacles, min_radius, max_radius)
         SeekerEnv.__init__(self, num_envs, num_steps)
         self.num_obstacles, self.min_radius, self.max_radius = num_obstacles, min_radius, max_radius
         self.draw_safe_action_set = draw_safe_action_set
@@ -57,10 +55,6 @@ class NavigateSeekerEnv(SeekerEnv, SafeActionEnv):
             cols.append(torch.zeros(self.num_envs, pad, dtype=self.goal.dtype))
         return torch.cat([c.to(self.state.dtype) for c in cols], dim=1).detach()
 
-    def _obstacle_columns(self) -> Tensor:
-        return torch.cat([torch.cat([b.center, b.radius.unsqueeze(1)], dim=1) for b in self.obstacles], dim=1) \
-            if self.obstacles else torch.zeros(self.num_envs, 0)
-
     def _wrap_obs(self, obs4: Tensor) -> Tensor:
         return torch.cat([obs4, self._obstacle_columns().to(obs4.dtype)], dim=1)
 
@@ -71,43 +65,6 @@ class NavigateSeekerEnv(SeekerEnv, SafeActionEnv):
         self.sample_obstacles()
         self.collided = torch.zeros_like(self.collided)
         self.reached = torch.zeros_like(self.reached)
-
-    def sample_goal(self):
-        """navigate_seeker.py:107-115."""
-        too_close = torch.ones(self.num_envs, dtype=torch.bool)
-        while bool(too_close.any()):
-            self.goal[too_close] = rng.rand(int(too_close.sum()), 2).to(self.goal.dtype) * 16.0 - 8.0
-            too_close = torch.linalg.vector_norm(self.goal - self.state[:, :2], dim=1) < self.max_radius * 2
-
-    def sample_obstacles(self):
-        """navigate_seeker.py:117-176."""
-        for i in range(self.num_obstacles):
-            obstructing = torch.ones(self.num_envs, dtype=torch.bool)
-            while bool(obstructing.any()):
-                self._sample_one_obstacle(i, obstructing)
-                obstructing = self._check_obstruction(i)
-
-    def _sample_one_obstacle(self, i: int, obstructing: Tensor):
-        sample = self.additional_observation_set.sample()
-        pos = self.state[:, :2].detach()
-        if i == 0:
-            diff = self.goal - pos
-            ray = diff / torch.linalg.vector_norm(diff, dim=1, keepdim=True)
-            normal_ray = torch.stack([ray[:, 1], -ray[:, 0]], dim=1)
-            center = (pos + self.goal) / 2 + rng.rand(self.num_envs, 1) * normal_ray * self.min_radius / 2
-            radius = rng.rand(self.num_envs) * (self.max_radius - self.min_radius) + self.min_radius
-        else:
-            center, radius = sample[:, i * 3:i * 3 + 2], sample[:, i * 3 + 2]
-        ball = self.obstacles[i]
-        ball.center = torch.where(obstructing.unsqueeze(1), center.to(ball.center.dtype), ball.center)
-        ball.radius = torch.where(obstructing, radius.to(ball.radius.dtype), ball.radius)
-
-    def _check_obstruction(self, i: int) -> Tensor:
-        ball = self.obstacles[i]
-        obstructing = ball.contains(self.state[:, :2].detach()) | ball.contains(self.goal)
-        for other in self.obstacles[:i]:
-            obstructing |= ball.intersects(other)
-        return obstructing
 
     def reset(self, seed=None):
         obs4, info = super().reset(seed)

@@ -52,13 +52,15 @@ class Safeguard:
             if self.action_constrained and not dynamic:
                 z = env.safe_action_set()
                 sa = getattr(env, "_ctrl64", None) or (f64(z.center[0]), f64(z.generator[0]))
-            if self.state_constrained:
+            dynamic_state = bool(getattr(env, "DYNAMIC_STATE_SET", False))      # NavigateQuadrotor: rebuilt per step in the kernels
+            if self.state_constrained and not dynamic_state:
                 z = env.safe_state_set()
                 ss = getattr(env, "_rci64", None) or (f64(z.center[0]), f64(z.generator[0]))
             G_w = f64(self.noise_mat[0]) @ f64(env.noise_set.generator[0])
             self._consts = build_consts(env.ENV_NAME, self.SG_KIND, gate_mode=_lib.GATE[self.gate], safe_action=sa,
                                         safe_state=ss, G_w=G_w, B0=f64(self.action_mat[0]), dynamic_action_set=dynamic,
-                                        n_obstacles=int(getattr(env, "num_obstacles", 0)), **self._rm_flags())
+                                        n_obstacles=int(getattr(env, "num_obstacles", 0)), dynamic_state_set=dynamic_state,
+                                        **self._rm_flags())
             # strict (the reference's behaviour): an infeasible program yields NaN and raises; non-strict: the raw action is
             # executed there, flagged FL_INFEASIBLE, so that long rollouts and the weights stay finite
             self._consts.infeasible_raw = 0 if self.strict else 1

@@ -15,6 +15,7 @@ template <class T> static SafeConsts<T> conv(const sgbpo_consts& c) {
   k.sg_kind = c.sg_kind; k.gate_mode = c.gate_mode;
   k.rm_linear = c.rm_linear; k.rm_zonotopic = c.rm_zonotopic; k.rm_passthrough = c.rm_passthrough;
   k.action_constrained = c.action_constrained; k.state_constrained = c.state_constrained; k.state_model = c.state_model; k.disable_clamp = c.disable_clamp; k.n_obstacles = c.n_obstacles; k.act_set_mode = c.act_set_mode;
+  k.infeasible_raw = c.infeasible_raw;
   for (int i = 0; i < MAXN; ++i) {
     k.box_min[i] = T(c.box_min[i]); k.box_max[i] = T(c.box_max[i]); k.noise_center[i] = T(c.noise_center[i]);
     k.cs_hat[i] = T(c.cs_hat[i]); k.rb[i] = T(c.rb[i]); k.c_s[i] = T(c.c_s[i]);
@@ -96,6 +97,7 @@ static void lin(int64_t N, const sgbpo_consts* c, const T* s, T* cc, T* A, T* B,
     case 0: FN<0, T>(__VA_ARGS__); break; case 1: FN<1, T>(__VA_ARGS__); break;  \
     case 2: FN<2, T>(__VA_ARGS__); break; case 3: FN<3, T>(__VA_ARGS__); break;  \
     case 4: FN<4, T>(__VA_ARGS__); break; case 5: FN<5, T>(__VA_ARGS__); break;  \
+    case 6: FN<6, T>(__VA_ARGS__); break;                                        \
     default: return -1; }
 
 template <class T>
@@ -112,7 +114,27 @@ static int lin_t(int env_id, int64_t N, const sgbpo_consts* c, const void* s, vo
   return 0;
 }
 
+template <class T>
+static void navquad_set_t(int64_t N, const sgbpo_consts* c, const T* s, const T* aux, T* center, T* gen, int32_t* status) {
+  using TASK = Task<ENV_NAVIGATE_QUADROTOR>;
+  const SafeConsts<T> k = conv<T>(*c);
+  for (int64_t i = 0; i < N; ++i) {
+    T cf[6], B[6][MAXM];
+    linearise_cB<TASK, T, T>(s + i * 6, k.noise_center, cf, B);
+    StateDyn<T> sd;
+    navquad_safe_state_set<T>(cf, B, aux + i * NAVQUAD_NAUX, k, sd);
+    for (int q = 0; q < 6; ++q) center[i * 6 + q] = sd.center[q];
+    for (int q = 0; q < 36; ++q) gen[i * 36 + q] = sd.gen[q];
+    status[i] = sd.degenerate ? 1 : 0;
+  }
+}
+
 extern "C" {
+int hm_navquad_set(int dtype, int64_t N, const sgbpo_consts* c, const void* s, const void* aux, void* center, void* gen, int32_t* status) {
+  if (dtype) navquad_set_t<double>(N, c, (const double*)s, (const double*)aux, (double*)center, (double*)gen, status);
+  else navquad_set_t<float>(N, c, (const float*)s, (const float*)aux, (float*)center, (float*)gen, status);
+  return 0;
+}
 int hm_step(int env_id, int dtype, int64_t N, const sgbpo_consts* c, const sgbpo_step_shared* sh, const void* s,
             const void* a, const void* w, const void* aux, const void* dirs, const void* rs, void* s_next, void* a_exec,
             void* obs, void* reward, int32_t* flags, const void* g_s_next, const void* g_a_exec, const void* g_obs,

@@ -8,7 +8,7 @@ import numpy as np
 from safegbpo_b200._lib import Consts, StepShared
 
 HERE = Path(__file__).resolve().parent / "hostmath"
-DIMS = {0: (2, 1, 3, 0), 1: (4, 1, 5, 0), 2: (4, 1, 5, 0), 3: (6, 2, 8, 2), 4: (3, 2, 23, 0), 5: (2, 2, 4, 11)}
+DIMS = {0: (2, 1, 3, 0), 1: (4, 1, 5, 0), 2: (4, 1, 5, 0), 3: (6, 2, 8, 2), 4: (3, 2, 23, 0), 5: (2, 2, 4, 11), 6: (6, 2, 8, 13)}
 _lib = None
 
 
@@ -60,3 +60,15 @@ def linearise(env_id, consts: Consts, s, dtype=np.float64):
                             _p(s), _p(c), _p(A), _p(B), _p(E))
     assert rc == 0
     return c, A, B, E
+
+
+def navquad_safe_state_set(consts: Consts, s, aux, dtype=np.float64):
+    """NavigateQuadrotor's per-step safe state set (P6-P8) on the host: (center (N,6), generator (N,6,6), status (N))."""
+    s, aux = np.ascontiguousarray(s, dtype=dtype), np.ascontiguousarray(aux, dtype=dtype)
+    N = s.shape[0]
+    center, gen, status = np.zeros((N, 6), dtype), np.zeros((N, 6, 6), dtype), np.zeros(N, np.int32)
+    lib().hm_navquad_set.restype = C.c_int
+    rc = lib().hm_navquad_set(C.c_int(1 if dtype == np.float64 else 0), C.c_int64(N), C.byref(consts), _p(s), _p(aux), _p(center),
+                              _p(gen), _p(status))
+    assert rc == 0
+    return center, gen, status

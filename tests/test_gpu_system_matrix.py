@@ -1,7 +1,7 @@
 """Configuration matrix of the reference's tests/system_tests.py (SHAC rows): every environment x safeguard combination
 the reference runs end to end must construct through the drop-in classes with the reference's constructor arguments
 (conf/envs.py, conf/safeguard.py) and complete one full SHAC learning episode (collect, policy update, critic fit,
-Polyak) with finite losses.  NavigateQuadrotor is the one environment not built yet."""
+Polyak) with finite losses."""
 import math
 
 import pytest
@@ -16,6 +16,7 @@ ENVS = {
     "BalanceQuadrotor": dict(num_envs=16, num_steps=240),
     "ManageHousehold": dict(num_envs=8, num_steps=720),
     "NavigateSeeker": dict(num_envs=64, num_steps=400, num_obstacles=1, min_radius=2.0, max_radius=4.0),
+    "NavigateQuadrotor": dict(num_envs=16, num_steps=240, num_obstacles=1, min_radius=2.0, max_radius=3.0),
 }
 SAFEGUARDS = {
     "none": None,
@@ -29,7 +30,7 @@ SAFEGUARDS = {
     "rm_orthogonal": ("RayMask", dict(regularisation_coefficient=0.1, linear_projection=True, zonotopic_approximation=False, passthrough=False)),
 }
 # system_tests.py: SHAC x {none, BP} on Pendulum / Quadrotor, SHAC + BP on every environment, SHAC + ray mask variants on Quadrotor
-MATRIX = [("BalancePendulum", "none"), ("BalanceQuadrotor", "none")] + [(e, "bp") for e in ENVS] + \
+MATRIX = [("BalancePendulum", "none"), ("BalanceQuadrotor", "none"), ("NavigateQuadrotor", "none")] + [(e, "bp") for e in ENVS] + \
          [("BalanceQuadrotor", s) for s in ("rm", "rm_passthrough", "rm_orthogonal")] + \
          [("BalancePendulum", "rm"), ("ManageHousehold", "rm"), ("SwingUpCartPole", "rm_orthogonal")] + \
          [("BalanceQuadrotor", "bp_always"), ("BalanceQuadrotor", "rm_orthogonal_always")]
@@ -41,11 +42,13 @@ def _classes():
     from safegbpo_b200.envs.balance_quadrotor import BalanceQuadrotorEnv
     from safegbpo_b200.envs.manage_household import ManageHouseholdEnv
     from safegbpo_b200.envs.navigate_seeker import NavigateSeekerEnv
+    from safegbpo_b200.envs.navigate_quadrotor import NavigateQuadrotorEnv
     from safegbpo_b200.envs.swingup_cartpole import SwingUpCartPoleEnv
     from safegbpo_b200.safeguards.boundary_projection import BoundaryProjectionSafeguard
     from safegbpo_b200.safeguards.ray_mask import RayMaskSafeguard
     return ({"BalancePendulum": BalancePendulumEnv, "BalanceCartPole": BalanceCartPoleEnv, "SwingUpCartPole": SwingUpCartPoleEnv,
-             "BalanceQuadrotor": BalanceQuadrotorEnv, "ManageHousehold": ManageHouseholdEnv, "NavigateSeeker": NavigateSeekerEnv},
+             "BalanceQuadrotor": BalanceQuadrotorEnv, "ManageHousehold": ManageHouseholdEnv, "NavigateSeeker": NavigateSeekerEnv,
+             "NavigateQuadrotor": NavigateQuadrotorEnv},
             {"BoundaryProjection": BoundaryProjectionSafeguard, "RayMask": RayMaskSafeguard})
 
 
@@ -130,7 +133,15 @@ def _assert_flagged_environments_are_infeasible(env, base, algo, seen, sg):
         return                                                  # (action-set-only programs are always feasible: nothing to check)
     k = env.consts()
     c_f, _, B, _ = ops.linearise(state, base.env_id, k)
-    z = base.safe_state_set()
+    dynamic = bool(getattr(base, "DYNAMIC_STATE_SET", False))      # NavigateQuadrotor: one safe state set per environment and step
+    if dynamic:
+        keep = base.state
+        base.state = state
+        z = base.safe_state_set()
+        status = base.last_safe_state_status
+        base.state = keep
+    else:
+        z = base.safe_state_set()
     G = z.generator[0].double().cpu().numpy()
     c_s = z.center[0].double().cpu().numpy()
     W = (env.noise_mat[0].double() @ base.noise_set.generator[0].double()).cpu().numpy()
@@ -138,5 +149,9 @@ def _assert_flagged_environments_are_infeasible(env, base, algo, seen, sg):
     if W.shape[1] == 0:
         W = np.zeros((G.shape[0], 1))
     for i in bad_t.nonzero().flatten()[:6].tolist():
+        if dynamic:
+            if int(status[i]) != 0:
+                continue                  # degenerate set (the reference's rank-deficient fallback blocks): no safe action by construction
+            G, c_s = z.generator[i].double().cpu().numpy(), z.center[i].double().cpu().numpy()
         budget = p1_feasibility_budget(G, W, c_s, c_f[i].double().cpu().numpy(), B[i].double().cpu().numpy())
         assert budget > 1.0 - 1e-6, f"environment {i}: flagged infeasible but the independent LP finds budget {budget:.6f} <= 1"
