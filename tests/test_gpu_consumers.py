@@ -75,9 +75,13 @@ def test_evaluate_policy_matches_manual_loop(cuda_default):
 def test_log_prob_matches_the_change_of_variables():
     """Policy.log_prob (reference policy.py:112-141): inside (-1, 1) the tanh change of variables, at +-1 the Gaussian tail."""
     from safegbpo_b200.learning_algorithms.components.policy import Policy
+    prev = torch.get_default_dtype()
     torch.set_default_dtype(torch.float64)
     torch.manual_seed(0)
-    pol = Policy(3, 2, net_arch=[16, 16])
+    try:
+        pol = Policy(3, 2, net_arch=[16, 16])
+    finally:
+        torch.set_default_dtype(prev)
     x = torch.randn(64, 3)
     with torch.no_grad():
         mean, std = pol.model(x), torch.exp(pol.log_std)

@@ -128,6 +128,12 @@ def test_fused_equals_eager(cuda_default, env_name, sg, opts, width, num_steps, 
     env_f, wrap_f, algo_f = build(env_name, sg, opts, width, num_steps, N, H, "on", dev)
     algo_f.policy.load_state_dict(algo_e.policy.state_dict())
     algo_f.target_value_function.load_state_dict(algo_e.target_value_function.state_dict())
+    for wrap, env in ((wrap_e, env_e), (wrap_f, env_f)):
+        if wrap is not env:
+            # keep the reference's failure value (NaN) for infeasible programs: both paths must then agree on WHICH environments
+            # fail; the non-strict default (raw action executed, rollout continues) would let one borderline float32 verdict
+            # send the two trajectories apart
+            wrap.consts().infeasible_raw = 0
     # start inside the feasible box (RCI resets put cartpole far outside; keep programs feasible for the comparison)
     half = env_e.state_set.generator[0].diagonal()
     spread = 0.1 if env_name == "BalancePendulum" else 0.6      # the pendulum's RCI set is a small part of the box

@@ -14,9 +14,9 @@ def test_operand_views(mode):
     from safegbpo_b200 import _lib
     dev = torch.device("cuda:0")
     g = torch.Generator(device="cpu").manual_seed(5 + mode)
-    x = torch.randn(128, 128, generator=g).to(dev)
-    z = (torch.randn(128, 128, generator=g) * 0.5).to(dev)
-    d = torch.zeros(128, 128, device=dev)
+    x = torch.randn(128, 128, generator=g, dtype=torch.float32, device="cpu").to(dev)      # (explicit: the kernel reads float32)
+    z = (torch.randn(128, 128, generator=g, dtype=torch.float32, device="cpu") * 0.5).to(dev)
+    d = torch.zeros(128, 128, device=dev, dtype=torch.float32)
     _lib.check(_lib.lib().sgbpo_tc_selftest(mode, C.c_void_p(x.data_ptr()), C.c_void_p(z.data_ptr()), C.c_void_p(d.data_ptr()),
                                             _lib.stream_ptr()), "sgbpo_tc_selftest")
     torch.cuda.synchronize()
