@@ -77,19 +77,19 @@ def test_log_prob_matches_the_change_of_variables():
     from safegbpo_b200.learning_algorithms.components.policy import Policy
     prev = torch.get_default_dtype()
     torch.set_default_dtype(torch.float64)
-    torch.manual_seed(0)
     try:
-        pol = Policy(3, 2, net_arch=[16, 16])
+        with torch.device("cpu"), torch.no_grad():
+            torch.manual_seed(0)
+            pol = Policy(3, 2, net_arch=[16, 16])
+            x = torch.randn(64, 3)
+            mean, std = pol.model(x), torch.exp(pol.log_std)
+            u = mean + std * torch.randn(64, 2)
+            a = torch.tanh(u)
+            ref = (torch.distributions.Normal(mean, std).log_prob(u) - torch.log(1 - a ** 2)).sum(1)
+            np.testing.assert_allclose(pol.log_prob(a, x).numpy(), ref.numpy(), rtol=1e-8, atol=1e-8)
+            sat = torch.ones(64, 2)
+            tiny = torch.finfo(torch.float64).eps
+            tail = torch.log(1 - torch.distributions.Normal(mean, std).cdf(torch.atanh(sat.clamp(max=1 - tiny))) + tiny).sum(1)
+            np.testing.assert_allclose(pol.log_prob(sat, x).numpy(), tail.numpy(), rtol=1e-8, atol=1e-8)
     finally:
         torch.set_default_dtype(prev)
-    x = torch.randn(64, 3)
-    with torch.no_grad():
-        mean, std = pol.model(x), torch.exp(pol.log_std)
-        u = mean + std * torch.randn(64, 2)
-        a = torch.tanh(u)
-        ref = (torch.distributions.Normal(mean, std).log_prob(u) - torch.log(1 - a ** 2)).sum(1)
-        np.testing.assert_allclose(pol.log_prob(a, x).numpy(), ref.numpy(), rtol=1e-8, atol=1e-8)
-        sat = torch.ones(64, 2)
-        tail = torch.log(1 - torch.distributions.Normal(mean, std).cdf(torch.atanh(sat.clamp(max=1 - torch.finfo(torch.float64).eps)))
-                         + torch.finfo(torch.float64).eps).sum(1)
-        np.testing.assert_allclose(pol.log_prob(sat, x).numpy(), tail.numpy(), rtol=1e-8, atol=1e-8)
