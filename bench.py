@@ -435,7 +435,7 @@ def correctness_gates(args, algo, env, base, episode, dtype, dev):
             infeas = (fl & _lib.FL_INFEASIBLE) != 0
             ok = guard & ~infeas
             viol = torch.zeros_like(ok)
-            if k is not None and k.state_constrained:
+            if k is not None and k.state_constrained and k.state_model not in (2, 3):      # (no device verdict for the lifted / unreduced models)
                 viol |= ok & ((fl & _lib.FL_NEXT_IN_SET) == 0)
             if k is not None and k.action_constrained:
                 viol |= ok & ((fl & _lib.FL_ACTION_IN_SET) == 0)
@@ -540,14 +540,16 @@ def fused_roofline(args, engine, episode, dtype):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     # algorithmic bytes: B_alg per env-step covers fwd+bwd of the rollout buffers; split per kernel
     b_alg = ALG_BYTES[args.env] * scale
-    per_kernel_bytes = {"rollout_fwd": 0.45 * b_alg * N * H, "rollout_bwd": 0.55 * b_alg * N * H,
-                        "mlp_rows": (engine.base.obs_dim + 1) * 4 * scale * N * H}
+    n_s, n_a = engine.base.state_dim, engine.base.action_dim
+    jac_bytes = (2 * n_s + n_a) * 4 * scale * N * H          # the step-Jacobian kernel re-reads (s_t, a_t, w_t): part of the reverse share
+    per_kernel_bytes = {"rollout_fwd": 0.45 * b_alg * N * H, "rollout_bwd": 0.55 * b_alg * N * H - (jac_bytes if ms.get("rollout_jac") else 0),
+                        "rollout_jac": jac_bytes, "mlp_rows": (engine.base.obs_dim + 1) * 4 * scale * N * H}
     achieved = per_kernel_bytes[dominant] / (ms[dominant] * 1e-3) / 1e9
     total_alg = b_alg * N * H
     all_ms = sum(v for v in ms.values() if v)
     traffic = None          # DRAM bytes per launch of the dominant kernel from the committed ncu capture of THIS workload
     try:
-        t = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())
+        t = json.loads((ROOT / "profiles" / "r2_traffic.json").read_text())
         w = t["workload"]
         if (w["env"], w["safeguard"], w["num_envs_per_gpu"], w["horizon"], w["dtype"]) == \
                 (args.env, args.safeguard, args.num_envs, args.horizon, args.dtype):
@@ -557,12 +559,13 @@ def fused_roofline(args, engine, episode, dtype):
     return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "kernel": dominant, "kernel_ms": ms, "alg_bytes_per_launch": per_kernel_bytes[dominant],
             "all_kernels_achieved_gbs": total_alg / (all_ms * 1e-3) / 1e9,
-            "note": "the per-environment chain of this workload (4096 envs x 64 sequential steps, policy MLP inside) is issue/"
-                    "latency-bound, not HBM-bound: ncu shows ~0.5 issue slots/cycle/SMSP and <3% DRAM utilisation "
-                    "(profiles/r1_ncu_full_summary.md); traffic exceeds the algorithmic bytes on purpose: the forward "
-                    "kernel stashes the policy activations (1.5 KB/env-step) so the reverse pass does not recompute two "
-                    "of its three GEMMs, and the hidden-layer weight-gradient operands are streamed for one GEMM; the "
-                    "HBM-bound regime of the same per-step kernels is reported under roofline_stress",
+            "engines": {"forward": "tcgen05" if engine.engine_fwd else "fma-tiles", "reverse": "parallel-tcgen05" if engine.engine_bwd else "sequential-fma"},
+            "note": "rollout_bwd = the whole reverse pass after the step Jacobians (row-batched tcgen05 policy backward in Jacobian "
+                    "mode, per-environment scan, row-batched tcgen05 policy backward in gradient mode).  This workload (4096 envs x "
+                    "64 SEQUENTIAL steps with a 34 kFLOP policy inside every step) is latency/issue-bound in its forward kernel, not "
+                    "HBM-bound: see profiles/r2_ncu_summary.md; traffic exceeds the algorithmic bytes on purpose (the forward kernel "
+                    "stashes the two ELU outputs, 1 KB per env-step, so that the reverse pass is batched over all H x N rows); the "
+                    "HBM-bound regime of the per-step kernels is reported under roofline_stress",
             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
             "launches_per_step": engine.launches_per_episode}
 

@@ -147,7 +147,11 @@ template <> struct Task<ENV_BALANCE_QUADROTOR> {
     const S thrust = a[0] * C<S>(6.0 / 7.0) + C<S>(9.81);
     const S roll_cmd = a[1] * C<S>(3.14159265358979323846 / 12.0);
     const S dx = s[0] - S(aux[0]), dz = s[1] - S(aux[1]);
-    const S dist = sg_sqrt(dx * dx + dz * dz);
+    const S q2 = dx * dx + dz * dz;
+    // At distance exactly 0 the state IS the goal, which only happens on the reset step (goal = reset position,
+    // quadrotor.py:119): the reference's post-reset state carries no autograd graph there, so torch.sqrt's infinite slope is
+    // never evaluated.  Forward-mode duals would form 0 * inf = NaN; the distance is a constant 0 instead.
+    const S dist = primal(q2) == T(0) ? C<S>(0.0) : sg_sqrt(q2);
     return -(C<S>(2.5) * dist) - C<S>(0.1) * (s[2] * s[2]) - C<S>(0.1) * (s[3] * s[3]) - C<S>(0.1) * (s[4] * s[4])
            - C<S>(0.1) * (s[5] * s[5]) - C<S>(0.002) * (thrust * thrust) - C<S>(0.001) * (roll_cmd * roll_cmd);
   }
