@@ -246,6 +246,22 @@ int sgbpo_episode_stats(int dtype, int64_t n_rewards, const void* rewards, int64
 int sgbpo_shac_loss(int dtype, int rows, int64_t N, const void* disc, const int32_t* term_int, const void* values,
                     const void* rewards, const void* norm, void* loss, void* stream);
 
+/* ---- random inputs of one episode in one launch (fused_rollout.py, rng_order = "batched"): eps [H][N][m] ~ N(0,1)
+ * (policy.py:84-85), noise [H][N][n] = lo + span * u (box.py:73-74), dirs [H][N][m][2m] unit columns (ray_mask.py:184-185) or
+ * NULL, reset_states [n_resets][N][n] = reset_center + reset_gen (2u - 1) (simulator.py:73 + the task's reset distribution).
+ * Counter-based Philox4x32-10 keyed by (seed, *episode, element): the same numbers whatever the launch shape. */
+#define SGBPO_MAX_RESET_GENS 24
+typedef struct sgbpo_episode_inputs_args {
+  int64_t N;
+  int32_t H, n, m, n_resets, n_reset_gens, want_dirs;
+  uint64_t seed;
+  const void* episode;       /* device int64: episode counter */
+  void* eps; void* noise; void* dirs; void* reset_states;
+  double noise_lo[SGBPO_MAXN], noise_span[SGBPO_MAXN];
+  double reset_center[SGBPO_MAXN], reset_gen[SGBPO_MAXN][SGBPO_MAX_RESET_GENS];
+} sgbpo_episode_inputs_args;
+int sgbpo_episode_inputs(int dtype, const sgbpo_episode_inputs_args* args, void* stream);
+
 /* ---- tensor-core operand-view self-test (diagnostic; tests/test_gpu_tc_mma.py): X, Z, D are 128 x 128 float32 device
  * matrices; mode 0: D = X Z^T, 1: D = X Z, 2: D = X^T Z, each through the fp16 hi/lo split tcgen05 path the rollout
  * kernels use (K-major / MN-major shared-memory views of one stored operand). */

@@ -77,6 +77,15 @@ class RolloutGrads(C.Structure):
                 ("g_log_std", C.c_void_p), ("g_w_hid", C.c_void_p)]
 
 
+class EpisodeInputs(C.Structure):
+    """Mirror of ``struct sgbpo_episode_inputs_args``."""
+    _fields_ = [("N", C.c_int64), ("H", C.c_int32), ("n", C.c_int32), ("m", C.c_int32), ("n_resets", C.c_int32),
+                ("n_reset_gens", C.c_int32), ("want_dirs", C.c_int32), ("seed", C.c_uint64), ("episode", C.c_void_p),
+                ("eps", C.c_void_p), ("noise", C.c_void_p), ("dirs", C.c_void_p), ("reset_states", C.c_void_p),
+                ("noise_lo", C.c_double * MAXN), ("noise_span", C.c_double * MAXN),
+                ("reset_center", C.c_double * MAXN), ("reset_gen", (C.c_double * 24) * MAXN)]
+
+
 ENV_IDS = {"BalancePendulum": 0, "BalanceCartPole": 1, "SwingUpCartPole": 2, "BalanceQuadrotor": 3,
            "ManageHousehold": 4, "NavigateSeeker": 5, "NavigateQuadrotor": 6}
 SG_NONE, SG_BOUNDARY_PROJECTION, SG_RAY_MASK = 0, 1, 2
@@ -113,6 +122,7 @@ _SIGNATURES = {
     "sgbpo_episode_stats": (C.c_int, [C.c_int, C.c_int64, _VP, C.c_int64, _VP, C.c_int, C.c_int, _VP, _VP, _VP, _VP]),
     "sgbpo_shac_loss": (C.c_int, [C.c_int, C.c_int, C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "sgbpo_tc_selftest": (C.c_int, [C.c_int, _VP, _VP, _VP, _VP]),
+    "sgbpo_episode_inputs": (C.c_int, [C.c_int, C.POINTER(EpisodeInputs), _VP]),
 }
 EXPORTED = tuple(_SIGNATURES)
 _lib = None

@@ -12,3 +12,6 @@ class BalancePendulumEnv(PendulumEnv, RCIEnv):
 
     def _after_reset(self):
         self.state = self.rci.sample()
+
+    def _reset_distribution(self):
+        return self._rci64

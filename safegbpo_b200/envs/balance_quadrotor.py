@@ -13,3 +13,6 @@ class BalanceQuadrotorEnv(QuadrotorEnv, RCIEnv):
     def _after_reset(self):
         self.state = self.rci.sample()
         self.goal = self.state[:, 0:2].detach().clone()
+
+    def _reset_distribution(self):
+        return self._rci64

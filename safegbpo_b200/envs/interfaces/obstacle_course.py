@@ -22,6 +22,9 @@ class ObstacleCourse:
             torch.tensor([0.0, 0.0, mid] * num_obstacles).unsqueeze(0).repeat(num_envs, 1),
             torch.diag_embed(torch.tensor([8.0, 8.0, (max_radius - min_radius) / 2] * num_obstacles).repeat(num_envs, 1)))
 
+    def _reset_distribution(self):
+        return None          # goal and obstacles are re-sampled by host rejection loops at every reset
+
     def _obstacle_columns(self) -> Tensor:
         return torch.cat([torch.cat([b.center, b.radius.unsqueeze(1)], dim=1) for b in self.obstacles], dim=1) \
             if self.obstacles else torch.zeros(self.num_envs, 0)

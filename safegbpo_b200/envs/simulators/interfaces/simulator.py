@@ -71,6 +71,12 @@ class Simulator:
         for k, v in snap.items():
             setattr(self, k, v)
 
+    def _reset_distribution(self):
+        """The distribution reset() draws the state from, as a zonotope (center (n,), generator (n, p)) of float64 numpy arrays:
+        state = center + generator (2u - 1), u ~ U[0, 1]^p -- or None when reset() is more than that (host rejection sampling).
+        The whole-horizon engine draws the reset states of a horizon in its one input-generation launch from it."""
+        return (self.state_set.center[0].double().cpu().numpy(), self.state_set.generator[0].double().cpu().numpy())
+
     def _adopt_reset(self, state: Tensor):
         """Side effects reset() has besides `state` for a reset that produced `state` (e.g. goal = position)."""
 

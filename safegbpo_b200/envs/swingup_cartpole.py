@@ -17,5 +17,9 @@ class SwingUpCartPoleEnv(CartPoleEnv, SafeStateEnv):
         self.state = rng.rand(self.num_envs, 4) * 0.1 - 0.05      # swingup_cartpole.py:62-63
         self.state[:, 1] = math.pi
 
+    def _reset_distribution(self):
+        import numpy as np
+        return np.array([0.0, math.pi, 0.0, 0.0]), np.diag([0.05, 0.0, 0.05, 0.05])
+
     def safe_state_set(self) -> sets.Zonotope:
         return self.state_set

@@ -175,6 +175,34 @@ class FusedRollout:
             return 0, 1
         return (1 if base.num_envs >= FusedRollout.TC_FORWARD_MIN_ENVS else 0), 1
 
+    # ---- native input generation (rng_order = "batched"): one Philox launch instead of ~20 library launches ----------------
+    def _native_inputs(self) -> bool:
+        return (self.rng_mode == "batched" and rng._source is None and os.environ.get("SGBPO_NATIVE_RNG", "1") != "0"
+                and self.base._reset_distribution() is not None)
+
+    def _inputs_args(self, H: int, eps, noise, dirs, reset_states, counter) -> "_lib.EpisodeInputs":
+        base = self.base
+        a = _lib.EpisodeInputs()
+        a.N, a.H, a.n, a.m = base.num_envs, H, base.state_dim, base.action_dim
+        a.n_resets = 0 if reset_states is None else reset_states.shape[0]
+        a.want_dirs = int(dirs is not None)
+        a.seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+        a.episode = counter.data_ptr()
+        a.eps, a.noise = eps.data_ptr(), noise.data_ptr()
+        a.dirs = None if dirs is None else dirs.data_ptr()
+        a.reset_states = None if reset_states is None else reset_states.data_ptr()
+        ctr = base.noise_set.center[0].double().cpu().numpy()
+        half = base.noise_set.generator[0].diagonal().double().cpu().numpy()
+        c, G = base._reset_distribution()
+        if G.shape[1] > 24:
+            raise _lib.SgbpoError("reset distribution with more than 24 generators")
+        a.n_reset_gens = G.shape[1]
+        for i in range(base.state_dim):
+            a.noise_lo[i], a.noise_span[i], a.reset_center[i] = float(ctr[i] - half[i]), float(2.0 * half[i]), float(c[i])
+            for j in range(G.shape[1]):
+                a.reset_gen[i][j] = float(G[i, j])
+        return a
+
     def _timed(self, name, fn):
         if not self.profile:
             return fn()
@@ -259,7 +287,18 @@ class FusedRollout:
         resets, reset_aux = [], []
         household = base._shared() is not None
         per_reset_aux = hasattr(base, "obstacles")          # NavigateSeeker: reset() re-samples goal and obstacles on the host
-        if self.rng_mode == "batched":
+        if self._native_inputs():
+            z = lambda *shape: torch.empty(*shape, dtype=dt, device=dev)
+            eps_t, noise_t = z(H, N, m), z(H, N, n)
+            dirs_t = z(H, N, m, 2 * m) if want_dirs else None
+            rs = z(self._max_resets(H), N, n)
+            counter = torch.tensor([self._episodes], dtype=torch.int64, device=dev)
+            args = self._inputs_args(H, eps_t, noise_t, dirs_t, rs, counter)
+            check(_lib.lib().sgbpo_episode_inputs(dtype_code(dt), C.byref(args), stream_ptr()), "sgbpo_episode_inputs")
+            resets = [rs[r] for r in range(len(reset_at))]
+            if resets:
+                base._adopt_reset(resets[-1])
+        elif self.rng_mode == "batched":
             eps_t = rng.randn(H, N, m).to(dt)
             u = rng.rand(H, N, n).to(dt)
             ctr = base.noise_set.center[0].to(dt)
@@ -365,7 +404,12 @@ class FusedRollout:
         g["term_of_row"], g["term_int"], g["term_rows"] = si[2 * H:3 * H + 2], si[3 * H + 2:4 * H + 4], si[4 * H + 4:]
         g["disc_t"], g["grw"], g["norm_t"], g["term_w"] = sf[0:H + 2], sf[H + 2:2 * H + 2], sf[2 * H + 2:2 * H + 3], sf[2 * H + 3:]
         g["reset_states"] = z(RM, N, n)
+        g["rng_ctr"] = z(1, dtype=torch.int64)
+        g["rng_ctr_host"] = torch.zeros(1, dtype=torch.int64, device="cpu").pin_memory()
+        g["inputs_args"] = self._inputs_args(H, g["eps"], g["noise"], g["dirs"], g["reset_states"], g["rng_ctr"]) \
+            if self._native_inputs() else None
         g["gobs_term"] = z(KM, N, o)
+        g["roww"] = z(KM, N)
         sizes = [o * W, W * m, 2 * W, 2 * W, 2 * W, m, m] + ([W * W] if self.engine_bwd else [])
         g["flat"] = z(sum(sizes))
         g["parts"] = torch.split(g["flat"], sizes)
@@ -409,7 +453,9 @@ class FusedRollout:
         dt = base.state.dtype
         lib = _lib.lib()
         g["states"][0].copy_(g["s_start"])      # (separate input buffer: the body must be idempotent for capture)
-        if self.rng_mode == "batched":
+        if g["inputs_args"] is not None:        # eps, noise, directions and reset states in ONE launch of ours
+            check(lib.sgbpo_episode_inputs(dtype_code(dt), C.byref(g["inputs_args"]), stream_ptr()), "sgbpo_episode_inputs")
+        elif self.rng_mode == "batched":
             g["eps"].normal_()
             g["u"].uniform_()
             if g["dirs"] is not None:
@@ -420,16 +466,16 @@ class FusedRollout:
                 if g["dirs"] is not None:
                     g["dirs"][t].uniform_(-1.0, 1.0)
                 g["u"][t].uniform_()
-        torch.addcmul(g["noise_lo"], g["u"], g["noise_span"], out=g["noise"])
-        if g["dirs"] is not None:
-            g["dirs"].div_(torch.linalg.vector_norm(g["dirs"], dim=2, keepdim=True))
-        if self.rng_mode == "batched":          # fixed number of reset-state draws per episode (see _draw_inputs)
+        if g["inputs_args"] is None:
+            torch.addcmul(g["noise_lo"], g["u"], g["noise_span"], out=g["noise"])
+            if g["dirs"] is not None:
+                g["dirs"].div_(torch.linalg.vector_norm(g["dirs"], dim=2, keepdim=True))
+        if self.rng_mode == "batched" and g["inputs_args"] is None:          # fixed number of reset-state draws per episode (see _draw_inputs)
             snap = base._reset_snapshot()
             for r in range(g["RM"]):
                 base.reset()
                 g["reset_states"][r].copy_(base.state)
             base._reset_restore(snap)
-        g["term"].copy_((g["term_int"] != 0).unsqueeze(1).expand(-1, N))
         check(lib.sgbpo_rollout_fwd(base.env_id, dtype_code(dt), C.byref(self._consts()), C.byref(self.policy_pack.desc),
                                     C.byref(g["r"]), stream_ptr()), "sgbpo_rollout_fwd")
         if self.vf_native:
@@ -460,9 +506,8 @@ class FusedRollout:
         # critic input-gradient on the (at most KM) terminal rows; unused slots carry weight 0
         x = g["obs"].index_select(0, g["term_rows"]).detach()
         if self.vf_vjp_native:         # one launch: forward + transposed pass of the target critic (csrc mlp_rows_vjp_kernel)
-            roww = g["term_w"].unsqueeze(1).expand(g["KM"], N).contiguous()
             check(_lib.lib().sgbpo_mlp_rows_vjp(dtype_code(dt), g["KM"] * N, C.byref(self.vf_pack.desc), C.c_void_p(x.data_ptr()),
-                                                C.c_void_p(roww.data_ptr()), C.c_void_p(g["gobs_term"].data_ptr()), stream_ptr()),
+                                                C.c_void_p(g["roww"].data_ptr()), C.c_void_p(g["gobs_term"].data_ptr()), stream_ptr()),
                   "sgbpo_mlp_rows_vjp")
         else:
             x = x.clone().requires_grad_(True)
@@ -514,6 +559,9 @@ class FusedRollout:
         g["sched_f_host"].copy_(torch.tensor(disc + grw + [float(norm)] + term_w, dtype=g["sched_f_host"].dtype, device="cpu"))
         g["sched_i"].copy_(g["sched_i_host"], non_blocking=True)
         g["sched_f"].copy_(g["sched_f_host"], non_blocking=True)
+        # tensors derived from the schedule (only when it changes: most episodes repeat the previous one)
+        g["term"].copy_((g["term_int"] != 0).unsqueeze(1).expand(-1, N))
+        g["roww"].copy_(g["term_w"].unsqueeze(1).expand(g["KM"], N))
 
     def _collect_graph(self, H: int, steps_end: int, pending_end: bool, reset_at, terminal_rows) -> float:
         base, algo = self.base, self.algo
@@ -531,6 +579,8 @@ class FusedRollout:
         g["row0_ready"] = False
         if g["aux0"] is not None:
             g["aux0"].copy_(base._aux())
+        g["rng_ctr_host"][0] = self._episodes
+        g["rng_ctr"].copy_(g["rng_ctr_host"], non_blocking=True)
         if g["fwd_graph"] is None:
             rng_state = torch.cuda.get_rng_state()
             g["fwd_graph"] = self._capture(self._fwd_body, g)
