@@ -559,7 +559,7 @@ def fused_roofline(args, engine, episode, dtype):
     return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "kernel": dominant, "kernel_ms": ms, "alg_bytes_per_launch": per_kernel_bytes[dominant],
             "all_kernels_achieved_gbs": total_alg / (all_ms * 1e-3) / 1e9,
-            "engines": {"forward": "tcgen05" if engine.engine_fwd else "fma-tiles", "reverse": "parallel-tcgen05" if engine.engine_bwd else "sequential-fma"},
+            "engines": {"forward": {0: "fma-tiles", 1: "tcgen05", 2: "warp-mma"}[engine.engine_fwd], "reverse": "parallel-tcgen05" if engine.engine_bwd else "sequential-fma"},
             "note": "rollout_bwd = the whole reverse pass after the step Jacobians (row-batched tcgen05 policy backward in Jacobian "
                     "mode, per-environment scan, row-batched tcgen05 policy backward in gradient mode).  This workload (4096 envs x "
                     "64 SEQUENTIAL steps with a 34 kFLOP policy inside every step) is latency/issue-bound in its forward kernel, not "

@@ -142,6 +142,8 @@ typedef struct sgbpo_rollout {
   int64_t N;
   int32_t H;
   int32_t engine;            /* bit 0, forward: 0 = FMA register tiles (float32 / float64, widths 32-128), 1 = tcgen05 kernel;
+                              * bit 2, forward: warp-MMA kernel (mma.sync on register fragments, no block-wide barrier in the time
+                              * loop; float32 policies [in -> 128 -> 128 -> m] of the first four environments; exclusive with bit 0);
                               * bit 1, reverse pass: 0 = sequential FMA kernel, 1 = parallel tensor-core reverse pass
                               * (row-batched policy backward + per-environment scan).  The tensor-core engines cover float32
                               * policies [in -> 128 -> 128 -> m]: sgbpo_rollout_engine_supported.  Both forward engines
@@ -165,7 +167,11 @@ typedef struct sgbpo_rollout {
    * of its three GEMMs; 1 KB per environment step of HBM traffic is far cheaper on this path. */
   void* stash_h1;            /* [H][N][width]  LayerNorm output of hidden layer 1 = operand of Linear2.weight.grad */
   void* stash_e1;            /* [H][N][width]  ELU output of hidden layer 1 */
-  void* stash_e2;            /* [H][N][width]  ELU output of hidden layer 2 */
+  void* stash_e2;            /* [H][N][width]  ELU output of hidden layer 2.  With reverse engine 1 (engine bit 1) both ELU stashes
+                              * are stored in 128-row tiles of 16-byte column chunks instead -- element (row = t N + env, col) at
+                              * ((row / 128 * width / 4 + col / 4) * 128 + row % 128) * 4 + col % 4 -- so that the row-batched
+                              * reverse kernels read them with contiguous 512-byte requests and one 64 KB TMA bulk copy per
+                              * tile; the buffers must then hold ceil(H N / 128) * 128 rows. */
   void* stash_stats;         /* [H][N][4]      LayerNorm mean1, rstd1, mean2, rstd2 */
   const void* reset_aux;     /* [R][N][naux] aux (goal, obstacles) in effect after reset r, or NULL: reset_states[r][:, :naux]
                               * (forward engine 1 and sgbpo_rollout_jac) */
@@ -184,7 +190,8 @@ typedef struct sgbpo_rollout_grads {
   /* parameter gradients, accumulated (caller zero-fills), in torch's layouts:
    * g_w_in [width][in_dim], g_w_out [out_dim][width], g_b_hid/g_gamma/g_beta [2][width], g_b_out/g_log_std [out_dim] */
   void* g_w_in; void* g_w_out; void* g_b_hid; void* g_gamma; void* g_beta; void* g_b_out; void* g_log_std;
-  void* g_w_hid;               /* reverse engine 1: [width][width] Linear2.weight.grad accumulated in-kernel (dz2_out unused) */
+  void* g_w_hid;               /* reverse engine 1: [width][width] Linear2.weight.grad accumulated in-kernel (dz2_out unused);
+                                * 16-byte aligned (flushed with vector reductions) */
 } sgbpo_rollout_grads;
 
 /* forward over the whole horizon: policy MLP + safeguarded step per environment per t (one launch) */
@@ -261,6 +268,27 @@ typedef struct sgbpo_episode_inputs_args {
   double reset_center[SGBPO_MAXN], reset_gen[SGBPO_MAXN][SGBPO_MAX_RESET_GENS];
 } sgbpo_episode_inputs_args;
 int sgbpo_episode_inputs(int dtype, const sgbpo_episode_inputs_args* args, void* stream);
+
+/* ---- containment verdicts per environment (replaces the host LPs of src/sets/zonotope.py:143-239 -- programs P9 -- and
+ * src/sets/box.py:90-102).  The outer set is passed as the K facets  h_k . d <= 1  of the verdict program's feasible region in the
+ * offset d = point - outer_center (safegbpo_b200/sets/verdicts.py enumerates them once per outer set on the host):
+ *   point in zonotope            value_i = max_k h_k . d_i                       = the LP value  min |gamma|_inf  (zonotope gauge)
+ *   zonotope (fixed generators)  value_i = max_k h_k . d_i  (facets of the LP's feasible region)   value <= 1 <=> LP value <= 1
+ *   zonotope (per-env generators, inner_gen != NULL, N x n x q row-major)
+ *                                value_i = max_k [h_k . d_i + sum_j |h_k . g_ij|]   exact containment in the outer polytope
+ * verdict_i = value_i <= 1 + tol (NaN -> 0).  outer_center is n values, or N x n when center_per_env != 0. */
+typedef struct sgbpo_contains_args {
+  int64_t N;
+  int32_t n, K, q, center_per_env;
+  const void* facets;        /* K x n */
+  const void* outer_center;
+  const void* points;        /* N x n: the point, or the centre of the inner zonotope */
+  const void* inner_gen;     /* NULL or N x n x q */
+  void* value;               /* N (may be NULL) */
+  int32_t* verdict;          /* N (may be NULL) */
+  double tol;
+} sgbpo_contains_args;
+int sgbpo_contains(int dtype, const sgbpo_contains_args* args, void* stream);
 
 /* ---- tensor-core operand-view self-test (diagnostic; tests/test_gpu_tc_mma.py): X, Z, D are 128 x 128 float32 device
  * matrices; mode 0: D = X Z^T, 1: D = X Z, 2: D = X^T Z, each through the fp16 hi/lo split tcgen05 path the rollout

@@ -86,6 +86,13 @@ class EpisodeInputs(C.Structure):
                 ("reset_center", C.c_double * MAXN), ("reset_gen", (C.c_double * 24) * MAXN)]
 
 
+class ContainsArgs(C.Structure):
+    """Mirror of ``struct sgbpo_contains_args``."""
+    _fields_ = [("N", C.c_int64), ("n", C.c_int32), ("K", C.c_int32), ("q", C.c_int32), ("center_per_env", C.c_int32),
+                ("facets", C.c_void_p), ("outer_center", C.c_void_p), ("points", C.c_void_p), ("inner_gen", C.c_void_p),
+                ("value", C.c_void_p), ("verdict", C.c_void_p), ("tol", C.c_double)]
+
+
 ENV_IDS = {"BalancePendulum": 0, "BalanceCartPole": 1, "SwingUpCartPole": 2, "BalanceQuadrotor": 3,
            "ManageHousehold": 4, "NavigateSeeker": 5, "NavigateQuadrotor": 6}
 SG_NONE, SG_BOUNDARY_PROJECTION, SG_RAY_MASK = 0, 1, 2
@@ -123,6 +130,7 @@ _SIGNATURES = {
     "sgbpo_shac_loss": (C.c_int, [C.c_int, C.c_int, C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "sgbpo_tc_selftest": (C.c_int, [C.c_int, _VP, _VP, _VP, _VP]),
     "sgbpo_episode_inputs": (C.c_int, [C.c_int, C.POINTER(EpisodeInputs), _VP]),
+    "sgbpo_contains": (C.c_int, [C.c_int, C.POINTER(ContainsArgs), _VP]),
 }
 EXPORTED = tuple(_SIGNATURES)
 _lib = None

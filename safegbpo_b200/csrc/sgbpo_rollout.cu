@@ -4,6 +4,9 @@
 #include "sgbpo_rollout_tc.cuh"
 
 namespace sgbpo {
+namespace wm {      // sgbpo_rollout_wm.cuh, instantiated in sgbpo_rollout_wm_env*.cu
+template <int ENV> int rollout_wm_fwd_env(const sgbpo_consts* c, const sgbpo_mlp* pol, const sgbpo_rollout* r, cudaStream_t st);
+}
 int launch_rows_tc(int64_t M, const sgbpo_mlp* net, const void* x, void* out, cudaStream_t st);   // sgbpo_mlp_tc.cu
 #define ROLLOUT_DISPATCH(FN, ...)                                                       \
   switch (env_id) {                                                                     \
@@ -25,6 +28,9 @@ int launch_rows_tc(int64_t M, const sgbpo_mlp* net, const void* x, void* out, cu
   }
 static int tc_fwd_dispatch(int env_id, const sgbpo_consts* c, const sgbpo_mlp* pol, const sgbpo_rollout* r, cudaStream_t st) {
   ROLLOUT_TC_DISPATCH(rollout_tc_fwd_env, c, pol, r, st)
+}
+static int wm_fwd_dispatch(int env_id, const sgbpo_consts* c, const sgbpo_mlp* pol, const sgbpo_rollout* r, cudaStream_t st) {
+  ROLLOUT_DISPATCH(wm::rollout_wm_fwd_env, c, pol, r, st)
 }
 static int tc_jac_dispatch(int env_id, const sgbpo_consts* c, const sgbpo_rollout* r, cudaStream_t st) {
   ROLLOUT_TC_DISPATCH(rollout_jac_env, c, r, st)
@@ -66,7 +72,8 @@ int sgbpo_rollout_fwd(int env_id, int dtype, const sgbpo_consts* consts, const s
   if (r->N <= 0 || r->H <= 0) return SGBPO_OK;
   if (!r->eps || !r->noise || !r->states || !r->obs || !r->actions || !r->exec_actions || !r->rewards || !r->flags)
     return fail2(SGBPO_E_ARG, "sgbpo_rollout_fwd: null buffer");
-  const int fwd_engine = r->engine & 1;
+  const int fwd_engine = (r->engine & 4) ? 2 : (r->engine & 1);
+  if ((r->engine & 5) == 5) return fail2(SGBPO_E_ARG, "sgbpo_rollout_fwd: engine bits 0 and 2 are exclusive");
   if (fwd_engine == 0) {
     const int n_stash = (r->stash_h1 != nullptr) + (r->stash_e1 != nullptr) + (r->stash_e2 != nullptr) + (r->stash_stats != nullptr);
     if (n_stash != 0 && n_stash != 4 && !(n_stash == 3 && !r->stash_h1))
@@ -74,7 +81,11 @@ int sgbpo_rollout_fwd(int env_id, int dtype, const sgbpo_consts* consts, const s
     if (n_stash != 0 && policy->n_hidden != 2) return fail2(SGBPO_E_UNSUPPORTED, "activation stash: policies with two hidden layers");
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (r->engine < 0 || r->engine > 3) return fail2(SGBPO_E_ARG, "sgbpo_rollout_fwd: unknown engine");
+  if (r->engine < 0 || r->engine > 7) return fail2(SGBPO_E_ARG, "sgbpo_rollout_fwd: unknown engine");
+  if (fwd_engine == 2) {
+    if (dtype != SGBPO_F32) return fail2(SGBPO_E_UNSUPPORTED, "warp-MMA rollout: float32 only");
+    return wm_fwd_dispatch(env_id, consts, policy, r, st);
+  }
   if (fwd_engine == 1) {
     if (dtype != SGBPO_F32) return fail2(SGBPO_E_UNSUPPORTED, "tensor-core rollout: float32 only");
     return tc_fwd_dispatch(env_id, consts, policy, r, st);

@@ -50,7 +50,17 @@ template <class T> struct RolloutArgs {
   int32_t* flags;         // [H][N]
   // activation stash (fwd writes, bwd reads): [H][N][W] x 3 and [H][N][4]
   T* stash_h1; T* stash_e1; T* stash_e2; T* stash_stats;
+  int stash_tiled;        // e1 / e2 in the 128-row tile layout the parallel reverse pass reads (stash_index)
 };
+
+// Position of (row = t * N + env, col) in an activation stash.  Row-major [row][W], or -- for the parallel reverse pass, whose
+// threads own one row and 32 consecutive columns -- 128-row tiles of 16-byte column chunks, [row / 128][col / 4][row % 128][col % 4]:
+// consecutive rows of a chunk are contiguous, so a warp (32 rows, one chunk) reads 512 contiguous bytes per request.
+template <int W>
+__device__ __forceinline__ size_t stash_index(bool tiled, int64_t row, int col) {
+  return tiled ? ((((size_t)(row >> 7) * (W / 4) + (size_t)(col >> 2)) << 7) + (size_t)(row & 127)) * 4 + (size_t)(col & 3)
+               : (size_t)row * W + col;
+}
 
 template <class T> struct BackwardArgs {
   const T* grw;           // [H]   d loss / d reward[t]  (0 on rows replaced by the critic value)
@@ -70,12 +80,16 @@ template <class T> struct BackwardArgs {
 // register tile <-> global [t][env][W]: per row, the warp touches W contiguous values (128-byte segments)
 template <class T, int W, int R>
 __device__ __forceinline__ void stream_tile(T* __restrict__ dst, int t, int64_t N, int64_t env0, int lane,
-                                            const T (&v)[R][W / 32]) {
+                                            const T (&v)[R][W / 32], bool tiled = false) {
+  // (row, lane + 32 j) -> stash_index, with the lane and j parts hoisted: one add per store
+  const size_t lane_off = tiled ? (size_t)(lane >> 2) * 512 + (lane & 3) : (size_t)lane, j_stride = tiled ? 8 * 512 : 32;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     if (env0 + r < N) {
+      const int64_t row = (int64_t)t * N + env0 + r;
+      T* p = dst + (tiled ? ((size_t)(row >> 7) * (W / 4) * 512 + (size_t)(row & 127) * 4) : (size_t)row * W) + lane_off;
 #pragma unroll
-      for (int j = 0; j < W / 32; ++j) dst[((int64_t)t * N + env0 + r) * W + lane + 32 * j] = v[r][j];
+      for (int j = 0; j < W / 32; ++j) p[j * j_stride] = v[r][j];
     }
   }
 }
@@ -165,12 +179,12 @@ rollout_fwd_kernel(const __grid_constant__ RolloutArgs<T> A, const __grid_consta
       tile_gemm<T, W, R>(obsT, NO, net.w_in, net.b_hid, lane, h);
       elu_layernorm<T, W, R, true>(h, net.gamma, net.beta, lane, ev, m1, r1);
       store_tile<T, W, R>(bufA, lane, h);
-      stream_tile<T, W, R>(A.stash_e1, t, N, env0, lane, ev);
+      stream_tile<T, W, R>(A.stash_e1, t, N, env0, lane, ev, A.stash_tiled != 0);
       if (A.stash_h1) stream_tile<T, W, R>(A.stash_h1, t, N, env0, lane, h);
       __syncwarp();
       tile_gemm<T, W, R>(bufA, W, net.w_hid, net.b_hid + W, lane, h);
       elu_layernorm<T, W, R, true>(h, net.gamma + W, net.beta + W, lane, ev, m2, r2);
-      stream_tile<T, W, R>(A.stash_e2, t, N, env0, lane, ev);
+      stream_tile<T, W, R>(A.stash_e2, t, N, env0, lane, ev, A.stash_tiled != 0);
       if (valid) {
         T st[4] = {T(0), T(0), T(0), T(0)};
 #pragma unroll
@@ -819,6 +833,7 @@ template <class T> RolloutArgs<T> convert_rollout(const sgbpo_rollout& r) {
   a.states = (T*)r.states; a.obs = (T*)r.obs; a.actions = (T*)r.actions; a.exec_actions = (T*)r.exec_actions;
   a.rewards = (T*)r.rewards; a.flags = r.flags;
   a.stash_h1 = (T*)r.stash_h1; a.stash_e1 = (T*)r.stash_e1; a.stash_e2 = (T*)r.stash_e2; a.stash_stats = (T*)r.stash_stats;
+  a.stash_tiled = (r.engine & 2) ? 1 : 0;
   return a;
 }
 template <class T> BackwardArgs<T> convert_backward(const sgbpo_rollout_grads& g) {

@@ -91,10 +91,13 @@ __device__ __forceinline__ void normalise4(float (&e)[CW], float sum, const floa
   rstd_out = rs;
 }
 
-__device__ __forceinline__ void store_cols(float* __restrict__ dst, const float (&e)[CW]) {      // 32 contiguous floats, 16-byte aligned
+// this thread's 32 columns of a stash row: contiguous (row-major stash) or eight 16-byte chunks 2 KB apart (tiled stash, where
+// the 32 rows of a warp make each chunk store one contiguous 512-byte request)
+__device__ __forceinline__ void store_cols_stash(float* __restrict__ base, bool tiled, int64_t row, int part, const float (&e)[CW]) {
 #pragma unroll
   for (int c4 = 0; c4 < CW / 4; ++c4)
-    *reinterpret_cast<float4*>(dst + 4 * c4) = make_float4(e[4 * c4], e[4 * c4 + 1], e[4 * c4 + 2], e[4 * c4 + 3]);
+    *reinterpret_cast<float4*>(base + sgbpo::stash_index<W>(tiled, row, part * CW + 4 * c4)) =
+        make_float4(e[4 * c4], e[4 * c4 + 1], e[4 * c4 + 2], e[4 * c4 + 3]);
 }
 __device__ __forceinline__ void load_cols(const float* __restrict__ src, float (&e)[CW]) {
 #pragma unroll
@@ -226,7 +229,7 @@ rollout_tc_fwd_kernel(const __grid_constant__ RolloutArgs<float> A, const __grid
           for (int i = 0; i < NS; ++i) rs[i] = A.reset_states[((int64_t)ridx * N + env) * NS + i];
         }
       }
-      const size_t stash_off = ((size_t)t * N + (valid ? env : 0)) * W + part * CW;
+      const int64_t stash_row = (int64_t)t * N + (valid ? env : 0);
       // ---- layer 1 on the FMA pipe (K = policy input width) ------------------------------------------------------------
       float e[CW];
 #pragma unroll
@@ -247,7 +250,7 @@ rollout_tc_fwd_kernel(const __grid_constant__ RolloutArgs<float> A, const __grid
       float sum = 0.f;
 #pragma unroll
       for (int c = 0; c < CW; ++c) { e[c] = elu1_fast(e[c]); sum += e[c]; }
-      if (A.stash_e1 && valid) store_cols(A.stash_e1 + stash_off, e);
+      if (A.stash_e1 && valid) store_cols_stash(A.stash_e1, A.stash_tiled != 0, stash_row, part, e);
       float st[4];
       normalise4(e, sum, S.g1, S.be1, S.red_a, S.red_b, part, trow, qbar, st[0], st[1]);
       // ---- layer 2 on the tensor cores -----------------------------------------------------------------------------------
@@ -275,7 +278,7 @@ rollout_tc_fwd_kernel(const __grid_constant__ RolloutArgs<float> A, const __grid
           sum += (e[4 * c4 + 0] + e[4 * c4 + 1]) + (e[4 * c4 + 2] + e[4 * c4 + 3]);
         }
       }
-      if (A.stash_e2 && valid) store_cols(A.stash_e2 + stash_off, e);
+      if (A.stash_e2 && valid) store_cols_stash(A.stash_e2, A.stash_tiled != 0, stash_row, part, e);
       normalise4(e, sum, S.g2, S.be2, S.red_a, S.red_b, part, trow, qbar, st[2], st[3]);
       // ---- output layer: partial dot products, exchanged over the row's four threads -----------------------------------
 #pragma unroll
@@ -426,13 +429,14 @@ template <int NSP> struct BwdSmem {
   uint64_t* bar;
   uint64_t* tma_bar;
   uint32_t* tmem_slot;
-  float* stage;              // (Jacobian mode) the NEXT tile's e2 rows, landed by TMA bulk copies while this tile computes
-  static constexpr int STAGE_PITCH = W + 4;           // floats per staged row: 528 B, conflict-free 16-byte reads down a column of rows
+  float* stage;              // (Jacobian mode) the NEXT tile of the e2 stash, landed by ONE 64 KB TMA bulk copy while this tile computes
+                             // (the stash is stored in 128-row tiles of 16-byte column chunks, sgbpo::stash_index: a tile is contiguous in
+                             // HBM and, staged as it is, a warp's 16-byte reads of one chunk are 512 contiguous bytes -> conflict-free)
   __host__ __device__ static int nop(int no) { return (no + 3) & ~3; }
   __host__ __device__ static size_t bytes(int in_dim, int no, int out_dim, bool grad) {
     return (grad ? 6 : 4) * (size_t)PART_BYTES + sizeof(float) * ((size_t)in_dim * W + 3 * W + (size_t)out_dim * W + (size_t)ROWS * nop(no) +
                                                                      (size_t)out_dim * ROWS + 2 * NSP * ROWS + W) + 8 + 48 +
-           (grad ? 0 : sizeof(float) * (size_t)ROWS * STAGE_PITCH);
+           (grad ? 0 : 128 + sizeof(float) * (size_t)ROWS * W);
   }
   __device__ void carve(unsigned char* smem, int in_dim, int no, int out_dim, bool grad) {
     w_hi = smem; w_lo = w_hi + PART_BYTES; a_hi = w_lo + PART_BYTES; a_lo = a_hi + PART_BYTES;
@@ -450,7 +454,7 @@ template <int NSP> struct BwdSmem {
     bar = reinterpret_cast<uint64_t*>(maxS + 2);
     tma_bar = bar + 1;
     tmem_slot = reinterpret_cast<uint32_t*>(tma_bar + 1);
-    stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~uintptr_t(15));    // bulk-copy destination: 16-byte aligned
+    stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 127) & ~uintptr_t(127));  // bulk-copy destination
   }
 };
 
@@ -466,10 +470,11 @@ __device__ __forceinline__ float2 row_sum_pair(float a, float b, float* red, int
   return t;
 }
 
-template <int C> __device__ __forceinline__ void load_cols_n(const float* __restrict__ src, float (&e)[C]) {
+// this thread's C columns [part * C, +C) of row `trow` of a stash tile (global or staged in shared memory): chunk stride 2 KB
+template <int C> __device__ __forceinline__ void load_cols_n(const float* __restrict__ tile, int trow, int part, float (&e)[C]) {
 #pragma unroll
   for (int c4 = 0; c4 < C / 4; ++c4) {
-    const float4 v = *reinterpret_cast<const float4*>(src + 4 * c4);
+    const float4 v = *reinterpret_cast<const float4*>(tile + ((size_t)(part * (C / 4) + c4) * ROWS + trow) * 4);
     e[4 * c4] = v.x; e[4 * c4 + 1] = v.y; e[4 * c4 + 2] = v.z; e[4 * c4 + 3] = v.w;
   }
 }
@@ -575,16 +580,13 @@ policy_rows_bwd_kernel(const __grid_constant__ RowsBwdArgs R, const __grid_const
   const uint32_t h_hi_addr = smem_u32(S.h_hi), h_lo_addr = smem_u32(S.h_lo);
   uint32_t phase = 0, tma_phase = 0;
   const int64_t n_tiles = (R.M + ROWS - 1) / ROWS;
-  // TMA staging (Jacobian mode): the owner thread of a row issues one bulk copy of its 512-byte e2 row into the padded stage;
-  // thread 0 arms the transaction barrier with the tile's byte count.  Issued for tile i + 1 as soon as every thread holds
-  // tile i's e2 in registers, so the copy runs under tile i's arithmetic and MMA.
+  // TMA staging (Jacobian mode): thread 0 arms the transaction barrier and issues one bulk copy of the whole 64 KB e2 tile (the
+  // stash buffers are padded to whole tiles).  Issued for tile i + 1 as soon as every thread holds tile i's e2 in registers, so
+  // the copy runs under tile i's arithmetic and MMA.
   auto stage_tile = [&](int64_t tile) {
-    if (!owner) return;
-    const int64_t row0 = tile * ROWS;
-    const int64_t rows_here = R.M - row0 < ROWS ? R.M - row0 : ROWS;
-    if (tid == 0) mbar_expect_tx(tma_bar_addr, (uint32_t)rows_here * W * 4);
-    if (trow < rows_here)
-      bulk_g2s(smem_u32(S.stage + trow * BwdSmem<NSP>::STAGE_PITCH), R.e2 + (size_t)(row0 + trow) * W, W * 4, tma_bar_addr);
+    if (tid != 0) return;
+    mbar_expect_tx(tma_bar_addr, (uint32_t)(ROWS * W * 4));
+    bulk_g2s(smem_u32(S.stage), R.e2 + (size_t)tile * ROWS * W, ROWS * W * 4, tma_bar_addr);
   };
   if (!GRAD && (int64_t)blockIdx.x < n_tiles) stage_tile(blockIdx.x);
 
@@ -604,7 +606,9 @@ policy_rows_bwd_kernel(const __grid_constant__ RowsBwdArgs R, const __grid_const
     tmem_ld_cols<C>(tmem_row + 128, z);
     float* dst = R.g_w_hid + (size_t)trow * W + part * C;
 #pragma unroll
-    for (int i = 0; i < C; ++i) atomicAdd(dst + i, z[i] * inv_scale);
+    for (int i = 0; i < C; i += 4)          // 16-byte vector reductions: a quarter of the atomic requests of every CTA's flush
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(z[i] * inv_scale), "f"(z[i + 1] * inv_scale),
+                   "f"(z[i + 2] * inv_scale), "f"(z[i + 3] * inv_scale) : "memory");
     tc_fence_before();
   };
 
@@ -619,11 +623,11 @@ policy_rows_bwd_kernel(const __grid_constant__ RowsBwdArgs R, const __grid_const
 #pragma unroll
     for (int c = 0; c < C; ++c) e2[c] = 0.f;
     if (GRAD) {
-      if (valid) load_cols_n<C>(R.e2 + row_off * W + part * C, e2);
+      if (valid) load_cols_n<C>(R.e2 + (size_t)tile * ROWS * W, trow, part, e2);
     } else {
       mbar_wait(tma_bar_addr, tma_phase);            // this tile's rows have landed in the stage
       tma_phase ^= 1;
-      if (valid) load_cols_n<C>(S.stage + trow * BwdSmem<NSP>::STAGE_PITCH + part * C, e2);
+      if (valid) load_cols_n<C>(S.stage, trow, part, e2);
       fence_async_smem();                            // generic-proxy reads of the stage before the async-proxy refill
       __syncthreads();
       if (tile + gridDim.x < n_tiles) stage_tile(tile + gridDim.x);
@@ -639,7 +643,7 @@ policy_rows_bwd_kernel(const __grid_constant__ RowsBwdArgs R, const __grid_const
       float h1[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) h1[c] = 0.f;
-      if (valid) load_cols_n<C>(R.e1 + row_off * W + part * C, h1);
+      if (valid) load_cols_n<C>(R.e1 + (size_t)tile * ROWS * W, trow, part, h1);
 #pragma unroll
       for (int c4 = 0; c4 < C / 4; ++c4) {
         const float4 g = *reinterpret_cast<const float4*>(S.g1 + part * C + 4 * c4);
@@ -759,7 +763,7 @@ policy_rows_bwd_kernel(const __grid_constant__ RowsBwdArgs R, const __grid_const
       float e1[C];              // (loaded while the MMAs execute)
 #pragma unroll
       for (int c = 0; c < C; ++c) e1[c] = 0.f;
-      if (valid) load_cols_n<C>(R.e1 + row_off * W + part * C, e1);
+      if (valid) load_cols_n<C>(R.e1 + (size_t)tile * ROWS * W, trow, part, e1);
       mbar_wait(bar_addr, phase);
       phase ^= 1;
       tc_fence_after();
@@ -1064,6 +1068,7 @@ template <int ENV> int rollout_tc_bwd(const sgbpo_mlp* pol, const sgbpo_rollout*
   PolicyTc p;
   if (!tc_policy(pol, p) || pol->out_dim != NA) return fail2(SGBPO_E_UNSUPPORTED, "tensor-core reverse pass: float32 policy [in -> 128 -> 128 -> m]");
   if (!r->jac || !r->pol_jac || !r->dmu || !g->g_w_hid) return fail2(SGBPO_E_ARG, "tensor-core reverse pass: jac, pol_jac, dmu and g_w_hid buffers are required");
+  if (reinterpret_cast<uintptr_t>(g->g_w_hid) % 16) return fail2(SGBPO_E_ARG, "tensor-core reverse pass: g_w_hid must be 16-byte aligned");
   RowsBwdArgs R;
   R.M = r->N * (int64_t)r->H;
   R.e1 = (const float*)r->stash_e1; R.e2 = (const float*)r->stash_e2; R.stats = (const float*)r->stash_stats;

@@ -28,6 +28,7 @@ FUSED_ENVS = {"BalancePendulum", "BalanceCartPole", "SwingUpCartPole", "BalanceQ
 # environments whose whole-horizon path exists only on the tensor-core engines (float32, policy [o -> 128 -> 128 -> m]): the
 # household's per-step series and the seeker's obstacle columns / per-reset goal + obstacles are handled by rollout_tc_fwd_kernel
 TC_ONLY_ENVS = {"ManageHousehold", "NavigateSeeker"}
+WARP_MMA_ENVS = {"BalancePendulum", "BalanceCartPole", "SwingUpCartPole", "BalanceQuadrotor"}   # forward engine 2 (csrc/sgbpo_rollout_wm.cuh)
 WIDTHS = (32, 64, 128)
 
 
@@ -144,7 +145,7 @@ class FusedRollout:
         # FMA kernel, 1 = parallel tensor-core reverse pass.  SGBPO_ROLLOUT_ENGINE = 0 | 1 | 2 forces (fwd, reverse) =
         # (0, 0) | (1, 1) | (0, 1) for A/B measurements and tests.
         self.engine_fwd, self.engine_bwd = self.pick_engine(self.base, self.policy_pack)
-        self.engine = self.engine_fwd | (self.engine_bwd << 1)
+        self.engine = {0: 0, 1: 1, 2: 4}[self.engine_fwd] | (self.engine_bwd << 1)       # sgbpo_rollout.engine bits
         lib = _lib.lib()
         self.jac_stride = lib.sgbpo_rollout_jac_stride(self.base.env_id) if self.engine_bwd else 0
         self.pol_jac_stride = lib.sgbpo_rollout_pol_jac_stride(self.base.env_id) if self.engine_bwd else 0
@@ -160,7 +161,7 @@ class FusedRollout:
         self.forward_only = False              # model-free consumers (consumers.RolloutCollector): no activation stash, no reverse pass
         self.kernel_ms = {"rollout_fwd": [], "mlp_rows": [], "rollout_jac": [], "rollout_bwd": []}
 
-    TC_FORWARD_MIN_ENVS = 12288       # measured cross-over of the two forward kernels on one B200 (profiles/r2_engines.md)
+    TC_FORWARD_MIN_ENVS = 12288       # measured cross-over of the warp-MMA and tcgen05 forward kernels on one B200 (profiles/r2_engines.md)
 
     @staticmethod
     def pick_engine(base, pack: "PackedMlp") -> tuple[int, int]:
@@ -173,7 +174,12 @@ class FusedRollout:
             return 1, 1
         if force == "2":
             return 0, 1
-        return (1 if base.num_envs >= FusedRollout.TC_FORWARD_MIN_ENVS else 0), 1
+        wm_ok = base.ENV_NAME in WARP_MMA_ENVS and base.obs_dim < 16
+        if force == "3":
+            return (2 if wm_ok else 0), 1
+        # forward: tcgen05 CTA tiles (128 environments per CTA) once they fill the GPU, below that the warp-MMA kernel
+        # (8 environments per warp, no block-wide barrier in the time loop); FMA tiles where neither applies
+        return (1 if base.num_envs >= FusedRollout.TC_FORWARD_MIN_ENVS else (2 if wm_ok else 0)), 1
 
     # ---- native input generation (rng_order = "batched"): one Philox launch instead of ~20 library launches ----------------
     def _native_inputs(self) -> bool:
@@ -202,6 +208,11 @@ class FusedRollout:
             for j in range(G.shape[1]):
                 a.reset_gen[i][j] = float(G[i, j])
         return a
+
+    def _stash_shape(self, H: int, N: int, W: int):
+        """ELU-output stashes: [H][N][W] for the sequential reverse pass; for the parallel one 128-row tiles of 16-byte column
+        chunks (csrc stash_index), padded to whole tiles."""
+        return (-(-(H * N) // 128) * 128, W) if self.engine_bwd else (H, N, W)
 
     def _timed(self, name, fn):
         if not self.profile:
@@ -384,7 +395,8 @@ class FusedRollout:
                  rewards=z(H + 2, N), values=z(H + 2, N), flags=z(H, N, dtype=torch.int32),
                  term=z(H + 2, N, dtype=torch.bool), reward_sum=z(()), n_interv=z((), dtype=torch.int64),
                  bad=z((), dtype=torch.int32), aux0=None if base._aux() is None else z(N, base._aux().shape[1]),
-                 h1=None if self.engine_bwd else z(H, N, W), e1=z(H, N, W), e2=z(H, N, W), stats=z(H, N, 4),
+                 h1=None if self.engine_bwd else z(H, N, W), e1=z(*self._stash_shape(H, N, W)), e2=z(*self._stash_shape(H, N, W)),
+                 stats=z(H, N, 4),
                  dz2=None if self.engine_bwd else z(H, N, W), jac=z(H, N, self.jac_stride) if self.engine_bwd else None,
                  pol_jac=z(H, N, self.pol_jac_stride) if self.engine_bwd else None, dmu=z(H, N, m) if self.engine_bwd else None, loss=z(()),
                  fwd_graph=None, bwd_graph=None,
@@ -410,10 +422,12 @@ class FusedRollout:
             if self._native_inputs() else None
         g["gobs_term"] = z(KM, N, o)
         g["roww"] = z(KM, N)
-        sizes = [o * W, W * m, 2 * W, 2 * W, 2 * W, m, m] + ([W * W] if self.engine_bwd else [])
+        # (Linear2.weight.grad first: the reverse kernels flush it with 16-byte vector reductions, so it must be 16-byte aligned)
+        sizes = ([W * W] if self.engine_bwd else []) + [o * W, W * m, 2 * W, 2 * W, 2 * W, m, m]
         g["flat"] = z(sum(sizes))
-        g["parts"] = torch.split(g["flat"], sizes)
-        g["dw_hid"] = g["parts"][7].view(W, W) if self.engine_bwd else z(W, W)
+        parts = torch.split(g["flat"], sizes)
+        g["dw_hid"] = parts[0].view(W, W) if self.engine_bwd else z(W, W)
+        g["parts"] = parts[1:] if self.engine_bwd else parts
         g["ctr"] = base.noise_set.center[0].to(dt).clone()
         g["half"] = base.noise_set.generator[0].diagonal().to(dt).clone()
         g["noise_lo"], g["noise_span"] = g["ctr"] - g["half"], 2.0 * g["half"]
@@ -719,10 +733,10 @@ class FusedRollout:
         r.states, r.obs, r.actions, r.exec_actions = states.data_ptr(), obs.data_ptr(), actions.data_ptr(), exec_actions.data_ptr()
         r.rewards, r.flags = rewards.data_ptr(), flags.data_ptr()
         W = self.policy_pack.width
-        if not self.forward_only and (self._grad_bufs is None or self._grad_bufs["e1"].shape != (H, N, W)
-                                      or self._grad_bufs["e1"].dtype != dt):
+        if not self.forward_only and (self._grad_bufs is None or self._grad_bufs["key"] != (H, N, W, dt)):
             mk = lambda *shape: torch.empty(*shape, dtype=dt, device=dev)
-            self._grad_bufs = dict(e1=mk(H, N, W), e2=mk(H, N, W), stats=mk(H, N, 4))
+            self._grad_bufs = dict(key=(H, N, W, dt), e1=mk(*self._stash_shape(H, N, W)), e2=mk(*self._stash_shape(H, N, W)),
+                                   stats=mk(H, N, 4))
             if self.engine_bwd:
                 self._grad_bufs.update(jac=mk(H, N, self.jac_stride), pol_jac=mk(H, N, self.pol_jac_stride), dmu=mk(H, N, m))
             else:
@@ -822,14 +836,15 @@ class FusedRollout:
             gobs_term = torch.stack(gterm).contiguous()
         term_of_row_t = torch.tensor(term_of_row, dtype=torch.int32, device=dev)
         tc = bool(self.engine_bwd)
-        sizes = [o * W, W * m, 2 * W, 2 * W, 2 * W, m, m] + ([W * W] if tc else [])
+        sizes = ([W * W] if tc else []) + [o * W, W * m, 2 * W, 2 * W, 2 * W, m, m]
         flat = torch.zeros(sum(sizes), dtype=dt, device=dev)
         parts = torch.split(flat, sizes)
+        dw_part, parts = (parts[0], parts[1:]) if tc else (None, parts)
         g = RolloutGrads()
         g.grw, g.gobs_term, g.term_of_row = grw.data_ptr(), gobs_term.data_ptr(), term_of_row_t.data_ptr()
         (g.g_w_in, g.g_w_out, g.g_b_hid, g.g_gamma, g.g_beta, g.g_b_out, g.g_log_std) = [x.data_ptr() for x in parts[:7]]
         if tc:
-            g.g_w_hid = parts[7].data_ptr()
+            g.g_w_hid = dw_part.data_ptr()
             self._timed("rollout_jac", lambda: check(
                 _lib.lib().sgbpo_rollout_jac(base.env_id, dtype_code(dt), C.byref(self._consts()), C.byref(last["r"]), stream_ptr()),
                 "sgbpo_rollout_jac"))
@@ -840,7 +855,7 @@ class FusedRollout:
                                          C.byref(self.policy_pack.desc), C.byref(last["r"]), C.byref(g), stream_ptr()),
             "sgbpo_rollout_bwd"))
         if tc:
-            dw_hid = parts[7].view(W, W)
+            dw_hid = dw_part.view(W, W)
         else:
             dw_hid = _tall_skinny_gram(self._grad_bufs["dz2"].view(H * N, W), self._grad_bufs["h1"].view(H * N, W))   # Linear.weight.grad [out][in]
         g_w_in, g_w_out, g_b_hid, g_gamma, g_beta, g_b_out, g_log_std = parts[:7]

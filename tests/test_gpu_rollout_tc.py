@@ -50,7 +50,7 @@ def _episode(env_name, sg, opts, N, H, num_steps, dtype, engine, dev, state, wei
         algo.policy_optim.zero_grad()
         algo.collect_trajectories()
         eng = algo._fused_engine
-        want = {0: (0, 0), 1: (1, 1), 2: (0, 1)}[engine] if dtype == torch.float32 else (0, 0)
+        want = {0: (0, 0), 1: (1, 1), 2: (0, 1), 3: (2, 1)}[engine] if dtype == torch.float32 else (0, 0)
         assert eng is not None and (eng.engine_fwd, eng.engine_bwd) == want
         loss = eng.backward()
         torch.cuda.synchronize()
@@ -87,7 +87,7 @@ def test_tensor_core_engine_vs_float64(cuda_default, env_name, sg, opts, N, H, n
     dev = cuda_default
     ref, state, weights, draws = _episode(env_name, sg, opts, N, H, num_steps, torch.float64, 0, dev, None, None, None, spread)
     fma, *_ = _episode(env_name, sg, opts, N, H, num_steps, torch.float32, 0, dev, state, weights, draws, spread)
-    for engine in (1, 2):        # tensor-core forward + parallel reverse pass; FMA forward + parallel reverse pass
+    for engine in (1, 2, 3):     # tcgen05 forward / FMA forward / warp-MMA forward, each + parallel reverse pass
         tc, *_ = _episode(env_name, sg, opts, N, H, num_steps, torch.float32, engine, dev, state, weights, draws, spread)
         fin = torch.isfinite(ref["obs"]).all(dim=2).all(dim=0) & torch.isfinite(fma["obs"]).all(dim=2).all(dim=0) \
             & torch.isfinite(tc["obs"]).all(dim=2).all(dim=0)
@@ -104,7 +104,8 @@ def test_tensor_core_engine_vs_float64(cuda_default, env_name, sg, opts, N, H, n
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("engine,r_rows", [(1, None), (2, 4), (0, 4), (0, 8)], ids=["tcgen05", "fma-fwd+tc-reverse", "fma-R4", "fma-R8"])
+@pytest.mark.parametrize("engine,r_rows", [(1, None), (2, 4), (3, None), (0, 4), (0, 8)],
+                         ids=["tcgen05", "fma-fwd+tc-reverse", "warp-mma-fwd+tc-reverse", "fma-R4", "fma-R8"])
 def test_headline_instantiations_gradients_vs_float64(cuda_default, engine, r_rows):
     """BASELINE configs[1] shapes (BalanceCartPole + boundary projection, policy [128, 128], H = 64, N = 1024): the
     policy gradients of the instantiations the benchmark times -- rollout_tc_bwd_kernel and
@@ -135,6 +136,19 @@ def test_tensor_core_kernels_are_tcgen05():
         body = sass[sass.index(kernel):]
         body = body[:body.index("Function :", 10)] if "Function :" in body[10:] else body
         assert "UTCHMMA" in body and "LDTM" in body, kernel
+
+
+def test_warp_mma_kernel_uses_tensor_core_mma():
+    """Forward engine 2 issues warp-level tensor-core MMAs (HMMA.16816.F32) and has no block-wide barrier in its time loop."""
+    import subprocess
+    from safegbpo_b200 import _lib
+    obj = _lib.PKG / "build" / "sgbpo_rollout_wm_env1.o"
+    if not obj.exists():
+        pytest.skip("object files are not shipped to the GPU box (the CPU run checks them)")
+    sass = subprocess.run(["cuobjdump", "-sass", str(obj)], capture_output=True, text=True).stdout
+    body = sass[sass.index("rollout_wm_fwd_kernel"):]
+    assert body.count("HMMA.16816.F32") >= 288
+    assert body.count("BAR.SYNC") <= 2             # the parameter staging barrier only
 
 
 def _build_any(env_name, N, H, num_steps, fused, dev):
