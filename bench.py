@@ -310,19 +310,23 @@ def run_ours(args):
         return loss, avg_reward
 
     def timed(k, from_host):
-        times = []
-        for _ in range(k):
-            flush.fill_(1.0)                          # L2 flush between timed iterations
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        """K episodes back to back as a training loop issues them (the only host wait is the episode's own read of its reward
+        scalar), bracketed by barrier + synchronize on both sides.  Every episode sits between two CUDA events on the launching
+        stream and the L2-flush fill between two episodes sits OUTSIDE them, so the sum of the K intervals is the device time of
+        exactly K episodes."""
+        events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        for e0, e1 in events:
+            flush.fill_(1.0)                          # L2 flush between timed iterations (not timed)
             e0.record()
             episode(from_host)
             e1.record()
-            torch.cuda.synchronize()
-            times.append(e0.elapsed_time(e1))
-        return times
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        return [e0.elapsed_time(e1) for e0, e1 in events]
 
     base.state = s0_host.to(dev)
     base.steps, base._reset_pending = 0, False

@@ -401,6 +401,7 @@ class FusedRollout:
                  pol_jac=z(H, N, self.pol_jac_stride) if self.engine_bwd else None, dmu=z(H, N, m) if self.engine_bwd else None, loss=z(()),
                  fwd_graph=None, bwd_graph=None,
                  scal=z(2, dtype=torch.float64), scal_host=torch.zeros(2, dtype=torch.float64, device="cpu").pin_memory(),
+                 loss_host=torch.zeros((), dtype=dt, device="cpu").pin_memory(),
                  side=torch.cuda.Stream(), ev_fwd=torch.cuda.Event(), ev_side=torch.cuda.Event())
         # per-episode schedule (reset-all events of Q6, terminal rows, discounts): two small pinned host blocks
         # copied into static device tensors before every replay, so episodes WITH resets replay the same graphs
@@ -505,6 +506,14 @@ class FusedRollout:
                                       _lib.FL_INTERVENED, _lib.FL_NONFINITE | _lib.FL_INFEASIBLE,
                                       C.c_void_p(g["scal"].data_ptr()), C.c_void_p(g["n_interv"].data_ptr()),
                                       C.c_void_p(g["bad"].data_ptr()), stream_ptr()), "sgbpo_episode_stats")
+        # the episode's loss VALUE is complete here (shac.py:131-142 reads rewards, values and the schedule only); computing it
+        # at the end of the forward graph lets it leave with the reward scalar, so update_policy's float(loss) does not wait
+        # for the reverse pass and the host prepares the next episode while the reverse pass runs
+        if not self.forward_only:
+            check(lib.sgbpo_shac_loss(dtype_code(dt), H + 2, N, C.c_void_p(g["disc_t"].data_ptr()),
+                                      C.c_void_p(g["term_int"].data_ptr()), C.c_void_p(g["values"].data_ptr()),
+                                      C.c_void_p(g["rewards"].data_ptr()), C.c_void_p(g["norm_t"].data_ptr()),
+                                      C.c_void_p(g["loss"].data_ptr()), stream_ptr()), "sgbpo_shac_loss")
 
     def _bwd_body(self, g):
         """Loss, terminal-value gradient, fused reverse pass, weight-gradient GEMM (capturable)."""
@@ -513,10 +522,6 @@ class FusedRollout:
         dt = base.state.dtype
         W = self.policy_pack.width
         o = base.obs_dim
-        check(_lib.lib().sgbpo_shac_loss(dtype_code(dt), H + 2, N, C.c_void_p(g["disc_t"].data_ptr()),
-                                         C.c_void_p(g["term_int"].data_ptr()), C.c_void_p(g["values"].data_ptr()),
-                                         C.c_void_p(g["rewards"].data_ptr()), C.c_void_p(g["norm_t"].data_ptr()),
-                                         C.c_void_p(g["loss"].data_ptr()), stream_ptr()), "sgbpo_shac_loss")
         # critic input-gradient on the (at most KM) terminal rows; unused slots carry weight 0
         x = g["obs"].index_select(0, g["term_rows"]).detach()
         if self.vf_vjp_native:         # one launch: forward + transposed pass of the target critic (csrc mlp_rows_vjp_kernel)
@@ -614,6 +619,7 @@ class FusedRollout:
         with torch.cuda.stream(g["side"]):
             g["side"].wait_event(g["ev_fwd"])
             g["scal_host"].copy_(g["scal"], non_blocking=True)
+            g["loss_host"].copy_(g["loss"], non_blocking=True)
             g["ev_side"].record(g["side"])
         buf.observations.tensor, buf.values.tensor, buf.rewards.tensor = g["obs"], g["values"], g["rewards"]
         buf.actions.tensor, buf.terminals.tensor = g["actions"], g["term"]
@@ -689,7 +695,7 @@ class FusedRollout:
         if not g.get("bwd_enqueued"):
             g["bwd_graph"].replay()
         g["bwd_enqueued"] = False
-        return g["loss"]
+        return g["loss_host"].clone()        # (host copy made behind the forward graph: reading it does not wait for the reverse pass)
 
     # ------------------------------------------------------------------------------------------------------
     def collect_trajectories(self) -> float:

@@ -56,7 +56,7 @@ def main():
     print(json.dumps(out))
 
 
-if __name__ == "__main__" and "--timeline" not in sys.argv:
+if __name__ == "__main__" and "--timeline" not in sys.argv and "--gpu-timeline" not in sys.argv:
     main()
 
 
@@ -94,3 +94,59 @@ def host_timeline():
 
 if __name__ == "__main__" and "--timeline" in sys.argv:
     host_timeline()
+
+
+def gpu_timeline():
+    """Device timeline of back-to-back graph-replayed episodes (torch.profiler / CUPTI): per kernel start, duration and the idle
+    gap before it.  Shows where an episode's device time goes besides its kernels (launch gaps inside the graphs, the gap
+    between the graphs, small copies)."""
+    import bench
+    from torch.profiler import profile, ProfilerActivity
+    torch.set_default_dtype(torch.float32)
+    torch.set_default_device(torch.device("cuda", 0))
+    torch.manual_seed(0)
+    from safegbpo_b200.learning_algorithms.shac import SHAC
+    from safegbpo_b200.safeguards.boundary_projection import BoundaryProjectionSafeguard
+    from safegbpo_b200.envs import balance_cartpole
+    env = BoundaryProjectionSafeguard(balance_cartpole.BalanceCartPoleEnv(num_envs=4096, num_steps=1000000), strict=False)
+    algo = SHAC(env=env, policy_kwargs={"net_arch": bench.POLICY_ARCH}, policy_optim_kwargs={"lr": 4e-4},
+                vf_kwargs={"net_arch": bench.VF_ARCH}, vf_optim_kwargs={"lr": 2e-3}, regularisation_coefficient=0.1,
+                len_trajectories=64, fused="on", rng_order="batched")
+
+    def episode():
+        algo.buffer.reset()
+        algo.policy_optim.zero_grad()
+        algo.collect_trajectories()
+        return algo.update_policy()
+
+    for _ in range(8):
+        episode()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        for _ in range(4):
+            episode()
+        torch.cuda.synchronize()
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    evs.sort(key=lambda e: e.time_range.start)
+    t0, prev_end = evs[0].time_range.start, None
+    rows = []
+    for e in evs:
+        s, d = e.time_range.start - t0, e.time_range.end - e.time_range.start
+        gap = 0.0 if prev_end is None else s - prev_end
+        rows.append((s, d, gap, e.name[:70]))
+        prev_end = max(prev_end or 0.0, s + d)
+    # the third episode: between the 3rd and 4th forward kernels
+    starts = [i for i, r in enumerate(rows) if "rollout_wm_fwd" in r[3] or "rollout_fwd_kernel" in r[3] or "rollout_tc_fwd" in r[3]]
+    a, b = starts[2], starts[3]
+    first = a
+    while first > 0 and rows[first - 1][0] > rows[starts[1]][0] and "adam" not in rows[first - 1][3]:
+        first -= 1
+    ep = rows[first:b]
+    busy, gaps = sum(r[1] for r in ep), sum(r[2] for r in ep[1:])
+    print(f"episode span {ep[-1][0] + ep[-1][1] - ep[0][0]:.1f} us, kernels {busy:.1f} us, gaps {gaps:.1f} us, {len(ep)} device activities")
+    for s, d, gap, name in ep:
+        print(f"  +{s - ep[0][0]:8.1f} us  dur {d:7.1f}  gap before {gap:6.1f}  {name}")
+
+
+if __name__ == "__main__" and "--gpu-timeline" in sys.argv:
+    gpu_timeline()
