@@ -292,6 +292,8 @@ def run_ours(args):
     half = base.state_set.generator[0].diagonal().cpu()
     ctr = base.state_set.center[0].cpu()
     s0_host = (ctr + (torch.rand(N, n, generator=gen, device="cpu", dtype=dtype) * 2 - 1) * half * STATE_SPREAD).pin_memory()
+    if hasattr(base, "obstacles"):     # obstacle courses: the states reset() drew together with their goals and obstacles
+        s0_host = base.state.detach().to("cpu", dtype).pin_memory()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     launches = {"n": 0}
 
@@ -450,6 +452,11 @@ def correctness_gates(args, algo, env, base, episode, dtype, dev):
             tot["intervened"] += int(((fl & _lib.FL_INTERVENED) != 0).sum())
             tot["safety_violations"] += int(viol.sum())
         tot["infeasible_fraction_of_guarded"] = tot["infeasible"] / max(tot["guard_used"], 1)
+        if args.safeguard == "ray_mask":
+            # the reference's radial maps as shipped (ray_mask.py:108-113) return action_dist / safe_dist WITHOUT the
+            # paper's factor safe_dist, so its executed actions are not confined to the safe set; the path reproduces the shipped
+            # arithmetic (parity), and the exits are counted here, not gated
+            tot["set_exits_reference_quirk_Q2"] = tot.pop("safety_violations")
         out["episodes"] = tot
     try:
         out["oracle_slice"] = oracle_slice_check(args, env, base, dtype, dev)

@@ -149,9 +149,9 @@ class FusedRollout:
         lib = _lib.lib()
         self.jac_stride = lib.sgbpo_rollout_jac_stride(self.base.env_id) if self.engine_bwd else 0
         self.pol_jac_stride = lib.sgbpo_rollout_pol_jac_stride(self.base.env_id) if self.engine_bwd else 0
-        # rollout_fwd, mlp_rows(_tc), episode_stats, shac_loss, mlp_rows_vjp, [rollout_jac,] rollout_bwd, grad_norm, adam_apply
-        # (reverse engine 1: rollout_jac, policy_rows_bwd<jac>, rollout_scan, policy_rows_bwd<grad> instead of rollout_bwd)
-        self.launches_per_episode = 11 if self.engine_bwd else 8
+        # [episode_inputs,] rollout_fwd, mlp_rows(_tc), episode_stats, shac_loss, mlp_rows_vjp, [rollout_jac,] rollout_bwd,
+        # grad_norm, adam_apply (reverse engine 1: rollout_jac, policy_rows_bwd<jac>, rollout_scan, policy_rows_bwd<grad>
+        # instead of rollout_bwd)
         self.use_graphs = True                 # replay the episode as two CUDA graphs when its schedule allows
         self.graph_warmup = 2                  # eager episodes before capture (optimizer state, cuBLAS handles)
         self._episodes = 0
@@ -160,6 +160,10 @@ class FusedRollout:
         self.speculative_backward = True       # graph path: enqueue the backward graph right behind the forward graph
         self.forward_only = False              # model-free consumers (consumers.RolloutCollector): no activation stash, no reverse pass
         self.kernel_ms = {"rollout_fwd": [], "mlp_rows": [], "rollout_jac": [], "rollout_bwd": []}
+
+    @property
+    def launches_per_episode(self) -> int:
+        return (11 if self.engine_bwd else 8) + (1 if self._native_inputs() else 0)
 
     TC_FORWARD_MIN_ENVS = 12288       # measured cross-over of the warp-MMA and tcgen05 forward kernels on one B200 (profiles/r2_engines.md)
 
