@@ -199,13 +199,21 @@ __device__ inline bool grid_sum(double (&v)[NV], int which) {      // which = 2 
   __syncthreads();
   if (!last) return false;
   __threadfence();
+  // the last CTA sums the per-CTA partials: every thread fetches one (independent loads, fixed tree order -> deterministic)
+#pragma unroll
+  for (int q = 0; q < NV; ++q)
+    sh[q][threadIdx.x] = threadIdx.x < gridDim.x ? ((volatile double*)g_ep_part[which][q])[threadIdx.x] : 0.0;
+  __syncthreads();
+  for (int s = EP_THREADS / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+#pragma unroll
+      for (int q = 0; q < NV; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + s];
+    }
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int q = 0; q < NV; ++q) {
-      double a = 0.0;
-      for (unsigned int b = 0; b < gridDim.x; ++b) a += ((volatile double*)g_ep_part[which][q])[b];
-      v[q] = a;
-    }
+    for (int q = 0; q < NV; ++q) v[q] = sh[q][0];
     g_ep_ticket[which] = 0;
   }
   return threadIdx.x == 0;
@@ -234,11 +242,18 @@ template <class T>
 __global__ void shac_loss_kernel(int rows, int64_t N, const T* __restrict__ disc, const int32_t* __restrict__ term_int,
                                  const T* __restrict__ values, const T* __restrict__ rewards, const T* __restrict__ norm, T* loss, int slot) {
   double v[1] = {0.0};
-  const int64_t total = (int64_t)rows * N, stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-    const int t = (int)(e / N);
-    const double d = (double)disc[t];
-    if (d != 0.0) v[0] += d * (double)(term_int[t] != 0 ? values[e] : rewards[e]);
+  for (int t = blockIdx.x; t < rows; t += gridDim.x) {      // one CTA per buffer row: no division per element, rows of weight 0
+    const double d = (double)disc[t];                        // are skipped whole, the loads of a row are independent
+    if (d == 0.0) continue;
+    const T* __restrict__ src = (term_int[t] != 0 ? values : rewards) + (int64_t)t * N;
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    int64_t e = threadIdx.x;
+    for (; e + 3 * (int64_t)blockDim.x < N; e += 4 * (int64_t)blockDim.x) {
+      const T x0 = src[e], x1 = src[e + blockDim.x], x2 = src[e + 2 * blockDim.x], x3 = src[e + 3 * blockDim.x];
+      a[0] += (double)x0; a[1] += (double)x1; a[2] += (double)x2; a[3] += (double)x3;
+    }
+    for (; e < N; e += blockDim.x) a[0] += (double)src[e];
+    v[0] += d * ((a[0] + a[1]) + (a[2] + a[3]));
   }
   if (!grid_sum<1>(v, 2 * slot + 1)) return;
   *loss = (T)(-v[0] / (double)norm[0]);
