@@ -18,12 +18,14 @@ import numpy as np
 import torch
 from torch import Tensor
 
+from abc import ABC
+
 from .... import _lib, ops, rng
 from .... import sets
 from ....consts import build_consts
 
 
-class Simulator:
+class Simulator(ABC):             # (an ABC like the reference's: safeguard.py:229 registers Safeguard as a virtual subclass)
     EVAL_ENVS: int = 1
     ENV_NAME: str = ""            # key into _lib.ENV_IDS
 

@@ -138,3 +138,6 @@ class Safeguard:
 
     def __dir__(self):
         return sorted(set(super().__dir__()) | set(dir(self.env)))
+
+
+Simulator.register(Safeguard)      # safeguard.py:229: a wrapped environment is a Simulator for isinstance checks
