@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import time
 from typing import Optional
 
 import numpy as np
@@ -158,6 +159,7 @@ class FusedRollout:
         self._g = None                         # static buffers + captured graphs
         self.profile = False                   # record CUDA events around each of our kernels
         self.speculative_backward = True       # graph path: enqueue the backward graph right behind the forward graph
+        self.merged_graph = os.environ.get("SGBPO_MERGED_GRAPH", "1") != "0"      # ... as ONE graph with the critic branch forked off
         self.forward_only = False              # model-free consumers (consumers.RolloutCollector): no activation stash, no reverse pass
         self.kernel_ms = {"rollout_fwd": [], "mlp_rows": [], "rollout_jac": [], "rollout_bwd": []}
 
@@ -406,6 +408,7 @@ class FusedRollout:
                  fwd_graph=None, bwd_graph=None,
                  scal=z(2, dtype=torch.float64), scal_host=torch.zeros(2, dtype=torch.float64, device="cpu").pin_memory(),
                  loss_host=torch.zeros((), dtype=dt, device="cpu").pin_memory(),
+                 done_host=torch.full((1,), -1, dtype=torch.int64, device="cpu").pin_memory(), branch=torch.cuda.Stream(), ep_graph=None,
                  side=torch.cuda.Stream(), ev_fwd=torch.cuda.Event(), ev_side=torch.cuda.Event())
         # per-episode schedule (reset-all events of Q6, terminal rows, discounts): two small pinned host blocks
         # copied into static device tensors before every replay, so episodes WITH resets replay the same graphs
@@ -467,6 +470,27 @@ class FusedRollout:
 
     def _fwd_body(self, g):
         """Everything of collect_trajectories that touches the device, on static buffers (capturable)."""
+        self._fwd_head(g)
+        self._fwd_tail(g)
+
+    def _episode_body(self, g):
+        """One whole episode as ONE graph with a fork: after the forward kernel the critic values, episode scalars and loss value
+        (branch stream, ending in the host copies of the scalars) run concurrently with the reverse pass (capture stream).  Both
+        branches only need the forward kernel's buffers; the branch's tcgen05 critic shares the SMs with the small-footprint
+        kernels of the reverse pass (critic input gradient, step Jacobians, scan), and the row-batched reverse kernels take over
+        the SMs as its CTAs retire."""
+        self._fwd_head(g)
+        main, br = torch.cuda.current_stream(), g["branch"]
+        br.wait_stream(main)
+        with torch.cuda.stream(br):
+            self._fwd_tail(g)
+            g["scal_host"].copy_(g["scal"], non_blocking=True)
+            g["loss_host"].copy_(g["loss"], non_blocking=True)
+            g["done_host"].copy_(g["rng_ctr"], non_blocking=True)      # last: its arrival tells the host the scalars are there
+        self._bwd_body(g)
+        main.wait_stream(br)
+
+    def _fwd_head(self, g):
         base, algo, H = self.base, self.algo, g["H"]
         N, o = base.num_envs, base.obs_dim
         dt = base.state.dtype
@@ -497,6 +521,12 @@ class FusedRollout:
             base._reset_restore(snap)
         check(lib.sgbpo_rollout_fwd(base.env_id, dtype_code(dt), C.byref(self._consts()), C.byref(self.policy_pack.desc),
                                     C.byref(g["r"]), stream_ptr()), "sgbpo_rollout_fwd")
+
+    def _fwd_tail(self, g):
+        base, algo, H = self.base, self.algo, g["H"]
+        N, o = base.num_envs, base.obs_dim
+        dt = base.state.dtype
+        lib = _lib.lib()
         if self.vf_native:
             check(lib.sgbpo_mlp_rows(dtype_code(dt), H * N, C.byref(self.vf_pack.desc), C.c_void_p(g["obs"][1].data_ptr()),
                                      C.c_void_p(g["values"][1].data_ptr()), stream_ptr()), "sgbpo_mlp_rows")
@@ -526,6 +556,11 @@ class FusedRollout:
         dt = base.state.dtype
         W = self.policy_pack.width
         o = base.obs_dim
+        g["flat"].zero_()
+        if self.engine_bwd:            # step Jacobians of all H x N steps in one parallel launch (first: no shared memory, so in the
+            # merged episode graph it shares the SMs with the critic kernel of the other branch)
+            check(_lib.lib().sgbpo_rollout_jac(base.env_id, dtype_code(dt), C.byref(self._consts()), C.byref(g["r"]), stream_ptr()),
+                  "sgbpo_rollout_jac")
         # critic input-gradient on the (at most KM) terminal rows; unused slots carry weight 0
         x = g["obs"].index_select(0, g["term_rows"]).detach()
         if self.vf_vjp_native:         # one launch: forward + transposed pass of the target critic (csrc mlp_rows_vjp_kernel)
@@ -536,10 +571,6 @@ class FusedRollout:
             x = x.clone().requires_grad_(True)
             v = (algo.target_value_function(x.view(-1, o)).view(g["KM"], N) * g["term_w"].unsqueeze(1)).sum()
             g["gobs_term"].copy_(torch.autograd.grad(v, x)[0])
-        g["flat"].zero_()
-        if self.engine_bwd:            # step Jacobians of all H x N steps in one parallel launch, then the parallel reverse pass
-            check(_lib.lib().sgbpo_rollout_jac(base.env_id, dtype_code(dt), C.byref(self._consts()), C.byref(g["r"]), stream_ptr()),
-                  "sgbpo_rollout_jac")
         check(_lib.lib().sgbpo_rollout_bwd(base.env_id, dtype_code(dt), C.byref(self._consts()),
                                            C.byref(self.policy_pack.desc), C.byref(g["r"]), C.byref(g["gr"]), stream_ptr()),
               "sgbpo_rollout_bwd")
@@ -604,6 +635,12 @@ class FusedRollout:
             g["aux0"].copy_(base._aux())
         g["rng_ctr_host"][0] = self._episodes
         g["rng_ctr"].copy_(g["rng_ctr_host"], non_blocking=True)
+        merged = (self.merged_graph and self.speculative_backward and not self.forward_only and g["bwd_graph"] is not None
+                  and g["inputs_args"] is not None)
+        if merged and g["ep_graph"] is None:
+            g["ep_graph"] = self._capture(self._episode_body, g)
+        if merged:
+            return self._replay_episode_graph(g, H, steps_end, pending_end, reset_at, terminal_rows)
         if g["fwd_graph"] is None:
             rng_state = torch.cuda.get_rng_state()
             g["fwd_graph"] = self._capture(self._fwd_body, g)
@@ -625,6 +662,22 @@ class FusedRollout:
             g["scal_host"].copy_(g["scal"], non_blocking=True)
             g["loss_host"].copy_(g["loss"], non_blocking=True)
             g["ev_side"].record(g["side"])
+        g["ev_side"].synchronize()
+        return self._finish_collect(g, H, steps_end, pending_end, reset_at, terminal_rows)
+
+    def _replay_episode_graph(self, g, H, steps_end, pending_end, reset_at, terminal_rows) -> float:
+        g["ep_graph"].replay()
+        g["bwd_enqueued"] = True
+        # the scalars are copied to pinned memory by the graph's branch; the host waits for the LAST of those copies (the episode
+        # counter) to land instead of for the whole graph, so it still runs ahead of the reverse pass
+        t0, want = time.perf_counter(), self._episodes
+        while int(g["done_host"][0]) != want:
+            if time.perf_counter() - t0 > 120.0:
+                raise _lib.SgbpoError("episode graph: the scalar read-back did not arrive (device fault?)")
+        return self._finish_collect(g, H, steps_end, pending_end, reset_at, terminal_rows)
+
+    def _finish_collect(self, g, H, steps_end, pending_end, reset_at, terminal_rows) -> float:
+        base, buf = self.base, self.algo.buffer
         buf.observations.tensor, buf.values.tensor, buf.rewards.tensor = g["obs"], g["values"], g["rewards"]
         buf.actions.tensor, buf.terminals.tensor = g["actions"], g["term"]
         if g.get("t_full") is None:
@@ -643,7 +696,6 @@ class FusedRollout:
             w = self.wrapper
             w.safe_action = g["exec_actions"][H - 1]
             w._interventions = w._interventions + g["n_interv"]
-        g["ev_side"].synchronize()
         self.last = dict(graph=True, terminal_rows=terminal_rows, flags=g["flags"], states=g["states"], exec_actions=g["exec_actions"])
         if self.wrapper is not None:
             if w.strict:
