@@ -289,6 +289,269 @@ rollout_wm_fwd_kernel(const __grid_constant__ RolloutArgs<float> A, const __grid
   }
 }
 
+// ---- pair-split variant: TWO warps share 8 environments, each computes 64 of the 128 hidden columns ------------------------------
+// Per step the two warps exchange (through a pair-private shared-memory block, under a 64-thread named barrier): the observations
+// (owner -> both), the LayerNorm half statistics (mean_h, M2_h: combined exactly, var = (M2_0 + M2_1 + 32 (mean_0 - mean_1)^2) / 128),
+// the A fragments of their 4 k-tiles of layer 2 and the partial output-layer dot products.  The MLP part of the per-step dependency
+// chain halves (144 instead of 288 HMMA per warp, 16 instead of 32 elementwise values per lane); the environment step stays on the
+// owner lanes of the pair's first warp.
+constexpr int PAIRS = 4, NTH = NT / 2, KTH = KT / 2;       // 8 warps per CTA = 4 pairs = 32 environments
+
+struct PairSmem {          // one per pair
+  float obs[R][16];        // policy input rows (k-padded): [obs, 1, 0...]
+  float2 stat[2][2][R];    // [layer][warp half][row] (mean_h, M2_h)
+  float mu[2][R][4];       // [warp half][row][q] partial output-layer sums
+  uint4 frag[2][KTH][32];  // [warp half][local k-tile][lane] A fragments (hi/lo stacked) of layer 2
+};
+
+__device__ __forceinline__ void pair_sync(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory"); }
+
+// ELU + stash + half-row statistics of this lane's 16 values (row g, its warp's 64 columns); h is left centred on the HALF mean
+__device__ __forceinline__ void elu_half_stats(float (&h)[NTH][2], float* __restrict__ stash, size_t nt_stride, bool store,
+                                               float& mean_h, float& m2_h) {
+  float s[2] = {0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < NTH; ++j) {
+    h[j][0] = elu_fast(h[j][0]);
+    h[j][1] = elu_fast(h[j][1]);
+    s[j & 1] += h[j][0] + h[j][1];
+    if (store) *reinterpret_cast<float2*>(stash + j * nt_stride) = make_float2(h[j][0], h[j][1]);
+  }
+  mean_h = quad_sum(s[0] + s[1]) * (2.f / W);
+  float q[2] = {0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < NTH; ++j) {
+    h[j][0] -= mean_h;
+    h[j][1] -= mean_h;
+    q[j & 1] = fmaf(h[j][0], h[j][0], q[j & 1]);
+    q[j & 1] = fmaf(h[j][1], h[j][1], q[j & 1]);
+  }
+  m2_h = quad_sum(q[0] + q[1]);
+}
+// combine the two half statistics (exact pooled mean / variance) and apply LayerNorm to the half-centred values
+__device__ __forceinline__ void layernorm_half(float (&h)[NTH][2], float mean_h, float m2_h, float2 other, const float* __restrict__ gamma,
+                                               const float* __restrict__ beta, int col0, float& mean, float& rstd) {
+  const float d = mean_h - other.x;
+  mean = 0.5f * (mean_h + other.x);
+  rstd = rsqrtf((m2_h + other.y + (W / 4) * d * d) * (1.f / W) + 1e-5f);
+  const float shift = mean_h - mean;
+#pragma unroll
+  for (int j = 0; j < NTH; ++j) {
+    const float2 gm = *reinterpret_cast<const float2*>(gamma + col0 + j * 8);
+    const float2 bt = *reinterpret_cast<const float2*>(beta + col0 + j * 8);
+    h[j][0] = ((h[j][0] + shift) * rstd) * gm.x + bt.x;
+    h[j][1] = ((h[j][1] + shift) * rstd) * gm.y + bt.y;
+  }
+}
+
+template <int ENV>
+__global__ void __launch_bounds__(PAIRS * 64, 1)
+rollout_wm2_fwd_kernel(const __grid_constant__ RolloutArgs<float> A, const __grid_constant__ MlpParams<float> P,
+                       const __grid_constant__ SafeConsts<float> k) {
+  using TASK = Task<ENV>;
+  using T = float;
+  constexpr int NS = TASK::NS, NA = TASK::NA, NO = TASK::NO, NAUX = TASK::NAUX;
+  static_assert(NO < 16 && NA <= 4, "one k-tile input layer, at most 4 policy outputs");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WmSmem S;
+  S.carve(smem_raw, NA);
+  PairSmem* PS = reinterpret_cast<PairSmem*>(smem_raw + ((WmSmem::bytes(NA) + 15) & ~size_t(15)));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
+  const int pair = warp >> 1, half = warp & 1;
+  PairSmem& X = PS[pair];
+
+  for (int idx = tid; idx < (KT + 1) * NT * 32; idx += PAIRS * 64) {
+    const int l = idx & 31, nt = (idx >> 5) % NT, kt = (idx >> 5) / NT;          // kt == KT: the input layer
+    const int n = nt * 8 + (l >> 2), k0 = 2 * (l & 3);
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int kk = k0 + (j & 1) + (j >> 1) * 8;
+      if (kt < KT) v[j] = P.weight[1][(size_t)n * W + kt * 16 + kk];
+      else v[j] = kk < NO ? P.weight[0][(size_t)n * NO + kk] : (kk == NO ? P.bias[0][n] : 0.f);
+    }
+    uint4 f;
+    split_pair(v[0], v[1], f.x, f.z);
+    split_pair(v[2], v[3], f.y, f.w);
+    (kt < KT ? S.w2f + ((size_t)kt * NT + nt) * 32 : S.w1f + (size_t)nt * 32)[l] = f;
+  }
+  for (int i = tid; i < W; i += PAIRS * 64) {
+    S.b2[i] = P.bias[1][i];
+    S.g1[i] = P.ln_weight[0][i]; S.be1[i] = P.ln_bias[0][i];
+    S.g2[i] = P.ln_weight[1][i]; S.be2[i] = P.ln_bias[1][i];
+  }
+  for (int i = tid; i < NA * W; i += PAIRS * 64) S.w_out[i] = P.weight[2][i];
+  for (int i = tid; i < NA; i += PAIRS * 64) S.b_out[i] = P.bias[2][i];
+
+  const int64_t N = A.N;
+  const int64_t env = ((int64_t)blockIdx.x * PAIRS + pair) * R + g;
+  const bool owner = half == 0 && tig == 0;
+  const bool row_ok = env < N, valid = owner && row_ok;
+  const bool tiled = A.stash_tiled != 0, stash = A.stash_e1 != nullptr;
+  const size_t nt_stride = tiled ? 1024 : 8;
+  const int col0 = half * (W / 2) + 2 * tig;              // this lane's first column (n-tile 8 half, pair 2 tig)
+
+  T s[NS], aux[NAUX > 0 ? NAUX : 1], ob[NO];
+  T sigma[NA];
+#pragma unroll
+  for (int q = 0; q < NA; ++q) sigma[q] = sg_exp(P.log_std[q]);
+#pragma unroll
+  for (int i = 0; i < NS; ++i) s[i] = valid ? A.states[env * NS + i] : T(0);
+  if (NAUX > 0) {
+#pragma unroll
+    for (int i = 0; i < NAUX; ++i) aux[i] = valid ? A.aux0[env * NAUX + i] : T(0);
+  }
+#pragma unroll
+  for (int i = 0; i < NO; ++i) ob[i] = valid ? A.obs[env * NO + i] : T(0);
+  if (half == 0) {
+    for (int i = lane; i < R * 16; i += 32) X.obs[i / 16][i % 16] = (i % 16) == NO ? 1.f : 0.f;
+    __syncwarp();
+    if (tig == 0) {
+#pragma unroll
+      for (int i = 0; i < NO; ++i) X.obs[g][i] = ob[i];
+    }
+  }
+  __syncthreads();
+
+  for (int t = 0; t < A.H; ++t) {
+    T epsv[NA], wv[NS], dv[NA * 2 * NA], rs[NS];
+    const int ridx = A.reset_idx ? A.reset_idx[t] : -1;
+    if (valid) {
+#pragma unroll
+      for (int q = 0; q < NA; ++q) epsv[q] = A.eps[((int64_t)t * N + env) * NA + q];
+#pragma unroll
+      for (int i = 0; i < NS; ++i) wv[i] = A.noise[((int64_t)t * N + env) * NS + i];
+      if (A.dirs) {
+#pragma unroll
+        for (int i = 0; i < NA * 2 * NA; ++i) dv[i] = A.dirs[((int64_t)t * N + env) * (NA * 2 * NA) + i];
+      }
+      if (ridx >= 0) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) rs[i] = A.reset_states[((int64_t)ridx * N + env) * NS + i];
+      }
+    }
+    pair_sync(pair);                                   // B0: the observations of this step are in X.obs
+    // ---- input layer, this warp's 8 n-tiles -------------------------------------------------------------------------------------
+    uint32_t a[4];
+    {
+      const float2 p01 = *reinterpret_cast<const float2*>(&X.obs[g][2 * tig]);
+      const float2 p23 = *reinterpret_cast<const float2*>(&X.obs[g][8 + 2 * tig]);
+      split_pair(p01.x, p01.y, a[0], a[1]);
+      split_pair(p23.x, p23.y, a[2], a[3]);
+    }
+    float h[NTH][2];
+#pragma unroll
+    for (int j = 0; j < NTH; ++j) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint4 b = S.w1f[(half * NTH + j) * 32 + lane];
+      hmma(acc, a, b.x, b.y);
+      hmma(acc, a, b.z, b.w);
+      h[j][0] = acc[0] + acc[2];
+      h[j][1] = acc[1] + acc[3];
+    }
+    const int64_t row = (int64_t)t * N + (row_ok ? env : 0);
+    const size_t stash_off = stash_index<W>(tiled, row, col0);
+    float st[4], mean_h, m2_h;
+    elu_half_stats(h, stash ? A.stash_e1 + stash_off : nullptr, nt_stride, stash && row_ok, mean_h, m2_h);
+    if (tig == 0) X.stat[0][half][g] = make_float2(mean_h, m2_h);
+    pair_sync(pair);                                   // B1
+    layernorm_half(h, mean_h, m2_h, X.stat[0][half ^ 1][g], S.g1, S.be1, col0, st[0], st[1]);
+    // ---- A fragments of this warp's 4 k-tiles, exchanged with the partner ---------------------------------------------------------
+    uint4 own[KTH], oth[KTH];
+#pragma unroll
+    for (int j = 0; j < KTH; ++j) {
+      split_pair(h[2 * j][0], h[2 * j][1], own[j].x, own[j].y);
+      split_pair(h[2 * j + 1][0], h[2 * j + 1][1], own[j].z, own[j].w);
+      X.frag[half][j][lane] = own[j];
+    }
+    pair_sync(pair);                                   // B2
+#pragma unroll
+    for (int j = 0; j < KTH; ++j) oth[j] = X.frag[half ^ 1][j][lane];
+    {
+      float acc[NTH][4];
+#pragma unroll
+      for (int j = 0; j < NTH; ++j) {
+        const float2 b = *reinterpret_cast<const float2*>(S.b2 + col0 + j * 8);
+        acc[j][0] = b.x; acc[j][1] = b.y; acc[j][2] = 0.f; acc[j][3] = 0.f;
+      }
+#pragma unroll
+      for (int kt = 0; kt < KT; ++kt) {
+        const uint4 f = ((kt / KTH) == 0) == (half == 0) ? own[kt % KTH] : oth[kt % KTH];
+        a[0] = f.x; a[1] = f.y; a[2] = f.z; a[3] = f.w;
+        const uint4* bf = S.w2f + ((size_t)kt * NT + half * NTH) * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < NTH; ++j) {
+          const uint4 b = bf[j * 32];
+          hmma(acc[j], a, b.x, b.y);
+          hmma(acc[j], a, b.z, b.w);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NTH; ++j) {
+        h[j][0] = acc[j][0] + acc[j][2];
+        h[j][1] = acc[j][1] + acc[j][3];
+      }
+    }
+    elu_half_stats(h, stash ? A.stash_e2 + stash_off : nullptr, nt_stride, stash && row_ok, mean_h, m2_h);
+    if (tig == 0) X.stat[1][half][g] = make_float2(mean_h, m2_h);
+    pair_sync(pair);                                   // B3
+    layernorm_half(h, mean_h, m2_h, X.stat[1][half ^ 1][g], S.g2, S.be2, col0, st[2], st[3]);
+    if (stash && valid) *reinterpret_cast<float4*>(A.stash_stats + row * 4) = make_float4(st[0], st[1], st[2], st[3]);
+    // ---- output layer: partial sums over this warp's columns --------------------------------------------------------------------
+    T mu[NA];
+#pragma unroll
+    for (int q = 0; q < NA; ++q) {
+      float o[2] = {0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < NTH; ++j) {
+        const float2 w = *reinterpret_cast<const float2*>(S.w_out + q * W + col0 + j * 8);
+        o[j & 1] = fmaf(h[j][0], w.x, o[j & 1]);
+        o[j & 1] = fmaf(h[j][1], w.y, o[j & 1]);
+      }
+      mu[q] = quad_sum(o[0] + o[1]);
+      if (tig == 0) X.mu[half][g][q] = mu[q];
+    }
+    pair_sync(pair);                                   // B4
+    // ---- environment step on the owner lanes of the pair's first warp -----------------------------------------------------------------
+    if (owner) {
+      T act[NA];
+#pragma unroll
+      for (int q = 0; q < NA; ++q) act[q] = valid ? sg_tanh((mu[q] + X.mu[1][g][q] + S.b_out[q]) + sigma[q] * epsv[q]) : T(0);
+      if (!valid) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) wv[i] = T(0);
+      }
+      if (NAUX > 0 && ridx >= 0 && valid) {
+#pragma unroll
+        for (int i = 0; i < NAUX; ++i) aux[i] = rs[i];
+      }
+      T sn[NS], ae[NA], rew;
+      int fl;
+      const StepShared<T>* sh = A.shared ? A.shared + t : nullptr;
+      StepShared<T> empty;
+      if (!sh) { memset(&empty, 0, sizeof(empty)); sh = &empty; }
+      safeguarded_step<TASK, T, T>(s, act, wv, aux, A.dirs ? dv : nullptr, sh, k, ridx >= 0, rs, sn, ae, ob, rew, fl);
+#pragma unroll
+      for (int i = 0; i < NS; ++i) s[i] = sn[i];
+#pragma unroll
+      for (int i = 0; i < NO; ++i) X.obs[g][i] = ob[i];
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) A.states[((int64_t)(t + 1) * N + env) * NS + i] = sn[i];
+#pragma unroll
+        for (int i = 0; i < NO; ++i) A.obs[((int64_t)(t + 1) * N + env) * NO + i] = ob[i];
+#pragma unroll
+        for (int q = 0; q < NA; ++q) {
+          A.actions[((int64_t)t * N + env) * NA + q] = act[q];
+          A.exec_actions[((int64_t)t * N + env) * NA + q] = ae[q];
+        }
+        A.rewards[(int64_t)t * N + env] = rew;
+        A.flags[(int64_t)t * N + env] = fl;
+      }
+    }
+  }
+}
+
 template <int ENV>
 int rollout_wm_fwd(const sgbpo_consts* c, const sgbpo_mlp* pol, const sgbpo_rollout* r, cudaStream_t st) {
   using TASK = Task<ENV>;
@@ -297,6 +560,20 @@ int rollout_wm_fwd(const sgbpo_consts* c, const sgbpo_mlp* pol, const sgbpo_roll
   const int n_stash = (r->stash_e1 != nullptr) + (r->stash_e2 != nullptr) + (r->stash_stats != nullptr);
   if (n_stash != 0 && n_stash != 3) return fail2(SGBPO_E_ARG, "warp-MMA forward: pass e1, e2 and stats stash buffers or none");
   if (r->stash_h1) return fail2(SGBPO_E_UNSUPPORTED, "warp-MMA forward does not write the h1 stash (sequential reverse pass)");
+  // two warps per 8 environments while one CTA per SM holds the whole batch (the pair kernel keeps 162 registers per thread: one
+  // CTA of 4 pairs per SM), one warp per 8 environments beyond that; SGBPO_WM_SPLIT=1|2 forces
+  const char* split = getenv("SGBPO_WM_SPLIT");
+  const bool pairs_fit = (r->N + PAIRS * R - 1) / (PAIRS * R) <= sm_count();
+  if (split ? split[0] == '2' : pairs_fit) {
+    auto kern2 = rollout_wm2_fwd_kernel<ENV>;
+    const size_t smem2 = ((WmSmem::bytes(TASK::NA) + 15) & ~size_t(15)) + PAIRS * sizeof(PairSmem);
+    cudaError_t e2 = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e2 != cudaSuccess) return cuda_fail2(e2, "cudaFuncSetAttribute(rollout_wm2_fwd)");
+    const int64_t grid2 = (r->N + PAIRS * R - 1) / (PAIRS * R);
+    kern2<<<(unsigned)grid2, PAIRS * 64, smem2, st>>>(convert_rollout<float>(*r), convert_mlp<float>(*pol), convert_consts<float>(*c));
+    e2 = cudaGetLastError();
+    return e2 == cudaSuccess ? SGBPO_OK : cuda_fail2(e2, "rollout_wm2_fwd_kernel");
+  }
   auto kern = rollout_wm_fwd_kernel<ENV>;
   const size_t smem = WmSmem::bytes(TASK::NA);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
