@@ -146,9 +146,13 @@ def test_warp_mma_kernel_uses_tensor_core_mma():
     if not obj.exists():
         pytest.skip("object files are not shipped to the GPU box (the CPU run checks them)")
     sass = subprocess.run(["cuobjdump", "-sass", str(obj)], capture_output=True, text=True).stdout
-    body = sass[sass.index("rollout_wm_fwd_kernel"):]
-    assert body.count("HMMA.16816.F32") >= 288
-    assert body.count("BAR.SYNC") <= 2             # the parameter staging barrier only
+    funcs = {}
+    for chunk in sass.split("Function : ")[1:]:
+        funcs[chunk.split("\n", 1)[0].strip()] = chunk
+    one = next(v for k, v in funcs.items() if "rollout_wm_fwd_kernel" in k)
+    two = next(v for k, v in funcs.items() if "rollout_wm2_fwd_kernel" in k)
+    assert one.count("HMMA.16816.F32") >= 288 and one.count("BAR.SYNC") <= 2      # the parameter staging barrier only
+    assert two.count("HMMA.16816.F32") >= 144 and "BAR.SYNC" in two               # pair-split: named 64-thread barriers
 
 
 def _build_any(env_name, N, H, num_steps, fused, dev):
