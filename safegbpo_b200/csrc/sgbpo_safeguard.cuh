@@ -99,19 +99,16 @@ SG_HD bool gate_projectable(const T* c_f, const T (*B)[MAXM], const SafeConsts<T
     ok = ok && (sg_abs(ctr[i]) <= half[i] + sup);
   }
 #pragma unroll
-  for (int a = 0; a < NA; ++a) {       // axes = normalised generators (NaN for a zero column -> false, as shipped)
-    T nrm = T(0);
-#pragma unroll
-    for (int i = 0; i < NS; ++i) nrm += B[i][a] * B[i][a];
-    nrm = sg_sqrt(nrm);
-    T proj = T(0), sup = T(0);
+  for (int a = 0; a < NA; ++a) {       // axes = normalised generators b / |b|:  |ctr . b| / |b| <= |b| + sum_i |half_i b_i| / |b|,
+    // evaluated multiplied through by |b| (no square root, no divisions); a zero column is NaN -> false in the reference
+    T nrm2 = T(0), proj = T(0), sup = T(0);
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
-      const T dir = B[i][a] / nrm;
-      proj += ctr[i] * dir;
-      sup += sg_abs(half[i] * dir);
+      nrm2 += B[i][a] * B[i][a];
+      proj += ctr[i] * B[i][a];
+      sup += sg_abs(half[i] * B[i][a]);
     }
-    ok = ok && (sg_abs(proj) <= nrm + sup);
+    ok = ok && nrm2 > T(0) && (sg_abs(proj) <= nrm2 + sup);
   }
   return ok;
 }
@@ -162,7 +159,29 @@ SG_HD Interval<S> safe_interval_m1(const S* c_f, const S (*B)[MAXM], const SafeC
     iv.lo = sg_max(iv.lo, S(k.a_lo[0]));
     iv.hi = sg_min(iv.hi, S(k.a_hi[0]));
   }
-  if (k.state_constrained) {
+  if (k.state_constrained && k.state_model == SM_INVERTIBLE) {
+    // |e_i - b_i a| <= rb_i per row (for_each_state_row_m1's two rows), with ONE reciprocal per row and no dependence between
+    // the rows' divisions:  b > 0: -(rb - e)/b <= a <= (rb + e)/b;  b < 0: (rb + e)/b <= a <= -(rb - e)/b
+    constexpr int NS = TASK::NS;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      S e = S(k.cs_hat[i]), b = S(T(0));
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        e = e - S(k.Ginv[i * NS + j]) * c_f[j];
+        b = b + S(k.Ginv[i * NS + j]) * B[j][0];
+      }
+      const T bp = primal(b);
+      if (bp != T(0)) {
+        const S r = C<S>(1.0) / b;
+        const S q1 = (S(k.rb[i]) + e) * r, q2 = -((S(k.rb[i]) - e) * r);
+        iv.hi = sg_min(iv.hi, bp > T(0) ? q1 : q2);
+        iv.lo = sg_max(iv.lo, bp > T(0) ? q2 : q1);
+      } else if (primal(S(k.rb[i]) - e) < T(0) || primal(S(k.rb[i]) + e) < T(0)) {
+        iv.feasible = false;
+      }
+    }
+  } else if (k.state_constrained) {
     for_each_state_row_m1<TASK>(c_f, B, k, [&](const S& alpha, const S& gamma, int) {
       const T al = primal(alpha);
       if (al > T(0)) iv.hi = sg_min(iv.hi, gamma / alpha);
