@@ -615,6 +615,10 @@ policy_rows_bwd_kernel(const __grid_constant__ RowsBwdArgs R, const __grid_const
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row = tile * ROWS + trow;
     const bool valid = row < R.M;
+    if (tid == 0 && tile + gridDim.x < n_tiles) {      // the next tile's stash blocks (64 KB contiguous each) on their way into L2
+      bulk_prefetch_l2(R.e1 + (size_t)(tile + gridDim.x) * ROWS * W, ROWS * W * 4);
+      if (GRAD) bulk_prefetch_l2(R.e2 + (size_t)(tile + gridDim.x) * ROWS * W, ROWS * W * 4);
+    }
     const size_t row_off = valid ? (size_t)row : 0;
     float4 st = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) st = *reinterpret_cast<const float4*>(R.stats + row_off * 4);

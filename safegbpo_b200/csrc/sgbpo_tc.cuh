@@ -93,6 +93,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// L2 prefetch of a contiguous block (TMA unit, no destination): turns the DRAM latency of the next tile's loads into L2 latency
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {      // 16-byte multiples
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 // named barrier over `count` threads (ids 1..15; id 0 is __syncthreads)
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
