@@ -169,7 +169,7 @@ mlp_rows_tc_kernel(int64_t M, const float* __restrict__ x, float* __restrict__ o
       }
     }
 #pragma unroll
-    for (int c = 0; c < CW; ++c) { e[c] = elu1(e[c]); sum += e[c]; }
+    for (int c = 0; c < CW; ++c) { e[c] = elu1_fast(e[c]); sum += e[c]; }
     normalise<NSPLIT>(e, sum, vec + 1 * W, vec + 2 * W, red_a, red_b, part, trow);
     // ---- hidden-hidden layers on the tensor cores ---------------------------------------------------------------
     for (int l = 0; l < n_hh; ++l) {
@@ -210,8 +210,8 @@ mlp_rows_tc_kernel(int64_t M, const float* __restrict__ x, float* __restrict__ o
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4) {
           const float4 b4 = *reinterpret_cast<const float4*>(bias + q * 32 + 4 * i4);
-          const float v0 = elu1(z[4 * i4 + 0] + b4.x), v1 = elu1(z[4 * i4 + 1] + b4.y);
-          const float v2 = elu1(z[4 * i4 + 2] + b4.z), v3 = elu1(z[4 * i4 + 3] + b4.w);
+          const float v0 = elu1_fast(z[4 * i4 + 0] + b4.x), v1 = elu1_fast(z[4 * i4 + 1] + b4.y);
+          const float v2 = elu1_fast(z[4 * i4 + 2] + b4.z), v3 = elu1_fast(z[4 * i4 + 3] + b4.w);
           e[q * 32 + 4 * i4 + 0] = v0; e[q * 32 + 4 * i4 + 1] = v1; e[q * 32 + 4 * i4 + 2] = v2; e[q * 32 + 4 * i4 + 3] = v3;
           sum += (v0 + v1) + (v2 + v3);
         }

@@ -978,9 +978,22 @@ rollout_scan_kernel(const __grid_constant__ ScanArgs A) {
       for (int i = 0; i < NO; ++i) gobs[i] = fmaf(pj[q * NOP + i], ga_pre, gobs[i]);
     }
   };
+  // ... and the rows of steps t - 4, t - 5 are pulled into L2 meanwhile (the Jacobian-mode kernel that ran in between has evicted
+  // what rollout_jac_kernel wrote), so the register loads one step ahead see L2 latency, which one step of arithmetic covers
+  auto prefetch_l2 = [&](int t) {
+    if (t < 0) return;
+    const size_t row = (size_t)t * A.N + e;
+    const char* p = reinterpret_cast<const char*>(A.jac + row * JS::STRIDE);
+#pragma unroll
+    for (int o = 0; o < JS::STRIDE * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(A.pol_jac + row * (NA * NOP)));
+  };
   StepIn bufa, bufb;
+  for (int t = A.H - 2; t >= A.H - 5; --t) prefetch_l2(t);
   fetch(A.H - 1, bufa);
   for (int t = A.H - 1; t >= 0; t -= 2) {
+    prefetch_l2(t - 5);
+    prefetch_l2(t - 6);
     if (t > 0) fetch(t - 1, bufb);
     step(t, bufa);
     if (t > 0) {

@@ -136,7 +136,7 @@ def gpu_timeline():
         rows.append((s, d, gap, e.name[:70]))
         prev_end = max(prev_end or 0.0, s + d)
     # the third episode: between the 3rd and 4th forward kernels
-    starts = [i for i, r in enumerate(rows) if "rollout_wm_fwd" in r[3] or "rollout_fwd_kernel" in r[3] or "rollout_tc_fwd" in r[3]]
+    starts = [i for i, r in enumerate(rows) if "rollout_wm" in r[3] or "rollout_fwd_kernel" in r[3] or "rollout_tc_fwd" in r[3]]
     a, b = starts[2], starts[3]
     first = a
     while first > 0 and rows[first - 1][0] > rows[starts[1]][0] and "adam" not in rows[first - 1][3]:
