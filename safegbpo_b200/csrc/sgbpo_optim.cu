@@ -118,6 +118,60 @@ adam_apply_kernel(const __grid_constant__ OptArgs<T> A, double beta1, double bet
   }
 }
 
+// small models (the policies of this path: ~18 k parameters): ONE CTA does both phases -- sum of squares, clip coefficient and bias
+// corrections, then the update -- instead of two launches with a grid-wide ticket in between
+constexpr int OPT_SMALL_THREADS = 1024, OPT_SMALL_MAX = 64 * 1024;
+template <class T, class STEP_T>
+__global__ void __launch_bounds__(OPT_SMALL_THREADS)
+clip_adam_small_kernel(const __grid_constant__ OptArgs<T> A, double lr, double beta1, double beta2, double eps, double max_norm,
+                       T* __restrict__ total_norm_out) {
+  __shared__ T scratch[OPT_SMALL_THREADS / 32];
+  __shared__ T s_coef, s_step[SGBPO_OPT_MAX_TENSORS], s_bc2[SGBPO_OPT_MAX_TENSORS];
+  T acc = T(0);
+  for (int i = 0; i < A.n; ++i) {
+    const T* __restrict__ g = A.grad[i];
+    for (int64_t j = threadIdx.x; j < A.numel[i]; j += OPT_SMALL_THREADS) acc += g[j] * g[j];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    T t = scratch[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) {
+      const T total_norm = sqrt(t);
+      const T coef = T(max_norm) / (total_norm + T(1e-6));
+      s_coef = (coef < T(1) || coef != coef) ? coef : T(1);
+      if (total_norm_out) *total_norm_out = total_norm;
+    }
+  }
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + A.n) {
+    const int i = threadIdx.x - 32;
+    STEP_T* sp = reinterpret_cast<STEP_T*>(A.step[i]);
+    const double step = (double)(*sp) + 1.0;
+    *sp = (STEP_T)step;
+    s_step[i] = (T)(lr / (1.0 - pow(beta1, step)));
+    s_bc2[i] = (T)sqrt(1.0 - pow(beta2, step));
+  }
+  __syncthreads();
+  const T coef = s_coef, one_m_b1 = T(1.0 - beta1), b2 = T(beta2), one_m_b2 = T(1.0 - beta2), eps_t = T(eps);
+  for (int i = 0; i < A.n; ++i) {
+    const T step_size = s_step[i], bc2_sqrt = s_bc2[i];
+    T* __restrict__ p = A.param[i]; T* __restrict__ g = A.grad[i]; T* __restrict__ m = A.exp_avg[i]; T* __restrict__ v = A.exp_avg_sq[i];
+    for (int64_t j = threadIdx.x; j < A.numel[i]; j += OPT_SMALL_THREADS) {
+      const T gj = g[j] * coef;
+      const T mj = m[j] + (gj - m[j]) * one_m_b1;
+      const T vj = v[j] * b2 + gj * gj * one_m_b2;
+      g[j] = gj;
+      m[j] = mj;
+      v[j] = vj;
+      p[j] = p[j] - step_size * (mj / (sqrt(vj) / bc2_sqrt + eps_t));
+    }
+  }
+}
+
 static int opt_fail(int code, const char* msg) {
   snprintf(g_err, sizeof(g_err), "%s", msg);
   return code;
@@ -134,6 +188,18 @@ static int launch_clip_adam(const sgbpo_optim* o, int step_dtype, void* total_no
     a.param[i] = (T*)o->param[i]; a.grad[i] = (T*)o->grad[i]; a.exp_avg[i] = (T*)o->exp_avg[i];
     a.exp_avg_sq[i] = (T*)o->exp_avg_sq[i]; a.step[i] = o->step[i]; a.numel[i] = o->numel[i];
     total += o->numel[i];
+  }
+  if (total <= OPT_SMALL_MAX && !(getenv("SGBPO_OPT_SMALL") && getenv("SGBPO_OPT_SMALL")[0] == '0')) {
+    if (step_dtype == SGBPO_F32)
+      clip_adam_small_kernel<T, float><<<1, OPT_SMALL_THREADS, 0, st>>>(a, o->lr, o->beta1, o->beta2, o->eps, o->max_norm, (T*)total_norm_out);
+    else
+      clip_adam_small_kernel<T, double><<<1, OPT_SMALL_THREADS, 0, st>>>(a, o->lr, o->beta1, o->beta2, o->eps, o->max_norm, (T*)total_norm_out);
+    const cudaError_t e1 = cudaGetLastError();
+    if (e1 != cudaSuccess) {
+      snprintf(g_err, sizeof(g_err), "clip_adam_small_kernel: %s", cudaGetErrorString(e1));
+      return SGBPO_E_CUDA;
+    }
+    return SGBPO_OK;
   }
   int64_t grid = (total + 4 * OPT_THREADS - 1) / (4 * OPT_THREADS);
   grid = grid < 1 ? 1 : (grid > OPT_MAX_CTAS ? OPT_MAX_CTAS : grid);

@@ -165,7 +165,7 @@ class FusedRollout:
 
     @property
     def launches_per_episode(self) -> int:
-        return (11 if self.engine_bwd else 8) + (1 if self._native_inputs() else 0)
+        return (10 if self.engine_bwd else 7) + (1 if self._native_inputs() else 0)     # (clip + Adam: one launch for small policies)
 
     TC_FORWARD_MIN_ENVS = 12288       # measured cross-over of the warp-MMA and tcgen05 forward kernels on one B200 (profiles/r2_engines.md)
 
