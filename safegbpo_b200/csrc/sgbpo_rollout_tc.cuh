@@ -910,6 +910,14 @@ struct ScanArgs {
   float* g_b_out;  float* g_log_std;       // [NA] accumulated (atomics)
 };
 
+constexpr int SCAN_STAGES = 4;
+template <int ENV> struct ScanRing {       // words per thread and stage: the step's Jacobian row + policy Jacobian, pitch = 4 (mod 32)
+  static constexpr int NOP = (Task<ENV>::NO + 3) & ~3;
+  static constexpr int WORDS = JacShape<ENV>::STRIDE + Task<ENV>::NA * NOP + 4 * ((2 * Task<ENV>::NA + 3) / 4);   // + actions, eps
+  static constexpr int PITCH = WORDS + ((4 - WORDS % 32) + 32) % 32;
+  static size_t bytes(int block) { return (size_t)SCAN_STAGES * block * PITCH * 4; }
+};
+
 template <int ENV>
 __global__ void __launch_bounds__(128)
 rollout_scan_kernel(const __grid_constant__ ScanArgs A) {
@@ -926,38 +934,86 @@ rollout_scan_kernel(const __grid_constant__ ScanArgs A) {
   for (int i = 0; i < NO; ++i) gobs[i] = 0.f;
 #pragma unroll
   for (int q = 0; q < NA; ++q) { sb[q] = 0.f; sl[q] = 0.f; sigma[q] = expf(A.log_std[q]); }
-  // the loads of step t - 1 do not depend on the recursion: they are issued before step t's arithmetic (two register buffers,
-  // the time loop unrolled by two so that both are statically indexed)
-  struct StepIn { float4 rec[JS::STRIDE / 4]; float4 pj[NA * NOP / 4]; float act[NA], eps[NA], term[NO], gr; };
-  auto fetch = [&](int t, StepIn& in) {
-    const size_t row = (size_t)t * A.N + e;
-    const float4* src = reinterpret_cast<const float4*>(A.jac + row * JS::STRIDE);
+  // The rows of the recursion do not depend on it: they stream through a SCAN_STAGES-deep ring in shared memory (cp.async), so the
+  // loads of step t - SCAN_STAGES are in flight while step t computes -- one step of arithmetic (~150 instructions) does not cover
+  // an L2 round trip, four do.  The 32 rows of a warp are contiguous in HBM, so the lanes copy them COOPERATIVELY (lane l takes the
+  // 16-byte chunks l, l + 32, ... of the block: 512 contiguous bytes per instruction instead of 32 different lines) into the
+  // per-thread slots; a __syncwarp orders the copies against the owner's reads.  The slot pitch is 4 (mod 32) words: a quarter
+  // warp's 16-byte reads touch all 32 banks once.
+  constexpr int REC4 = JS::STRIDE / 4, PJ4 = NA * NOP / 4, P4 = ScanRing<ENV>::PITCH / 4;
+  extern __shared__ float4 scan_ring[];
+  float4* mine = scan_ring + (size_t)threadIdx.x * P4;
+  const size_t stage_stride = (size_t)blockDim.x * P4;
+  const int lane = threadIdx.x & 31;
+  const int64_t env0 = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31);          // first environment of this warp
+  const uint32_t warp_ring = smem_u32(scan_ring + (size_t)(threadIdx.x & ~31) * P4);
+  auto issue = [&](int t, int stage) {
+    if (t >= 0) {
+      const size_t row = (size_t)t * A.N + e;
+      const float4* src = reinterpret_cast<const float4*>(A.jac + ((size_t)t * A.N + env0) * JS::STRIDE);
+      const float4* ps = reinterpret_cast<const float4*>(A.pol_jac + ((size_t)t * A.N + env0) * (NA * NOP));
+      const uint32_t wdst = warp_ring + (uint32_t)(stage * stage_stride * 16);
+      const uint32_t dst = smem_u32(mine + stage * stage_stride);
 #pragma unroll
-    for (int i = 0; i < JS::STRIDE / 4; ++i) in.rec[i] = src[i];
-    const float4* ps = reinterpret_cast<const float4*>(A.pol_jac + row * (NA * NOP));
+      for (int i = 0; i < REC4; ++i) {
+        const int c = i * 32 + lane, th = c / REC4, off = c % REC4;
+        if (env0 + th < A.N)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(wdst + (uint32_t)(th * P4 + off) * 16), "l"(src + c) : "memory");
+      }
 #pragma unroll
-    for (int i = 0; i < NA * NOP / 4; ++i) in.pj[i] = ps[i];
+      for (int i = 0; i < PJ4; ++i) {
+        const int c = i * 32 + lane, th = c / PJ4, off = c % PJ4;
+        if (env0 + th < A.N)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(wdst + (uint32_t)(th * P4 + REC4 + off) * 16), "l"(ps + c) : "memory");
+      }
 #pragma unroll
-    for (int q = 0; q < NA; ++q) { in.act[q] = A.actions[row * NA + q]; in.eps[q] = A.eps[row * NA + q]; }
+      for (int q = 0; q < NA; ++q) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 16 * (REC4 + PJ4) + 4 * q), "l"(A.actions + row * NA + q) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 16 * (REC4 + PJ4) + 4 * (NA + q)), "l"(A.eps + row * NA + q) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");        // (an empty group keeps the wait count uniform)
+  };
+  // (the per-step scalars shared by all environments -- grw[t], term_of_row[t + 1] -- are L1 hits after the first touch of their
+  // line; the terminal-value gradient rows are read where a terminal row occurs, once or twice per horizon)
+  struct Small { float act[NA], eps[NA], term[NO], gr; };
+  auto fetch_small = [&](int t, Small& in) {
     const int kt = A.term_of_row ? A.term_of_row[t + 1] : -1;
 #pragma unroll
     for (int i = 0; i < NO; ++i) in.term[i] = kt >= 0 ? A.gobs_term[((size_t)kt * A.N + e) * A.in_dim + i] : 0.f;
     in.gr = A.grw[t];
   };
-  auto step = [&](int t, const StepIn& in) {
+#pragma unroll
+  for (int sidx = 0; sidx < SCAN_STAGES; ++sidx) issue(A.H - 1 - sidx, sidx);
+  Small cur, nxt;
+  fetch_small(A.H - 1, cur);
+  int stage = 0;
+  for (int t = A.H - 1; t >= 0; --t) {
+    if (t > 0) fetch_small(t - 1, nxt);
+    asm volatile("cp.async.wait_group %0;" ::"n"(SCAN_STAGES - 1) : "memory");
+    __syncwarp();                            // every lane's share of this stage has landed
     const size_t row = (size_t)t * A.N + e;
     float rec[JS::STRIDE], pj[NA * NOP];
+    const float4* in4 = mine + stage * stage_stride;
 #pragma unroll
-    for (int i = 0; i < JS::STRIDE / 4; ++i) { rec[4 * i] = in.rec[i].x; rec[4 * i + 1] = in.rec[i].y; rec[4 * i + 2] = in.rec[i].z; rec[4 * i + 3] = in.rec[i].w; }
+    for (int i = 0; i < REC4; ++i) { const float4 v = in4[i]; rec[4 * i] = v.x; rec[4 * i + 1] = v.y; rec[4 * i + 2] = v.z; rec[4 * i + 3] = v.w; }
 #pragma unroll
-    for (int i = 0; i < NA * NOP / 4; ++i) { pj[4 * i] = in.pj[i].x; pj[4 * i + 1] = in.pj[i].y; pj[4 * i + 2] = in.pj[i].z; pj[4 * i + 3] = in.pj[i].w; }
+    for (int i = 0; i < PJ4; ++i) { const float4 v = in4[REC4 + i]; pj[4 * i] = v.x; pj[4 * i + 1] = v.y; pj[4 * i + 2] = v.z; pj[4 * i + 3] = v.w; }
+    {
+      const float* sc = reinterpret_cast<const float*>(in4 + REC4 + PJ4);
+#pragma unroll
+      for (int q = 0; q < NA; ++q) { cur.act[q] = sc[q]; cur.eps[q] = sc[NA + q]; }
+    }
+    __syncwarp();                            // every lane holds its row in registers before any lane refills the slots
+    issue(t - SCAN_STAGES, stage);
+    stage = stage + 1 == SCAN_STAGES ? 0 : stage + 1;
     float go[NO];
 #pragma unroll
-    for (int i = 0; i < NO; ++i) go[i] = gobs[i] + in.term[i];
+    for (int i = 0; i < NO; ++i) go[i] = gobs[i] + cur.term[i];
     float v[KD];
 #pragma unroll
     for (int d = 0; d < KD; ++d) {
-      float x = in.gr * rec[(NS + NO) * KD + d];
+      float x = cur.gr * rec[(NS + NO) * KD + d];
 #pragma unroll
       for (int i = 0; i < NS; ++i) x = fmaf(gs[i], rec[i * KD + d], x);
 #pragma unroll
@@ -970,37 +1026,16 @@ rollout_scan_kernel(const __grid_constant__ ScanArgs A) {
     for (int i = 0; i < NO; ++i) gobs[i] = 0.f;
 #pragma unroll
     for (int q = 0; q < NA; ++q) {
-      const float ga_pre = valid ? v[NS + q] * (1.f - in.act[q] * in.act[q]) : 0.f;      // d loss / d (mu + sigma eps)
+      const float ga_pre = valid ? v[NS + q] * (1.f - cur.act[q] * cur.act[q]) : 0.f;      // d loss / d (mu + sigma eps)
       if (valid) A.dmu[row * NA + q] = ga_pre;
       sb[q] += ga_pre;
-      sl[q] += ga_pre * in.eps[q] * sigma[q];
+      sl[q] += ga_pre * cur.eps[q] * sigma[q];
 #pragma unroll
       for (int i = 0; i < NO; ++i) gobs[i] = fmaf(pj[q * NOP + i], ga_pre, gobs[i]);
     }
-  };
-  // ... and the rows of steps t - 4, t - 5 are pulled into L2 meanwhile (the Jacobian-mode kernel that ran in between has evicted
-  // what rollout_jac_kernel wrote), so the register loads one step ahead see L2 latency, which one step of arithmetic covers
-  auto prefetch_l2 = [&](int t) {
-    if (t < 0) return;
-    const size_t row = (size_t)t * A.N + e;
-    const char* p = reinterpret_cast<const char*>(A.jac + row * JS::STRIDE);
-#pragma unroll
-    for (int o = 0; o < JS::STRIDE * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(A.pol_jac + row * (NA * NOP)));
-  };
-  StepIn bufa, bufb;
-  for (int t = A.H - 2; t >= A.H - 5; --t) prefetch_l2(t);
-  fetch(A.H - 1, bufa);
-  for (int t = A.H - 1; t >= 0; t -= 2) {
-    prefetch_l2(t - 5);
-    prefetch_l2(t - 6);
-    if (t > 0) fetch(t - 1, bufb);
-    step(t, bufa);
-    if (t > 0) {
-      if (t > 1) fetch(t - 2, bufa);
-      step(t - 1, bufb);
-    }
+    cur = nxt;
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
   for (int q = 0; q < NA; ++q) {
     float b = sb[q], l = sl[q];
@@ -1107,8 +1142,14 @@ template <int ENV> int rollout_tc_bwd(const sgbpo_mlp* pol, const sgbpo_rollout*
     S.jac = (const float*)r->jac; S.pol_jac = (const float*)r->pol_jac; S.actions = (const float*)r->actions; S.eps = (const float*)r->eps;
     S.grw = (const float*)g->grw; S.gobs_term = (const float*)g->gobs_term; S.term_of_row = g->term_of_row;
     S.log_std = p.log_std; S.dmu = (float*)r->dmu; S.g_b_out = (float*)g->g_b_out; S.g_log_std = (float*)g->g_log_std;
-    const int block = r->N >= 148 * 128 ? 128 : 32;
-    rollout_scan_kernel<ENV><<<(int)((r->N + block - 1) / block), block, 0, st>>>(S);
+    int block = r->N >= 148 * 128 ? 128 : 32;
+    while (block > 32 && ScanRing<ENV>::bytes(block) > 200 * 1024) block >>= 1;
+    const size_t ring = ScanRing<ENV>::bytes(block);
+    if (ring > 48 * 1024) {
+      const cudaError_t ea = cudaFuncSetAttribute(rollout_scan_kernel<ENV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
+      if (ea != cudaSuccess) return cuda_fail2(ea, "cudaFuncSetAttribute(rollout_scan)");
+    }
+    rollout_scan_kernel<ENV><<<(int)((r->N + block - 1) / block), block, ring, st>>>(S);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail2(e, "rollout_scan_kernel");
   }
