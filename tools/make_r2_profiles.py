@@ -117,12 +117,13 @@ bench value: ncu serialises launches and replays each kernel; the live per-kerne
   228 MB written (the two ELU stashes, 1 KB per env-step, in the reverse pass's tile layout) = 11x the 20.9 MB of algorithmic bytes, on
   purpose (HBM is 6 % busy).
 * **Reverse pass, 4096 envs**: Jacobian-mode `policy_rows_bwd_kernel` 103 us (first round-2 version: 163 us), gradient mode 238 us
-  (351 us), scan 54 us.  With the stash in 128-row tiles of 16-byte chunks the `lg_throttle` stall is gone (2.0 -> < 0.3) and
+  (351 us), scan 35 us (55 us before its rows streamed through a cooperative cp.async ring).  With the stash in 128-row tiles of 16-byte chunks the `lg_throttle` stall is gone (2.0 -> < 0.3) and
   `long_scoreboard` fell from 3.6 to 2.6 (gradient mode) / 2.2 to 1.6 (Jacobian mode); issue rate 0.29 -> 0.43 / 0.34 -> 0.52.  The
   gradient kernel is now bound by its instruction count (106 M warp instructions: the four column-sum transposes through shared memory are
   35 % of them) and the MMA round trip (`mbar_wait` 8 % of samples).  DRAM traffic = the stash read once per mode (273 / 281 MB).  The scan
-  (one thread per environment, 64 sequential steps) is pure latency: 0.11 issue slots, `long_scoreboard` 6.6 even with its rows
-  prefetched into L2 -- one step of arithmetic does not cover an L2 round trip; a shared-memory ring of 3-4 steps (cp.async) is the fix.
+  (one thread per environment, 64 sequential steps) is pure latency; what made it slow was not the depth of its prefetch but the shape
+  of its loads: every thread read its own 240-byte row, i.e. each load instruction of a warp touched 32 different lines.  Now the warp
+  fills a 4-stage shared-memory ring cooperatively (512 contiguous bytes per cp.async instruction).
 * **65 536 envs** (`r2_full_64k`): tcgen05 forward 2.46 ms writing 4.5 GB of stash (1.8 TB/s), Jacobian mode 1.44 ms reading 4.36 GB
   (3.0 TB/s = 46 % of the measured HBM peak), gradient mode 3.18 ms (1.4 TB/s), critic 1.85 ms, scan 0.30 ms (5.5 TB/s of Jacobian
   rows: HBM-bound there).  At this size the row-batched kernels are the episode (reverse 47 %, critic 18 %) and the Jacobian mode is
@@ -192,6 +193,7 @@ Round 1 (FMA forward, sequential FMA reverse): 133 M env-steps/s at 4096 envs, 2
 | angle wrap without sin / cos / atan2 | 1.11 | 0.41 | 0.42 |
 | gate without sqrt / divisions, one reciprocal per interval row | 1.05 | 0.35 | 0.42 |
 | hardware-exponential ELU in the critic, L2 prefetches, one-launch clip + Adam | 1.02 | 0.35 | 0.41 |
+| scan rows through a cooperative cp.async ring | 1.00 | 0.35 | 0.39 |
 
 Column split 8 instead of 4 in the row-batched kernels (`SGBPO_ROWS_BWD_SPLIT=8`) was measured slower (gradient mode 0.416 vs 0.351 ms
 with the row-major stash) and stays off.
