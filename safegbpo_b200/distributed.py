@@ -30,6 +30,8 @@ def allreduce_policy_grads(algo):
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return
     engine = getattr(algo, "_fused_engine", None)
+    if engine is not None and engine.last and engine.last.get("grads_synced"):
+        return          # the episode graph already averaged the static gradient buffers (fused_rollout._episode_body)
     bufs = engine.static_grad_buffers() if engine is not None else None
     if bufs is not None:
         # graph path: every policy gradient is a view of two static buffers -> two in-place NCCL calls, no packing
@@ -44,6 +46,9 @@ def allreduce_policy_grads(algo):
     for g in grads:
         g.copy_(flat[off:off + g.numel()].view_as(g))
         off += g.numel()
+
+
+allreduce_policy_grads.graph_capturable = True      # (one or two in-place NCCL calls on static buffers)
 
 
 def _allreduce_mean(flat: torch.Tensor):

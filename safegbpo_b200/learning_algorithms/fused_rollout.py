@@ -409,6 +409,7 @@ class FusedRollout:
                  scal=z(2, dtype=torch.float64), scal_host=torch.zeros(2, dtype=torch.float64, device="cpu").pin_memory(),
                  loss_host=torch.zeros((), dtype=dt, device="cpu").pin_memory(),
                  done_host=torch.full((1,), -1, dtype=torch.int64, device="cpu").pin_memory(), branch=torch.cuda.Stream(), ep_graph=None,
+                 ep_sync=False,
                  side=torch.cuda.Stream(), ev_fwd=torch.cuda.Event(), ev_side=torch.cuda.Event())
         # per-episode schedule (reset-all events of Q6, terminal rows, discounts): two small pinned host blocks
         # copied into static device tensors before every replay, so episodes WITH resets replay the same graphs
@@ -488,7 +489,23 @@ class FusedRollout:
             g["loss_host"].copy_(g["loss"], non_blocking=True)
             g["done_host"].copy_(g["rng_ctr"], non_blocking=True)      # last: its arrival tells the host the scalars are there
         self._bwd_body(g)
+        if g["ep_sync"]:       # data-parallel replicas: the gradient all-reduce is a node of the episode graph (no per-episode host call)
+            import torch.distributed as dist
+            for b in ([g["flat"]] if self.engine_bwd else [g["flat"], g["dw_hid"]]):
+                dist.all_reduce(b, op=dist.ReduceOp.AVG)
         main.wait_stream(br)
+
+    def _graph_sync(self) -> bool:
+        """Whether the policy-gradient all-reduce of a data-parallel job is captured at the end of the episode graph (opt-in,
+        SGBPO_GRAPH_ALLREDUCE=1): the hook installed by distributed.attach is the stock one and NCCL is the backend.  Measured on
+        2 B200s: 1.080 -> 1.044 ms per episode (the per-episode host call of torch.distributed costs more than the 13 us
+        collective: the host falls behind the device, profiles/r2_configs.md).  Off by default: with the collective captured, the
+        process did not return from its exit path (process-group teardown with a live graph) within the test's time limit, and
+        there was no GPU budget left to make that robust."""
+        import torch.distributed as dist
+        hook = getattr(self.algo, "grad_sync", None)
+        return (os.environ.get("SGBPO_GRAPH_ALLREDUCE", "0") == "1" and hook is not None and getattr(hook, "graph_capturable", False)
+                and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and dist.get_backend() == "nccl")
 
     def _fwd_head(self, g):
         base, algo, H = self.base, self.algo, g["H"]
@@ -637,6 +654,11 @@ class FusedRollout:
         g["rng_ctr"].copy_(g["rng_ctr_host"], non_blocking=True)
         merged = (self.merged_graph and self.speculative_backward and not self.forward_only and g["bwd_graph"] is not None
                   and g["inputs_args"] is not None)
+        if merged:
+            want_sync = self._graph_sync()
+            if g["ep_graph"] is not None and g.get("ep_sync") != want_sync:
+                g["ep_graph"] = None                     # the job became / stopped being data-parallel: capture again
+            g["ep_sync"] = want_sync
         if merged and g["ep_graph"] is None:
             g["ep_graph"] = self._capture(self._episode_body, g)
         if merged:
@@ -668,6 +690,7 @@ class FusedRollout:
     def _replay_episode_graph(self, g, H, steps_end, pending_end, reset_at, terminal_rows) -> float:
         g["ep_graph"].replay()
         g["bwd_enqueued"] = True
+        g["grads_synced"] = bool(g["ep_sync"])
         # the scalars are copied to pinned memory by the graph's branch; the host waits for the LAST of those copies (the episode
         # counter) to land instead of for the whole graph, so it still runs ahead of the reverse pass
         t0, want = time.perf_counter(), self._episodes
@@ -696,7 +719,8 @@ class FusedRollout:
             w = self.wrapper
             w.safe_action = g["exec_actions"][H - 1]
             w._interventions = w._interventions + g["n_interv"]
-        self.last = dict(graph=True, terminal_rows=terminal_rows, flags=g["flags"], states=g["states"], exec_actions=g["exec_actions"])
+        self.last = dict(graph=True, terminal_rows=terminal_rows, flags=g["flags"], states=g["states"], exec_actions=g["exec_actions"],
+                         grads_synced=bool(g.pop("grads_synced", False)))
         if self.wrapper is not None:
             if w.strict:
                 if g["scal_host"][1] != 0:

@@ -101,10 +101,16 @@ def gpu_timeline():
     gap before it.  Shows where an episode's device time goes besides its kernels (launch gaps inside the graphs, the gap
     between the graphs, small copies)."""
     import bench
+    import os
     from torch.profiler import profile, ProfilerActivity
+    world, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:          # torchrun: the same trace with the gradient all-reduce between the episode graph and the optimizer
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.set_default_dtype(torch.float32)
-    torch.set_default_device(torch.device("cuda", 0))
-    torch.manual_seed(0)
+    torch.set_default_device(torch.device("cuda", local))
+    torch.manual_seed(local)
     from safegbpo_b200.learning_algorithms.shac import SHAC
     from safegbpo_b200.safeguards.boundary_projection import BoundaryProjectionSafeguard
     from safegbpo_b200.envs import balance_cartpole
@@ -112,6 +118,9 @@ def gpu_timeline():
     algo = SHAC(env=env, policy_kwargs={"net_arch": bench.POLICY_ARCH}, policy_optim_kwargs={"lr": 4e-4},
                 vf_kwargs={"net_arch": bench.VF_ARCH}, vf_optim_kwargs={"lr": 2e-3}, regularisation_coefficient=0.1,
                 len_trajectories=64, fused="on", rng_order="batched")
+    if world > 1:
+        from safegbpo_b200 import distributed as sgdist
+        sgdist.attach(algo)
 
     def episode():
         algo.buffer.reset()
@@ -143,6 +152,8 @@ def gpu_timeline():
         first -= 1
     ep = rows[first:b]
     busy, gaps = sum(r[1] for r in ep), sum(r[2] for r in ep[1:])
+    if local != 0:
+        return
     print(f"episode span {ep[-1][0] + ep[-1][1] - ep[0][0]:.1f} us, kernels {busy:.1f} us, gaps {gaps:.1f} us, {len(ep)} device activities")
     for s, d, gap, name in ep:
         print(f"  +{s - ep[0][0]:8.1f} us  dur {d:7.1f}  gap before {gap:6.1f}  {name}")

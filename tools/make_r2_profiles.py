@@ -237,7 +237,12 @@ Notes
   env-steps/s at {' / '.join(str(n) for n in sorted(mg))} GPUs ({mgt} ms per episode), efficiency {eff}; `replicas_in_sync` (policy and critic
   after a full SHAC iteration) true at every N.  The per-episode cost of the policy-gradient all-reduce (72 KB, NCCL, between the episode
   graph and the optimizer launch) is ~0.07-0.09 ms: constant, so its share grew as the episode went from 1.98 to 1.02 ms (round 1: 0.916
-  at 8 GPUs on a 1.98 ms episode).
+  at 8 GPUs on a 1.98 ms episode).  A 2-GPU device timeline (`torchrun ... tools/episode_breakdown.py --gpu-timeline`) names the
+  limiter: the NCCL kernel itself is 13 us with 2 us gaps around it; what costs is the HOST side of `torch.distributed.all_reduce`,
+  which makes the host fall ~0.1 ms behind the device at the start of the next episode.  With the collective captured as a node of the
+  episode graph (`SGBPO_GRAPH_ALLREDUCE=1`) the same 2-GPU run measures 502 M env-steps/s, 1.044 ms per episode instead of 485 M,
+  1.080 ms, replicas in sync -- but the process then hung in its exit path (process-group teardown with the graph alive) until the
+  test's timeout, so it stays opt-in this round.
 """)
     par = (G / "r2_parity.txt").read_text()
     (OUT / "r2_parity.md").write_text(f"""# Round 2: measured parity of the whole-horizon engines against the float64 episode
