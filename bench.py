@@ -223,7 +223,43 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
 
+    def _nvml_loop(self) -> bool:
+        """The counters nvidia-smi prints, read in-process through NVML (nvidia_ml_py): spawning nvidia-smi every 50 ms enumerates
+        every GPU of the box and takes driver locks, which stalls rank 0's launches -- and, through the gradient all-reduce, every
+        other rank's timed episode -- for milliseconds.  Returns False when NVML is not usable (then nvidia-smi is polled)."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            handle = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            return False
+        self.source = "nvml"
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)))
+                get = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+                mask = int(get(handle))
+                for name, bit in bits.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+        return True
+
     def run(self):
+        self.source = "nvidia-smi"
+        if self._nvml_loop():
+            return
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -242,7 +278,8 @@ class ClockSampler(threading.Thread):
 
     def summary(self):
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "source": getattr(self, "source", "nvidia-smi")}
 
 
 def run_ours(args):

@@ -274,6 +274,10 @@ class FusedRollout:
         (simulator.py:100-106), which buffer rows are terminal, and the shared step counter per step."""
         base = self.base
         pending, steps = base._reset_pending, base.steps
+        key = (bool(pending), int(steps), H, int(base.num_steps))
+        cached = self.__dict__.get("_sched_cache")
+        if cached is not None and cached[0] == key:          # (host time per episode matters: the lists are read-only downstream)
+            return cached[1]
         reset_at, terminal_rows, pre_steps, post_steps = [], [False] * (H + 2), [], []
         for t in range(H):
             pre_steps.append(steps)               # household: T_out index used by execute_action (household.py:176)
@@ -285,7 +289,9 @@ class FusedRollout:
             pending = steps >= base.num_steps
             terminal_rows[t + 1] = pending
         terminal_rows[H] = True
-        return reset_at, terminal_rows, pre_steps, post_steps, pending, steps
+        out = (reset_at, terminal_rows, pre_steps, post_steps, pending, steps)
+        self.__dict__["_sched_cache"] = (key, out)
+        return out
 
     def _max_resets(self, H: int) -> int:
         """Upper bound on reset-all events inside one horizon (a reset follows every num_steps steps)."""
