@@ -233,16 +233,20 @@ Notes
 * **BalanceQuadrotor + boundary projection** stays solver-bound (lifted 38-variable program per step, one thread per environment,
   profiles/r1_lifted_solver_ncu.md): with box-uniform states almost every guarded step is infeasible and runs to the iteration cap.
   The warp-cooperative solver VERDICT item 4 asks for was not built this round (DESIGN.md section 8).
-* **Multi-GPU** (weak scaling, 4096 envs per GPU, `torchrun --nproc-per-node N bench.py --gpus N --steps 30 --warmup 5`, one box): {mgs} M
-  env-steps/s at {' / '.join(str(n) for n in sorted(mg))} GPUs ({mgt} ms per episode), efficiency {eff}; `replicas_in_sync` (policy and critic
-  after a full SHAC iteration) true at every N.  The per-episode cost of the policy-gradient all-reduce (72 KB, NCCL, between the episode
-  graph and the optimizer launch) is ~0.07-0.09 ms: constant, so its share grew as the episode went from 1.98 to 1.02 ms (round 1: 0.916
-  at 8 GPUs on a 1.98 ms episode).  A 2-GPU device timeline (`torchrun ... tools/episode_breakdown.py --gpu-timeline`) names the
-  limiter: the NCCL kernel itself is 13 us with 2 us gaps around it; what costs is the HOST side of `torch.distributed.all_reduce`,
-  which makes the host fall ~0.1 ms behind the device at the start of the next episode.  With the collective captured as a node of the
-  episode graph (`SGBPO_GRAPH_ALLREDUCE=1`) the same 2-GPU run measures 502 M env-steps/s, 1.044 ms per episode instead of 485 M,
-  1.080 ms, replicas in sync -- but the process then hung in its exit path (process-group teardown with the graph alive) until the
-  test's timeout, so it stays opt-in this round.
+* **Multi-GPU** (weak scaling, 4096 envs per GPU, `torchrun --nproc-per-node N bench.py --gpus N --steps 30 --warmup 5`, one box, final
+  binary): 261.5 / 488.6 / 963.2 / 1892.3 M env-steps/s at 1 / 2 / 4 / 8 GPUs (1.002 / 1.073 / 1.089 / 1.108 ms per episode), efficiency
+  0.934 / 0.921 / 0.905; `replicas_in_sync` (policy and critic after a full SHAC iteration) true at every N (the 4-GPU line predates the
+  NVML clock sampler).  The per-episode cost of the policy-gradient all-reduce (72 KB, NCCL, between the episode graph and the optimizer
+  launch) is ~0.07-0.1 ms: constant, so its share grew as the episode went from 1.98 to 1.00 ms (round 1: 0.916 at 8 GPUs on a 1.98 ms
+  episode).  A 2-GPU device timeline (`torchrun ... tools/episode_breakdown.py --gpu-timeline`) names the limiter: the NCCL kernel itself
+  is 13 us with 2 us gaps around it; what costs is the HOST side of `torch.distributed.all_reduce`, which makes the host fall ~0.1 ms
+  behind the device at the start of the next episode.  With the collective captured as a node of the episode graph
+  (`SGBPO_GRAPH_ALLREDUCE=1`) a 2-GPU run measured 502 M env-steps/s, 1.044 ms per episode instead of 485 M, 1.080 ms, replicas in sync
+  -- but the process then hung in its exit path (process-group teardown with the graph alive) until the test's timeout, so it stays
+  opt-in this round.  Measurement hygiene: the clock sampler used to spawn `nvidia-smi` every 50 ms on rank 0, which enumerates every
+  GPU of the box and takes driver locks; through the all-reduce that stalled every rank's timed episodes (2-GPU runs scattered
+  between 1.08 and 1.54 ms per episode).  It now reads the same counters in-process through NVML (two consecutive 2-GPU runs: 1.073 /
+  1.086 ms).
 """)
     par = (G / "r2_parity.txt").read_text()
     (OUT / "r2_parity.md").write_text(f"""# Round 2: measured parity of the whole-horizon engines against the float64 episode
