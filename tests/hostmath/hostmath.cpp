@@ -142,6 +142,21 @@ int hm_step(int env_id, int dtype, int64_t N, const sgbpo_consts* c, const sgbpo
   return dtype ? step_t<double>(env_id, N, c, sh, s, a, w, aux, dirs, rs, s_next, a_exec, obs, reward, flags, g_s_next, g_a_exec, g_obs, g_reward, gs, ga)
                : step_t<float>(env_id, N, c, sh, s, a, w, aux, dirs, rs, s_next, a_exec, obs, reward, flags, g_s_next, g_a_exec, g_obs, g_reward, gs, ga);
 }
+// wrap_angle (sgbpo_dual.cuh): value and derivative (one dual direction) of n angles
+int hm_wrap_angle(int dtype, int64_t n, const void* x, void* y, void* dy) {
+  for (int64_t i = 0; i < n; ++i) {
+    if (dtype) {
+      Dual<double, 1> d = Dual<double, 1>::seed(((const double*)x)[i], 0);
+      const Dual<double, 1> r = wrap_angle(d);
+      ((double*)y)[i] = r.v; ((double*)dy)[i] = r.d[0];
+    } else {
+      Dual<float, 1> d = Dual<float, 1>::seed(((const float*)x)[i], 0);
+      const Dual<float, 1> r = wrap_angle(d);
+      ((float*)y)[i] = r.v; ((float*)dy)[i] = r.d[0];
+    }
+  }
+  return 0;
+}
 int hm_linearise(int env_id, int dtype, int64_t N, const sgbpo_consts* c, const void* s, void* cc, void* A, void* B, void* E) {
   return dtype ? lin_t<double>(env_id, N, c, s, cc, A, B, E) : lin_t<float>(env_id, N, c, s, cc, A, B, E);
 }

@@ -72,3 +72,12 @@ def navquad_safe_state_set(consts: Consts, s, aux, dtype=np.float64):
                               _p(gen), _p(status))
     assert rc == 0
     return center, gen, status
+
+
+def wrap_angle(x, dtype=np.float64):
+    """csrc/sgbpo_dual.cuh::wrap_angle on the host: (wrapped value, derivative)."""
+    x = np.ascontiguousarray(x, dtype=dtype)
+    y, dy = np.empty_like(x), np.empty_like(x)
+    lib().hm_wrap_angle.restype = C.c_int
+    lib().hm_wrap_angle(int(dtype == np.float64), C.c_int64(x.size), _p(x), _p(y), _p(dy))
+    return y, dy
