@@ -38,6 +38,23 @@ def test_reference_hand_cases():
     assert np.max(H @ np.array([2.0, 0.0])) <= 1.0 + 1e-12 and np.max(H @ np.array([1.5, 1.0])) > 1.0
 
 
+def test_shared_generator_facets_give_the_zonotope_lp_verdict():
+    """Zonotope program with fixed inner generators: the facets of the LP's feasible region in the centre offset (what DeviceVerdict
+    uploads) decide exactly like the reference's Sadraddini-Tedrake LP (zonotope.py:213-236)."""
+    from safegbpo_b200.consts import merge_parallel_generators, polytope_facets
+    rs = np.random.default_rng(3)
+    for n, p, q in [(2, 4, 2), (3, 5, 3)]:
+        c, G = _rand_zonotope(rs, n, p)
+        Gi = 0.15 * rs.normal(size=(n, q))
+        centers = c + (G @ rs.uniform(-1.25, 1.25, size=(p, 60))).T
+        H = polytope_facets(merge_parallel_generators(G), Gi)
+        value = np.max((centers - c) @ H.T, axis=1)
+        want = np.array([osets.zonotope_in_zonotope_norm(ci, Gi, c, G) for ci in centers])
+        clear = np.abs(want - 1.0) > 1e-7
+        assert np.array_equal((value <= 1.0)[clear], (want <= 1.0)[clear]), (n, p, q)
+        assert 0.05 < (want <= 1.0).mean() < 0.99
+
+
 @pytest.fixture
 def dev():
     if not torch.cuda.is_available():
