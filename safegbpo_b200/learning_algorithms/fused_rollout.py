@@ -1,14 +1,16 @@
 """Whole-horizon fused engine behind ``SHAC.collect_trajectories`` / ``SHAC.update_policy``.
 
 Host side of csrc/sgbpo_rollout*.cu: resolves the episode schedule (reset-all of Q6, terminal rows,
-household series), draws the random inputs in the reference's order, launches
+household series), draws the random inputs (the reference's order, or one Philox launch), launches
 
-    sgbpo_rollout_fwd  ->  sgbpo_mlp_rows (target critic over all rows)          [collect_trajectories]
-    (critic input-gradient on the terminal rows) -> sgbpo_rollout_bwd -> one GEMM   [update_policy backward]
+    [sgbpo_episode_inputs] -> sgbpo_rollout_fwd -> sgbpo_mlp_rows (target critic over all rows)
+                           -> sgbpo_episode_stats -> sgbpo_shac_loss                                  [collect_trajectories]
+    sgbpo_rollout_jac -> sgbpo_mlp_rows_vjp (terminal rows) -> sgbpo_rollout_bwd                      [update_policy backward]
 
-and maps the results back onto the reference's objects (CoupledBuffer tensors, ``policy.*.grad``).
-Everything numeric runs in libsgbpo.so except two plain library calls: the critic's input gradient on the
-K terminal rows (torch autograd on N x o inputs) and dW_hid = h1^T dz2 (cuBLAS through torch.matmul).
+and maps the results back onto the reference's objects (CoupledBuffer tensors, ``policy.*.grad``).  Episodes whose schedule allows
+it are replayed as CUDA graphs (two per episode, then one with the critic branch forked beside the reverse pass).  Everything
+numeric runs in libsgbpo.so; with the sequential reverse engine (float64, other widths) two plain library calls remain: the
+critic's input gradient where the network does not fit the kernel, and dW_hid = h1^T dz2 (cuBLAS through torch.matmul).
 """
 from __future__ import annotations
 
@@ -142,9 +144,9 @@ class FusedRollout:
         self._grad_bufs = None
         self.last = None
         # Engines (include/sgbpo.h, sgbpo_rollout.engine): forward 0 = FMA register tiles, 1 = tcgen05 kernel (one CTA per 128
-        # environments: wins once there are more 128-environment tiles than SMs can hide latency for); reverse 0 = sequential
-        # FMA kernel, 1 = parallel tensor-core reverse pass.  SGBPO_ROLLOUT_ENGINE = 0 | 1 | 2 forces (fwd, reverse) =
-        # (0, 0) | (1, 1) | (0, 1) for A/B measurements and tests.
+        # environments: wins once those tiles fill the GPU), 2 = warp-MMA kernel (8 environments per warp / pair of warps: wins
+        # below that); reverse 0 = sequential FMA kernel, 1 = parallel tensor-core reverse pass.  SGBPO_ROLLOUT_ENGINE =
+        # 0 | 1 | 2 | 3 forces (fwd, reverse) = (0, 0) | (1, 1) | (0, 1) | (2, 1) for A/B measurements and tests.
         self.engine_fwd, self.engine_bwd = self.pick_engine(self.base, self.policy_pack)
         self.engine = {0: 0, 1: 1, 2: 4}[self.engine_fwd] | (self.engine_bwd << 1)       # sgbpo_rollout.engine bits
         lib = _lib.lib()
